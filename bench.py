@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""Benchmark of the HiDeNN-FEM quadrature hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dtype f64|f32]
+
+A "step" = one evaluation of EnergyLoss2D (domain + Neumann edges) forward AND backward
+(r-adaptive: gradients w.r.t. nodal values and nodal coordinates) over the whole mesh, through the
+drop-in Python API with the reference's own loop body (zero_grad -> loss_fn(model) -> backward).
+Workload C4: 2x1 plate with three holes, >= 10 M unstructured triangles per GPU
+(jittered nodes, hashed diagonals), gauss_order=4 (ng=4), FP64.  N>1: the global plate has N x 10 M
+elements split into column strips (contiguous element blocks + halo nodes), one packed all-reduce
+per step ("weak" scaling).
+
+Prints ONE JSON line (rank 0).  metric = element-quadrature evals/s = Ne*ng/t_step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+NG = 4
+METRIC = "element-quadrature evals/s (fwd+bwd)"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--elems", type=int, default=10_000_000, help="elements per GPU")
+    ap.add_argument("--ordering", default="morton", choices=["natural", "morton", "random"])
+    ap.add_argument("--tile-nodes", type=int, default=0)
+    ap.add_argument("--cpu-sample-elems", type=int, default=1_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extra", action="store_true", help="also time the random-ordering and FP32 variants (N=1)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:       # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.join(timeout=1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# ------------------------------------------------------------------------------------------------
+def balanced_splits(nx, ny, world, holes, length=2.0, height=1.0):
+    """Column split points giving every rank about the same number of kept elements."""
+    if world == 1:
+        return [0, nx - 1]
+    hx, hy = length / (nx - 1), height / (ny - 1)
+    y = np.arange(ny) * hy
+    cnt = np.zeros(nx - 1, np.int64)
+    prev = None
+    for ix in range(nx):
+        x = ix * hx
+        ins = np.zeros(ny, bool)
+        for (cx, cy, r) in holes:
+            ins |= (x - cx) ** 2 + (y - cy) ** 2 <= r * r
+        if prev is not None:
+            bad = prev[:-1] | prev[1:] | ins[:-1] | ins[1:]      # cell touches an inside node -> at most 2 elements lost
+            cnt[ix - 1] = 2 * (ny - 1) - 2 * int(bad.sum())
+        prev = ins
+    cum = np.concatenate([[0], np.cumsum(cnt)])
+    splits = [0]
+    for r in range(1, world):
+        splits.append(int(np.searchsorted(cum, cum[-1] * r / world)))
+    splits.append(nx - 1)
+    return splits
+
+
+def make_workload(args, rank, world, device, dtype, ordering, n_elems_per_gpu, tile_nodes=0):
+    from hidenn_fem_b200 import meshgen, dist as hd
+    from hidenn_fem_b200.models import PiecewiseLinearShapeNN2D
+    from hidenn_fem_b200.loss import EnergyLoss2D
+    nx, ny = meshgen.plate_dims_for_elements(n_elems_per_gpu * world)
+    splits = balanced_splits(nx, ny, world, meshgen.DEFAULT_HOLES)
+    m = meshgen.plate_mesh(nx, ny, jitter=0.25, diag="random", seed=0, ordering=ordering,
+                           col_range=(splits[rank], splits[rank + 1]))
+    T = torch.tensor
+    torch.manual_seed(0)
+    model = PiecewiseLinearShapeNN2D(T(m.node_coords, dtype=dtype), T(m.connectivity), T(m.boundary_mask),
+                                     T(m.dirichlet_mask), 0.0, T(m.neumann_edges))
+    # u_free = 1e-5*randn as in the reference ctor (models.py:274), seeded per global node so strips agree
+    u0 = 1e-5 * (2.0 * meshgen._hash_u01(np.stack([m.global_node_id * 2, m.global_node_id * 2 + 1], 1) + (1 << 50), 7) - 1.0)
+    with torch.no_grad():
+        model.u_free.copy_(T(u0[~m.dirichlet_mask], dtype=torch.float32))
+    if dtype == torch.float64:
+        model = model.double()
+    model.tile_nodes = tile_nodes
+    model = model.to(device)
+    if world > 1:
+        halo = hd.setup_strip_halo(m, m.boundary_mask, m.dirichlet_mask, device, dtype)
+        loss_fn = hd.DistributedEnergyLoss2D(E=10e9, nu=0.3, length=2.0, height=1.0, device=device, dtype=dtype, halo=halo)
+    else:
+        loss_fn = EnergyLoss2D(E=10e9, nu=0.3, length=2.0, height=1.0, device=device, dtype=dtype)
+    return m, model, loss_fn, (nx, ny)
+
+
+def time_steps(model, loss_fn, steps, warmup, world):
+    import torch.distributed as dist
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        loss = loss_fn(model)
+        loss.backward()
+        return loss
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t.item())
+    return ms / steps, float(loss.item())
+
+
+def time_kernel(model, loss_fn, steps, warmup):
+    """Dominant kernel alone (tile kernel, HIDENN_TILES_ONLY) with CUDA events on the launch stream."""
+    import ctypes as C
+    from hidenn_fem_b200 import _lib
+    plan = model._plan()
+    dt = model.dtype
+    consts = loss_fn._consts(model, None)
+    xb, ub = model._fixed_pair()
+    xf, uf = model.node_coords_free.detach(), model.u_free.detach()
+    gx, gu = torch.empty_like(xf), torch.empty_like(uf)
+    out = torch.empty(4, device=xf.device, dtype=dt)
+    scratch = loss_fn._scratch(plan, xf.device, dt)
+    f = _lib.fn("hidenn_tri_energy", dt)
+    s = _lib.stream_ptr()
+
+    def launch():
+        _lib.check(f(plan.handle, _lib.ptr(xf), _lib.ptr(xb), _lib.ptr(uf), _lib.ptr(ub), _lib.ptr(consts), _lib.ptr(None),
+                     C.c_int(1 | 2 | 4 | 16), _lib.ptr(out), _lib.ptr(gx), _lib.ptr(gu), _lib.ptr(None), _lib.ptr(scratch), s))
+    for _ in range(warmup):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def time_e2e(model, loss_fn, steps, warmup):
+    """Through the C-ABI host-buffer entry point: pinned host parameters in, loss + both gradients out,
+    every step (hidenn_tri_energy_host_*)."""
+    import ctypes as C
+    from hidenn_fem_b200 import _lib
+    plan = model._plan()
+    dt = model.dtype
+    consts = loss_fn._consts(model, None).cpu()
+    xb, ub = model._fixed_pair()
+    xf = model.node_coords_free.detach().cpu().pin_memory()
+    uf = model.u_free.detach().cpu().pin_memory()
+    xb, ub = xb.cpu().pin_memory(), ub.cpu().pin_memory()
+    out = torch.empty(4, dtype=dt).pin_memory()
+    gx, gu = torch.empty_like(xf).pin_memory(), torch.empty_like(uf).pin_memory()
+    f = _lib.fn("hidenn_tri_energy_host", dt)
+    s = _lib.stream_ptr()
+    h2d = (xf.numel() + uf.numel() + xb.numel() + ub.numel() + consts.numel()) * xf.element_size()
+    d2h = (gx.numel() + gu.numel() + 4) * xf.element_size()
+
+    def call():
+        _lib.check(f(plan.handle, _lib.ptr(xf), _lib.ptr(xb), _lib.ptr(uf), _lib.ptr(ub), _lib.ptr(consts), C.c_int(7),
+                     _lib.ptr(out), _lib.ptr(gx), _lib.ptr(gu), s))
+    for _ in range(max(1, min(warmup, 3))):
+        call()
+    torch.cuda.synchronize()
+    n = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        call()          # synchronous: returns when loss and gradients are in host memory
+    t = (time.perf_counter() - t0) / n
+    return t * 1e3, h2d, d2h, float(out[0])
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(n_elems, dtype):
+    """The reference's CPU torch path restated in oracle/torch_port.py, same generator, bounded size."""
+    from hidenn_fem_b200 import meshgen
+    from oracle import torch_port as tp
+    from oracle import closed_form as cf
+    torch.set_num_threads(os.cpu_count() or 1)
+    nx, ny = meshgen.plate_dims_for_elements(n_elems)
+    m = meshgen.plate_mesh(nx, ny, jitter=0.25, diag="random", seed=0, ordering="morton")
+    T = torch.tensor
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    u0 = 1e-5 * (2.0 * meshgen._hash_u01(np.stack([m.global_node_id * 2, m.global_node_id * 2 + 1], 1) + (1 << 50), 7) - 1.0)
+    port = tp.TriPort(T(m.node_coords.astype(npdt)), T(m.connectivity), T(m.boundary_mask), T(m.dirichlet_mask), 0.0,
+                      T(m.neumann_edges), u_free=T(u0[~m.dirichlet_mask].astype(npdt)))
+    xg, wg = cf.triangle_gauss_points(4, npdt)
+    xi1, w1 = cf.interval_gauss_points(2, npdt)
+    Cm = T(cf.plane_stress_C(10e9, 0.3, npdt))
+    xg, wg, xi1, w1 = T(xg), T(wg), T(xi1), T(w1)
+
+    def step():
+        port.x_free.grad = None
+        port.u_free.grad = None
+        loss = tp.tri_energy(port, Cm, xg, wg, xi1, w1)
+        loss.backward()
+        return float(loss.detach())
+    return step, m.connectivity.shape[0]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    step, ne = cpu_reference_step_factory(args.cpu_sample_elems, dtype)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    k = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        step()
+    t = (time.perf_counter() - t0) / k
+    val = ne * NG / t
+    cores = torch.get_num_threads()
+    sample = f"{ne} triangles of the same plate generator (C4 scaled down), 1 step = loss+backward, mean of {k}"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": "C4 2D plate linear elasticity energy+gradient (EnergyLoss2D fwd+bwd, r-adaptive), CPU sample",
+                   "elements": ne, "gauss_points": NG},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    sz = 8 if dtype == torch.float64 else 4
+
+    t0 = time.time()
+    m, model, loss_fn, dims = make_workload(args, rank, world, device, dtype, args.ordering, args.elems, args.tile_nodes)
+    plan = model._plan()
+    setup_s = time.time() - t0
+    ne_local = m.connectivity.shape[0]
+    nn_local = m.node_coords.shape[0]
+
+    sampler = ClockSampler(physical_index(local))
+    sampler.start()
+    ms_step, loss_val = time_steps(model, loss_fn, args.steps, args.warmup, world)
+    clocks = sampler.stop()
+    ms_kernel = time_kernel(model, loss_fn, args.steps, args.warmup)
+
+    ne_tot = torch.tensor([ne_local, nn_local], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ne_tot)
+    ne_total, nn_total = int(ne_tot[0].item()), int(ne_tot[1].item())
+    value = ne_total * NG / (ms_step * 1e-3)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+    # algorithmic bytes of one launch: int32 connectivity + read x,u + write dx,du of the free rows
+    nfree_x, nfree_u = plan.info["n_free_x"], plan.info["n_free_u"]
+    alg_bytes = 12 * ne_local + 2 * sz * (2 * nn_local) + 2 * sz * (nfree_x + nfree_u)
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "tri_tile_kernel<%s>" % ("double" if sz == 8 else "float"),
+                "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
+                "bytes_per_element": alg_bytes / ne_local, "peak_source": peak_src}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            roofline["traffic"] = json.load(open(tpath)).get(args.dtype)
+        except Exception:
+            pass
+
+    e2e = None
+    if not args.no_e2e and world == 1:
+        ms_e2e, h2d, d2h, l_e2e = time_e2e(model, loss_fn, args.steps, args.warmup)
+        e2e = {"value": ne_local * NG / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": ms_e2e, "api": "hidenn_tri_energy_host_%s (pinned host buffers)" % args.dtype,
+               "loss_matches_resident": bool(abs(l_e2e - loss_val) <= 1e-9 * abs(loss_val))}
+    elif world > 1:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "host-buffer entry point measured at N=1 only"}
+
+    extra = {}
+    if args.extra and world == 1:
+        for tag, dt2, ordr in (("f64_random_numbering", torch.float64, "random"), ("f32_morton", torch.float32, "morton"),
+                               ("f64_natural", torch.float64, "natural")):
+            del model, loss_fn
+            torch.cuda.empty_cache()
+            m2, model, loss_fn, _ = make_workload(args, 0, 1, device, dt2, ordr, args.elems, args.tile_nodes)
+            ms2, _ = time_steps(model, loss_fn, args.steps, args.warmup, 1)
+            k2 = time_kernel(model, loss_fn, args.steps, args.warmup)
+            s2 = 8 if dt2 == torch.float64 else 4
+            p2 = model._plan()
+            ab = 12 * m2.connectivity.shape[0] + 2 * s2 * 2 * m2.node_coords.shape[0] + 2 * s2 * (p2.info["n_free_x"] + p2.info["n_free_u"])
+            extra[tag] = {"ms_per_step": ms2, "kernel_ms": k2, "evals_per_s": m2.connectivity.shape[0] * NG / (ms2 * 1e-3),
+                          "roofline_frac": ab / (k2 * 1e-3) / 1e9 / peak}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        step, ne_s = cpu_reference_step_factory(args.cpu_sample_elems, dtype)
+        step()
+        best = 1e30
+        for _ in range(3):
+            t1 = time.perf_counter()
+            step()
+            best = min(best, time.perf_counter() - t1)
+        cpu_baseline = {"value": ne_s * NG / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{ne_s} triangles, same generator, torch-autograd port of the reference path "
+                                  f"(oracle/torch_port.py), 1 warm-up + best of 3, {best * 1e3:.0f} ms/step"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic",
+            "config": {"workload": "C4 examples/example4.py 2D plate linear elasticity, EnergyLoss2D energy+gradient "
+                                   "(fwd+bwd, r-adaptive), unstructured triangles (jitter 0.25, hashed diagonals), gauss_order=4",
+                       "elements_total": ne_total, "nodes_total": nn_total, "elements_per_gpu": ne_local,
+                       "grid_nodes": list(dims), "ordering": args.ordering, "partition": "column strips + halo nodes" if world > 1 else "none",
+                       "l2_policy": "inputs+outputs+plan per launch (> 400 MB) exceed the 126 MB L2; no flush needed",
+                       "tile_nodes": plan.info["max_local"], "n_tiles": plan.info["n_tiles"],
+                       "halo_recompute": plan.info["elem_visits"] / max(1, ne_local), "setup_s": setup_s},
+            "loss": loss_val,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": args.steps * (2 + 2 + (4 if world > 1 else 0)),
+            "gpu_launches_note": "per step: tri_tile_kernel + tri_edge_finalize_kernel + 2 scale_inplace_kernel"
+                                 + (" + 4 halo pack/unpack" if world > 1 else ""),
+        }
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,96 @@
+"""ctypes binding of include/hidenn_b200.h (the C-ABI of the CUDA library).
+
+There is deliberately no fallback: if the shared library is missing, or no CUDA device is
+visible when a compute entry point is needed, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhidenn_b200.so")
+HEADERS = [os.path.join(os.path.dirname(HERE), "include", h) for h in ("hidenn_b200.h", "hidenn_b200_grid.h")]
+
+_lib = None
+
+c_void_p, c_int, c_i64 = C.c_void_p, C.c_int, C.c_int64
+
+
+class HidennError(RuntimeError):
+    pass
+
+
+def declared_symbols():
+    """Every function the public headers declare (used by the CPU export test)."""
+    names = []
+    for h in HEADERS:
+        if not os.path.exists(h):
+            continue
+        txt = open(h).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        names += re.findall(r"\b(hidenn_[a-z0-9_]+)\s*\(", txt)
+    return sorted(set(names))
+
+
+def lib():
+    """Load (building in-tree if sources are newer) and return the ctypes handle."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH) or os.environ.get("HIDENN_REBUILD"):
+        from . import build as _build
+        _build.build()
+    if not os.path.exists(LIB_PATH):
+        raise HidennError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                          "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.hidenn_last_error.restype = C.c_char_p
+    for name in declared_symbols():
+        if name in ("hidenn_last_error", "hidenn_tri_plan_destroy"):
+            continue
+        getattr(L, name).restype = c_int
+    L.hidenn_tri_plan_destroy.restype = None
+    L.hidenn_tri_plan_destroy.argtypes = [c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().hidenn_last_error().decode()
+        raise HidennError(f"{what}: {msg}" if what else msg)
+
+
+def require_cuda():
+    n = lib().hidenn_device_count()
+    if n <= 0:
+        raise HidennError("no CUDA device visible: the HiDeNN B200 path has no CPU fallback "
+                          f"({lib().hidenn_last_error().decode()})")
+    return n
+
+
+def ptr(t):
+    """Raw pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def suffix(dtype):
+    if dtype == torch.float64:
+        return "f64"
+    if dtype == torch.float32:
+        return "f32"
+    raise HidennError(f"unsupported dtype {dtype}: the kernels are FP64 and FP32")
+
+
+def fn(name, dtype):
+    return getattr(lib(), f"{name}_{suffix(dtype)}")

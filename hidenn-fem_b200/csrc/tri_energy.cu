@@ -1,0 +1,417 @@
+// Fused triangle energy forward + backward (sm_100a, FP64 / FP32 CUDA cores; HBM-bound gather/reduce,
+// deliberately no tensor cores).
+//
+// One launch replaces EnergyLoss2D.__call__ + loss.backward() of the reference
+// (/root/reference/src/loss.py:55-116 over /root/reference/src/models.py:292-376):
+//   gather connectivity + nodal coordinates/values (staged in shared memory)
+//   -> shape functions / J / det J / J^-1 / B-matrix -> plane-stress energy density
+//   -> element energy (block reduction, fixed order) and the 12 nodal gradient partials
+//   -> per-tile node->element CSR fold in shared memory (deterministic, no float atomics)
+//   -> coalesced AoS pair stores straight into the Parameter-layout gradient arrays.
+// Per-element formulas: SURVEY.md Appendix A.1 with  d psi/dJ = -(P Jinv)^T G  (DESIGN.md §4).
+#include "../../include/hidenn_b200.h"
+#include "common.cuh"
+#include "tri_plan.h"
+
+namespace hidenn {
+
+constexpr int kTileBlock = 256;
+
+template <typename R> struct TriConsts {
+    R c00, c01, c02, c11, c12, c22, W;
+    R fb[6];
+};
+
+template <typename R>
+__device__ __forceinline__ void tri_element(const typename Real2<R>::type v0, const typename Real2<R>::type v1,
+                                            const typename Real2<R>::type v2, const typename Real2<R>::type U0,
+                                            const typename Real2<R>::type U1, const typename Real2<R>::type U2,
+                                            const TriConsts<R>& K, R& energy, typename Real2<R>::type gu[3],
+                                            typename Real2<R>::type gx[3]) {
+    const R a = v0.x - v2.x, b = v1.x - v2.x, c = v0.y - v2.y, d = v1.y - v2.y;
+    const R det = a * d - b * c;
+    const R inv = rcp(det);
+    const R j00 = d * inv, j01 = -b * inv, j10 = -c * inv, j11 = a * inv;     // J^-1 (reference uses J^-1, not J^-T)
+    const R p0 = U0.x - U2.x, p1 = U1.x - U2.x, q0 = U0.y - U2.y, q1 = U1.y - U2.y;
+    const R G00 = p0 * j00 + p1 * j01, G01 = p0 * j10 + p1 * j11;
+    const R G10 = q0 * j00 + q1 * j01, G11 = q0 * j10 + q1 * j11;
+    const R e0 = G00, e1 = G11, e2 = G01 + G10;
+    const R s0 = K.c00 * e0 + K.c01 * e1 + K.c02 * e2;
+    const R s1 = K.c01 * e0 + K.c11 * e1 + K.c12 * e2;
+    const R s2 = K.c02 * e0 + K.c12 * e1 + K.c22 * e2;
+    const R psi = R(0.5) * (e0 * s0 + e1 * s1 + e2 * s2);
+    const R bw = U0.x * K.fb[0] + U0.y * K.fb[1] + U1.x * K.fb[2] + U1.y * K.fb[3] + U2.x * K.fb[4] + U2.y * K.fb[5];
+    const R dens = K.W * psi - bw;
+    const R A = fabs(det);
+    energy = A * dens;
+    const R M00 = s0 * j00 + s2 * j10, M01 = s0 * j01 + s2 * j11;
+    const R M10 = s2 * j00 + s1 * j10, M11 = s2 * j01 + s1 * j11;
+    const R AW = A * K.W;
+    gu[0] = mk2<R>(AW * M00 - A * K.fb[0], AW * M10 - A * K.fb[1]);
+    gu[1] = mk2<R>(AW * M01 - A * K.fb[2], AW * M11 - A * K.fb[3]);
+    gu[2] = mk2<R>(-AW * (M00 + M01) - A * K.fb[4], -AW * (M10 + M11) - A * K.fb[5]);
+    const R K00 = -(M00 * G00 + M10 * G10), K01 = -(M00 * G01 + M10 * G11);
+    const R K10 = -(M01 * G00 + M11 * G10), K11 = -(M01 * G01 + M11 * G11);
+    const R sd = det < R(0) ? -dens : dens;
+    const R D00 = sd * d + AW * K00, D01 = -sd * c + AW * K01;
+    const R D10 = -sd * b + AW * K10, D11 = sd * a + AW * K11;
+    gx[0] = mk2<R>(D00, D10);
+    gx[1] = mk2<R>(D01, D11);
+    gx[2] = mk2<R>(-(D00 + D01), -(D10 + D11));
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kTileBlock)
+tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ x_free,
+                const typename Real2<R>::type* __restrict__ x_fixed, const typename Real2<R>::type* __restrict__ u_free,
+                const typename Real2<R>::type* __restrict__ u_fixed, const R* __restrict__ consts, const int flags,
+                typename Real2<R>::type* __restrict__ gx_free, typename Real2<R>::type* __restrict__ gu_free,
+                R* __restrict__ tile_energy) {
+    using R2 = typename Real2<R>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TileDesc td = P.tiles[blockIdx.x];
+    R2* s_xy = reinterpret_cast<R2*>(smem_raw);
+    R2* s_uv = s_xy + td.n_local;
+    R2* s_pu = s_uv + td.n_local;
+    R2* s_px = s_pu + td.n_entries;
+    R* s_red = reinterpret_cast<R*>(s_px + td.n_entries);
+    uint16_t* s_off = reinterpret_cast<uint16_t*>(s_red + 8);
+    const int tid = threadIdx.x;
+
+    // phase 1: stage tile nodes (coalesced slot reads, AoS pair gathers) and fold offsets
+    for (int i = tid; i < td.n_local; i += kTileBlock) {
+        const int xs = __ldg(P.t_xslot + td.node_off + i);
+        const int us = __ldg(P.t_uslot + td.node_off + i);
+        s_xy[i] = load_slot<R2>(x_free, x_fixed, xs);
+        s_uv[i] = load_slot<R2>(u_free, u_fixed, us);
+    }
+    for (int i = tid; i <= td.n_owned; i += kTileBlock) s_off[i] = __ldg(P.entry_off + td.off_off + i);
+
+    TriConsts<R> K;
+    K.c00 = __ldg(consts + HIDENN_TRI_C00); K.c01 = __ldg(consts + HIDENN_TRI_C01); K.c02 = __ldg(consts + HIDENN_TRI_C02);
+    K.c11 = __ldg(consts + HIDENN_TRI_C11); K.c12 = __ldg(consts + HIDENN_TRI_C12); K.c22 = __ldg(consts + HIDENN_TRI_C22);
+    K.W = __ldg(consts + HIDENN_TRI_W);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) K.fb[k] = __ldg(consts + HIDENN_TRI_FB + k);
+    __syncthreads();
+
+    // phase 2: elements -> energy + gradient partials scattered to their fold slots
+    R e_acc = R(0);
+    constexpr unsigned LM = (1u << kLidBits) - 1u;
+    for (int i = tid; i < td.n_elem; i += kTileBlock) {
+        const unsigned long long w = __ldg(P.elem_pack + td.elem_off + i);
+        const unsigned l0 = (unsigned)(w) & LM, l1 = (unsigned)(w >> kLidBits) & LM, l2 = (unsigned)(w >> (2 * kLidBits)) & LM;
+        R e;
+        R2 gu[3], gx[3];
+        tri_element<R>(s_xy[l0], s_xy[l1], s_xy[l2], s_uv[l0], s_uv[l1], s_uv[l2], K, e, gu, gx);
+        if ((w >> kOwnerBit) & 1ull) e_acc += e;
+        const unsigned r0 = (unsigned)(w >> (3 * kLidBits)) & 255u, r1 = (unsigned)(w >> (3 * kLidBits + kRankBits)) & 255u,
+                       r2 = (unsigned)(w >> (3 * kLidBits + 2 * kRankBits)) & 255u;
+        if (r0 != (unsigned)kRankSkip) { const unsigned p = s_off[l0] + r0; s_pu[p] = gu[0]; s_px[p] = gx[0]; }
+        if (r1 != (unsigned)kRankSkip) { const unsigned p = s_off[l1] + r1; s_pu[p] = gu[1]; s_px[p] = gx[1]; }
+        if (r2 != (unsigned)kRankSkip) { const unsigned p = s_off[l2] + r2; s_pu[p] = gu[2]; s_px[p] = gx[2]; }
+    }
+    __syncthreads();
+
+    // phase 3: owned nodes fold their CSR segment in fixed order and store the final gradients
+    for (int i = tid; i < td.n_owned; i += kTileBlock) {
+        const unsigned b = s_off[i], e = s_off[i + 1];
+        R ax = R(0), ay = R(0), bx = R(0), by = R(0);
+        for (unsigned k = b; k < e; ++k) {
+            const R2 u = s_pu[k], x = s_px[k];
+            ax += u.x; ay += u.y; bx += x.x; by += x.y;
+        }
+        const int xs = __ldg(P.t_xslot + td.node_off + i);
+        const int us = __ldg(P.t_uslot + td.node_off + i);
+        if ((flags & HIDENN_NEED_GU) && us >= 0) gu_free[us] = mk2<R>(ax, ay);
+        if ((flags & HIDENN_NEED_GX) && xs >= 0) gx_free[xs] = mk2<R>(bx, by);
+    }
+
+    // tile energy (fixed-order block sum)
+    const R tot = block_sum<R, kTileBlock>(e_acc, s_red);
+    if (tid == 0) tile_energy[blockIdx.x] = tot;
+}
+
+// Energy-only variant (torch.no_grad() evaluations, e.g. logging): no fold, no gradient traffic.
+template <typename R>
+__global__ void __launch_bounds__(kTileBlock)
+tri_tile_energy_only_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ x_free,
+                            const typename Real2<R>::type* __restrict__ x_fixed,
+                            const typename Real2<R>::type* __restrict__ u_free,
+                            const typename Real2<R>::type* __restrict__ u_fixed, const R* __restrict__ consts,
+                            R* __restrict__ tile_energy) {
+    using R2 = typename Real2<R>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TileDesc td = P.tiles[blockIdx.x];
+    R2* s_xy = reinterpret_cast<R2*>(smem_raw);
+    R2* s_uv = s_xy + td.n_local;
+    R* s_red = reinterpret_cast<R*>(s_uv + td.n_local);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < td.n_local; i += kTileBlock) {
+        s_xy[i] = load_slot<R2>(x_free, x_fixed, __ldg(P.t_xslot + td.node_off + i));
+        s_uv[i] = load_slot<R2>(u_free, u_fixed, __ldg(P.t_uslot + td.node_off + i));
+    }
+    TriConsts<R> K;
+    K.c00 = __ldg(consts + HIDENN_TRI_C00); K.c01 = __ldg(consts + HIDENN_TRI_C01); K.c02 = __ldg(consts + HIDENN_TRI_C02);
+    K.c11 = __ldg(consts + HIDENN_TRI_C11); K.c12 = __ldg(consts + HIDENN_TRI_C12); K.c22 = __ldg(consts + HIDENN_TRI_C22);
+    K.W = __ldg(consts + HIDENN_TRI_W);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) K.fb[k] = __ldg(consts + HIDENN_TRI_FB + k);
+    __syncthreads();
+    R e_acc = R(0);
+    constexpr unsigned LM = (1u << kLidBits) - 1u;
+    for (int i = tid; i < td.n_elem; i += kTileBlock) {
+        const unsigned long long w = __ldg(P.elem_pack + td.elem_off + i);
+        if (!((w >> kOwnerBit) & 1ull)) continue;
+        const unsigned l0 = (unsigned)(w) & LM, l1 = (unsigned)(w >> kLidBits) & LM, l2 = (unsigned)(w >> (2 * kLidBits)) & LM;
+        R e;
+        R2 gu[3], gx[3];
+        tri_element<R>(s_xy[l0], s_xy[l1], s_xy[l2], s_uv[l0], s_uv[l1], s_uv[l2], K, e, gu, gx);
+        e_acc += e;
+    }
+    const R tot = block_sum<R, kTileBlock>(e_acc, s_red);
+    if (tid == 0) tile_energy[blockIdx.x] = tot;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Neumann edge term (src/loss.py:91-110, src/models.py:359-376) + final fixed-order reduction.
+// One CTA: the edge count is O(sqrt(Ne)).  Edge nodes are folded node-centrically (each node by one
+// thread, entries in ascending edge order) and *added* to the gradients the tile kernel stored.
+// ---------------------------------------------------------------------------------------------
+constexpr int kEdgeBlock = 1024;
+
+template <typename R> struct EdgeEval {
+    R ds, S;
+    typename Real2<R>::type dir, x0, x1, U0, U1;
+};
+
+template <typename R>
+__device__ __forceinline__ EdgeEval<R> edge_eval(const TriPlanDev& P, int e, const typename Real2<R>::type* x_free,
+                                                 const typename Real2<R>::type* x_fixed,
+                                                 const typename Real2<R>::type* u_free,
+                                                 const typename Real2<R>::type* u_fixed, const R* consts,
+                                                 const R* t_table, int ng1) {
+    using R2 = typename Real2<R>::type;
+    EdgeEval<R> E;
+    const int4 s = __ldg(reinterpret_cast<const int4*>(P.e_slots) + e);
+    E.x0 = load_slot<R2>(x_free, x_fixed, s.x); E.U0 = load_slot<R2>(u_free, u_fixed, s.y);
+    E.x1 = load_slot<R2>(x_free, x_fixed, s.z); E.U1 = load_slot<R2>(u_free, u_fixed, s.w);
+    const R dx = E.x1.x - E.x0.x, dy = E.x1.y - E.x0.y;
+    E.ds = sqrt(dx * dx + dy * dy);
+    E.dir = mk2<R>(dx / E.ds, dy / E.ds);
+    R S = R(0);
+    for (int q = 0; q < ng1; ++q) {
+        const R xi = consts[HIDENN_TRI_XI1 + q], w = consts[HIDENN_TRI_W1 + q];
+        const R ux = (R(1) - xi) * E.U0.x + xi * E.U1.x, uy = (R(1) - xi) * E.U0.y + xi * E.U1.y;
+        R tx, ty;
+        if (t_table) { tx = t_table[(e * ng1 + q) * 2]; ty = t_table[(e * ng1 + q) * 2 + 1]; }
+        else { tx = consts[HIDENN_TRI_TX]; ty = consts[HIDENN_TRI_TY]; }
+        S += w * (ux * tx + uy * ty);
+    }
+    E.S = S;
+    return E;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kEdgeBlock)
+tri_edge_finalize_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ x_free,
+                         const typename Real2<R>::type* __restrict__ x_fixed,
+                         const typename Real2<R>::type* __restrict__ u_free,
+                         const typename Real2<R>::type* __restrict__ u_fixed, const R* __restrict__ consts,
+                         const R* __restrict__ t_table, const int flags, const R* __restrict__ tile_energy,
+                         R* __restrict__ out, typename Real2<R>::type* __restrict__ gx_free,
+                         typename Real2<R>::type* __restrict__ gu_free, R* __restrict__ gt_out) {
+    using R2 = typename Real2<R>::type;
+    __shared__ double s_red[kEdgeBlock / 32];
+    const int tid = threadIdx.x;
+    const bool with_edges = (flags & HIDENN_WITH_EDGES) && P.n_edges > 0;
+    const int ng1 = with_edges ? (int)consts[HIDENN_TRI_NG1] : 0;
+
+    double e_edge = 0.0;
+    if (with_edges) {
+        for (int e = tid; e < P.n_edges; e += kEdgeBlock) {
+            const EdgeEval<R> E = edge_eval<R>(P, e, x_free, x_fixed, u_free, u_fixed, consts, t_table, ng1);
+            e_edge += (double)(E.S * E.ds);
+            if (gt_out) {   // d loss / d t_q = -w_q ds u_q
+                for (int q = 0; q < ng1; ++q) {
+                    const R xi = consts[HIDENN_TRI_XI1 + q], w = consts[HIDENN_TRI_W1 + q];
+                    gt_out[(e * ng1 + q) * 2] = -w * E.ds * ((R(1) - xi) * E.U0.x + xi * E.U1.x);
+                    gt_out[(e * ng1 + q) * 2 + 1] = -w * E.ds * ((R(1) - xi) * E.U0.y + xi * E.U1.y);
+                }
+            }
+        }
+        if (flags & (HIDENN_NEED_GX | HIDENN_NEED_GU)) {
+            for (int k = tid; k < P.n_enodes; k += kEdgeBlock) {
+                R gux = R(0), guy = R(0), gxx = R(0), gxy = R(0);
+                for (int j = P.en_off[k]; j < P.en_off[k + 1]; ++j) {
+                    const int ent = P.en_ent[j], e = ent >> 1, end = ent & 1;
+                    const EdgeEval<R> E = edge_eval<R>(P, e, x_free, x_fixed, u_free, u_fixed, consts, t_table, ng1);
+                    R fx = R(0), fy = R(0);
+                    for (int q = 0; q < ng1; ++q) {
+                        const R xi = consts[HIDENN_TRI_XI1 + q], w = consts[HIDENN_TRI_W1 + q];
+                        const R nsh = end ? xi : (R(1) - xi);
+                        R tx, ty;
+                        if (t_table) { tx = t_table[(e * ng1 + q) * 2]; ty = t_table[(e * ng1 + q) * 2 + 1]; }
+                        else { tx = consts[HIDENN_TRI_TX]; ty = consts[HIDENN_TRI_TY]; }
+                        fx += w * nsh * tx; fy += w * nsh * ty;
+                    }
+                    gux -= E.ds * fx; guy -= E.ds * fy;
+                    // d(-E_edge)/dx: end 0: +S*dir, end 1: -S*dir
+                    const R sg = end ? -E.S : E.S;
+                    gxx += sg * E.dir.x; gxy += sg * E.dir.y;
+                }
+                const int xs = P.en_xslot[k], us = P.en_uslot[k];
+                if ((flags & HIDENN_NEED_GU) && us >= 0) { R2 g = gu_free[us]; g.x += gux; g.y += guy; gu_free[us] = g; }
+                if ((flags & HIDENN_NEED_GX) && xs >= 0) { R2 g = gx_free[xs]; g.x += gxx; g.y += gxy; gx_free[xs] = g; }
+            }
+        }
+    }
+    // domain energy: fixed-order strided + tree sum of the tile partials, accumulated in double
+    double e_dom = 0.0;
+    for (int t = tid; t < P.n_tiles; t += kEdgeBlock) e_dom += (double)tile_energy[t];
+    const double dom = block_sum<double, kEdgeBlock>(e_dom, s_red);
+    __syncthreads();
+    const double edg = block_sum<double, kEdgeBlock>(e_edge, s_red);
+    if (tid == 0) {
+        out[0] = (R)(dom - edg);
+        out[1] = (R)dom;
+        out[2] = (R)edg;
+        out[3] = R(0);
+    }
+}
+
+template <typename R>
+__global__ void scale_inplace_kernel(R* __restrict__ g, int64_t n, const R* __restrict__ scale) {
+    const R s = __ldg(scale);
+    if (s == R(1)) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) g[i] *= s;
+}
+
+template <typename R> static size_t smem_for(const hidenn_tri_plan* p) {
+    size_t b = (size_t)p->dev.max_local * 4 * sizeof(R) + (size_t)p->dev.max_entries * 4 * sizeof(R);
+    b += ((size_t)(p->dev.max_owned + 1) * 2 + 15) / 16 * 16;
+    b += 64 * 8;
+    return b;
+}
+
+template <typename R>
+static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed,
+                             const R* consts, const R* t_table, int flags, R* out, R* gx, R* gu, R* gt, R* scratch,
+                             void* stream_v) {
+    using R2 = typename Real2<R>::type;
+    HIDENN_REQUIRE(p != nullptr, "tri_energy: plan is NULL");
+    HIDENN_REQUIRE(p->device >= 0, "tri_energy: host-only plan (device=-1) cannot run kernels; there is no CPU fallback");
+    HIDENN_REQUIRE(consts && out && scratch, "tri_energy: NULL consts/out/scratch");
+    HIDENN_REQUIRE(x_fixed || p->n_fixed_x == 0, "tri_energy: x_fixed NULL");
+    HIDENN_REQUIRE(u_fixed || p->n_fixed_u == 0, "tri_energy: u_fixed NULL (the reference raises too when u_fixed=None)");
+    HIDENN_REQUIRE(!(flags & HIDENN_NEED_GX) || gx, "tri_energy: gx_free NULL");
+    HIDENN_REQUIRE(!(flags & HIDENN_NEED_GU) || gu, "tri_energy: gu_free NULL");
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    const bool grad = flags & (HIDENN_NEED_GX | HIDENN_NEED_GU);
+    if (p->dev.n_tiles > 0) {
+        if (grad) {
+            const size_t smem = smem_for<R>(p);
+            static thread_local size_t configured[2] = {0, 0};
+            size_t& cfg = configured[sizeof(R) == 8 ? 0 : 1];
+            if (smem > cfg) {
+                HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cfg = smem;
+            }
+            tri_tile_kernel<R><<<p->dev.n_tiles, kTileBlock, smem, stream>>>(
+                p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags,
+                (R2*)gx, (R2*)gu, scratch);
+        } else {
+            const size_t smem = (size_t)p->dev.max_local * 4 * sizeof(R) + 64 * 8;
+            static thread_local size_t configured[2] = {0, 0};
+            size_t& cfg = configured[sizeof(R) == 8 ? 0 : 1];
+            if (smem > cfg) {
+                HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_energy_only_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cfg = smem;
+            }
+            tri_tile_energy_only_kernel<R><<<p->dev.n_tiles, kTileBlock, smem, stream>>>(
+                p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, scratch);
+        }
+        HIDENN_CUDA_OK(cudaGetLastError());
+    }
+    if (flags & HIDENN_TILES_ONLY) return 0;
+    tri_edge_finalize_kernel<R><<<1, kEdgeBlock, 0, stream>>>(p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free,
+                                                              (const R2*)u_fixed, consts, t_table, flags, scratch, out,
+                                                              (R2*)gx, (R2*)gu, gt);
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename R>
+static int tri_energy_host(hidenn_tri_plan* p, const R* xf, const R* xb, const R* uf, const R* ub, const R* consts_h, int flags,
+                           R* out_h, R* gx_h, R* gu_h, void* stream_v) {
+    HIDENN_REQUIRE(p != nullptr && p->device >= 0, "tri_energy_host: needs a device plan");
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    HIDENN_CUDA_OK(cudaSetDevice(p->device));
+    const size_t nfx = 2 * (size_t)p->n_free_x, nbx = 2 * (size_t)p->n_fixed_x, nfu = 2 * (size_t)p->n_free_u, nbu = 2 * (size_t)p->n_fixed_u;
+    const size_t nsc = (size_t)p->dev.n_tiles + 8;
+    auto al = [](size_t n) { return (n + 31) / 32 * 32; };
+    const size_t total = al(nfx) * 2 + al(nbx) + al(nfu) * 2 + al(nbu) + al(HIDENN_TRI_NCONST) + al(4) + al(nsc);
+    if (plan_ensure_arena(p, total * sizeof(R))) return 1;
+    R* base = reinterpret_cast<R*>(p->arena);
+    R* d_xf = base; base += al(nfx);
+    R* d_xb = base; base += al(nbx);
+    R* d_uf = base; base += al(nfu);
+    R* d_ub = base; base += al(nbu);
+    R* d_gx = base; base += al(nfx);
+    R* d_gu = base; base += al(nfu);
+    R* d_c = base; base += al(HIDENN_TRI_NCONST);
+    R* d_out = base; base += al(4);
+    R* d_sc = base;
+    HIDENN_CUDA_OK(cudaMemcpyAsync(d_xf, xf, nfx * sizeof(R), cudaMemcpyHostToDevice, stream));
+    if (nbx) HIDENN_CUDA_OK(cudaMemcpyAsync(d_xb, xb, nbx * sizeof(R), cudaMemcpyHostToDevice, stream));
+    HIDENN_CUDA_OK(cudaMemcpyAsync(d_uf, uf, nfu * sizeof(R), cudaMemcpyHostToDevice, stream));
+    if (nbu) HIDENN_CUDA_OK(cudaMemcpyAsync(d_ub, ub, nbu * sizeof(R), cudaMemcpyHostToDevice, stream));
+    HIDENN_CUDA_OK(cudaMemcpyAsync(d_c, consts_h, HIDENN_TRI_NCONST * sizeof(R), cudaMemcpyHostToDevice, stream));
+    if (tri_energy_launch<R>(p, d_xf, d_xb, d_uf, d_ub, d_c, nullptr, flags, d_out, d_gx, d_gu, nullptr, d_sc, stream_v)) return 1;
+    HIDENN_CUDA_OK(cudaMemcpyAsync(out_h, d_out, 4 * sizeof(R), cudaMemcpyDeviceToHost, stream));
+    if ((flags & HIDENN_NEED_GX) && gx_h) HIDENN_CUDA_OK(cudaMemcpyAsync(gx_h, d_gx, nfx * sizeof(R), cudaMemcpyDeviceToHost, stream));
+    if ((flags & HIDENN_NEED_GU) && gu_h) HIDENN_CUDA_OK(cudaMemcpyAsync(gu_h, d_gu, nfu * sizeof(R), cudaMemcpyDeviceToHost, stream));
+    HIDENN_CUDA_OK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+template <typename R> static int scale_launch(R* g, int64_t n, const R* s, void* stream_v) {
+    HIDENN_REQUIRE(g && s, "scale_inplace: NULL");
+    if (n <= 0) return 0;
+    const int block = 256;
+    const int grid = (int)std::min<int64_t>((n + block * 4 - 1) / (block * 4), 148 * 16);
+    scale_inplace_kernel<R><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(g, n, s);
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace hidenn
+
+using namespace hidenn;
+
+extern "C" int hidenn_tri_energy_f64(const hidenn_tri_plan* plan, const double* x_free, const double* x_fixed,
+                                     const double* u_free, const double* u_fixed, const double* consts,
+                                     const double* t_table, int flags, double* out, double* gx_free, double* gu_free,
+                                     double* gt_out, double* scratch, void* stream) {
+    return tri_energy_launch<double>(plan, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx_free, gu_free,
+                                     gt_out, scratch, stream);
+}
+extern "C" int hidenn_tri_energy_f32(const hidenn_tri_plan* plan, const float* x_free, const float* x_fixed,
+                                     const float* u_free, const float* u_fixed, const float* consts, const float* t_table,
+                                     int flags, float* out, float* gx_free, float* gu_free, float* gt_out, float* scratch,
+                                     void* stream) {
+    return tri_energy_launch<float>(plan, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx_free, gu_free,
+                                    gt_out, scratch, stream);
+}
+extern "C" int hidenn_tri_energy_host_f64(hidenn_tri_plan* plan, const double* a, const double* b, const double* c,
+                                          const double* d, const double* k, int flags, double* out, double* gx, double* gu,
+                                          void* stream) {
+    return tri_energy_host<double>(plan, a, b, c, d, k, flags, out, gx, gu, stream);
+}
+extern "C" int hidenn_tri_energy_host_f32(hidenn_tri_plan* plan, const float* a, const float* b, const float* c,
+                                          const float* d, const float* k, int flags, float* out, float* gx, float* gu,
+                                          void* stream) {
+    return tri_energy_host<float>(plan, a, b, c, d, k, flags, out, gx, gu, stream);
+}
+extern "C" int hidenn_scale_inplace_f64(double* g, int64_t n, const double* s, void* stream) { return scale_launch<double>(g, n, s, stream); }
+extern "C" int hidenn_scale_inplace_f32(float* g, int64_t n, const float* s, void* stream) { return scale_launch<float>(g, n, s, stream); }

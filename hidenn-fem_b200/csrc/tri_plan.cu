@@ -1,0 +1,432 @@
+// Host-side plan builder for the triangle path (static topology, once per mesh).
+//
+// Replaces, for the hot path, what the reference redoes on every call:
+//   * masked index_put assembly of coords / u_full   (/root/reference/src/models.py:292-305)  -> slot maps
+//   * coords[connectivity[idx]] gathers               (/root/reference/src/models.py:228-238)  -> tile-local packs
+//   * autograd's scatter-add backward of those gathers                                         -> per-tile node->element CSR
+//
+// Tiling: recursive coordinate bisection of the nodes (initial coordinates) into compact blobs of
+// ~tile_nodes owned nodes; a tile visits every element incident to an owned node ("owner computes",
+// halo elements recomputed), so each nodal gradient is folded and written by exactly one CTA in a
+// fixed order: deterministic, no float atomics, no second pass.
+#include "../../include/hidenn_b200.h"
+#include "common.cuh"
+#include "tri_plan.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <future>
+#include <memory>
+#include <numeric>
+#include <thread>
+
+namespace hidenn {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+template <typename T> static int upload(hidenn_tri_plan* p, const std::vector<T>& h, const T** d) {
+    void* ptr = nullptr;
+    size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    HIDENN_CUDA_OK(cudaMalloc(&ptr, bytes));
+    p->dev_allocs.push_back(ptr);
+    p->dev_bytes += bytes;
+    if (!h.empty()) HIDENN_CUDA_OK(cudaMemcpy(ptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *d = reinterpret_cast<const T*>(ptr);
+    return 0;
+}
+
+struct Rcb {
+    const double* xy;
+    std::vector<int32_t>& idx;
+    std::vector<int64_t>& tile_begin;   // size n_tiles+1 filled by leaves
+    void run(int64_t lo, int64_t hi, int64_t t_lo, int64_t t_hi, int depth) {
+        const int64_t nt = t_hi - t_lo;
+        if (nt <= 1) {
+            tile_begin[t_lo] = lo;
+            return;
+        }
+        double mn[2] = {1e300, 1e300}, mx[2] = {-1e300, -1e300};
+        for (int64_t i = lo; i < hi; ++i) {
+            const double* p = xy + 2 * (int64_t)idx[i];
+            mn[0] = std::min(mn[0], p[0]); mx[0] = std::max(mx[0], p[0]);
+            mn[1] = std::min(mn[1], p[1]); mx[1] = std::max(mx[1], p[1]);
+        }
+        const int ax = (mx[1] - mn[1] > mx[0] - mn[0]) ? 1 : 0;
+        const int64_t tl = nt / 2;
+        const int64_t nl = (hi - lo) * tl / nt;
+        const double* c = xy;
+        auto cmp = [c, ax](int32_t a, int32_t b) {
+            const double va = c[2 * (int64_t)a + ax], vb = c[2 * (int64_t)b + ax];
+            return va < vb || (va == vb && a < b);
+        };
+        std::nth_element(idx.begin() + lo, idx.begin() + lo + nl, idx.begin() + hi, cmp);
+        if (depth < 3 && hi - lo > 200000) {
+            auto f = std::async(std::launch::async, [=] { this->run(lo, lo + nl, t_lo, t_lo + tl, depth + 1); });
+            run(lo + nl, hi, t_lo + tl, t_hi, depth + 1);
+            f.get();
+        } else {
+            run(lo, lo + nl, t_lo, t_lo + tl, depth + 1);
+            run(lo + nl, hi, t_lo + tl, t_hi, depth + 1);
+        }
+    }
+};
+
+struct TileBuild {
+    std::vector<int32_t> nodes;     // owned (ascending) then halo (ascending)
+    int32_t n_owned = 0;
+    std::vector<int32_t> elems;     // ascending global element id
+    std::vector<unsigned long long> pack;
+    std::vector<uint16_t> off;      // n_owned+1
+    int err = 0;
+};
+
+int plan_ensure_generic(hidenn_tri_plan* p) {
+    if (p->generic_uploaded) return 0;
+    HIDENN_REQUIRE(p->device >= 0, "host-only plan (device=-1) cannot run kernels");
+    HIDENN_CUDA_OK(cudaSetDevice(p->device));
+    if (upload(p, p->conn32, &p->dev.conn32)) return 1;
+    if (upload(p, p->xslot, &p->dev.xslot)) return 1;
+    if (upload(p, p->uslot, &p->dev.uslot)) return 1;
+    if (upload(p, p->n2e_off, &p->dev.n2e_off)) return 1;
+    if (upload(p, p->n2e_ent, &p->dev.n2e_ent)) return 1;
+    if (upload(p, p->edges32, &p->dev.edges32)) return 1;
+    p->generic_uploaded = true;
+    return 0;
+}
+
+int plan_ensure_arena(hidenn_tri_plan* p, size_t bytes) {
+    if (p->arena_bytes >= bytes) return 0;
+    HIDENN_CUDA_OK(cudaSetDevice(p->device));
+    if (p->arena) cudaFree(p->arena);
+    p->arena = nullptr;
+    p->arena_bytes = 0;
+    HIDENN_CUDA_OK(cudaMalloc(&p->arena, bytes));
+    p->arena_bytes = bytes;
+    return 0;
+}
+
+}  // namespace hidenn
+
+using namespace hidenn;
+
+extern "C" const char* hidenn_last_error(void) { return hidenn::g_err.c_str(); }
+extern "C" int hidenn_version(void) { return HIDENN_B200_VERSION; }
+extern "C" int hidenn_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        set_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+        return -1;
+    }
+    return n;
+}
+
+extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t Nn, const double* coords,
+                                      const uint8_t* bmask, const uint8_t* dmask, const int64_t* edges, int64_t Ned,
+                                      int tile_nodes, int real_bytes, int device, hidenn_tri_plan** out) {
+    HIDENN_REQUIRE(out != nullptr, "plan_create: out is NULL");
+    *out = nullptr;
+    HIDENN_REQUIRE(conn && coords && bmask && dmask, "plan_create: NULL input");
+    HIDENN_REQUIRE(Ne >= 0 && Nn > 0 && Nn < (int64_t)2147483000 && Ne < (int64_t)500000000, "plan_create: sizes out of range");
+    HIDENN_REQUIRE(real_bytes == 8 || real_bytes == 4, "plan_create: real_bytes must be 8 or 4");
+    HIDENN_REQUIRE(Ned == 0 || edges != nullptr, "plan_create: edges NULL");
+    if (tile_nodes <= 0) tile_nodes = real_bytes == 8 ? 288 : 576;
+    HIDENN_REQUIRE(tile_nodes >= 8 && tile_nodes <= 2048, "plan_create: tile_nodes must be in [8,2048]");
+
+    for (int64_t i = 0; i < 3 * Ne; ++i)
+        HIDENN_REQUIRE(conn[i] >= 0 && conn[i] < Nn, "plan_create: connectivity index out of range");
+    for (int64_t i = 0; i < 2 * Ned; ++i)
+        HIDENN_REQUIRE(edges[i] >= 0 && edges[i] < Nn, "plan_create: edge node index out of range");
+
+    std::unique_ptr<hidenn_tri_plan> p(new hidenn_tri_plan());
+    p->device = device;
+    p->real_bytes = real_bytes;
+    p->n_elems = Ne;
+    p->n_nodes = Nn;
+
+    // slot maps (src/models.py:261-262, 274: free rows in ascending node order)
+    p->xslot.resize(Nn);
+    p->uslot.resize(Nn);
+    {
+        int32_t fx = 0, bx = 0, fu = 0, bu = 0;
+        for (int64_t n = 0; n < Nn; ++n) {
+            p->xslot[n] = bmask[n] ? ~(bx++) : fx++;
+            p->uslot[n] = dmask[n] ? ~(bu++) : fu++;
+        }
+        p->n_free_x = fx; p->n_fixed_x = bx; p->n_free_u = fu; p->n_fixed_u = bu;
+    }
+    p->conn32.resize(3 * Ne);
+    for (int64_t i = 0; i < 3 * Ne; ++i) p->conn32[i] = (int32_t)conn[i];
+
+    // global node -> (element, corner) CSR, ascending element id inside each node
+    p->n2e_off.assign(Nn + 1, 0);
+    for (int64_t i = 0; i < 3 * Ne; ++i) p->n2e_off[p->conn32[i] + 1]++;
+    for (int64_t n = 0; n < Nn; ++n) p->n2e_off[n + 1] += p->n2e_off[n];
+    p->n2e_ent.resize(3 * Ne);
+    {
+        std::vector<int64_t> cur(p->n2e_off.begin(), p->n2e_off.end() - 1);
+        for (int64_t e = 0; e < Ne; ++e)
+            for (int c = 0; c < 3; ++c) p->n2e_ent[cur[p->conn32[3 * e + c]]++] = (int32_t)(e * 4 + c);
+    }
+    for (int64_t n = 0; n < Nn; ++n)
+        HIDENN_REQUIRE(p->n2e_off[n + 1] - p->n2e_off[n] < kRankSkip, "plan_create: node valence >= 255 not supported");
+
+    // RCB tiling of the nodes
+    const int64_t n_tiles = (Nn + tile_nodes - 1) / tile_nodes;
+    std::vector<int32_t> order(Nn);
+    std::iota(order.begin(), order.end(), 0);
+    std::vector<int64_t> tile_begin(n_tiles + 1, 0);
+    tile_begin[n_tiles] = Nn;
+    {
+        Rcb r{coords, order, tile_begin};
+        r.run(0, Nn, 0, n_tiles, 0);
+    }
+
+    // per-tile packs, in parallel over tiles
+    std::vector<TileBuild> tb(n_tiles);
+    const int32_t* c32 = p->conn32.data();
+    const int64_t* n2o = p->n2e_off.data();
+    const int32_t* n2e = p->n2e_ent.data();
+    auto build_range = [&](int64_t t0, int64_t t1) {
+        std::vector<int32_t> cand, halo;
+        for (int64_t t = t0; t < t1; ++t) {
+            TileBuild& B = tb[t];
+            B.nodes.assign(order.begin() + tile_begin[t], order.begin() + tile_begin[t + 1]);
+            std::sort(B.nodes.begin(), B.nodes.end());
+            B.n_owned = (int32_t)B.nodes.size();
+            cand.clear();
+            for (int32_t n : B.nodes)
+                for (int64_t k = n2o[n]; k < n2o[n + 1]; ++k) cand.push_back(n2e[k] >> 2);
+            std::sort(cand.begin(), cand.end());
+            cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+            B.elems = cand;
+            halo.clear();
+            auto owned_id = [&](int32_t n) -> int32_t {
+                auto it = std::lower_bound(B.nodes.begin(), B.nodes.begin() + B.n_owned, n);
+                return (it != B.nodes.begin() + B.n_owned && *it == n) ? (int32_t)(it - B.nodes.begin()) : -1;
+            };
+            for (int32_t e : B.elems)
+                for (int c = 0; c < 3; ++c) {
+                    int32_t n = c32[3 * (int64_t)e + c];
+                    if (owned_id(n) < 0) halo.push_back(n);
+                }
+            std::sort(halo.begin(), halo.end());
+            halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+            B.nodes.insert(B.nodes.end(), halo.begin(), halo.end());
+            if ((int64_t)B.nodes.size() > kMaxLocal) { B.err = 1; continue; }
+            B.off.resize(B.n_owned + 1);
+            int64_t acc = 0;
+            for (int32_t l = 0; l < B.n_owned; ++l) {
+                B.off[l] = (uint16_t)acc;
+                acc += n2o[B.nodes[l] + 1] - n2o[B.nodes[l]];
+                if (acc > kMaxEntries) { B.err = 2; break; }
+            }
+            if (B.err) continue;
+            B.off[B.n_owned] = (uint16_t)acc;
+            B.pack.resize(B.elems.size());
+            for (size_t i = 0; i < B.elems.size(); ++i) {
+                const int32_t e = B.elems[i];
+                unsigned long long w = 0;
+                for (int c = 0; c < 3; ++c) {
+                    const int32_t n = c32[3 * (int64_t)e + c];
+                    int32_t lid = owned_id(n);
+                    unsigned long long rank = kRankSkip;
+                    if (lid >= 0) {
+                        const int32_t key = e * 4 + c;
+                        for (int64_t k = n2o[n]; k < n2o[n + 1]; ++k)
+                            if (n2e[k] == key) { rank = (unsigned long long)(k - n2o[n]); break; }
+                    } else {
+                        auto it = std::lower_bound(B.nodes.begin() + B.n_owned, B.nodes.end(), n);
+                        lid = (int32_t)(it - B.nodes.begin());
+                    }
+                    w |= (unsigned long long)lid << (kLidBits * c);
+                    w |= rank << (3 * kLidBits + kRankBits * c);
+                }
+                // the tile that owns corner 0 adds the element's energy
+                if (owned_id(c32[3 * (int64_t)e]) >= 0) w |= 1ull << kOwnerBit;
+                B.pack[i] = w;
+            }
+        }
+    };
+    {
+        unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        if (n_tiles < 64) nthr = 1;
+        std::vector<std::thread> th;
+        const int64_t per = (n_tiles + nthr - 1) / nthr;
+        for (unsigned i = 0; i < nthr; ++i) {
+            const int64_t a = i * per, b = std::min<int64_t>(n_tiles, a + per);
+            if (a < b) th.emplace_back(build_range, a, b);
+        }
+        for (auto& t : th) t.join();
+    }
+    int32_t max_local = 0, max_entries = 0, max_owned = 0, max_elem = 0;
+    int64_t node_visits = 0, elem_visits = 0, off_total = 0;
+    for (auto& B : tb) {
+        HIDENN_REQUIRE(B.err != 1, "plan_create: a tile has more than 4095 local nodes; use a smaller tile_nodes");
+        HIDENN_REQUIRE(B.err != 2, "plan_create: a tile has more than 65535 fold entries; use a smaller tile_nodes");
+        node_visits += (int64_t)B.nodes.size();
+        elem_visits += (int64_t)B.elems.size();
+        off_total += B.n_owned + 1;
+    }
+    HIDENN_REQUIRE(node_visits < 2147483000LL && elem_visits < 2147483000LL, "plan_create: mesh too large for int32 tile offsets");
+    p->tiles.resize(n_tiles);
+    p->t_node.reserve(node_visits);
+    p->t_elem.reserve(elem_visits);
+    p->elem_pack.reserve(elem_visits);
+    p->entry_off.reserve(off_total);
+    for (int64_t t = 0; t < n_tiles; ++t) {
+        TileBuild& B = tb[t];
+        TileDesc d{};
+        d.node_off = (int32_t)p->t_node.size();
+        d.n_owned = B.n_owned;
+        d.n_local = (int32_t)B.nodes.size();
+        d.elem_off = (int32_t)p->t_elem.size();
+        d.n_elem = (int32_t)B.elems.size();
+        d.off_off = (int32_t)p->entry_off.size();
+        d.n_entries = B.off.empty() ? 0 : B.off[B.n_owned];
+        p->tiles[t] = d;
+        p->t_node.insert(p->t_node.end(), B.nodes.begin(), B.nodes.end());
+        p->t_elem.insert(p->t_elem.end(), B.elems.begin(), B.elems.end());
+        p->elem_pack.insert(p->elem_pack.end(), B.pack.begin(), B.pack.end());
+        p->entry_off.insert(p->entry_off.end(), B.off.begin(), B.off.end());
+        max_local = std::max(max_local, d.n_local);
+        max_entries = std::max(max_entries, d.n_entries);
+        max_owned = std::max(max_owned, d.n_owned);
+        max_elem = std::max(max_elem, d.n_elem);
+        std::vector<int32_t>().swap(B.nodes);
+        std::vector<int32_t>().swap(B.elems);
+        std::vector<unsigned long long>().swap(B.pack);
+    }
+    p->node_visits = node_visits;
+    p->elem_visits = elem_visits;
+
+    std::vector<int32_t> t_xslot(node_visits), t_uslot(node_visits);
+    for (int64_t i = 0; i < node_visits; ++i) {
+        t_xslot[i] = p->xslot[p->t_node[i]];
+        t_uslot[i] = p->uslot[p->t_node[i]];
+    }
+
+    // Neumann edges: slot quads + node-centric CSR (each edge node folded by one thread)
+    p->edges32.resize(2 * Ned);
+    std::vector<int32_t> e_slots(4 * Ned);
+    for (int64_t e = 0; e < Ned; ++e) {
+        const int32_t a = (int32_t)edges[2 * e], b = (int32_t)edges[2 * e + 1];
+        p->edges32[2 * e] = a; p->edges32[2 * e + 1] = b;
+        e_slots[4 * e + 0] = p->xslot[a]; e_slots[4 * e + 1] = p->uslot[a];
+        e_slots[4 * e + 2] = p->xslot[b]; e_slots[4 * e + 3] = p->uslot[b];
+    }
+    std::vector<int32_t> enodes(p->edges32);
+    std::sort(enodes.begin(), enodes.end());
+    enodes.erase(std::unique(enodes.begin(), enodes.end()), enodes.end());
+    const int32_t n_en = (int32_t)enodes.size();
+    std::vector<int32_t> en_xslot(n_en), en_uslot(n_en), en_off(n_en + 1, 0), en_ent(2 * Ned);
+    for (int32_t k = 0; k < n_en; ++k) { en_xslot[k] = p->xslot[enodes[k]]; en_uslot[k] = p->uslot[enodes[k]]; }
+    auto en_id = [&](int32_t n) { return (int32_t)(std::lower_bound(enodes.begin(), enodes.end(), n) - enodes.begin()); };
+    for (int64_t i = 0; i < 2 * Ned; ++i) en_off[en_id(p->edges32[i]) + 1]++;
+    for (int32_t k = 0; k < n_en; ++k) en_off[k + 1] += en_off[k];
+    {
+        std::vector<int32_t> cur(en_off.begin(), en_off.end() - 1);
+        for (int64_t i = 0; i < 2 * Ned; ++i) en_ent[cur[en_id(p->edges32[i])]++] = (int32_t)i;   // edge*2+end, ascending
+    }
+
+    // upload (device == -1: host-only plan for index tests, no compute possible)
+    TriPlanDev& D0 = p->dev;
+    D0.n_tiles = (int32_t)n_tiles;
+    D0.max_local = max_local; D0.max_entries = max_entries; D0.max_owned = max_owned; D0.max_elem = max_elem;
+    D0.n_edges = (int32_t)Ned; D0.n_enodes = n_en;
+    if (device == -1) {
+        *out = p.release();
+        return 0;
+    }
+    int ndev = 0;
+    HIDENN_CUDA_OK(cudaGetDeviceCount(&ndev));
+    HIDENN_REQUIRE(device >= 0 && device < ndev, "plan_create: no such CUDA device (this library has no CPU fallback)");
+    HIDENN_CUDA_OK(cudaSetDevice(device));
+    TriPlanDev& D = p->dev;
+    D.n_tiles = (int32_t)n_tiles;
+    D.max_local = max_local; D.max_entries = max_entries; D.max_owned = max_owned; D.max_elem = max_elem;
+    D.n_edges = (int32_t)Ned; D.n_enodes = n_en;
+    D.n_elems = Ne; D.n_nodes = Nn; D.n_free_x = p->n_free_x; D.n_free_u = p->n_free_u;
+    hidenn_tri_plan* pp = p.get();
+    int rc = 0;
+    rc |= upload(pp, p->tiles, &D.tiles);
+    rc |= upload(pp, t_xslot, &D.t_xslot);
+    rc |= upload(pp, t_uslot, &D.t_uslot);
+    rc |= upload(pp, p->elem_pack, &D.elem_pack);
+    rc |= upload(pp, p->entry_off, &D.entry_off);
+    rc |= upload(pp, e_slots, &D.e_slots);
+    rc |= upload(pp, en_xslot, &D.en_xslot);
+    rc |= upload(pp, en_uslot, &D.en_uslot);
+    rc |= upload(pp, en_off, &D.en_off);
+    rc |= upload(pp, en_ent, &D.en_ent);
+    if (rc) {
+        for (void* q : p->dev_allocs) cudaFree(q);
+        return 1;
+    }
+    *out = p.release();
+    return 0;
+}
+
+extern "C" void hidenn_tri_plan_destroy(hidenn_tri_plan* p) {
+    if (!p) return;
+    if (p->device >= 0) cudaSetDevice(p->device);
+    for (void* q : p->dev_allocs) cudaFree(q);
+    if (p->arena) cudaFree(p->arena);
+    delete p;
+}
+
+static size_t tile_smem_bytes(const hidenn_tri_plan* p, int rb) {
+    // node pairs (xy, uv) + fold partial pairs (gu, gx) + entry offsets + block-reduce scratch
+    size_t b = (size_t)p->dev.max_local * 4 * rb + (size_t)p->dev.max_entries * 4 * rb;
+    b += ((size_t)(p->dev.max_owned + 1) * 2 + 15) / 16 * 16;
+    b += 64 * 8;
+    return b;
+}
+
+extern "C" int hidenn_tri_plan_info(const hidenn_tri_plan* p, int64_t* info) {
+    HIDENN_REQUIRE(p && info, "plan_info: NULL");
+    info[0] = p->dev.n_tiles;
+    info[1] = p->elem_visits;
+    info[2] = p->node_visits;
+    info[3] = p->dev.max_local;
+    info[4] = p->dev.max_entries;
+    info[5] = p->dev.n_tiles + 8;
+    info[6] = (int64_t)tile_smem_bytes(p, 8);
+    info[7] = (int64_t)tile_smem_bytes(p, 4);
+    info[8] = p->n_free_x;
+    info[9] = p->n_free_u;
+    info[10] = p->dev.n_edges;
+    info[11] = p->dev.n_enodes;
+    info[12] = (int64_t)p->dev_bytes;
+    info[13] = p->dev.max_elem;
+    info[14] = p->n_elems;
+    info[15] = p->n_nodes;
+    return 0;
+}
+
+extern "C" int hidenn_tri_plan_slots(const hidenn_tri_plan* p, int32_t* xs, int32_t* us) {
+    HIDENN_REQUIRE(p && xs && us, "plan_slots: NULL");
+    std::memcpy(xs, p->xslot.data(), p->xslot.size() * sizeof(int32_t));
+    std::memcpy(us, p->uslot.data(), p->uslot.size() * sizeof(int32_t));
+    return 0;
+}
+
+extern "C" int hidenn_tri_plan_decode(const hidenn_tri_plan* p, int64_t* out_elem, int64_t* out_nodes, uint8_t* out_owner) {
+    HIDENN_REQUIRE(p && out_elem && out_nodes && out_owner, "plan_decode: NULL");
+    for (size_t t = 0; t < p->tiles.size(); ++t) {
+        const TileDesc& d = p->tiles[t];
+        for (int32_t i = 0; i < d.n_elem; ++i) {
+            const unsigned long long w = p->elem_pack[d.elem_off + i];
+            const int64_t v = d.elem_off + i;
+            out_elem[v] = p->t_elem[v];
+            for (int c = 0; c < 3; ++c) {
+                const int lid = (int)((w >> (kLidBits * c)) & ((1u << kLidBits) - 1));
+                out_nodes[3 * v + c] = p->t_node[d.node_off + lid];
+            }
+            out_owner[v] = (uint8_t)((w >> kOwnerBit) & 1ull);
+        }
+    }
+    return 0;
+}

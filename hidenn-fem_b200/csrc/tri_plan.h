@@ -1,0 +1,86 @@
+// Triangle plan: tile packs for the owner-computes fused energy kernel.
+#pragma once
+#include <stdint.h>
+#include <vector>
+
+namespace hidenn {
+
+// One CTA processes one tile: a compact blob of "owned" nodes (it alone writes their gradients)
+// plus every element incident to them (halo elements are recomputed by the neighbouring tile too).
+struct TileDesc {          // 32 B
+    int32_t node_off;      // first entry of this tile in t_xslot / t_uslot
+    int32_t n_owned;       // local ids [0,n_owned) are owned, [n_owned,n_local) are halo (read only)
+    int32_t n_local;
+    int32_t elem_off;      // first entry in elem_pack
+    int32_t n_elem;
+    int32_t off_off;       // first entry in entry_off (n_owned+1 values)
+    int32_t n_entries;     // sum of owned valences = shared-memory partial slots
+    int32_t pad;
+};
+
+// elem_pack bit layout (uint64): local node ids 3 x 12 bit, fold ranks 3 x 8 bit (255 = halo corner,
+// contribution dropped), bit 60 = this visit owns the element's energy.
+constexpr int kLidBits = 12;
+constexpr int kRankBits = 8;
+constexpr int kRankSkip = 255;
+constexpr int kOwnerBit = 60;
+constexpr int kMaxLocal = (1 << kLidBits) - 1;
+constexpr int kMaxEntries = 65535;
+
+struct TriPlanDev {
+    const TileDesc* tiles;
+    int32_t n_tiles;
+    const int32_t* t_xslot;      // [node visits]
+    const int32_t* t_uslot;
+    const unsigned long long* elem_pack;   // [element visits]
+    const uint16_t* entry_off;
+    int32_t max_local, max_entries, max_owned, max_elem;
+    // Neumann edges
+    int32_t n_edges;
+    const int32_t* e_slots;      // [Ned,4]: xslot0, uslot0, xslot1, uslot1
+    int32_t n_enodes;
+    const int32_t* en_xslot;     // [n_enodes]
+    const int32_t* en_uslot;
+    const int32_t* en_off;       // [n_enodes+1]
+    const int32_t* en_ent;       // edge*2 + end
+    // global views (generic forward / fold); uploaded lazily
+    const int32_t* conn32;       // [Ne,3]
+    const int32_t* xslot;        // [Nn]
+    const int32_t* uslot;
+    const int64_t* n2e_off;      // [Nn+1]
+    const int32_t* n2e_ent;      // element*4 + corner, ascending element id per node
+    const int32_t* edges32;      // [Ned,2]
+    int64_t n_elems, n_nodes, n_free_x, n_free_u;
+};
+
+}  // namespace hidenn
+
+struct hidenn_tri_plan {
+    int device = 0;
+    int real_bytes = 8;
+    int64_t n_elems = 0, n_nodes = 0, n_free_x = 0, n_free_u = 0, n_fixed_x = 0, n_fixed_u = 0;
+    int64_t elem_visits = 0, node_visits = 0;
+    // host copies (tests / decode)
+    std::vector<hidenn::TileDesc> tiles;
+    std::vector<int32_t> t_node;            // global node id of every tile-local node
+    std::vector<int32_t> t_elem;            // global element id of every tile element visit
+    std::vector<unsigned long long> elem_pack;
+    std::vector<uint16_t> entry_off;
+    std::vector<int32_t> xslot, uslot;
+    std::vector<int32_t> conn32;
+    std::vector<int64_t> n2e_off;
+    std::vector<int32_t> n2e_ent;
+    std::vector<int32_t> edges32;
+    hidenn::TriPlanDev dev{};
+    std::vector<void*> dev_allocs;
+    size_t dev_bytes = 0;
+    bool generic_uploaded = false;
+    // arena for the host-buffer entry points
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+};
+
+namespace hidenn {
+int plan_ensure_generic(hidenn_tri_plan* p);
+int plan_ensure_arena(hidenn_tri_plan* p, size_t bytes);
+}

@@ -1,0 +1,198 @@
+"""Multi-GPU: element-block partition with halo nodes + one packed all-reduce per evaluation.
+
+New capability (the reference is single-process); design of SURVEY.md §8(e):
+each rank owns a contiguous block of elements and holds every node those elements touch.  Nodes
+touched by more than one rank ("shared") receive partial gradients on each rank; ONE
+`all_reduce(sum)` over the packed buffer  [loss, (gx,gy,gu,gv) of every shared node]  completes
+them, so the collective moves O(sqrt(Ne)) values, not the full gradient.  The packing order is the
+ascending global node id, identical on every rank.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import meshgen
+from .loss import EnergyLoss2D
+
+
+# ------------------------------------------------------------------------------------------------
+# host-side index plan (pure integer work; unit-tested on CPU with gloo)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class HaloPlan:
+    shared_gid: np.ndarray      # [S] ascending global ids of all shared nodes (same on every rank)
+    local_pos: np.ndarray       # [s] positions in shared_gid of the shared nodes this rank holds
+    local_node: np.ndarray      # [s] their local node index
+    x_rows: np.ndarray          # [sx] rows of node_coords_free (only free ones)
+    x_pos: np.ndarray           # [sx] matching positions in shared_gid
+    u_rows: np.ndarray          # [su] rows of u_free
+    u_pos: np.ndarray           # [su]
+
+    @property
+    def buffer_len(self):
+        return 1 + 4 * self.shared_gid.shape[0]
+
+
+def shared_ids_from_candidates(cands: Sequence[np.ndarray]) -> np.ndarray:
+    """Global ids that appear in the candidate lists of at least two ranks."""
+    allc = np.concatenate([np.unique(c) for c in cands]) if len(cands) else np.zeros(0, np.int64)
+    ids, cnt = np.unique(allc, return_counts=True)
+    return ids[cnt >= 2]
+
+
+def build_halo_plan(global_node_id: np.ndarray, free_mask: np.ndarray, u_free_mask: np.ndarray,
+                    shared_gid: np.ndarray) -> HaloPlan:
+    order = np.argsort(global_node_id, kind="stable")
+    sorted_gid = global_node_id[order]
+    pos_in_local = np.searchsorted(sorted_gid, shared_gid)
+    pos_in_local = np.clip(pos_in_local, 0, max(sorted_gid.size - 1, 0))
+    have = sorted_gid[pos_in_local] == shared_gid if sorted_gid.size else np.zeros(shared_gid.shape, bool)
+    local_pos = np.nonzero(have)[0]
+    local_node = order[pos_in_local[have]]
+    xrow_of_node = np.cumsum(free_mask) - 1
+    urow_of_node = np.cumsum(u_free_mask) - 1
+    fx = free_mask[local_node]
+    fu = u_free_mask[local_node]
+    return HaloPlan(shared_gid, local_pos, local_node,
+                    xrow_of_node[local_node][fx].astype(np.int32), local_pos[fx].astype(np.int64),
+                    urow_of_node[local_node][fu].astype(np.int32), local_pos[fu].astype(np.int64))
+
+
+def gather_candidates(local_cand: np.ndarray, group=None) -> list:
+    """all_gather of variable-length int64 id lists (setup time only)."""
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    n = torch.tensor([local_cand.size], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    mx = int(max(int(s.item()) for s in sizes))
+    pad = torch.full((max(mx, 1),), -1, dtype=torch.int64, device=dev)
+    pad[:local_cand.size] = torch.from_numpy(local_cand.astype(np.int64)).to(dev)
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return [b[:int(s.item())].cpu().numpy() for b, s in zip(bufs, sizes)]
+
+
+# ------------------------------------------------------------------------------------------------
+# partitioners
+# ------------------------------------------------------------------------------------------------
+def strip_mesh(nx: int, ny: int, rank: int, world: int, **kw) -> meshgen.PlateMesh:
+    """Rank's contiguous block of cell columns of the global nx x ny plate (bit-identical to the
+    corresponding part of the global mesh; ordering applied inside the strip)."""
+    ncol = nx - 1
+    c0 = rank * ncol // world
+    c1 = (rank + 1) * ncol // world
+    return meshgen.plate_mesh(nx, ny, col_range=(c0, c1), **kw)
+
+
+def strip_candidates(mesh: meshgen.PlateMesh) -> np.ndarray:
+    """Nodes on the strip's first / last node column (only they can be shared with a neighbour)."""
+    ny = mesh.meta["ny"]
+    c0, c1 = mesh.meta["col_range"]
+    gix = mesh.global_node_id // ny
+    return mesh.global_node_id[(gix == c0) | (gix == c1)]
+
+
+def partition_elements(mesh: meshgen.PlateMesh, world: int, rank: int) -> meshgen.PlateMesh:
+    """General partition of an in-memory mesh: contiguous blocks of the (locality-ordered) element list;
+    the rank keeps the nodes its elements touch, renumbered ascending.  Neumann edges follow the rank
+    that owns both end nodes' element (an edge on the boundary belongs to exactly one element)."""
+    Ne = mesh.connectivity.shape[0]
+    e0, e1 = rank * Ne // world, (rank + 1) * Ne // world
+    conn = mesh.connectivity[e0:e1]
+    used = np.unique(conn)
+    new = -np.ones(mesh.node_coords.shape[0], np.int64)
+    new[used] = np.arange(used.size)
+    lconn = new[conn]
+    # edges of my elements
+    e_all = np.concatenate([conn[:, [0, 1]], conn[:, [1, 2]], conn[:, [2, 0]]], 0)
+    e_all = np.sort(e_all, 1)
+    key = e_all[:, 0] * mesh.node_coords.shape[0] + e_all[:, 1]
+    nk = mesh.neumann_edges[:, 0] * mesh.node_coords.shape[0] + mesh.neumann_edges[:, 1]
+    mine = np.isin(nk, key)
+    ledges = new[mesh.neumann_edges[mine]]
+    return meshgen.PlateMesh(mesh.node_coords[used], lconn, mesh.boundary_mask[used], mesh.dirichlet_mask[used],
+                             mesh.neumann_mask[used], ledges, mesh.global_node_id[used],
+                             meta=dict(mesh.meta, part=(rank, world)))
+
+
+# ------------------------------------------------------------------------------------------------
+# device-side exchange
+# ------------------------------------------------------------------------------------------------
+class HaloExchange:
+    """Packs [loss, shared-node gradients] with the C-ABI pack kernels, all-reduces once (NCCL), unpacks."""
+
+    def __init__(self, plan: HaloPlan, device, dtype, group=None):
+        self.plan = plan
+        self.group = group
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.HidennError("HaloExchange runs on CUDA tensors only (no CPU fallback)")
+        self.dtype = dtype
+        S = plan.shared_gid.shape[0]
+        self.S = S
+        self.buf = torch.zeros(1 + 4 * S, device=self.device, dtype=dtype)
+        t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a)).to(self.device, d)
+        self.x_rows, self.u_rows = t(plan.x_rows, torch.int32), t(plan.u_rows, torch.int32)
+        # staging is dense per kind: gx pairs at [1, 1+2S), gu pairs at [1+2S, 1+4S); rows scatter by position
+        self.x_pos, self.u_pos = t(plan.x_pos, torch.int64), t(plan.u_pos, torch.int64)
+        self.stage_x = torch.empty(max(self.x_rows.numel(), 1), 2, device=self.device, dtype=dtype)
+        self.stage_u = torch.empty(max(self.u_rows.numel(), 1), 2, device=self.device, dtype=dtype)
+
+    def exchange(self, out, gx, gu):
+        """out: device [4] (loss first); gx/gu: parameter-layout gradients or None. In place."""
+        s = _lib.stream_ptr()
+        dt = self.dtype
+        self.buf.zero_()
+        self.buf[0:1].copy_(out[0:1])
+        S = self.S
+        bx = self.buf[1:1 + 2 * S].view(S, 2)
+        bu = self.buf[1 + 2 * S:1 + 4 * S].view(S, 2)
+        if gx is not None and self.x_rows.numel():
+            _lib.check(_lib.fn("hidenn_halo_pack", dt)(_lib.ptr(gx), _lib.ptr(self.x_rows), C.c_int64(self.x_rows.numel()),
+                                                       _lib.ptr(self.stage_x), s))
+            bx[self.x_pos] = self.stage_x[:self.x_rows.numel()]
+        if gu is not None and self.u_rows.numel():
+            _lib.check(_lib.fn("hidenn_halo_pack", dt)(_lib.ptr(gu), _lib.ptr(self.u_rows), C.c_int64(self.u_rows.numel()),
+                                                       _lib.ptr(self.stage_u), s))
+            bu[self.u_pos] = self.stage_u[:self.u_rows.numel()]
+        dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+        out[0:1].copy_(self.buf[0:1])
+        if gx is not None and self.x_rows.numel():
+            self.stage_x[:self.x_rows.numel()] = bx[self.x_pos]
+            _lib.check(_lib.fn("hidenn_halo_unpack", dt)(_lib.ptr(gx), _lib.ptr(self.x_rows), C.c_int64(self.x_rows.numel()),
+                                                         _lib.ptr(self.stage_x), s))
+        if gu is not None and self.u_rows.numel():
+            self.stage_u[:self.u_rows.numel()] = bu[self.u_pos]
+            _lib.check(_lib.fn("hidenn_halo_unpack", dt)(_lib.ptr(gu), _lib.ptr(self.u_rows), C.c_int64(self.u_rows.numel()),
+                                                         _lib.ptr(self.stage_u), s))
+
+
+class DistributedEnergyLoss2D(EnergyLoss2D):
+    """EnergyLoss2D over a partitioned mesh: local fused kernels, then one packed all-reduce.
+    Every rank returns the global loss; shared-node gradients are complete (and bit-identical) on
+    all ranks that hold the node, so element-wise optimisers keep halo copies consistent."""
+
+    def __init__(self, *args, halo: Optional[HaloExchange] = None, **kw):
+        super().__init__(*args, **kw)
+        self.halo = halo
+
+    def _post_forward(self, model, out, gx, gu):
+        if self.halo is not None:
+            self.halo.exchange(out, gx, gu)
+
+
+def setup_strip_halo(mesh: meshgen.PlateMesh, boundary_mask: np.ndarray, dirichlet_mask: np.ndarray, device, dtype,
+                     group=None) -> HaloExchange:
+    cands = gather_candidates(strip_candidates(mesh), group)
+    shared = shared_ids_from_candidates(cands)
+    plan = build_halo_plan(mesh.global_node_id, ~boundary_mask, ~dirichlet_mask, shared)
+    return HaloExchange(plan, device, dtype, group)

@@ -1,0 +1,240 @@
+"""EnergyLoss2D -- drop-in mirror of /root/reference/src/loss.py on the fused B200 kernels.
+
+`loss_fn(model, b_force=None, t_force=None)` returns a 0-dim tensor whose `.backward()` fills
+`model.node_coords_free.grad` and `model.u_free.grad` exactly like the reference's autograd
+path, but the whole evaluation (gather, shape functions, Jacobian, B-matrix, energy, both
+gradients, deterministic node fold, Neumann edges, final reduction) is two CUDA launches.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Optional
+
+import torch
+
+from . import _lib
+from .utils import triangle_gauss_points, interval_gauss_points
+
+NCONST = 32
+I_C, I_W, I_FB, I_TX, I_TY, I_NG1, I_XI1, I_W1 = 0, 6, 7, 13, 14, 15, 16, 24
+NEED_GX, NEED_GU, WITH_EDGES = 1, 2, 4
+
+
+class _TriEnergyFn(torch.autograd.Function):
+    """Fused EnergyLoss2D.__call__ (reference loss.py:113-116).  Gradients are produced by the same
+    launch as the energy and handed to autograd in backward (scaled on device by grad_output)."""
+
+    @staticmethod
+    def forward(ctx, x_free, u_free, model, consts, with_edges, t_force, loss_obj):
+        plan = model._plan()
+        dt, dev = x_free.dtype, x_free.device
+        need_gx, need_gu = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        flags = (NEED_GX if need_gx else 0) | (NEED_GU if need_gu else 0) | (WITH_EDGES if with_edges else 0)
+        xb, ub = model._fixed_pair()
+        out = torch.empty(4, device=dev, dtype=dt)
+        gx = torch.empty_like(x_free) if need_gx else None
+        gu = torch.empty_like(u_free) if need_gu else None
+        scratch = loss_obj._scratch(plan, dev, dt)
+        t_table = gt = xq = t_live = None
+        if with_edges and t_force is not None and model.N_edges > 0:
+            # user traction at the physical edge points (reference loss.py:96,106); it may depend on x
+            with torch.enable_grad():
+                xq = loss_obj._edge_points(model).detach().requires_grad_(True)
+                t_live = t_force(xq)
+            t_table = t_live.detach().to(dt).contiguous()
+            if t_live.requires_grad and need_gx:
+                gt = torch.empty_like(t_table)
+        _lib.check(_lib.fn("hidenn_tri_energy", dt)(
+            plan.handle, _lib.ptr(x_free), _lib.ptr(xb), _lib.ptr(u_free), _lib.ptr(ub), _lib.ptr(consts), _lib.ptr(t_table),
+            C.c_int(flags), _lib.ptr(out), _lib.ptr(gx), _lib.ptr(gu), _lib.ptr(gt), _lib.ptr(scratch), _lib.stream_ptr()))
+        if gt is not None:
+            # chain d loss/d t_q through the user's traction to the edge end points (last line)
+            (gxq,) = torch.autograd.grad(t_live, xq, gt.reshape(t_live.shape))
+            loss_obj._scatter_edge_point_grads(model, gxq, gx)
+        loss_obj._post_forward(model, out, gx, gu)      # multi-GPU halo all-reduce hook (dist.py); no-op on one GPU
+        ctx.save_for_backward(gx if need_gx else None, gu if need_gu else None)
+        ctx.used = False
+        loss_obj.last_parts = out
+        return out[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        if ctx.used:
+            raise RuntimeError("EnergyLoss2D: backward called twice on the same loss; the fused path hands its "
+                               "gradient buffers to autograd without a copy -- evaluate the loss again instead")
+        ctx.used = True
+        gx, gu = ctx.saved_tensors
+        go = grad_out.reshape(1).contiguous()
+        for g in (gx, gu):
+            if g is not None:
+                if go.dtype != g.dtype:
+                    go = go.to(g.dtype)
+                _lib.check(_lib.fn("hidenn_scale_inplace", g.dtype)(_lib.ptr(g), C.c_int64(g.numel()), _lib.ptr(go),
+                                                                    _lib.stream_ptr()))
+        return gx, gu, None, None, None, None, None
+
+
+class EnergyLoss2D:
+    """Plane-stress total potential energy (reference loss.py:6-116), same constructor and methods."""
+
+    def __init__(self, E: float = 10e9, nu: float = 0.3, length: float = 1.0, height: float = 1.0,
+                 gauss_order: int = 4, gauss_order_1d: int = 2, device: Optional[torch.device] = None,
+                 dtype: torch.dtype = torch.float32):
+        self.E = E
+        self.nu = nu
+        self.length = length
+        self.height = height
+        self.gauss_order = gauss_order
+        self.gauss_order_1d = gauss_order_1d
+        self.device = device or torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.dtype = dtype
+        factor = E / (1 - nu ** 2)
+        self.C = torch.tensor([[1.0, nu, 0.0], [nu, 1.0, 0.0], [0.0, 0.0, (1.0 - nu) / 2.0]],
+                              dtype=dtype, device=self.device) * factor
+        self.xg, self.wg = triangle_gauss_points(order=self.gauss_order, device=self.device, dtype=self.dtype)
+        self.ng = self.xg.shape[0]
+        self.xg_1d, self.wg_1d = interval_gauss_points(order=self.gauss_order_1d, device=self.device, dtype=self.dtype)
+        self.ng1 = self.xg_1d.shape[0]
+        if self.ng1 > 8:
+            raise ValueError("gauss_order_1d > 8 is not supported by the edge kernel")
+        self._consts_cache = None
+        self._scratch_cache = {}
+        self._edge_cache = {}
+        self.last_parts = None     # device tensor [loss, domain, edge, 0] of the latest fused call
+
+    def _post_forward(self, model, out, gx, gu):
+        """Hook after the fused launch (overridden by dist.DistributedEnergyLoss2D)."""
+
+    # -- default forces (reference loss.py:43-51) ----------------------------------------------
+    def uniform_body_force(self, x: torch.Tensor) -> torch.Tensor:
+        return torch.zeros_like(x)
+
+    def uniform_edge_force(self, x: torch.Tensor, L: float = 1.0, F_total: float = 100e3) -> torch.Tensor:
+        t_x = torch.full((x.shape[0],), F_total / L, device=x.device, dtype=x.dtype)
+        return torch.stack([t_x, torch.zeros_like(t_x)], dim=1)
+
+    # -- constants handed to the kernels (include/hidenn_b200.h, HIDENN_TRI_*) --------------------
+    def _consts(self, model, b_force):
+        dt, dev = model.dtype, model.device
+        key = (self.C._version, self.wg._version, self.xg_1d._version, self.wg_1d._version, self.xg._version, dt, dev)
+        if self._consts_cache is None or self._consts_cache[0] != key:
+            Cm = self.C.to(device=dev, dtype=dt)
+            Cs = 0.5 * (Cm + Cm.T)
+            base = torch.zeros(NCONST, device=dev, dtype=dt)
+            base[I_C:I_C + 6] = torch.stack([Cs[0, 0], Cs[0, 1], Cs[0, 2], Cs[1, 1], Cs[1, 2], Cs[2, 2]])
+            base[I_W] = self.wg.to(device=dev, dtype=dt).sum()
+            base[I_TX] = 100e3 / 1.0          # uniform_edge_force defaults (reference loss.py:47-51, Q17)
+            base[I_NG1] = float(self.ng1)
+            base[I_XI1:I_XI1 + self.ng1] = self.xg_1d.to(device=dev, dtype=dt)
+            base[I_W1:I_W1 + self.ng1] = self.wg_1d.to(device=dev, dtype=dt)
+            self._consts_cache = (key, base)
+        base = self._consts_cache[1]
+        if b_force is None:
+            return base
+        # b_force sees the *reference* Gauss points (reference loss.py:60,80; Q4) -> constant 3x2 load matrix
+        xg = self.xg.to(device=dev, dtype=dt)
+        wg = self.wg.to(device=dev, dtype=dt)
+        b = b_force(xg).to(dt)
+        N = torch.stack([xg[:, 0], xg[:, 1], 1.0 - xg[:, 0] - xg[:, 1]], dim=1)
+        Fb = torch.einsum("g,gk,gi->ki", wg, N, b)
+        c = base.clone()
+        c[I_FB:I_FB + 6] = Fb.reshape(-1)
+        return c
+
+    def _scratch(self, plan, dev, dt):
+        key = (id(plan), dev, dt)
+        s = self._scratch_cache.get(key)
+        if s is None or s.numel() < plan.info["scratch"]:
+            s = torch.empty(plan.info["scratch"], device=dev, dtype=dt)
+            self._scratch_cache[key] = s
+        return s
+
+    def _edge_tables(self, model):
+        """Per-model static index tables for the user-traction path (small: O(#Neumann edges))."""
+        key = (id(model), model.device)
+        tb = self._edge_cache.get(key)
+        if tb is None:
+            dev = model.device
+            edges = model.neumann_edges.to(dev)
+            plan = model._plan()
+            xs, _ = plan.slots()
+            xs = torch.from_numpy(xs).to(dev).long()
+            e0, e1 = xs[edges[:, 0]], xs[edges[:, 1]]
+            # unique end nodes and a padded (node -> incident edge-end) table for a deterministic fold
+            ends = edges.reshape(-1)
+            uniq, inv = torch.unique(ends, sorted=True, return_inverse=True)
+            deg = torch.bincount(inv, minlength=uniq.numel())
+            maxdeg = int(deg.max().item()) if uniq.numel() else 0
+            order = torch.argsort(inv, stable=True)
+            start = torch.cumsum(deg, 0) - deg
+            pos = torch.arange(ends.numel(), device=dev) - start[inv[order]]
+            table = torch.full((uniq.numel(), max(maxdeg, 1)), -1, dtype=torch.long, device=dev)
+            table[inv[order], pos] = order
+            tb = dict(e0=e0, e1=e1, uniq_slot=xs[uniq], table=table)
+            self._edge_cache[key] = tb
+        return tb
+
+    def _edge_points(self, model):
+        """xq of reference loss.py:96 from the Parameters directly (no full-array assembly)."""
+        tb = self._edge_tables(model)
+        xf, xb = model.node_coords_free.detach(), model._fixed_pair()[0]
+
+        def pick(s):
+            free = s >= 0
+            out = torch.empty(s.shape[0], 2, device=xf.device, dtype=xf.dtype)
+            out[free] = xf[s[free]]
+            out[~free] = xb[(~s[~free])]
+            return out
+        x0, x1 = pick(tb["e0"]), pick(tb["e1"])
+        xi = self.xg_1d.to(device=xf.device, dtype=xf.dtype)[None, :, None]
+        return ((1.0 - xi) * x0[:, None, :] + xi * x1[:, None, :]).reshape(-1, 2)
+
+    def _scatter_edge_point_grads(self, model, gxq, gx):
+        tb = self._edge_tables(model)
+        dt = gx.dtype
+        ng1 = self.ng1
+        xi = self.xg_1d.to(device=gx.device, dtype=dt)[None, :, None]
+        g = gxq.to(dt).reshape(-1, ng1, 2)
+        g0 = ((1.0 - xi) * g).sum(1)
+        g1 = (xi * g).sum(1)
+        per_end = torch.stack([g0, g1], dim=1).reshape(-1, 2)          # [2*Ned,2] in edges.reshape(-1) order
+        table = tb["table"]
+        contrib = torch.where((table >= 0)[..., None], per_end[table.clamp(min=0)], torch.zeros((), dtype=dt, device=gx.device))
+        node_g = contrib.sum(1)                                          # fixed order -> deterministic
+        slot = tb["uniq_slot"]
+        free = slot >= 0
+        gx[slot[free]] += node_g[free]
+
+    # -- reference API ------------------------------------------------------------------------------
+    def _fused(self, model, b_force, t_force, with_edges):
+        model._check_ready()
+        if with_edges:
+            model.N_edges            # AttributeError if the model has no neumann_edges (reference Q9)
+        consts = self._consts(model, b_force)
+        loss = _TriEnergyFn.apply(model.node_coords_free, model.u_free, model, consts, with_edges, t_force, self)
+        return loss
+
+    def domain_energy(self, model, b_force: Optional[Callable[[torch.Tensor], torch.Tensor]] = None) -> torch.Tensor:
+        """reference loss.py:55-88 (strain energy minus body work), fused forward+backward."""
+        return self._fused(model, b_force, None, with_edges=False)
+
+    def edge_energy(self, model, t_force: Optional[Callable[[torch.Tensor], torch.Tensor]] = None) -> torch.Tensor:
+        """reference loss.py:91-110.  Stand-alone edge term: O(#edges) work through the generic
+        differentiable edge forward (the fused path of __call__ handles it inside the kernel)."""
+        x_i, x_ip1 = model.nm_edges[:]
+        N_edges = model.N_edges
+        dt, dev = model.dtype, model.device
+        xg1, wg1 = self.xg_1d.to(device=dev, dtype=dt), self.wg_1d.to(device=dev, dtype=dt)
+        xq = (1.0 - xg1[None, :, None]) * x_i[:, None, :] + xg1[None, :, None] * x_ip1[:, None, :]
+        xq_flat = xq.reshape(-1, 2)
+        wq_flat = wg1[None, :].expand(N_edges, self.ng1).reshape(-1)
+        x_eval = xg1[None, :].expand(N_edges, self.ng1).reshape(-1, 1)
+        edge_id = torch.repeat_interleave(torch.arange(N_edges, device=dev), repeats=self.ng1)
+        u_edge, ds = model(x_eval, edge_id, edge=True)
+        t_edge = t_force(xq_flat) if t_force is not None else self.uniform_edge_force(xq_flat)
+        return torch.sum((u_edge * t_edge).sum(dim=1) * (wq_flat * ds))
+
+    def __call__(self, model, b_force=None, t_force=None) -> torch.Tensor:
+        """reference loss.py:113-116: domain - edge, as one fused evaluation."""
+        return self._fused(model, b_force, t_force, with_edges=True)

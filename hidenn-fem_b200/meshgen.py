@@ -191,7 +191,7 @@ def plate_mesh(nx: int, ny: int, length: float = 2.0, height: float = 1.0,
                                seed=seed, ordering=ordering, col_range=(c0, c1)))
 
 
-def plate_dims_for_elements(n_elems: int, aspect: float = 2.0, hole_fraction: float = 0.0735):
+def plate_dims_for_elements(n_elems: int, aspect: float = 2.0, hole_fraction: float = 0.0745):
     """(nx, ny) nodes such that the plate keeps >= n_elems triangles after hole removal."""
     cells = n_elems / 2.0 / (1.0 - hole_fraction)
     ncy = int(np.ceil(np.sqrt(cells / aspect)))

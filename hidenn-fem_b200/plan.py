@@ -1,0 +1,88 @@
+"""TriPlan: Python handle of the static-topology plan (include/hidenn_b200.h, hidenn_tri_plan_*)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+INFO_KEYS = ("n_tiles", "elem_visits", "node_visits", "max_local", "max_entries", "scratch", "smem_f64", "smem_f32",
+             "n_free_x", "n_free_u", "n_edges", "n_edge_nodes", "plan_bytes", "max_elem", "n_elems", "n_nodes")
+
+
+def _np(a, dtype):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class TriPlan:
+    """Built once per mesh (connectivity, masks and Neumann edges never change during training;
+    /root/reference/src/models.py:248-282 keeps them as buffers)."""
+
+    def __init__(self, connectivity, n_nodes, coords_init, boundary_mask, dirichlet_mask, neumann_edges=None,
+                 tile_nodes=0, real_bytes=8, device=None):
+        L = _lib.lib()
+        conn = _np(connectivity, np.int64).reshape(-1, 3)
+        xy = _np(coords_init, np.float64).reshape(-1, 2)
+        bm = _np(boundary_mask, np.uint8)
+        dm = _np(dirichlet_mask, np.uint8)
+        if neumann_edges is None:
+            ed = np.zeros((0, 2), np.int64)
+        else:
+            ed = _np(neumann_edges, np.int64).reshape(-1, 2)
+        assert xy.shape[0] == n_nodes and bm.shape[0] == n_nodes and dm.shape[0] == n_nodes
+        if device is None or device == -1:
+            dev_index = -1
+        else:
+            device = torch.device(device)
+            if device.type != "cuda":
+                raise _lib.HidennError("TriPlan needs a CUDA device: the B200 path has no CPU fallback")
+            _lib.require_cuda()
+            dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        self.device_index = dev_index
+        self._h = C.c_void_p(0)
+        rc = L.hidenn_tri_plan_create(conn.ctypes.data_as(C.c_void_p), C.c_int64(conn.shape[0]), C.c_int64(n_nodes),
+                                      xy.ctypes.data_as(C.c_void_p), bm.ctypes.data_as(C.c_void_p),
+                                      dm.ctypes.data_as(C.c_void_p), ed.ctypes.data_as(C.c_void_p),
+                                      C.c_int64(ed.shape[0]), C.c_int(int(tile_nodes)), C.c_int(int(real_bytes)),
+                                      C.c_int(dev_index), C.byref(self._h))
+        _lib.check(rc, "hidenn_tri_plan_create")
+        info = (C.c_int64 * 16)()
+        _lib.check(L.hidenn_tri_plan_info(self._h, info), "hidenn_tri_plan_info")
+        self.info = dict(zip(INFO_KEYS, [int(v) for v in info]))
+        self.real_bytes = real_bytes
+        self.n_nodes = n_nodes
+        self.n_elems = conn.shape[0]
+
+    @property
+    def handle(self):
+        return self._h
+
+    def slots(self):
+        xs = np.empty(self.n_nodes, np.int32)
+        us = np.empty(self.n_nodes, np.int32)
+        _lib.check(_lib.lib().hidenn_tri_plan_slots(self._h, xs.ctypes.data_as(C.c_void_p), us.ctypes.data_as(C.c_void_p)))
+        return xs, us
+
+    def decode(self):
+        v = self.info["elem_visits"]
+        el = np.empty(v, np.int64)
+        nd = np.empty((v, 3), np.int64)
+        ow = np.empty(v, np.uint8)
+        _lib.check(_lib.lib().hidenn_tri_plan_decode(self._h, el.ctypes.data_as(C.c_void_p), nd.ctypes.data_as(C.c_void_p),
+                                                     ow.ctypes.data_as(C.c_void_p)))
+        return el, nd, ow
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.lib().hidenn_tri_plan_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

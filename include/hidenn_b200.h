@@ -1,0 +1,210 @@
+/*
+ * hidenn_b200.h -- C-ABI of the B200-native HiDeNN-FEM quadrature hot path.
+ *
+ * The reference (achraf-15/HiDeNN-FEM) has no FFI: its boundary for this path is the Python
+ * class API (src/models.py, src/loss.py).  This header is the native boundary a binding of
+ * that API calls; every entry point names the reference lines it replaces.  The Python
+ * mirror (hidenn-fem_b200/models.py, loss.py) binds it with ctypes; INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - Every function returns 0 on success, non-zero on error; hidenn_last_error() then
+ *     returns a thread-local message.
+ *   - "host"  pointers are ordinary CPU memory; "dev" pointers are CUDA device memory on the
+ *     plan's device.  No buffer ownership is transferred; nothing on the hot path allocates.
+ *   - `stream` is a cudaStream_t passed as void*; all hot-path calls are asynchronous on it.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ *   - Node coordinates / displacements are AoS pairs [N,2] exactly like the reference's
+ *     Parameters `node_coords_free`, `u_free` (src/models.py:261,274).
+ */
+#ifndef HIDENN_B200_H
+#define HIDENN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HIDENN_B200_VERSION 100
+
+/* layout of the `consts` device array handed to the triangle energy kernels (in the compute type) */
+#define HIDENN_TRI_C00 0      /* symmetrised plane-stress matrix 0.5*(C+C^T) of src/loss.py:29-32, 6 entries: */
+#define HIDENN_TRI_C01 1      /*   C00 C01 C02 C11 C12 C22                                                     */
+#define HIDENN_TRI_C02 2
+#define HIDENN_TRI_C11 3
+#define HIDENN_TRI_C12 4
+#define HIDENN_TRI_C22 5
+#define HIDENN_TRI_W 6        /* sum of the triangle Gauss weights (src/utils.py:13-81; 0.25 for order 4/6) */
+#define HIDENN_TRI_FB 7       /* Fb[k][i] = sum_g w_g N_k(g) b_i(g), 6 entries (src/loss.py:80-81,86)         */
+#define HIDENN_TRI_TX 13      /* uniform traction (src/loss.py:47-51): (1e5, 0)                              */
+#define HIDENN_TRI_TY 14
+#define HIDENN_TRI_NG1 15     /* number of 1D Gauss points on an edge (<= 8), stored as a real               */
+#define HIDENN_TRI_XI1 16     /* 8 slots: raw leggauss points on [-1,1] (src/utils.py:4-11)                  */
+#define HIDENN_TRI_W1 24      /* 8 slots: raw leggauss weights                                               */
+#define HIDENN_TRI_NCONST 32
+
+/* flags */
+#define HIDENN_NEED_GX 1      /* write d loss / d node_coords_free */
+#define HIDENN_NEED_GU 2      /* write d loss / d u_free           */
+#define HIDENN_WITH_EDGES 4   /* include the Neumann edge term (src/loss.py:91-110) */
+#define HIDENN_TILES_ONLY 16  /* measurement aid: launch only the tile kernel (per-tile energies stay in scratch) */
+
+const char* hidenn_last_error(void);
+int hidenn_version(void);
+/* number of CUDA devices visible; <0 on error (used by the loader to fail loudly) */
+int hidenn_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Triangle plan: static topology preprocessing, once per mesh (connectivity never changes
+ * during r-adaptation; src/models.py:252 keeps it as a buffer).  Replaces, for the hot path,
+ * the per-call masked index_put assembly of src/models.py:292-305 (slot maps), the
+ * connectivity gather of src/models.py:228-238 (tile-local uint packs) and autograd's
+ * scatter-add backward (node->element CSR inside each tile).
+ *
+ *   conn            host [Ne,3] int64   (src/models.py:252)
+ *   coords_init     host [Nn,2] double  initial coordinates, used ONLY for locality ordering
+ *   boundary_mask   host [Nn] uint8     1 = coordinate fixed (src/models.py:256-263)
+ *   dirichlet_mask  host [Nn] uint8     1 = displacement fixed (src/models.py:266-271)
+ *   edges           host [Ned,2] int64  Neumann edges (src/models.py:280-282); may be NULL/0
+ *   tile_nodes      owned nodes per tile; 0 = default for `real_bytes` (8 or 4)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hidenn_tri_plan hidenn_tri_plan;
+
+int hidenn_tri_plan_create(const int64_t* conn, int64_t n_elems, int64_t n_nodes,
+                           const double* coords_init,
+                           const uint8_t* boundary_mask, const uint8_t* dirichlet_mask,
+                           const int64_t* edges, int64_t n_edges,
+                           int tile_nodes, int real_bytes, int device,
+                           hidenn_tri_plan** out);
+void hidenn_tri_plan_destroy(hidenn_tri_plan* plan);
+
+/* info[0]=n_tiles [1]=tile element visits (incl. halo recompute) [2]=tile node visits
+ * [3]=max local nodes/tile [4]=max fold entries/tile [5]=scratch elements needed
+ * [6]=dynamic smem bytes f64 [7]=same f32 [8]=n_free_x [9]=n_free_u [10]=n_edges [11]=n_edge_nodes
+ * [12]=plan bytes on device [13]=max elements/tile [14]=n_elems [15]=n_nodes */
+int hidenn_tri_plan_info(const hidenn_tri_plan* plan, int64_t* info16);
+
+/* Bit-exact integer views for tests (host copies): slot maps of src/models.py:292-305.
+ * xslot[n] >= 0: row of node n in node_coords_free; < 0: ~row in node_coords_fixed. Same for uslot. */
+int hidenn_tri_plan_slots(const hidenn_tri_plan* plan, int32_t* xslot_host, int32_t* uslot_host);
+/* For every tile element visit: global element id and the three global node ids it will gather
+ * (decoded from the tile packs) -- lets tests check connectivity indexing bit-exactly.
+ * out_elem [visits], out_nodes [visits,3], out_owner [visits] (1 = this visit adds the energy). */
+int hidenn_tri_plan_decode(const hidenn_tri_plan* plan, int64_t* out_elem, int64_t* out_nodes, uint8_t* out_owner);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused energy + gradients:  EnergyLoss2D.__call__ (src/loss.py:113-116) =
+ * domain_energy (src/loss.py:55-88) over PiecewiseLinearShapeNN2D.forward
+ * (src/models.py:316-357) minus edge_energy (src/loss.py:91-110, src/models.py:359-376),
+ * and what loss.backward() leaves in node_coords_free.grad / u_free.grad.
+ *
+ *   x_free  dev [Nfree,2]   x_fixed dev [Nfixed,2]   (src/models.py:261-262)
+ *   u_free  dev [Nufree,2]  u_fixed dev [Nufixed,2]  (src/models.py:274-277, broadcast by caller)
+ *   consts  dev [HIDENN_TRI_NCONST]
+ *   t_table dev [Ned,ng1,2] traction at the physical edge Gauss points, or NULL = uniform
+ *   out     dev [4]: loss, domain energy, edge energy, (unused)
+ *   gx_free dev [Nfree,2], gu_free dev [Nufree,2]: overwritten (every row), not accumulated
+ *   gt_out  dev [Ned,ng1,2] or NULL: d loss / d t_table (for tractions that depend on x)
+ *   scratch dev [info[5]] reals
+ * ------------------------------------------------------------------------------------------ */
+int hidenn_tri_energy_f64(const hidenn_tri_plan* plan,
+                          const double* x_free, const double* x_fixed,
+                          const double* u_free, const double* u_fixed,
+                          const double* consts, const double* t_table, int flags,
+                          double* out, double* gx_free, double* gu_free, double* gt_out,
+                          double* scratch, void* stream);
+int hidenn_tri_energy_f32(const hidenn_tri_plan* plan,
+                          const float* x_free, const float* x_fixed,
+                          const float* u_free, const float* u_fixed,
+                          const float* consts, const float* t_table, int flags,
+                          float* out, float* gx_free, float* gu_free, float* gt_out,
+                          float* scratch, void* stream);
+
+/* Host-buffer convenience (the end-to-end drop-in for a CPU caller): copies the four parameter
+ * arrays host->device, runs the fused step, copies loss and both gradients back and waits.
+ * Host buffers should be pinned for full PCIe speed.  `work` is a plan-owned device arena. */
+int hidenn_tri_energy_host_f64(hidenn_tri_plan* plan,
+                               const double* x_free_h, const double* x_fixed_h,
+                               const double* u_free_h, const double* u_fixed_h,
+                               const double* consts_h, int flags,
+                               double* out_h, double* gx_free_h, double* gu_free_h, void* stream);
+int hidenn_tri_energy_host_f32(hidenn_tri_plan* plan,
+                               const float* x_free_h, const float* x_fixed_h,
+                               const float* u_free_h, const float* u_fixed_h,
+                               const float* consts_h, int flags,
+                               float* out_h, float* gx_free_h, float* gu_free_h, void* stream);
+
+/* g[i] *= *scale for i<n unless *scale == 1 (then every block exits at once): applies autograd's
+ * grad_output to gradients computed in the forward launch without a host sync. */
+int hidenn_scale_inplace_f64(double* g, int64_t n, const double* scale_dev, void* stream);
+int hidenn_scale_inplace_f32(float* g, int64_t n, const float* scale_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Generic pointwise forward(x_ref, elem_id) and its VJP (src/models.py:316-357; callers
+ * src/loss.py:65, src/plots.py:183-187).
+ *   elem_id dev [M] int64, x_ref dev [M,2]
+ *   u_h dev [M,2], detJ dev [M] (signed), grad_u dev [M,2,2]
+ * VJP: cotangents cu [M,2], cd [M], cG [M,2,2] (any may be NULL) -> per-row corner contributions
+ *   row_gx dev [M,3,2], row_gu dev [M,3,2]  (folded to nodes by hidenn_tri_fold_rows)
+ * ------------------------------------------------------------------------------------------ */
+int hidenn_tri_eval_fwd_f64(const hidenn_tri_plan* plan, const double* x_free, const double* x_fixed,
+                            const double* u_free, const double* u_fixed,
+                            const double* x_ref, const int64_t* elem_id, int64_t M,
+                            double* u_h, double* detJ, double* grad_u, void* stream);
+int hidenn_tri_eval_fwd_f32(const hidenn_tri_plan* plan, const float* x_free, const float* x_fixed,
+                            const float* u_free, const float* u_fixed,
+                            const float* x_ref, const int64_t* elem_id, int64_t M,
+                            float* u_h, float* detJ, float* grad_u, void* stream);
+int hidenn_tri_eval_bwd_f64(const hidenn_tri_plan* plan, const double* x_free, const double* x_fixed,
+                            const double* u_free, const double* u_fixed,
+                            const double* x_ref, const int64_t* elem_id, int64_t M,
+                            const double* cu, const double* cd, const double* cG,
+                            double* row_gx, double* row_gu, void* stream);
+int hidenn_tri_eval_bwd_f32(const hidenn_tri_plan* plan, const float* x_free, const float* x_fixed,
+                            const float* u_free, const float* u_fixed,
+                            const float* x_ref, const int64_t* elem_id, int64_t M,
+                            const float* cu, const float* cd, const float* cG,
+                            float* row_gx, float* row_gu, void* stream);
+/* Deterministic fold of per-row corner contributions to the parameter gradients.
+ *   order dev [M] int64: a permutation that sorts rows by elem_id (stable), seg dev [Ne+1] int64:
+ *   row range of each element in that order.  Rows of one element are summed in that order,
+ *   elements of one node in ascending element id (global node->element CSR held by the plan). */
+int hidenn_tri_fold_rows_f64(const hidenn_tri_plan* plan, const double* row_gx, const double* row_gu,
+                             const int64_t* order, const int64_t* seg, int64_t M,
+                             double* elem_tmp, double* gx_free, double* gu_free, void* stream);
+int hidenn_tri_fold_rows_f32(const hidenn_tri_plan* plan, const float* row_gx, const float* row_gu,
+                             const int64_t* order, const int64_t* seg, int64_t M,
+                             float* elem_tmp, float* gx_free, float* gu_free, void* stream);
+/* Edge branch forward(x, edge_id, edge=True) (src/models.py:359-376): u_h [M,2], ds [M]. */
+int hidenn_tri_edge_fwd_f64(const hidenn_tri_plan* plan, const double* x_free, const double* x_fixed,
+                            const double* u_free, const double* u_fixed,
+                            const double* xi, const int64_t* edge_id, int64_t M,
+                            double* u_h, double* ds, void* stream);
+int hidenn_tri_edge_fwd_f32(const hidenn_tri_plan* plan, const float* x_free, const float* x_fixed,
+                            const float* u_free, const float* u_fixed,
+                            const float* xi, const int64_t* edge_id, int64_t M,
+                            float* u_h, float* ds, void* stream);
+
+/* Gather full arrays: coords / u_full properties (src/models.py:292-305) without masked index_put. */
+int hidenn_tri_assemble_f64(const hidenn_tri_plan* plan, int which /*0=coords,1=u*/,
+                            const double* free_vals, const double* fixed_vals, double* full, void* stream);
+int hidenn_tri_assemble_f32(const hidenn_tri_plan* plan, int which,
+                            const float* free_vals, const float* fixed_vals, float* full, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Halo pack / unpack for element-block partitions (new capability, the
+ * reference is single-device).  idx dev [n] int32 rows of a [N,2] gradient array.
+ * pack:   buf[2*i..] = g[idx[i]]        unpack: g[idx[i]] = buf[2*i..]
+ * ------------------------------------------------------------------------------------------ */
+int hidenn_halo_pack_f64(const double* g, const int32_t* idx, int64_t n, double* buf, void* stream);
+int hidenn_halo_unpack_f64(double* g, const int32_t* idx, int64_t n, const double* buf, void* stream);
+int hidenn_halo_pack_f32(const float* g, const int32_t* idx, int64_t n, float* buf, void* stream);
+int hidenn_halo_unpack_f32(float* g, const int32_t* idx, int64_t n, const float* buf, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIDENN_B200_H */

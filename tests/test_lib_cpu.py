@@ -1,0 +1,119 @@
+"""CPU: the C-ABI library loads, exports every declared symbol, and its integer plan data is bit-exact.
+No compute entry point is called here (there is no GPU and no CPU fallback)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from hidenn_fem_b200 import _lib, meshgen
+from hidenn_fem_b200.plan import TriPlan
+
+
+def test_exports_every_declared_symbol():
+    names = _lib.declared_symbols()
+    assert len(names) >= 28
+    L = _lib.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert L.hidenn_version() == 100
+
+
+@pytest.mark.parametrize("ordering", ["natural", "morton", "random"])
+@pytest.mark.parametrize("tile_nodes", [16, 64, 288])
+def test_plan_indexing_bit_exact(ordering, tile_nodes):
+    m = meshgen.plate_mesh(37, 19, jitter=0.25, diag="random", seed=5, ordering=ordering)
+    p = TriPlan(m.connectivity, m.node_coords.shape[0], m.node_coords, m.boundary_mask, m.dirichlet_mask,
+                m.neumann_edges, tile_nodes=tile_nodes, device=-1)
+    el, nd, ow = p.decode()
+    # every tile visit gathers exactly the nodes of the reference's connectivity[elem_id] (models.py:235)
+    assert np.array_equal(nd, m.connectivity[el])
+    # each element's energy is counted exactly once; every element is visited by 1..3 tiles
+    assert (np.bincount(el[ow == 1], minlength=p.n_elems) == 1).all()
+    visits = np.bincount(el, minlength=p.n_elems)
+    assert visits.min() >= 1 and visits.max() <= 3
+    # slot maps = rank among free / fixed rows in ascending node order (models.py:261-262,274)
+    xs, us = p.slots()
+    free = ~m.boundary_mask
+    assert np.array_equal(xs[free], np.arange(free.sum())) and np.array_equal(~xs[~free], np.arange((~free).sum()))
+    ufree = ~m.dirichlet_mask
+    assert np.array_equal(us[ufree], np.arange(ufree.sum())) and np.array_equal(~us[~ufree], np.arange((~ufree).sum()))
+    assert p.info["n_free_x"] == free.sum() and p.info["n_free_u"] == ufree.sum()
+    p.close()
+
+
+def test_plan_edge_cases():
+    # single element, no edges, nothing fixed
+    conn = np.array([[0, 1, 2]])
+    xy = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+    z = np.zeros(3, bool)
+    p = TriPlan(conn, 3, xy, z, z, None, device=-1)
+    assert p.info["n_tiles"] == 1 and p.info["elem_visits"] == 1 and p.info["n_edges"] == 0
+    # an isolated node (no element) still belongs to a tile so its gradient row gets written (as zero)
+    xy4 = np.vstack([xy, [[5.0, 5.0]]])
+    p = TriPlan(conn, 4, xy4, np.zeros(4, bool), np.zeros(4, bool), None, device=-1)
+    assert p.info["node_visits"] == 4
+    # empty mesh (no elements)
+    p = TriPlan(np.zeros((0, 3), np.int64), 3, xy, z, z, None, device=-1)
+    assert p.info["elem_visits"] == 0
+    # fan: one hub node of valence 40 (more than a typical tile row)
+    k = 40
+    ang = np.linspace(0, 2 * np.pi, k, endpoint=False)
+    xyf = np.vstack([[0.0, 0.0], np.stack([np.cos(ang), np.sin(ang)], 1)])
+    connf = np.stack([np.zeros(k, int), 1 + np.arange(k), 1 + (np.arange(k) + 1) % k], 1)
+    p = TriPlan(connf, k + 1, xyf, np.zeros(k + 1, bool), np.zeros(k + 1, bool), None, tile_nodes=8, device=-1)
+    el, nd, ow = p.decode()
+    assert np.array_equal(nd, connf[el]) and (np.bincount(el[ow == 1], minlength=k) == 1).all()
+
+
+def test_plan_rejects_bad_input():
+    xy = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]])
+    z = np.zeros(3, bool)
+    with pytest.raises(_lib.HidennError, match="out of range"):
+        TriPlan(np.array([[0, 1, 3]]), 3, xy, z, z, None, device=-1)
+    with pytest.raises(_lib.HidennError, match="edge node"):
+        TriPlan(np.array([[0, 1, 2]]), 3, xy, z, z, np.array([[0, 7]]), device=-1)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from hidenn_fem_b200.models import PiecewiseLinearShapeNN2D
+    from hidenn_fem_b200.loss import EnergyLoss2D
+    m = meshgen.plate_mesh(9, 5)
+    T = torch.tensor
+    model = PiecewiseLinearShapeNN2D(T(m.node_coords, dtype=torch.float32), T(m.connectivity), T(m.boundary_mask),
+                                     T(m.dirichlet_mask), 0.0, T(m.neumann_edges))
+    loss_fn = EnergyLoss2D(device=torch.device("cpu"))
+    with pytest.raises(_lib.HidennError, match="no CPU fallback"):
+        loss_fn(model)
+    with pytest.raises(_lib.HidennError):
+        TriPlan(m.connectivity, m.node_coords.shape[0], m.node_coords, m.boundary_mask, m.dirichlet_mask,
+                m.neumann_edges, device="cuda:0")
+
+
+def test_state_dict_names_match_reference():
+    from hidenn_fem_b200.models import PiecewiseLinearShapeNN2D
+    m = meshgen.plate_mesh(9, 5)
+    T = torch.tensor
+    model = PiecewiseLinearShapeNN2D(T(m.node_coords, dtype=torch.float32), T(m.connectivity), T(m.boundary_mask),
+                                     T(m.dirichlet_mask), 0.0, T(m.neumann_edges))
+    assert [n for n, _ in model.named_parameters()] == ["node_coords_free", "u_free"]
+    assert set(dict(model.named_buffers())) == {"initial_node_coords", "connectivity", "boundary_mask", "node_coords_fixed",
+                                               "free_mask", "dirichlet_mask", "u_free_mask", "u_fixed", "neumann_edges"}
+    assert model.Nnodes == m.node_coords.shape[0] and model.Nelems == m.connectivity.shape[0]
+    assert model.u_free.dtype == torch.float32 and model.dim_u == 2 and model.scale == 1e-5
+
+
+def test_quadrature_tables_match_reference_bits():
+    from hidenn_fem_b200 import utils
+    from helpers import gold
+    g = gold("quadrature")
+    for dt, tag in ((torch.float64, "f64"), (torch.float32, "f32")):
+        for o in (1, 3, 4, 6, 7):
+            rs, w = utils.triangle_gauss_points(o, device=torch.device("cpu"), dtype=dt)
+            assert np.array_equal(rs.numpy(), g[f"tri{o}_rs_{tag}"]) and np.array_equal(w.numpy(), g[f"tri{o}_w_{tag}"])
+        for o in (1, 2, 3, 4, 5):
+            x, w = utils.interval_gauss_points(o, dtype=dt)
+            assert np.array_equal(x.numpy(), g[f"int{o}_x_{tag}"]) and np.array_equal(w.numpy(), g[f"int{o}_w_{tag}"])
+    with pytest.raises(NotImplementedError):
+        utils.triangle_gauss_points(2, device=torch.device("cpu"))

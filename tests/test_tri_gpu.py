@@ -1,0 +1,255 @@
+"""GPU parity: fused triangle kernels (through the C-ABI) vs the oracle and the reference's golden fixtures.
+
+Tolerances (BASELINE.json north_star): FP64 1e-10, FP32 1e-5 relative (loss |d|/|ref|, gradients
+max-norm relative); element / connectivity indexing bit-exact (tests/test_lib_cpu.py)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import gold, relmax, tri_oracle, TRI_CASES
+from oracle import closed_form as cf
+import forces
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float64: 1e-10, torch.float32: 1e-5}
+
+
+def build(g, device="cuda", dtype=None, tile_nodes=0):
+    from hidenn_fem_b200.models import PiecewiseLinearShapeNN2D
+    T = torch.tensor
+    npdt = g["node_coords_free"].dtype if "node_coords_free" in g else np.float64
+    dt = dtype or (torch.float64 if npdt == np.float64 else torch.float32)
+    coords = T(g["node_coords"], dtype=dt)
+    model = PiecewiseLinearShapeNN2D(coords, T(g["connectivity"]), T(g["boundary_mask"]), T(g["dirichlet_mask"]),
+                                     float(g["u_fixed"]) if "u_fixed" in g else 0.0, T(g["neumann_edges"]))
+    if dt == torch.float64:
+        model = model.double()
+    model.tile_nodes = tile_nodes
+    model = model.to(device)
+    with torch.no_grad():
+        if "node_coords_free" in g:
+            model.node_coords_free.copy_(T(g["node_coords_free"]))
+            model.u_free.copy_(T(g["u_free"]))
+    return model
+
+
+def loss_of(g, dt, **kw):
+    from hidenn_fem_b200.loss import EnergyLoss2D
+    return EnergyLoss2D(E=10e9, nu=0.3, gauss_order=int(g.get("gauss_order", 4)), gauss_order_1d=int(g.get("gauss_order_1d", 2)),
+                        device=torch.device("cuda"), dtype=dt, **kw)
+
+
+@pytest.mark.parametrize("case", TRI_CASES)
+@pytest.mark.parametrize("tag", ["default", "forces"])
+@pytest.mark.parametrize("tile_nodes", [0, 16])
+def test_energy_and_grads_vs_reference_golden(case, tag, tile_nodes):
+    g = gold(case)
+    model = build(g, tile_nodes=tile_nodes)
+    dt = model.dtype
+    loss_fn = loss_of(g, dt)
+    bf, tf = (forces.b_force_test, forces.t_force_test) if tag == "forces" else (None, None)
+    loss = loss_fn(model, bf, tf)
+    loss.backward()
+    tol = TOL[dt]
+    ref = float(g[f"loss_{tag}"])
+    assert abs(loss.item() - ref) <= tol * abs(ref), (loss.item(), ref)
+    assert relmax(model.node_coords_free.grad.cpu().numpy(), g[f"gx_{tag}"]) < tol
+    assert relmax(model.u_free.grad.cpu().numpy(), g[f"gu_{tag}"]) < tol
+    parts = loss_fn.last_parts.cpu().numpy()
+    assert abs(parts[1] - float(g[f"domain_{tag}"])) <= tol * max(abs(float(g[f"domain_{tag}"])), abs(ref))
+    assert abs(parts[2] - float(g[f"edge_{tag}"])) <= tol * max(abs(float(g[f"edge_{tag}"])), abs(ref))
+
+
+@pytest.mark.parametrize("case", ["tri_f64_jitter", "tri_f32_jitter"])
+def test_domain_and_edge_separately(case):
+    g = gold(case)
+    model = build(g)
+    loss_fn = loss_of(g, model.dtype)
+    tol = TOL[model.dtype]
+    d = loss_fn.domain_energy(model, forces.b_force_test)
+    e = loss_fn.edge_energy(model, forces.t_force_test)
+    assert abs(d.item() - float(g["domain_forces"])) <= tol * abs(float(g["domain_forces"]))
+    assert abs(e.item() - float(g["edge_forces"])) <= tol * abs(float(g["edge_forces"]))
+    (d - e).backward()
+    assert relmax(model.node_coords_free.grad.cpu().numpy(), g["gx_forces"]) < tol
+    assert relmax(model.u_free.grad.cpu().numpy(), g["gu_forces"]) < tol
+
+
+@pytest.mark.parametrize("case", TRI_CASES)
+def test_generic_forward_and_vjp_vs_reference_golden(case):
+    g = gold(case)
+    model = build(g)
+    dt = model.dtype
+    tol = TOL[dt]
+    T = lambda a: torch.tensor(a, device="cuda")
+    u_h, det, G = model(T(g["pt_x"]), T(g["pt_e"]))
+    assert relmax(u_h.detach().cpu().numpy(), g["pt_u"]) < tol
+    assert relmax(det.detach().cpu().numpy(), g["pt_det"]) < tol
+    assert relmax(G.detach().cpu().numpy(), g["pt_G"]) < 5 * tol
+    ((u_h * T(g["pt_cu"])).sum() + (det * T(g["pt_cd"])).sum() + (G * T(g["pt_cG"])).sum()).backward()
+    assert relmax(model.node_coords_free.grad.cpu().numpy(), g["pt_gx"]) < 5 * tol
+    assert relmax(model.u_free.grad.cpu().numpy(), g["pt_gu"]) < 5 * tol
+    ue, ds = model(T(g["ed_x"]), T(g["ed_e"]), edge=True)
+    assert relmax(ue.detach().cpu().numpy(), g["ed_u"]) < tol and relmax(ds.detach().cpu().numpy(), g["ed_ds"]) < tol
+    ue2, ds2 = model.edge_forward_nograd(T(g["ed_x"]), T(g["ed_e"]))
+    assert relmax(ue2.cpu().numpy(), g["ed_u"]) < tol and relmax(ds2.cpu().numpy(), g["ed_ds"]) < tol
+    # coords / u_full properties (models.py:292-305)
+    fmask = ~g["boundary_mask"]
+    full = cf.assemble_full(g["node_coords_free"], g["node_coords_fixed"], fmask)
+    assert np.array_equal(model.coords.detach().cpu().numpy(), full)
+
+
+def _mesh_case(n_elems, dtype, ordering, jitter=0.25, invert=0.0, seed=0, u_scale=1e-5):
+    from hidenn_fem_b200 import meshgen
+    nx, ny = meshgen.plate_dims_for_elements(n_elems)
+    m = meshgen.plate_mesh(nx, ny, jitter=jitter, diag="random", seed=seed, ordering=ordering)
+    conn = meshgen.invert_some_elements(m.connectivity, invert, seed) if invert else m.connectivity
+    bmask = m.boundary_mask & ~m.neumann_mask
+    rng = np.random.default_rng(seed)
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    coords = m.node_coords.astype(npdt)
+    g = dict(node_coords=coords, connectivity=conn, boundary_mask=bmask, dirichlet_mask=m.dirichlet_mask,
+             neumann_edges=m.neumann_edges, u_fixed=np.asarray(0.0), gauss_order=4, gauss_order_1d=2,
+             node_coords_free=coords[~bmask], node_coords_fixed=coords[bmask],
+             u_free=(u_scale * rng.standard_normal((int((~m.dirichlet_mask).sum()), 2))).astype(npdt))
+    return g
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("ordering", ["natural", "random", "morton"])
+def test_parity_200k_vs_oracle(dtype, ordering):
+    """Mid-size unstructured mesh, incl. 20% inverted elements: CUDA vs closed-form oracle (FP64 evaluation of the
+    same FP32/FP64 inputs)."""
+    g = _mesh_case(200_000, dtype, ordering, invert=0.2, u_scale=1e-3)
+    model = build(g)
+    loss_fn = loss_of(g, dtype)
+    loss = loss_fn(model)
+    loss.backward()
+    g64 = dict(g)
+    lo, gx, gu = tri_oracle(g64, "default", dtype=np.float64)
+    tol = TOL[dtype]
+    assert abs(loss.item() - float(lo)) <= tol * abs(float(lo))
+    assert relmax(model.node_coords_free.grad.cpu().numpy(), gx) < tol
+    assert relmax(model.u_free.grad.cpu().numpy(), gu) < tol
+
+
+def test_determinism_and_plan_invariance():
+    g = _mesh_case(100_000, torch.float64, "random", u_scale=1e-3)
+    outs = []
+    for tile_nodes in (0, 0, 96):
+        model = build(g, tile_nodes=tile_nodes)
+        loss_fn = loss_of(g, torch.float64)
+        loss = loss_fn(model)
+        loss.backward()
+        outs.append((loss.item(), model.node_coords_free.grad.clone(), model.u_free.grad.clone()))
+    # same plan: bit-identical run to run (no float atomics anywhere)
+    assert outs[0][0] == outs[1][0]
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    # different tiling: gradients bit-identical (node fold order = ascending element id in every tiling);
+    # the energy sum is re-associated across tiles
+    assert torch.equal(outs[0][1], outs[2][1]) and torch.equal(outs[0][2], outs[2][2])
+    assert abs(outs[0][0] - outs[2][0]) <= 1e-13 * abs(outs[0][0])
+
+
+def test_no_grad_and_frozen_parameters():
+    g = gold("tri_f64_jitter")
+    model = build(g)
+    loss_fn = loss_of(g, torch.float64)
+    with torch.no_grad():
+        l0 = loss_fn(model)
+    assert abs(l0.item() - float(g["loss_default"])) <= 1e-10 * abs(float(g["loss_default"]))
+    assert not l0.requires_grad
+    # alternating scheme of examples/example4.py:92-103: freeze the mesh, then the displacements
+    model.node_coords_free.requires_grad = False
+    loss_fn(model).backward()
+    assert model.node_coords_free.grad is None
+    assert relmax(model.u_free.grad.cpu().numpy(), g["gu_default"]) < 1e-10
+    model.zero_grad()
+    model.node_coords_free.requires_grad = True
+    model.u_free.requires_grad = False
+    loss_fn(model).backward()
+    assert model.u_free.grad is None
+    assert relmax(model.node_coords_free.grad.cpu().numpy(), g["gx_default"]) < 1e-10
+
+
+def test_grad_accumulation_and_scaling():
+    g = gold("tri_f64_jitter")
+    model = build(g)
+    loss_fn = loss_of(g, torch.float64)
+    (3.0 * loss_fn(model)).backward()
+    loss_fn(model).backward()          # accumulates into .grad like the reference's autograd path
+    assert relmax(model.u_free.grad.cpu().numpy(), 4.0 * g["gu_default"]) < 1e-10
+    assert relmax(model.node_coords_free.grad.cpu().numpy(), 4.0 * g["gx_default"]) < 1e-10
+
+
+@pytest.mark.parametrize("tag,dtype", [("tri_traj_f64", torch.float64), ("tri_traj_f32", torch.float32)])
+def test_unchanged_training_loops_vs_reference(tag, dtype):
+    """The LBFGS / Adam loops of examples/example4.py:54-80, verbatim, on the drop-in classes."""
+    g = gold(tag)
+    g = dict(g, u_fixed=np.asarray(0.0))
+
+    def fresh():
+        m = build(g, dtype=dtype)
+        with torch.no_grad():
+            m.u_free.copy_(torch.tensor(g["u_free0"]))
+        return m
+    model = fresh()
+    loss_fn = loss_of(g, dtype)
+    optimizer = torch.optim.LBFGS(model.parameters())
+    losses = []
+    for epoch in range(3):
+        def closure():
+            optimizer.zero_grad()
+            loss = loss_fn(model)
+            loss.backward()
+            return loss
+        losses.append(optimizer.step(closure).item())
+    rtol = 1e-8 if dtype == torch.float64 else 5e-3
+    assert np.allclose(losses, g["lbfgs_losses"], rtol=rtol), (losses, g["lbfgs_losses"])
+    with torch.no_grad():
+        final = loss_fn(model).item()
+    assert abs(final - float(g["lbfgs_final"])) <= (1e-6 if dtype == torch.float64 else 2e-2) * abs(float(g["lbfgs_final"]))
+    model2 = fresh()
+    opt2 = torch.optim.Adam([{"params": model2.u_free, "lr": 1e-4}, {"params": model2.node_coords_free, "lr": 1e-5}], lr=1e-4)
+    ad = []
+    for _ in range(10):
+        opt2.zero_grad()
+        l = loss_fn(model2)
+        l.backward()
+        opt2.step()
+        ad.append(l.item())
+    assert np.allclose(ad, g["adam_losses"], rtol=1e-8 if dtype == torch.float64 else 1e-3), (ad, g["adam_losses"])
+    assert relmax(model2.u_free.detach().cpu().numpy(), g["adam_u"]) < (1e-8 if dtype == torch.float64 else 1e-3)
+
+
+def test_host_buffer_entry_point():
+    """hidenn_tri_energy_host_f64: the end-to-end call a CPU caller makes (pinned host buffers in, loss + grads out)."""
+    import ctypes as C
+    from hidenn_fem_b200 import _lib
+    g = gold("tri_f64_jitter")
+    model = build(g)
+    loss_fn = loss_of(g, torch.float64)
+    consts = loss_fn._consts(model, None).cpu()
+    plan = model._plan()
+    xb, ub = model._fixed_pair()
+    xf = model.node_coords_free.detach().cpu().pin_memory()
+    uf = model.u_free.detach().cpu().pin_memory()
+    xb, ub = xb.cpu(), ub.cpu()
+    out = torch.empty(4, dtype=torch.float64).pin_memory()
+    gx = torch.empty_like(xf).pin_memory()
+    gu = torch.empty_like(uf).pin_memory()
+    _lib.check(_lib.lib().hidenn_tri_energy_host_f64(plan.handle, _lib.ptr(xf), _lib.ptr(xb), _lib.ptr(uf), _lib.ptr(ub),
+                                                     _lib.ptr(consts), C.c_int(7), _lib.ptr(out), _lib.ptr(gx), _lib.ptr(gu),
+                                                     _lib.stream_ptr()))
+    assert abs(out[0].item() - float(g["loss_default"])) <= 1e-10 * abs(float(g["loss_default"]))
+    assert relmax(gx.numpy(), g["gx_default"]) < 1e-10 and relmax(gu.numpy(), g["gu_default"]) < 1e-10
+
+
+def test_cpu_tensor_raises():
+    from hidenn_fem_b200 import _lib
+    g = gold("tri_f64_jitter")
+    model = build(g, device="cpu")
+    loss_fn = loss_of(g, torch.float64)
+    with pytest.raises(_lib.HidennError, match="no CPU fallback"):
+        loss_fn(model)
