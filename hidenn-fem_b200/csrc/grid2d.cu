@@ -1,0 +1,185 @@
+// Structured Q1 (tensor-product) model kernels: two 1D lookups, bilinear interpolation, per-row VJP pieces and
+// the deterministic cell / node / grid-line folds.  Reference: /root/reference/src/models.py:180-212.
+#include "../../include/hidenn_b200_grid.h"
+#include "common.cuh"
+
+namespace hidenn {
+
+template <typename R> __device__ __forceinline__ int lookup_line(const R* __restrict__ grid, int64_t N, R x) {
+    int64_t lo = 0, hi = N;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(grid + mid) < x) lo = mid + 1; else hi = mid;
+    }
+    int64_t e = lo - 1;
+    e = e < 0 ? 0 : (e > N - 2 ? N - 2 : e);
+    return (int)e;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+q1_fwd_kernel(const R* __restrict__ gx, int64_t Nx, const R* __restrict__ gy, int64_t Ny, const R* __restrict__ uf,
+              const typename Real2<R>::type* __restrict__ x, int64_t M, R* __restrict__ u, int32_t* __restrict__ ixo,
+              int32_t* __restrict__ iyo) {
+    for (int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x; m < M; m += (int64_t)gridDim.x * 256) {
+        const typename Real2<R>::type p = x[m];
+        const int ix = lookup_line<R>(gx, Nx, p.x), iy = lookup_line<R>(gy, Ny, p.y);
+        const R x0 = __ldg(gx + ix), x1 = __ldg(gx + ix + 1), y0 = __ldg(gy + iy), y1 = __ldg(gy + iy + 1);
+        R hx = x1 - x0, hy = y1 - y0;
+        hx = hx < R(1e-10) ? R(1e-10) : hx;
+        hy = hy < R(1e-10) ? R(1e-10) : hy;
+        const R N1x = (x1 - p.x) / hx, N2x = (p.x - x0) / hx, N1y = (y1 - p.y) / hy, N2y = (p.y - y0) / hy;
+        const R u00 = __ldg(uf + (int64_t)ix * Ny + iy), u10 = __ldg(uf + (int64_t)(ix + 1) * Ny + iy);
+        const R u01 = __ldg(uf + (int64_t)ix * Ny + iy + 1), u11 = __ldg(uf + (int64_t)(ix + 1) * Ny + iy + 1);
+        u[m] = N1x * N1y * u00 + N2x * N1y * u10 + N1x * N2y * u01 + N2x * N2y * u11;
+        if (ixo) ixo[m] = ix;
+        if (iyo) iyo[m] = iy;
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+q1_bwd_kernel(const R* __restrict__ gx, const R* __restrict__ gy, int64_t Ny, const R* __restrict__ uf,
+              const typename Real2<R>::type* __restrict__ x, const int32_t* __restrict__ ixs, const int32_t* __restrict__ iys,
+              const R* __restrict__ r, int64_t M, R* __restrict__ rows) {
+    for (int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x; m < M; m += (int64_t)gridDim.x * 256) {
+        const typename Real2<R>::type p = x[m];
+        const int ix = ixs[m], iy = iys[m];
+        const R x0 = __ldg(gx + ix), x1 = __ldg(gx + ix + 1), y0 = __ldg(gy + iy), y1 = __ldg(gy + iy + 1);
+        const R hxr = x1 - x0, hyr = y1 - y0;
+        const bool ax = hxr >= R(1e-10), ay = hyr >= R(1e-10);
+        const R ihx = R(1) / (ax ? hxr : R(1e-10)), ihy = R(1) / (ay ? hyr : R(1e-10));
+        const R N1x = (x1 - p.x) * ihx, N2x = (p.x - x0) * ihx, N1y = (y1 - p.y) * ihy, N2y = (p.y - y0) * ihy;
+        const R u00 = __ldg(uf + (int64_t)ix * Ny + iy), u10 = __ldg(uf + (int64_t)(ix + 1) * Ny + iy);
+        const R u01 = __ldg(uf + (int64_t)ix * Ny + iy + 1), u11 = __ldg(uf + (int64_t)(ix + 1) * Ny + iy + 1);
+        const R rv = r[m];
+        R* o = rows + 8 * m;
+        o[0] = rv * N1x * N1y; o[1] = rv * N2x * N1y; o[2] = rv * N1x * N2y; o[3] = rv * N2x * N2y;
+        const R A = N1y * u00 + N2y * u01, B = N1y * u10 + N2y * u11;       // u = A N1x + B N2x
+        const R numx = A * (x1 - p.x) + B * (p.x - x0);
+        const R qx = ax ? numx * ihx * ihx : R(0);
+        o[4] = rv * (-B * ihx + qx);
+        o[5] = rv * (A * ihx - qx);
+        const R Cc = N1x * u00 + N2x * u10, D = N1x * u01 + N2x * u11;      // u = C N1y + D N2y
+        const R numy = Cc * (y1 - p.y) + D * (p.y - y0);
+        const R qy = ay ? numy * ihy * ihy : R(0);
+        o[6] = rv * (-D * ihy + qy);
+        o[7] = rv * (Cc * ihy - qy);
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+q1_fold_cells_kernel(const R* __restrict__ rows, const int64_t* __restrict__ order, const int64_t* __restrict__ seg, int64_t ncell,
+                     R* __restrict__ cell_tmp) {
+    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < ncell; c += (int64_t)gridDim.x * 256) {
+        R a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = R(0);
+        for (int64_t q = seg[c]; q < seg[c + 1]; ++q) {
+            const int64_t m = order[q];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += rows[8 * m + k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cell_tmp[8 * c + k] = a[k];
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+q1_fold_nodes_kernel(const R* __restrict__ cell_tmp, int64_t Nx, int64_t Ny, R* __restrict__ du) {
+    const int64_t total = Nx * Ny, cy = Ny - 1;
+    for (int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x; n < total; n += (int64_t)gridDim.x * 256) {
+        const int64_t i = n / Ny, j = n % Ny;
+        R a = R(0);
+        if (i < Nx - 1 && j < Ny - 1) a += cell_tmp[8 * (i * cy + j) + 0];
+        if (i > 0 && j < Ny - 1) a += cell_tmp[8 * ((i - 1) * cy + j) + 1];
+        if (i < Nx - 1 && j > 0) a += cell_tmp[8 * (i * cy + j - 1) + 2];
+        if (i > 0 && j > 0) a += cell_tmp[8 * ((i - 1) * cy + j - 1) + 3];
+        du[n] = a;
+    }
+}
+
+// one block per grid line: fixed-order strided partial sums + block tree
+template <typename R>
+__global__ void __launch_bounds__(256) q1_fold_lines_kernel(const R* __restrict__ cell_tmp, int64_t Nx, int64_t Ny, R* __restrict__ dgx,
+                                                             R* __restrict__ dgy) {
+    __shared__ R s_red[8];
+    const int64_t cy = Ny - 1, cx = Nx - 1;
+    const int64_t line = blockIdx.x;
+    R a = R(0);
+    if (line < Nx) {
+        const int64_t i = line;
+        for (int64_t j = threadIdx.x; j < cy; j += 256) {
+            if (i < cx) a += cell_tmp[8 * (i * cy + j) + 4];
+            if (i > 0) a += cell_tmp[8 * ((i - 1) * cy + j) + 5];
+        }
+    } else {
+        const int64_t j = line - Nx;
+        for (int64_t i = threadIdx.x; i < cx; i += 256) {
+            if (j < cy) a += cell_tmp[8 * (i * cy + j) + 6];
+            if (j > 0) a += cell_tmp[8 * (i * cy + j - 1) + 7];
+        }
+    }
+    const R tot = block_sum<R, 256>(a, s_red);
+    if (threadIdx.x == 0) {
+        if (line < Nx) dgx[line] = tot; else dgy[line - Nx] = tot;
+    }
+}
+
+static inline int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 32)); }
+
+template <typename R>
+static int q1_fwd(const R* gx, int64_t Nx, const R* gy, int64_t Ny, const R* uf, const R* x, int64_t M, R* u, int32_t* ix, int32_t* iy, void* s) {
+    HIDENN_REQUIRE(Nx >= 2 && Ny >= 2, "q1_interp_fwd: both grids need at least 2 nodes");
+    if (M <= 0) return 0;
+    HIDENN_REQUIRE(gx && gy && uf && x && u, "q1_interp_fwd: NULL");
+    q1_fwd_kernel<R><<<grid_for(M), 256, 0, (cudaStream_t)s>>>(gx, Nx, gy, Ny, uf, (const typename Real2<R>::type*)x, M, u, ix, iy);
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename R>
+static int q1_bwd(const R* gx, int64_t Nx, const R* gy, int64_t Ny, const R* uf, const R* x, const int32_t* ix, const int32_t* iy, const R* r,
+                  int64_t M, R* rows, void* s) {
+    (void)Nx;
+    if (M <= 0) return 0;
+    HIDENN_REQUIRE(gx && gy && uf && x && ix && iy && r && rows, "q1_interp_bwd: NULL");
+    q1_bwd_kernel<R><<<grid_for(M), 256, 0, (cudaStream_t)s>>>(gx, gy, Ny, uf, (const typename Real2<R>::type*)x, ix, iy, r, M, rows);
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename R>
+static int q1_fold(const R* rows, const int64_t* order, const int64_t* seg, int64_t Nx, int64_t Ny, R* cell_tmp, R* du, R* dgx, R* dgy, void* s) {
+    HIDENN_REQUIRE(Nx >= 2 && Ny >= 2 && order && seg && cell_tmp && du && dgx && dgy, "q1_fold_rows: bad arguments");
+    cudaStream_t st = (cudaStream_t)s;
+    const int64_t ncell = (Nx - 1) * (Ny - 1);
+    q1_fold_cells_kernel<R><<<grid_for(ncell), 256, 0, st>>>(rows, order, seg, ncell, cell_tmp);
+    q1_fold_nodes_kernel<R><<<grid_for(Nx * Ny), 256, 0, st>>>(cell_tmp, Nx, Ny, du);
+    q1_fold_lines_kernel<R><<<(int)(Nx + Ny), 256, 0, st>>>(cell_tmp, Nx, Ny, dgx, dgy);
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace hidenn
+
+using namespace hidenn;
+
+#define HIDENN_Q1_API(SUF, T)                                                                                                       \
+    extern "C" int hidenn_q1_interp_fwd_##SUF(const T* gx, int64_t Nx, const T* gy, int64_t Ny, const T* uf, const T* x, int64_t M,  \
+                                              T* u, int32_t* ix, int32_t* iy, void* s) {                                            \
+        return q1_fwd<T>(gx, Nx, gy, Ny, uf, x, M, u, ix, iy, s);                                                                   \
+    }                                                                                                                               \
+    extern "C" int hidenn_q1_interp_bwd_##SUF(const T* gx, int64_t Nx, const T* gy, int64_t Ny, const T* uf, const T* x,             \
+                                              const int32_t* ix, const int32_t* iy, const T* r, int64_t M, T* rows, void* s) {      \
+        return q1_bwd<T>(gx, Nx, gy, Ny, uf, x, ix, iy, r, M, rows, s);                                                             \
+    }                                                                                                                               \
+    extern "C" int hidenn_q1_fold_rows_##SUF(const T* rows, const int64_t* o, const int64_t* sg, int64_t Nx, int64_t Ny, T* tmp,     \
+                                             T* du, T* dgx, T* dgy, void* s) {                                                      \
+        return q1_fold<T>(rows, o, sg, Nx, Ny, tmp, du, dgx, dgy, s);                                                               \
+    }
+
+HIDENN_Q1_API(f64, double)
+HIDENN_Q1_API(f32, float)

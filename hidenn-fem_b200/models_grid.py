@@ -1,12 +1,415 @@
-"""1D and structured-2D models (placeholder until the grid kernels land)."""
+"""1D and structured-2D models -- drop-in mirrors of /root/reference/src/models.py:6-212 on the
+grid kernels (include/hidenn_b200_grid.h), plus the fused 1D bar energy of
+/root/reference/examples/example3.py:27-70.
+
+Constructor signatures, Parameter / buffer names and registration order follow the reference
+so `state_dict()` round-trips.  `forward` stays differentiable w.r.t. `x_eval` to second order
+(the reference's example3 calls `autograd.grad(u, xq, create_graph=True)`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
 import torch.nn as nn
+
+from . import _lib
+
+c_i64 = C.c_int64
+
+
+def _require_cuda(t, what):
+    if t.device.type != "cuda":
+        raise _lib.HidennError(f"{what}: tensors are on {t.device}; the B200 path has no CPU fallback")
+    _lib.suffix(t.dtype)
+
+
+def _scratch_1d(n, like):
+    L = _lib.lib()
+    L.hidenn_1d_scratch_size.restype = C.c_int64
+    return torch.empty(int(L.hidenn_1d_scratch_size(c_i64(n))), device=like.device, dtype=like.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# r-adaptive grid: softplus -> clamp -> cumsum -> normalise (models.py:45-53)
+# ------------------------------------------------------------------------------------------------
+class _GridFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, x0, xN):
+        _require_cuda(p, "grid")
+        p = p.contiguous()
+        n = p.shape[0]
+        dt = p.dtype
+        x0c, xNc = x0.to(dt).contiguous(), xN.to(dt).contiguous()
+        grid = torch.empty(n + 1, device=p.device, dtype=dt)
+        cum = torch.empty(n, device=p.device, dtype=dt)
+        sc = _scratch_1d(n, p)
+        _lib.check(_lib.fn("hidenn_1d_grid_fwd", dt)(_lib.ptr(p), c_i64(n), _lib.ptr(x0c), _lib.ptr(xNc), _lib.ptr(grid),
+                                                     _lib.ptr(cum), _lib.ptr(sc), _lib.stream_ptr()))
+        ctx.save_for_backward(p, cum, x0c, xNc)
+        return grid
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dgrid):
+        p, cum, x0c, xNc = ctx.saved_tensors
+        n = p.shape[0]
+        dp = torch.empty_like(p)
+        sc = _scratch_1d(n, p)
+        _lib.check(_lib.fn("hidenn_1d_grid_bwd", p.dtype)(_lib.ptr(dgrid.contiguous()), _lib.ptr(p), _lib.ptr(cum), _lib.ptr(x0c),
+                                                          _lib.ptr(xNc), c_i64(n), _lib.ptr(dp), _lib.ptr(sc), _lib.stream_ptr()))
+        return dp, None, None
+
+
+def _fold_1d(rows, elem, N):
+    """Deterministic fold of per-row (du_e, du_e+1, dg_e, dg_e+1) to nodes: stable sort by element."""
+    dt, dev = rows.dtype, rows.device
+    e64 = elem.to(torch.int64)
+    sorted_e, order = torch.sort(e64, stable=True)
+    seg = torch.searchsorted(sorted_e, torch.arange(N, device=dev, dtype=torch.int64))     # N-1 elements -> N bounds
+    tmp = torch.empty(max(N - 1, 1), 4, device=dev, dtype=dt)
+    du = torch.empty(N, device=dev, dtype=dt)
+    dg = torch.empty(N, device=dev, dtype=dt)
+    _lib.check(_lib.fn("hidenn_1d_fold_rows", dt)(_lib.ptr(rows), _lib.ptr(order), _lib.ptr(seg), c_i64(N), _lib.ptr(tmp),
+                                                  _lib.ptr(du), _lib.ptr(dg), _lib.stream_ptr()))
+    return du, dg
+
+
+class _Interp1DFn(torch.autograd.Function):
+    """u(x) of models.py:70-90.  backward is itself a differentiable Function so that
+    d u / d x (the element slope) can be differentiated again w.r.t. grid and u (example3.py:56)."""
+
+    @staticmethod
+    def forward(ctx, grid, u_full, x):
+        _require_cuda(grid, "forward")
+        dt = grid.dtype
+        xs = x.to(dt).contiguous()
+        g, uf = grid.contiguous(), u_full.to(dt).contiguous()
+        M = xs.numel()
+        u = torch.empty(xs.shape, device=g.device, dtype=dt)
+        elem = torch.empty(M, device=g.device, dtype=torch.int32)
+        _lib.check(_lib.fn("hidenn_1d_interp_fwd", dt)(_lib.ptr(g), c_i64(g.shape[0]), _lib.ptr(uf), _lib.ptr(xs), c_i64(M),
+                                                       _lib.ptr(u), _lib.ptr(elem), _lib.ptr(None), _lib.stream_ptr()))
+        ctx.save_for_backward(grid, u_full, x, elem)
+        return u
+
+    @staticmethod
+    def backward(ctx, r):
+        grid, u_full, x, elem = ctx.saved_tensors
+        dgrid, du, dx = _Interp1DBwdFn.apply(grid, u_full, x, elem, r)
+        return dgrid, du, dx
+
+
+class _Interp1DBwdFn(torch.autograd.Function):
+    """(d grid, d u_full, d x) = VJP of the interpolation for cotangent r; its own backward handles the
+    cotangent of d x (= r * slope), which is what the double-backward of example3.py needs."""
+
+    @staticmethod
+    def forward(ctx, grid, u_full, x, elem, r):
+        dt = grid.dtype
+        g, uf, xs, rr = grid.contiguous(), u_full.to(dt).contiguous(), x.to(dt).contiguous(), r.to(dt).contiguous()
+        M = xs.numel()
+        rows = torch.empty(M, 4, device=g.device, dtype=dt)
+        dx = torch.empty(xs.shape, device=g.device, dtype=dt)
+        _lib.check(_lib.fn("hidenn_1d_interp_bwd", dt)(_lib.ptr(g), c_i64(g.shape[0]), _lib.ptr(uf), _lib.ptr(xs), _lib.ptr(elem),
+                                                       _lib.ptr(rr), _lib.ptr(None), c_i64(M), _lib.ptr(rows), _lib.ptr(dx),
+                                                       _lib.stream_ptr()))
+        du, dg = _fold_1d(rows, elem, g.shape[0])
+        ctx.save_for_backward(grid, u_full, x, elem, r)
+        return dg, du.to(u_full.dtype), dx.to(x.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_dgrid, g_du, g_dx):
+        grid, u_full, x, elem, r = ctx.saved_tensors
+        if g_dgrid is not None or g_du is not None:
+            # Only the cotangent of d x is supported at second order (that is all the reference's losses use).
+            if (g_dgrid is not None and bool(g_dgrid.abs().max() > 0)) or (g_du is not None and bool(g_du.abs().max() > 0)):
+                raise NotImplementedError("second-order derivatives through d grid / d u are not implemented")
+        if g_dx is None:
+            return None, None, None, None, None
+        dt = grid.dtype
+        g, uf, xs = grid.contiguous(), u_full.to(dt).contiguous(), x.to(dt).contiguous()
+        M = xs.numel()
+        # d x = r * slope(grid, u):  cotangent on the slope is g_dx * r; cotangent on r is g_dx * slope
+        rs = (g_dx.to(dt) * r.to(dt)).contiguous()
+        rows = torch.empty(M, 4, device=g.device, dtype=dt)
+        _lib.check(_lib.fn("hidenn_1d_interp_bwd", dt)(_lib.ptr(g), c_i64(g.shape[0]), _lib.ptr(uf), _lib.ptr(xs), _lib.ptr(elem),
+                                                       _lib.ptr(None), _lib.ptr(rs), c_i64(M), _lib.ptr(rows), _lib.ptr(None),
+                                                       _lib.stream_ptr()))
+        du, dg = _fold_1d(rows, elem, g.shape[0])
+        slope = torch.empty(xs.shape, device=g.device, dtype=dt)
+        utmp = torch.empty(xs.shape, device=g.device, dtype=dt)
+        _lib.check(_lib.fn("hidenn_1d_interp_fwd", dt)(_lib.ptr(g), c_i64(g.shape[0]), _lib.ptr(uf), _lib.ptr(xs), c_i64(M),
+                                                       _lib.ptr(utmp), _lib.ptr(None), _lib.ptr(slope), _lib.stream_ptr()))
+        return dg, du.to(u_full.dtype), None, None, (g_dx.to(dt) * slope).to(r.dtype)
 
 
 class PiecewiseLinearShapeNN(nn.Module):
-    def __init__(self, *a, **k):
-        raise NotImplementedError
+    """1D P1 interpolant with optional r-adaptive nodes (reference models.py:6-90)."""
+
+    def __init__(self, node_coords, r_adapt=False, u0=None, uN=None):
+        super().__init__()
+        self.N = len(node_coords)
+        self.r_adapt = r_adapt
+        self.register_buffer("x0", node_coords[0:1])
+        self.register_buffer("xN", node_coords[-1:])
+        if self.r_adapt and self.N > 2:
+            self.x_increments = nn.Parameter(node_coords[1:] - node_coords[:-1])
+        else:
+            self.register_buffer("x_inner", node_coords[1:-1])
+        if u0 is not None:
+            self.register_buffer("u0_fixed", torch.tensor([u0], dtype=torch.float32))
+        else:
+            self.u0_fixed = None
+        if uN is not None:
+            self.register_buffer("uN_fixed", torch.tensor([uN], dtype=torch.float32))
+        else:
+            self.uN_fixed = None
+        if (self.u0_fixed is not None) and (self.uN_fixed is not None):
+            self.u = nn.Parameter(torch.zeros(self.N - 2))
+        elif (self.u0_fixed is not None) ^ (self.uN_fixed is not None):
+            self.u = nn.Parameter(torch.zeros(self.N - 1))
+        else:
+            self.u = nn.Parameter(torch.zeros(self.N))
+        self.epsilon = 1e-10
+
+    @property
+    def grid(self):
+        if self.r_adapt and self.N > 2:
+            return _GridFn.apply(self.x_increments, self.x0, self.xN)
+        return torch.cat([self.x0, self.x_inner, self.xN], dim=0)
+
+    @property
+    def u_full(self):
+        if self.u0_fixed is not None and self.uN_fixed is not None:
+            return torch.cat([self.u0_fixed, self.u.view(-1), self.uN_fixed])
+        elif self.u0_fixed is not None:
+            return torch.cat([self.u0_fixed, self.u.view(-1)])
+        elif self.uN_fixed is not None:
+            return torch.cat([self.u, self.uN_fixed])
+        return self.u.view(-1)
+
+    def lookup(self, x_eval):
+        """Element index of every point, bit-exact with clamp(searchsorted(grid,x)-1, 0, N-2) (models.py:73-74)."""
+        grid = self.grid.detach().contiguous()
+        _require_cuda(grid, "lookup")
+        xs = x_eval.to(grid.dtype).contiguous()
+        out = torch.empty(xs.numel(), device=grid.device, dtype=torch.int32)
+        _lib.check(_lib.fn("hidenn_1d_lookup", grid.dtype)(_lib.ptr(grid), c_i64(grid.shape[0]), _lib.ptr(xs), c_i64(xs.numel()),
+                                                           _lib.ptr(out), _lib.stream_ptr()))
+        return out.reshape(xs.shape)
+
+    def forward(self, x_eval):
+        return _Interp1DFn.apply(self.grid, self.u_full, x_eval)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused bar energy (examples/example3.py:27-70)
+# ------------------------------------------------------------------------------------------------
+class _BarEnergyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, grid, u_full, xi, wi, E, b_table, state):
+        _require_cuda(grid, "bar_energy")
+        dt = grid.dtype
+        g, uf = grid.contiguous(), u_full.to(dt).contiguous()
+        N = g.shape[0]
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        loss = torch.empty(1, device=g.device, dtype=dt)
+        du = torch.empty(N, device=g.device, dtype=dt) if need else None
+        dg = torch.empty(N, device=g.device, dtype=dt) if need else None
+        flag = torch.empty(1, device=g.device, dtype=torch.int32)
+        sc = _scratch_1d(N, g)
+        Ec = C.c_double(float(E)) if dt == torch.float64 else C.c_float(float(E))
+        _lib.check(_lib.fn("hidenn_1d_bar_energy", dt)(_lib.ptr(g), c_i64(N), _lib.ptr(uf), _lib.ptr(xi), _lib.ptr(wi),
+                                                       C.c_int(int(xi.numel())), Ec, _lib.ptr(b_table), C.c_int(1 if need else 0),
+                                                       _lib.ptr(loss), _lib.ptr(du), _lib.ptr(dg), _lib.ptr(flag), _lib.ptr(sc),
+                                                       _lib.stream_ptr()))
+        state.note_flag(flag)
+        ctx.save_for_backward(dg, du)
+        ctx.udtype = u_full.dtype
+        return loss[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        dg, du = ctx.saved_tensors
+        return (dg * go if dg is not None else None), ((du * go).to(ctx.udtype) if du is not None else None), \
+            None, None, None, None, None
+
+
+class _FlagState:
+    """Deferred check of the kernel's degenerate-lookup flag (no host sync on the hot path)."""
+
+    def __init__(self):
+        self.pending = []
+
+    def note_flag(self, flag):
+        host = torch.empty(1, dtype=torch.int32).pin_memory()
+        host.copy_(flag, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.pending.append((host, ev))
+        self.check(block=False)
+
+    def check(self, block=True):
+        keep = []
+        for host, ev in self.pending:
+            if block:
+                ev.synchronize()
+            if ev.query():
+                if int(host.item()) != 0:
+                    self.pending = []
+                    raise RuntimeError("bar_energy_loss: a Gauss point fell outside its own element (degenerate grid); "
+                                       "the fused path is invalid here -- use energy_loss_generic")
+            else:
+                keep.append((host, ev))
+        self.pending = keep
+
+
+_bar_state = _FlagState()
+
+
+def bar_energy_loss(model, xi, wi, b_force, E, L=10.0, b_builtin=False):
+    """Fused drop-in for `energy_loss(model, xi, wi, b_force, E, L)` of examples/example3.py:27-70.
+    `b_builtin=True` evaluates that example's own b_force (example3.py:16-24) inside the kernel instead of
+    calling the Python callable on the [Ne, ng] quadrature points."""
+    grid = model.grid
+    dt = grid.dtype
+    xi_c, wi_c = xi.to(device=grid.device, dtype=dt).contiguous(), wi.to(device=grid.device, dtype=dt).contiguous()
+    b_table = None
+    if not b_builtin:
+        with torch.no_grad():
+            g = grid.detach()
+            x_i, x_ip1 = g[:-1].unsqueeze(1), g[1:].unsqueeze(1)
+            xq = 0.5 * (x_ip1 - x_i) * xi_c + 0.5 * (x_ip1 + x_i)
+            b_table = b_force(xq).to(dt).contiguous()
+    return _BarEnergyFn.apply(grid, model.u_full, xi_c, wi_c, E, b_table, _bar_state)
+
+
+def energy_loss_generic(model, xi, wi, b_force, E, L=10.0):
+    """The reference's energy_loss verbatim in structure (examples/example3.py:27-70), running on the generic
+    differentiable forward (double backward through autograd.grad)."""
+    with torch.no_grad():
+        grid = model.grid
+        x_i, x_ip1 = grid[:-1].unsqueeze(1), grid[1:].unsqueeze(1)
+        xq = 0.5 * (x_ip1 - x_i) * xi + 0.5 * (x_ip1 + x_i)
+        wq = 0.5 * (x_ip1 - x_i) * wi
+    xq.requires_grad_(True)
+    u = model(xq)
+    du_dx = torch.autograd.grad(u, xq, grad_outputs=torch.ones_like(u), create_graph=True)[0]
+    return torch.sum(wq * (0.5 * E * du_dx ** 2 - b_force(xq) * u))
+
+
+def example3_b_force(x):
+    """examples/example3.py:16-24."""
+    N1 = 4 * torch.pi ** 2 * (x - 2.5) ** 2 - 2 * torch.pi
+    D1 = torch.exp(torch.pi * (x - 2.5) ** 2)
+    N2 = 8 * torch.pi ** 2 * (x - 7.5) ** 2 - 4 * torch.pi
+    D2 = torch.exp(torch.pi * (x - 7.5) ** 2)
+    return -N1 / D1 - N2 / D2
+
+
+# ------------------------------------------------------------------------------------------------
+# structured Q1 model (models.py:93-212)
+# ------------------------------------------------------------------------------------------------
+class _Q1InterpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gx, gy, u_full, x):
+        _require_cuda(gx, "forward")
+        dt = gx.dtype
+        gxc, gyc, uf, xs = gx.contiguous(), gy.to(dt).contiguous(), u_full.to(dt).contiguous(), x.to(dt).contiguous()
+        M = xs.shape[0]
+        u = torch.empty(M, device=gxc.device, dtype=dt)
+        ix = torch.empty(M, device=gxc.device, dtype=torch.int32)
+        iy = torch.empty(M, device=gxc.device, dtype=torch.int32)
+        _lib.check(_lib.fn("hidenn_q1_interp_fwd", dt)(_lib.ptr(gxc), c_i64(gxc.shape[0]), _lib.ptr(gyc), c_i64(gyc.shape[0]),
+                                                       _lib.ptr(uf), _lib.ptr(xs), c_i64(M), _lib.ptr(u), _lib.ptr(ix), _lib.ptr(iy),
+                                                       _lib.stream_ptr()))
+        ctx.save_for_backward(gxc, gyc, uf, xs, ix, iy)
+        ctx.udtype = u_full.dtype
+        return u
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, r):
+        gx, gy, uf, xs, ix, iy = ctx.saved_tensors
+        dt, dev = gx.dtype, gx.device
+        M = xs.shape[0]
+        Nx, Ny = gx.shape[0], gy.shape[0]
+        rows = torch.empty(M, 8, device=dev, dtype=dt)
+        s = _lib.stream_ptr()
+        _lib.check(_lib.fn("hidenn_q1_interp_bwd", dt)(_lib.ptr(gx), c_i64(Nx), _lib.ptr(gy), c_i64(Ny), _lib.ptr(uf), _lib.ptr(xs),
+                                                       _lib.ptr(ix), _lib.ptr(iy), _lib.ptr(r.to(dt).contiguous()), c_i64(M),
+                                                       _lib.ptr(rows), s))
+        ncell = (Nx - 1) * (Ny - 1)
+        cell = ix.to(torch.int64) * (Ny - 1) + iy.to(torch.int64)
+        sorted_c, order = torch.sort(cell, stable=True)
+        seg = torch.searchsorted(sorted_c, torch.arange(ncell + 1, device=dev, dtype=torch.int64))
+        tmp = torch.empty(ncell, 8, device=dev, dtype=dt)
+        du = torch.empty(Nx, Ny, device=dev, dtype=dt)
+        dgx = torch.empty(Nx, device=dev, dtype=dt)
+        dgy = torch.empty(Ny, device=dev, dtype=dt)
+        _lib.check(_lib.fn("hidenn_q1_fold_rows", dt)(_lib.ptr(rows), _lib.ptr(order), _lib.ptr(seg), c_i64(Nx), c_i64(Ny),
+                                                      _lib.ptr(tmp), _lib.ptr(du), _lib.ptr(dgx), _lib.ptr(dgy), s))
+        return dgx, dgy, du.to(ctx.udtype), None
 
 
 class StructuredShapeNN2D(nn.Module):
-    def __init__(self, *a, **k):
-        raise NotImplementedError
+    """Tensor-product Q1 interpolant on two r-adaptive 1D grids: the *first* class named
+    PiecewiseLinearShapeNN2D in the reference (models.py:93-212), which its second definition shadows."""
+
+    def __init__(self, grid_x, grid_y, boundary_mask_x=None, boundary_mask_y=None, r_adapt=False, u_fixed=None):
+        super().__init__()
+        self.Nx = grid_x.numel()
+        self.Ny = grid_y.numel()
+        self.r_adapt = r_adapt
+        self.register_buffer("initial_x_grid", grid_x.clone())
+        self.register_buffer("initial_y_grid", grid_y.clone())
+        self.register_buffer("x0", grid_x.flatten()[0:1])
+        self.register_buffer("xN", grid_x.flatten()[-1:])
+        self.register_buffer("y0", grid_y.flatten()[0:1])
+        self.register_buffer("yN", grid_y.flatten()[-1:])
+        if self.r_adapt and max(self.Nx, self.Ny) > 2:
+            self.increments_x = nn.Parameter(grid_x[1:] - grid_x[:-1])
+            self.increments_y = nn.Parameter(grid_y[1:] - grid_y[:-1])
+        else:
+            self.register_buffer("x_grid_inner", grid_x[1:-1])
+            self.register_buffer("y_grid_inner", grid_y[1:-1])
+        if boundary_mask_x is None:
+            boundary_mask_x = torch.zeros(self.Nx, dtype=torch.bool)
+            boundary_mask_x[0] = boundary_mask_x[-1] = True
+        if boundary_mask_y is None:
+            boundary_mask_y = torch.zeros(self.Ny, dtype=torch.bool)
+            boundary_mask_y[0] = boundary_mask_y[-1] = True
+        self.register_buffer("boundary_mask_x", boundary_mask_x)
+        self.register_buffer("boundary_mask_y", boundary_mask_y)
+        self.register_buffer("node_mask", self.boundary_mask_x[:, None] | self.boundary_mask_y[None, :])
+        if u_fixed is not None:
+            self.register_buffer("u_fixed", torch.tensor([u_fixed], dtype=torch.float32))
+        else:
+            self.u_fixed = None
+        self.u = nn.Parameter(torch.randn(self.Nx, self.Ny))
+        self.epsilon = 1e-10
+
+    @property
+    def grid(self):
+        if self.r_adapt and max(self.Nx, self.Ny) > 2:
+            x_full = _GridFn.apply(self.increments_x, self.x0, self.xN)
+            y_full = _GridFn.apply(self.increments_y, self.y0, self.yN)
+        else:
+            x_full = torch.cat([self.x0, self.x_grid_inner, self.xN], dim=0)
+            y_full = torch.cat([self.y0, self.y_grid_inner, self.yN], dim=0)
+        x_full = torch.where(self.boundary_mask_x, self.initial_x_grid, x_full)
+        y_full = torch.where(self.boundary_mask_y, self.initial_y_grid, y_full)
+        return x_full, y_full
+
+    @property
+    def u_full(self):
+        if self.u_fixed is not None:
+            return torch.where(self.node_mask, self.u_fixed, self.u)
+        return self.u
+
+    def forward(self, x_eval):
+        gx, gy = self.grid
+        return _Q1InterpFn.apply(gx, gy, self.u_full, x_eval)

@@ -1,0 +1,216 @@
+"""GPU parity of the 1D and structured-2D paths vs the reference's golden fixtures and the oracle.
+FP64 1e-10 / FP32 1e-5 on values; lookup indices bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import gold, relmax
+from oracle import closed_form as cf
+
+pytestmark = pytest.mark.gpu
+T = lambda a, **k: torch.tensor(a, device="cuda", **k)
+
+
+def make_1d(g, k, dt, r_adapt, u0=None, uN=None, npts=100, L=1.0):
+    from hidenn_fem_b200.models import PiecewiseLinearShapeNN
+    xg = torch.linspace(0, L, npts, dtype=dt)
+    model = PiecewiseLinearShapeNN(xg, r_adapt=r_adapt, u0=u0, uN=uN)
+    if dt == torch.float64:
+        model = model.double()
+    model = model.cuda()
+    with torch.no_grad():
+        model.u.copy_(T(g[k + "_u"]))
+        if r_adapt:
+            model.x_increments.copy_(T(g[k + "_p"]))
+    return model
+
+
+def test_lookup_bit_exact_gpu():
+    from hidenn_fem_b200.models import PiecewiseLinearShapeNN
+    g = gold("one_d")
+    m = PiecewiseLinearShapeNN(torch.tensor(g["lk_grid"])).cuda()
+    with torch.no_grad():
+        m.u.copy_(T([1.0, -2.0, 0.5, 3.0]))
+    x = T(g["lk_x"])
+    assert np.array_equal(m.lookup(x).cpu().numpy(), g["lk_idx"])
+    assert relmax(m(x).detach().cpu().numpy(), g["lk_u"]) < 1e-6
+    # large random check against numpy searchsorted on a non-uniform grid, incl. points exactly on nodes
+    rng = np.random.default_rng(0)
+    grid = np.sort(rng.random(5001))
+    xs = np.concatenate([rng.random(20000) * 1.2 - 0.1, grid[::7]])
+    m2 = PiecewiseLinearShapeNN(torch.tensor(grid)).cuda()
+    got = m2.lookup(T(xs)).cpu().numpy()
+    assert np.array_equal(got, cf.lookup_1d(grid, xs, grid.size))
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("mode", ["f", "r"])
+def test_example1_l2_step_and_adam(tag, mode):
+    g = gold("one_d")
+    dt = torch.float64 if tag == "f64" else torch.float32
+    k = f"ex1_{tag}_{mode}"
+    model = make_1d(g, k, dt, mode == "r")
+    tol = 1e-10 if dt == torch.float64 else 1e-5
+    assert relmax(model.grid.detach().cpu().numpy(), g[k + "_grid"]) < (1e-13 if dt == torch.float64 else 1e-6)
+    xt = torch.linspace(0, 1, 1000, dtype=dt).cuda()
+    ut = torch.sin(2 * torch.pi * xt)
+    pred = model(xt)
+    loss = ((pred - ut) ** 2).mean()
+    loss.backward()
+    assert relmax(pred.detach().cpu().numpy(), g[k + "_pred"]) < tol
+    assert abs(loss.item() - float(g[k + "_loss"])) <= tol * abs(float(g[k + "_loss"]))
+    assert relmax(model.u.grad.cpu().numpy(), g[k + "_gu"]) < tol
+    if mode == "r":
+        assert relmax(model.x_increments.grad.cpu().numpy(), g[k + "_gp"]) < (1e-9 if dt == torch.float64 else 3e-4)
+    # unchanged Adam loop of examples/example1.py:31-40
+    model.zero_grad()
+    opt = torch.optim.Adam(model.parameters(), lr=0.005)
+    tr = []
+    for _ in range(25):
+        opt.zero_grad()
+        l = ((model(xt) - ut) ** 2).mean()
+        l.backward()
+        opt.step()
+        tr.append(l.item())
+    assert np.allclose(tr, g[k + "_adam"], rtol=1e-7 if dt == torch.float64 else 2e-3)
+
+
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+@pytest.mark.parametrize("npts", [89, 300])
+@pytest.mark.parametrize("path", ["fused_builtin", "fused_callable", "generic"])
+def test_example3_bar_energy(tag, npts, path):
+    from hidenn_fem_b200 import models_grid as mg
+    from hidenn_fem_b200.utils import interval_gauss_points
+    g = gold("one_d")
+    dt = torch.float64 if tag == "f64" else torch.float32
+    k = f"ex3_{tag}_{npts}"
+    model = make_1d(g, k, dt, True, u0=0.0, uN=0.0, npts=npts, L=10.0)
+    xi, wi = interval_gauss_points(int(g[k + "_ng"]), device="cuda", dtype=dt)
+    if path == "fused_builtin":
+        loss = mg.bar_energy_loss(model, xi, wi, None, 175.0, b_builtin=True)
+    elif path == "fused_callable":
+        loss = mg.bar_energy_loss(model, xi, wi, mg.example3_b_force, 175.0)
+    else:
+        loss = mg.energy_loss_generic(model, xi, wi, mg.example3_b_force, E=175.0)
+    loss.backward()
+    tol = 1e-10 if dt == torch.float64 else 1e-4
+    assert abs(loss.item() - float(g[k + "_loss"])) <= tol * abs(float(g[k + "_loss"]))
+    assert relmax(model.u.grad.cpu().numpy(), g[k + "_gu"]) < tol
+    assert relmax(model.x_increments.grad.cpu().numpy(), g[k + "_gp"]) < (1e-9 if dt == torch.float64 else 2e-3)
+    mg._bar_state.check(block=True)
+    if path == "generic" or dt == torch.float32:
+        return
+    # unchanged Adam loop of examples/example3.py:89-96 on the fused loss
+    model.zero_grad()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    tr = []
+    for _ in range(15):
+        opt.zero_grad()
+        l = mg.bar_energy_loss(model, xi, wi, mg.example3_b_force, 175.0, b_builtin=(path == "fused_builtin"))
+        l.backward()
+        opt.step()
+        tr.append(l.item())
+    assert np.allclose(tr, g[k + "_adam"], rtol=1e-8)
+
+
+def test_bar_energy_1m_vs_oracle():
+    """Config C2: 1M elements FP64; oracle = closed form on the same grid."""
+    from hidenn_fem_b200 import models_grid as mg
+    from hidenn_fem_b200.models import PiecewiseLinearShapeNN
+    from hidenn_fem_b200.utils import interval_gauss_points
+    N = 1_000_001
+    xg = torch.linspace(0, 10.0, N, dtype=torch.float64)
+    model = PiecewiseLinearShapeNN(xg, r_adapt=True, u0=0.0, uN=0.0).double().cuda()
+    gen = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        model.u.copy_((1e-2 * torch.randn(N - 2, generator=gen, dtype=torch.float64)).cuda())
+        model.x_increments.add_((0.1 * 1e-5 * torch.randn(N - 1, generator=gen, dtype=torch.float64)).cuda())
+    xi, wi = interval_gauss_points(2, device="cuda", dtype=torch.float64)
+    loss = mg.bar_energy_loss(model, xi, wi, None, 175.0, b_builtin=True)
+    loss.backward()
+    mg._bar_state.check(block=True)
+    p = model.x_increments.detach().cpu().numpy()
+    u = model.u.detach().cpu().numpy()
+    grid, aux = cf.grid_1d(p, np.float64(0.0), np.float64(10.0))
+    assert relmax(model.grid.detach().cpu().numpy(), grid) < 1e-12
+    ufull = np.concatenate([[0.0], u, [0.0]])
+    xin, win = cf.interval_gauss_points(2)
+    lo, dG, dU = cf.bar_energy(grid, ufull, xin, win, 175.0)
+    assert abs(loss.item() - lo) <= 1e-10 * abs(lo)
+    assert relmax(model.u.grad.cpu().numpy(), dU[1:-1]) < 1e-10
+    dp = cf.grid_1d_backward(dG, p, aux)
+    assert relmax(model.x_increments.grad.cpu().numpy(), dp) < 1e-8
+
+
+@pytest.mark.parametrize("tag", ["f64", "f32"])
+@pytest.mark.parametrize("ftag", ["free", "fix"])
+def test_structured_q1(tag, ftag):
+    from hidenn_fem_b200.models import PiecewiseLinearShapeNN2D, StructuredShapeNN2D
+    g = gold("structured")
+    dt = torch.float64 if tag == "f64" else torch.float32
+    k = f"q1_{tag}_{ftag}"
+    Nx, Ny = 25, 19
+    gx, gy = torch.linspace(0, 1, Nx, dtype=dt), torch.linspace(0, 1, Ny, dtype=dt)
+    ufix = float(g[k + "_ufix"]) if ftag == "fix" else None
+    # the reference name with grid_x/grid_y keywords selects the structured class (models.py:93 vs :241)
+    model = PiecewiseLinearShapeNN2D(grid_x=gx, grid_y=gy, boundary_mask_x=None, boundary_mask_y=None, r_adapt=True, u_fixed=ufix)
+    assert isinstance(model, StructuredShapeNN2D)
+    if dt == torch.float64:
+        model = model.double()
+    model = model.cuda()
+    with torch.no_grad():
+        model.increments_x.copy_(T(g[k + "_px"]))
+        model.increments_y.copy_(T(g[k + "_py"]))
+        model.u.copy_(T(g[k + "_u"]))
+    gxx, gyy = model.grid
+    assert relmax(gxx.detach().cpu().numpy(), g[k + "_gx"]) < (1e-13 if dt == torch.float64 else 1e-6)
+    x, ut = T(g[k + "_x"]), T(g[k + "_ut"])
+    pred = model(x)
+    loss = ((pred - ut) ** 2).mean()
+    loss.backward()
+    tol = 1e-10 if dt == torch.float64 else 1e-5
+    assert relmax(pred.detach().cpu().numpy(), g[k + "_pred"]) < tol
+    assert abs(loss.item() - float(g[k + "_loss"])) <= tol * abs(float(g[k + "_loss"]))
+    assert relmax(model.u.grad.cpu().numpy(), g[k + "_gu"]) < tol
+    gt = 1e-9 if dt == torch.float64 else 2e-3
+    assert relmax(model.increments_x.grad.cpu().numpy(), g[k + "_gpx"]) < gt
+    assert relmax(model.increments_y.grad.cpu().numpy(), g[k + "_gpy"]) < gt
+    # Adam loop of examples/example2.py:37-48 with the fixed sample set of the fixture
+    model.zero_grad()
+    opt = torch.optim.Adam(model.parameters(), lr=0.005)
+    tr = []
+    for _ in range(15):
+        opt.zero_grad()
+        l = ((model(x) - ut) ** 2).mean()
+        l.backward()
+        opt.step()
+        tr.append(l.item())
+    assert np.allclose(tr, g[k + "_adam"], rtol=1e-7 if dt == torch.float64 else 2e-3)
+
+
+def test_structured_lookup_and_large_vs_oracle():
+    from hidenn_fem_b200.models import StructuredShapeNN2D
+    rng = np.random.default_rng(3)
+    Nx, Ny, M = 257, 193, 200_000
+    gx, gy = torch.linspace(0, 1, Nx, dtype=torch.float64), torch.linspace(0, 1, Ny, dtype=torch.float64)
+    model = StructuredShapeNN2D(gx, gy, r_adapt=True).double().cuda()
+    with torch.no_grad():
+        model.increments_x.mul_(T(1.0 + 0.3 * rng.standard_normal(Nx - 1)))
+        model.increments_y.mul_(T(1.0 + 0.3 * rng.standard_normal(Ny - 1)))
+    x = rng.random((M, 2)) * 1.1 - 0.05
+    ut = np.sin(2 * np.pi * x[:, 0]) * np.cos(2 * np.pi * x[:, 1])
+    pred = model(T(x))
+    loss = ((pred - T(ut)) ** 2).mean()
+    loss.backward()
+    gxx, gyy = (a.detach().cpu().numpy() for a in model.grid)
+    u = model.u.detach().cpu().numpy()
+    po, ix, iy = cf.q1_interp(gxx, gyy, u, x)
+    assert relmax(pred.detach().cpu().numpy(), po) < 1e-12
+    r = 2.0 * (po - ut) / M
+    dgx, dgy, dU = cf.q1_interp_backward(gxx, gyy, u, x, r)
+    assert relmax(model.u.grad.cpu().numpy(), dU) < 1e-10
+    # determinism: a second evaluation is bit-identical
+    g1 = model.u.grad.clone()
+    model.zero_grad()
+    ((model(T(x)) - T(ut)) ** 2).mean().backward()
+    assert torch.equal(g1, model.u.grad)
