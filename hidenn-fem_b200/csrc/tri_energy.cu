@@ -22,7 +22,19 @@ template <typename R> struct TriConsts {
     R fb[6];
 };
 
-template <typename R>
+// 1/x to full precision without the slow-path branch of the IEEE division: hardware seed + 2 Newton steps.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
+
+// BODY: a body force table is present (Fb != 0).  ISO: C has the plane-stress form c02 = c12 = 0.
+template <typename R, bool BODY, bool ISO>
 __device__ __forceinline__ void tri_element(const typename Real2<R>::type v0, const typename Real2<R>::type v1,
                                             const typename Real2<R>::type v2, const typename Real2<R>::type U0,
                                             const typename Real2<R>::type U1, const typename Real2<R>::type U2,
@@ -30,38 +42,64 @@ __device__ __forceinline__ void tri_element(const typename Real2<R>::type v0, co
                                             typename Real2<R>::type gx[3]) {
     const R a = v0.x - v2.x, b = v1.x - v2.x, c = v0.y - v2.y, d = v1.y - v2.y;
     const R det = a * d - b * c;
-    const R inv = rcp(det);
+    const R inv = fast_rcp(det);
     const R j00 = d * inv, j01 = -b * inv, j10 = -c * inv, j11 = a * inv;     // J^-1 (reference uses J^-1, not J^-T)
     const R p0 = U0.x - U2.x, p1 = U1.x - U2.x, q0 = U0.y - U2.y, q1 = U1.y - U2.y;
     const R G00 = p0 * j00 + p1 * j01, G01 = p0 * j10 + p1 * j11;
     const R G10 = q0 * j00 + q1 * j01, G11 = q0 * j10 + q1 * j11;
     const R e0 = G00, e1 = G11, e2 = G01 + G10;
-    const R s0 = K.c00 * e0 + K.c01 * e1 + K.c02 * e2;
-    const R s1 = K.c01 * e0 + K.c11 * e1 + K.c12 * e2;
-    const R s2 = K.c02 * e0 + K.c12 * e1 + K.c22 * e2;
+    R s0, s1, s2;
+    if (ISO) {
+        s0 = K.c00 * e0 + K.c01 * e1;
+        s1 = K.c01 * e0 + K.c11 * e1;
+        s2 = K.c22 * e2;
+    } else {
+        s0 = K.c00 * e0 + K.c01 * e1 + K.c02 * e2;
+        s1 = K.c01 * e0 + K.c11 * e1 + K.c12 * e2;
+        s2 = K.c02 * e0 + K.c12 * e1 + K.c22 * e2;
+    }
     const R psi = R(0.5) * (e0 * s0 + e1 * s1 + e2 * s2);
-    const R bw = U0.x * K.fb[0] + U0.y * K.fb[1] + U1.x * K.fb[2] + U1.y * K.fb[3] + U2.x * K.fb[4] + U2.y * K.fb[5];
-    const R dens = K.W * psi - bw;
+    R dens = K.W * psi;
+    if (BODY) dens -= U0.x * K.fb[0] + U0.y * K.fb[1] + U1.x * K.fb[2] + U1.y * K.fb[3] + U2.x * K.fb[4] + U2.y * K.fb[5];
     const R A = fabs(det);
     energy = A * dens;
-    const R M00 = s0 * j00 + s2 * j10, M01 = s0 * j01 + s2 * j11;
-    const R M10 = s2 * j00 + s1 * j10, M11 = s2 * j01 + s1 * j11;
     const R AW = A * K.W;
-    gu[0] = mk2<R>(AW * M00 - A * K.fb[0], AW * M10 - A * K.fb[1]);
-    gu[1] = mk2<R>(AW * M01 - A * K.fb[2], AW * M11 - A * K.fb[3]);
-    gu[2] = mk2<R>(-AW * (M00 + M01) - A * K.fb[4], -AW * (M10 + M11) - A * K.fb[5]);
-    const R K00 = -(M00 * G00 + M10 * G10), K01 = -(M00 * G01 + M10 * G11);
-    const R K10 = -(M01 * G00 + M11 * G10), K11 = -(M01 * G01 + M11 * G11);
+    // M = AW * P * Jinv  (P = d psi / d G = [[s0,s2],[s2,s1]])
+    const R t0 = AW * s0, t1 = AW * s1, t2 = AW * s2;
+    const R M00 = t0 * j00 + t2 * j10, M01 = t0 * j01 + t2 * j11;
+    const R M10 = t2 * j00 + t1 * j10, M11 = t2 * j01 + t1 * j11;
+    if (BODY) {
+        gu[0] = mk2<R>(M00 - A * K.fb[0], M10 - A * K.fb[1]);
+        gu[1] = mk2<R>(M01 - A * K.fb[2], M11 - A * K.fb[3]);
+        gu[2] = mk2<R>(-(M00 + M01) - A * K.fb[4], -(M10 + M11) - A * K.fb[5]);
+    } else {
+        gu[0] = mk2<R>(M00, M10);
+        gu[1] = mk2<R>(M01, M11);
+        gu[2] = mk2<R>(-(M00 + M01), -(M10 + M11));
+    }
+    // dE/dJ = s*adj(J)^T-like term * dens  -  M^T G
     const R sd = det < R(0) ? -dens : dens;
-    const R D00 = sd * d + AW * K00, D01 = -sd * c + AW * K01;
-    const R D10 = -sd * b + AW * K10, D11 = sd * a + AW * K11;
+    const R D00 = sd * d - (M00 * G00 + M10 * G10), D01 = -sd * c - (M00 * G01 + M10 * G11);
+    const R D10 = -sd * b - (M01 * G00 + M11 * G10), D11 = sd * a - (M01 * G01 + M11 * G11);
     gx[0] = mk2<R>(D00, D10);
     gx[1] = mk2<R>(D01, D11);
     gx[2] = mk2<R>(-(D00 + D01), -(D10 + D11));
 }
 
-template <typename R>
-__global__ void __launch_bounds__(kTileBlock)
+template <typename R, bool BODY> __device__ __forceinline__ TriConsts<R> load_consts(const R* __restrict__ consts) {
+    TriConsts<R> K;
+    K.c00 = __ldg(consts + HIDENN_TRI_C00); K.c01 = __ldg(consts + HIDENN_TRI_C01); K.c02 = __ldg(consts + HIDENN_TRI_C02);
+    K.c11 = __ldg(consts + HIDENN_TRI_C11); K.c12 = __ldg(consts + HIDENN_TRI_C12); K.c22 = __ldg(consts + HIDENN_TRI_C22);
+    K.W = __ldg(consts + HIDENN_TRI_W);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) K.fb[k] = BODY ? __ldg(consts + HIDENN_TRI_FB + k) : R(0);
+    return K;
+}
+
+constexpr int kPre = 3;   // element packs prefetched per thread before the first barrier (kPre*256 >= typical tile)
+
+template <typename R, bool BODY, bool ISO>
+__global__ void __launch_bounds__(kTileBlock, 3)
 tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ x_free,
                 const typename Real2<R>::type* __restrict__ x_fixed, const typename Real2<R>::type* __restrict__ u_free,
                 const typename Real2<R>::type* __restrict__ u_fixed, const R* __restrict__ consts, const int flags,
@@ -70,62 +108,85 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
     using R2 = typename Real2<R>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TileDesc td = P.tiles[blockIdx.x];
+    // shared layout: node pairs xy | uv, fold partial pairs gu | gx (n_entries + 1 dump slot), reduce scratch
     R2* s_xy = reinterpret_cast<R2*>(smem_raw);
-    R2* s_uv = s_xy + td.n_local;
-    R2* s_pu = s_uv + td.n_local;
-    R2* s_px = s_pu + td.n_entries;
-    R* s_red = reinterpret_cast<R*>(s_px + td.n_entries);
-    uint16_t* s_off = reinterpret_cast<uint16_t*>(s_red + 8);
+    R2* s_uv = s_xy + P.max_local;
+    R2* s_pu = s_uv + P.max_local;
+    R2* s_px = s_pu + (P.max_entries + 1);
+    R* s_red = reinterpret_cast<R*>(s_px + (P.max_entries + 1));
     const int tid = threadIdx.x;
 
-    // phase 1: stage tile nodes (coalesced slot reads, AoS pair gathers) and fold offsets
-    for (int i = tid; i < td.n_local; i += kTileBlock) {
-        const int xs = __ldg(P.t_xslot + td.node_off + i);
-        const int us = __ldg(P.t_uslot + td.node_off + i);
-        s_xy[i] = load_slot<R2>(x_free, x_fixed, xs);
-        s_uv[i] = load_slot<R2>(u_free, u_fixed, us);
-    }
-    for (int i = tid; i <= td.n_owned; i += kTileBlock) s_off[i] = __ldg(P.entry_off + td.off_off + i);
-
-    TriConsts<R> K;
-    K.c00 = __ldg(consts + HIDENN_TRI_C00); K.c01 = __ldg(consts + HIDENN_TRI_C01); K.c02 = __ldg(consts + HIDENN_TRI_C02);
-    K.c11 = __ldg(consts + HIDENN_TRI_C11); K.c12 = __ldg(consts + HIDENN_TRI_C12); K.c22 = __ldg(consts + HIDENN_TRI_C22);
-    K.W = __ldg(consts + HIDENN_TRI_W);
+    // phase 1: issue every global load of the tile up front -- element packs and fold offsets into registers,
+    // node slots -> AoS pair gathers -> shared memory
+    unsigned long long wpre[kPre];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) K.fb[k] = __ldg(consts + HIDENN_TRI_FB + k);
+    for (int k = 0; k < kPre; ++k) {
+        const int i = tid + k * kTileBlock;
+        wpre[k] = i < td.n_elem ? __ldg(P.elem_pack + td.elem_off + i) : 0ull;
+    }
+    int2 myslot[2];
+    unsigned myoff[2][2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = tid + k * kTileBlock;
+        myslot[k] = make_int2(-1, -1);
+        myoff[k][0] = myoff[k][1] = 0;
+        if (i < td.n_local) {
+            const int2 sl = __ldg(P.t_slots + td.node_off + i);
+            myslot[k] = sl;
+            s_xy[i] = load_slot<R2>(x_free, x_fixed, sl.x);
+            s_uv[i] = load_slot<R2>(u_free, u_fixed, sl.y);
+        }
+        if (i < td.n_owned) {
+            myoff[k][0] = __ldg(P.entry_off + td.off_off + i);
+            myoff[k][1] = __ldg(P.entry_off + td.off_off + i + 1);
+        }
+    }
+    for (int i = tid + 2 * kTileBlock; i < td.n_local; i += kTileBlock) {      // tiles with more than 512 local nodes
+        const int2 sl = __ldg(P.t_slots + td.node_off + i);
+        s_xy[i] = load_slot<R2>(x_free, x_fixed, sl.x);
+        s_uv[i] = load_slot<R2>(u_free, u_fixed, sl.y);
+    }
+    const TriConsts<R> K = load_consts<R, BODY>(consts);
     __syncthreads();
 
-    // phase 2: elements -> energy + gradient partials scattered to their fold slots
+    // phase 2: elements -> energy + gradient partials stored at their precomputed fold slots
     R e_acc = R(0);
-    constexpr unsigned LM = (1u << kLidBits) - 1u;
-    for (int i = tid; i < td.n_elem; i += kTileBlock) {
-        const unsigned long long w = __ldg(P.elem_pack + td.elem_off + i);
-        const unsigned l0 = (unsigned)(w) & LM, l1 = (unsigned)(w >> kLidBits) & LM, l2 = (unsigned)(w >> (2 * kLidBits)) & LM;
+    constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
+    auto do_element = [&](const unsigned long long w) {
+        const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
+        const unsigned l0 = lo & LM, l1 = (lo >> kLidBits) & LM, l2 = (lo >> (2 * kLidBits)) & LM;
+        const unsigned p0 = (unsigned)(w >> (3 * kLidBits)) & PM, p1 = (hi >> (3 * kLidBits + kPosBits - 32)) & PM,
+                       p2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
         R e;
         R2 gu[3], gx[3];
-        tri_element<R>(s_xy[l0], s_xy[l1], s_xy[l2], s_uv[l0], s_uv[l1], s_uv[l2], K, e, gu, gx);
-        if ((w >> kOwnerBit) & 1ull) e_acc += e;
-        const unsigned r0 = (unsigned)(w >> (3 * kLidBits)) & 255u, r1 = (unsigned)(w >> (3 * kLidBits + kRankBits)) & 255u,
-                       r2 = (unsigned)(w >> (3 * kLidBits + 2 * kRankBits)) & 255u;
-        if (r0 != (unsigned)kRankSkip) { const unsigned p = s_off[l0] + r0; s_pu[p] = gu[0]; s_px[p] = gx[0]; }
-        if (r1 != (unsigned)kRankSkip) { const unsigned p = s_off[l1] + r1; s_pu[p] = gu[1]; s_px[p] = gx[1]; }
-        if (r2 != (unsigned)kRankSkip) { const unsigned p = s_off[l2] + r2; s_pu[p] = gu[2]; s_px[p] = gx[2]; }
-    }
+        tri_element<R, BODY, ISO>(s_xy[l0], s_xy[l1], s_xy[l2], s_uv[l0], s_uv[l1], s_uv[l2], K, e, gu, gx);
+        e_acc += (hi >> 31) ? e : R(0);
+        s_pu[p0] = gu[0]; s_px[p0] = gx[0];
+        s_pu[p1] = gu[1]; s_px[p1] = gx[1];
+        s_pu[p2] = gu[2]; s_px[p2] = gx[2];
+    };
+#pragma unroll
+    for (int k = 0; k < kPre; ++k)
+        if (tid + k * kTileBlock < td.n_elem) do_element(wpre[k]);
+    for (int i = tid + kPre * kTileBlock; i < td.n_elem; i += kTileBlock) do_element(__ldg(P.elem_pack + td.elem_off + i));
     __syncthreads();
 
-    // phase 3: owned nodes fold their CSR segment in fixed order and store the final gradients
-    for (int i = tid; i < td.n_owned; i += kTileBlock) {
-        const unsigned b = s_off[i], e = s_off[i + 1];
+    // phase 3: owned nodes fold their slot range in fixed order and store the final gradients
+    auto fold_node = [&](const unsigned b, const unsigned e, const int2 sl) {
         R ax = R(0), ay = R(0), bx = R(0), by = R(0);
         for (unsigned k = b; k < e; ++k) {
             const R2 u = s_pu[k], x = s_px[k];
             ax += u.x; ay += u.y; bx += x.x; by += x.y;
         }
-        const int xs = __ldg(P.t_xslot + td.node_off + i);
-        const int us = __ldg(P.t_uslot + td.node_off + i);
-        if ((flags & HIDENN_NEED_GU) && us >= 0) gu_free[us] = mk2<R>(ax, ay);
-        if ((flags & HIDENN_NEED_GX) && xs >= 0) gx_free[xs] = mk2<R>(bx, by);
-    }
+        if ((flags & HIDENN_NEED_GU) && sl.y >= 0) gu_free[sl.y] = mk2<R>(ax, ay);
+        if ((flags & HIDENN_NEED_GX) && sl.x >= 0) gx_free[sl.x] = mk2<R>(bx, by);
+    };
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (tid + k * kTileBlock < td.n_owned) fold_node(myoff[k][0], myoff[k][1], myslot[k]);
+    for (int i = tid + 2 * kTileBlock; i < td.n_owned; i += kTileBlock)
+        fold_node(__ldg(P.entry_off + td.off_off + i), __ldg(P.entry_off + td.off_off + i + 1), __ldg(P.t_slots + td.node_off + i));
 
     // tile energy (fixed-order block sum)
     const R tot = block_sum<R, kTileBlock>(e_acc, s_red);
@@ -148,15 +209,11 @@ tri_tile_energy_only_kernel(const TriPlanDev P, const typename Real2<R>::type* _
     R* s_red = reinterpret_cast<R*>(s_uv + td.n_local);
     const int tid = threadIdx.x;
     for (int i = tid; i < td.n_local; i += kTileBlock) {
-        s_xy[i] = load_slot<R2>(x_free, x_fixed, __ldg(P.t_xslot + td.node_off + i));
-        s_uv[i] = load_slot<R2>(u_free, u_fixed, __ldg(P.t_uslot + td.node_off + i));
+        const int2 sl = __ldg(P.t_slots + td.node_off + i);
+        s_xy[i] = load_slot<R2>(x_free, x_fixed, sl.x);
+        s_uv[i] = load_slot<R2>(u_free, u_fixed, sl.y);
     }
-    TriConsts<R> K;
-    K.c00 = __ldg(consts + HIDENN_TRI_C00); K.c01 = __ldg(consts + HIDENN_TRI_C01); K.c02 = __ldg(consts + HIDENN_TRI_C02);
-    K.c11 = __ldg(consts + HIDENN_TRI_C11); K.c12 = __ldg(consts + HIDENN_TRI_C12); K.c22 = __ldg(consts + HIDENN_TRI_C22);
-    K.W = __ldg(consts + HIDENN_TRI_W);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) K.fb[k] = __ldg(consts + HIDENN_TRI_FB + k);
+    const TriConsts<R> K = load_consts<R, true>(consts);
     __syncthreads();
     R e_acc = R(0);
     constexpr unsigned LM = (1u << kLidBits) - 1u;
@@ -166,7 +223,7 @@ tri_tile_energy_only_kernel(const TriPlanDev P, const typename Real2<R>::type* _
         const unsigned l0 = (unsigned)(w) & LM, l1 = (unsigned)(w >> kLidBits) & LM, l2 = (unsigned)(w >> (2 * kLidBits)) & LM;
         R e;
         R2 gu[3], gx[3];
-        tri_element<R>(s_xy[l0], s_xy[l1], s_xy[l2], s_uv[l0], s_uv[l1], s_uv[l2], K, e, gu, gx);
+        tri_element<R, true, false>(s_xy[l0], s_xy[l1], s_xy[l2], s_uv[l0], s_uv[l1], s_uv[l2], K, e, gu, gx);
         e_acc += e;
     }
     const R tot = block_sum<R, kTileBlock>(e_acc, s_red);
@@ -288,10 +345,22 @@ __global__ void scale_inplace_kernel(R* __restrict__ g, int64_t n, const R* __re
 }
 
 template <typename R> static size_t smem_for(const hidenn_tri_plan* p) {
-    size_t b = (size_t)p->dev.max_local * 4 * sizeof(R) + (size_t)p->dev.max_entries * 4 * sizeof(R);
-    b += ((size_t)(p->dev.max_owned + 1) * 2 + 15) / 16 * 16;
-    b += 64 * 8;
-    return b;
+    return (size_t)p->dev.max_local * 4 * sizeof(R) + (size_t)(p->dev.max_entries + 1) * 4 * sizeof(R) + 128;
+}
+
+template <typename R, bool BODY, bool ISO>
+static int launch_tile(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed, const R* consts,
+                       int flags, R* gx, R* gu, R* scratch, cudaStream_t stream) {
+    using R2 = typename Real2<R>::type;
+    const size_t smem = smem_for<R>(p);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_kernel<R, BODY, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    tri_tile_kernel<R, BODY, ISO><<<p->dev.n_tiles, kTileBlock, smem, stream>>>(
+        p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch);
+    return 0;
 }
 
 template <typename R>
@@ -310,16 +379,13 @@ static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R*
     const bool grad = flags & (HIDENN_NEED_GX | HIDENN_NEED_GU);
     if (p->dev.n_tiles > 0) {
         if (grad) {
-            const size_t smem = smem_for<R>(p);
-            static thread_local size_t configured[2] = {0, 0};
-            size_t& cfg = configured[sizeof(R) == 8 ? 0 : 1];
-            if (smem > cfg) {
-                HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                cfg = smem;
-            }
-            tri_tile_kernel<R><<<p->dev.n_tiles, kTileBlock, smem, stream>>>(
-                p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags,
-                (R2*)gx, (R2*)gu, scratch);
+            const bool body = !(flags & HIDENN_HINT_NO_BODY_FORCE), iso = (flags & HIDENN_HINT_C_PLANE_STRESS) != 0;
+            int rc;
+            if (body && iso) rc = launch_tile<R, true, true>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream);
+            else if (body) rc = launch_tile<R, true, false>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream);
+            else if (iso) rc = launch_tile<R, false, true>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream);
+            else rc = launch_tile<R, false, false>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream);
+            if (rc) return rc;
         } else {
             const size_t smem = (size_t)p->dev.max_local * 4 * sizeof(R) + 64 * 8;
             static thread_local size_t configured[2] = {0, 0};

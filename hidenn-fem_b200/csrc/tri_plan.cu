@@ -132,7 +132,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     HIDENN_REQUIRE(Ne >= 0 && Nn > 0 && Nn < (int64_t)2147483000 && Ne < (int64_t)500000000, "plan_create: sizes out of range");
     HIDENN_REQUIRE(real_bytes == 8 || real_bytes == 4, "plan_create: real_bytes must be 8 or 4");
     HIDENN_REQUIRE(Ned == 0 || edges != nullptr, "plan_create: edges NULL");
-    if (tile_nodes <= 0) tile_nodes = real_bytes == 8 ? 288 : 576;
+    if (tile_nodes <= 0) tile_nodes = 288;
     HIDENN_REQUIRE(tile_nodes >= 8 && tile_nodes <= 2048, "plan_create: tile_nodes must be in [8,2048]");
 
     for (int64_t i = 0; i < 3 * Ne; ++i)
@@ -171,13 +171,17 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
             for (int c = 0; c < 3; ++c) p->n2e_ent[cur[p->conn32[3 * e + c]]++] = (int32_t)(e * 4 + c);
     }
     for (int64_t n = 0; n < Nn; ++n)
-        HIDENN_REQUIRE(p->n2e_off[n + 1] - p->n2e_off[n] < kRankSkip, "plan_create: node valence >= 255 not supported");
+        HIDENN_REQUIRE(p->n2e_off[n + 1] - p->n2e_off[n] < kMaxValence, "plan_create: node valence >= 255 not supported");
 
     // RCB tiling of the nodes
-    const int64_t n_tiles = (Nn + tile_nodes - 1) / tile_nodes;
+    int64_t n_tiles = 0;
     std::vector<int32_t> order(Nn);
+    std::vector<int64_t> tile_begin;
+    std::vector<TileBuild> tb;
+    for (int attempt = 0;; ++attempt) {
+    n_tiles = (Nn + tile_nodes - 1) / tile_nodes;
     std::iota(order.begin(), order.end(), 0);
-    std::vector<int64_t> tile_begin(n_tiles + 1, 0);
+    tile_begin.assign(n_tiles + 1, 0);
     tile_begin[n_tiles] = Nn;
     {
         Rcb r{coords, order, tile_begin};
@@ -185,7 +189,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     }
 
     // per-tile packs, in parallel over tiles
-    std::vector<TileBuild> tb(n_tiles);
+    tb.assign(n_tiles, TileBuild());
     const int32_t* c32 = p->conn32.data();
     const int64_t* n2o = p->n2e_off.data();
     const int32_t* n2e = p->n2e_ent.data();
@@ -232,19 +236,18 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
                 for (int c = 0; c < 3; ++c) {
                     const int32_t n = c32[3 * (int64_t)e + c];
                     int32_t lid = owned_id(n);
-                    unsigned long long rank = kRankSkip;
+                    unsigned long long pos = (unsigned long long)acc;     // dump slot for halo corners
                     if (lid >= 0) {
                         const int32_t key = e * 4 + c;
                         for (int64_t k = n2o[n]; k < n2o[n + 1]; ++k)
-                            if (n2e[k] == key) { rank = (unsigned long long)(k - n2o[n]); break; }
+                            if (n2e[k] == key) { pos = (unsigned long long)(B.off[lid] + (k - n2o[n])); break; }
                     } else {
                         auto it = std::lower_bound(B.nodes.begin() + B.n_owned, B.nodes.end(), n);
                         lid = (int32_t)(it - B.nodes.begin());
                     }
                     w |= (unsigned long long)lid << (kLidBits * c);
-                    w |= rank << (3 * kLidBits + kRankBits * c);
+                    w |= pos << (3 * kLidBits + kPosBits * c);
                 }
-                // the tile that owns corner 0 adds the element's energy
                 if (owned_id(c32[3 * (int64_t)e]) >= 0) w |= 1ull << kOwnerBit;
                 B.pack[i] = w;
             }
@@ -261,11 +264,16 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
         }
         for (auto& t : th) t.join();
     }
+    bool bad = false;
+    for (auto& B : tb) bad |= (B.err != 0);
+    if (!bad) break;
+    // a tile exceeded the pack limits (1023 local nodes / 2047 fold slots): shrink the tiles and retry
+    HIDENN_REQUIRE(attempt < 12 && tile_nodes > 8, "plan_create: cannot tile this mesh within the pack limits");
+    tile_nodes = std::max(8, tile_nodes * 3 / 4);
+    }
     int32_t max_local = 0, max_entries = 0, max_owned = 0, max_elem = 0;
     int64_t node_visits = 0, elem_visits = 0, off_total = 0;
     for (auto& B : tb) {
-        HIDENN_REQUIRE(B.err != 1, "plan_create: a tile has more than 4095 local nodes; use a smaller tile_nodes");
-        HIDENN_REQUIRE(B.err != 2, "plan_create: a tile has more than 65535 fold entries; use a smaller tile_nodes");
         node_visits += (int64_t)B.nodes.size();
         elem_visits += (int64_t)B.elems.size();
         off_total += B.n_owned + 1;
@@ -302,11 +310,8 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     p->node_visits = node_visits;
     p->elem_visits = elem_visits;
 
-    std::vector<int32_t> t_xslot(node_visits), t_uslot(node_visits);
-    for (int64_t i = 0; i < node_visits; ++i) {
-        t_xslot[i] = p->xslot[p->t_node[i]];
-        t_uslot[i] = p->uslot[p->t_node[i]];
-    }
+    std::vector<int2> t_slots(node_visits);
+    for (int64_t i = 0; i < node_visits; ++i) t_slots[i] = make_int2(p->xslot[p->t_node[i]], p->uslot[p->t_node[i]]);
 
     // Neumann edges: slot quads + node-centric CSR (each edge node folded by one thread)
     p->edges32.resize(2 * Ned);
@@ -352,8 +357,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     hidenn_tri_plan* pp = p.get();
     int rc = 0;
     rc |= upload(pp, p->tiles, &D.tiles);
-    rc |= upload(pp, t_xslot, &D.t_xslot);
-    rc |= upload(pp, t_uslot, &D.t_uslot);
+    rc |= upload(pp, t_slots, &D.t_slots);
     rc |= upload(pp, p->elem_pack, &D.elem_pack);
     rc |= upload(pp, p->entry_off, &D.entry_off);
     rc |= upload(pp, e_slots, &D.e_slots);
@@ -379,10 +383,7 @@ extern "C" void hidenn_tri_plan_destroy(hidenn_tri_plan* p) {
 
 static size_t tile_smem_bytes(const hidenn_tri_plan* p, int rb) {
     // node pairs (xy, uv) + fold partial pairs (gu, gx) + entry offsets + block-reduce scratch
-    size_t b = (size_t)p->dev.max_local * 4 * rb + (size_t)p->dev.max_entries * 4 * rb;
-    b += ((size_t)(p->dev.max_owned + 1) * 2 + 15) / 16 * 16;
-    b += 64 * 8;
-    return b;
+    return (size_t)p->dev.max_local * 4 * rb + (size_t)(p->dev.max_entries + 1) * 4 * rb + 128;
 }
 
 extern "C" int hidenn_tri_plan_info(const hidenn_tri_plan* p, int64_t* info) {

@@ -18,20 +18,20 @@ struct TileDesc {          // 32 B
     int32_t pad;
 };
 
-// elem_pack bit layout (uint64): local node ids 3 x 12 bit, fold ranks 3 x 8 bit (255 = halo corner,
-// contribution dropped), bit 60 = this visit owns the element's energy.
-constexpr int kLidBits = 12;
-constexpr int kRankBits = 8;
-constexpr int kRankSkip = 255;
-constexpr int kOwnerBit = 60;
-constexpr int kMaxLocal = (1 << kLidBits) - 1;
-constexpr int kMaxEntries = 65535;
+// elem_pack bit layout (uint64): local node ids 3 x 10 bit, fold-slot positions 3 x 11 bit (precomputed
+// off[node] + rank; halo corners point at the tile's dump slot = n_entries), bit 63 = this visit owns the
+// element's energy.
+constexpr int kLidBits = 10;
+constexpr int kPosBits = 11;
+constexpr int kOwnerBit = 63;
+constexpr int kMaxLocal = (1 << kLidBits) - 1;       // local ids 0..1022
+constexpr int kMaxEntries = (1 << kPosBits) - 1;     // fold slots 0..2046 + dump slot <= 2047
+constexpr int kMaxValence = 255;
 
 struct TriPlanDev {
     const TileDesc* tiles;
     int32_t n_tiles;
-    const int32_t* t_xslot;      // [node visits]
-    const int32_t* t_uslot;
+    const int2* t_slots;         // [node visits]: (xslot, uslot)
     const unsigned long long* elem_pack;   // [element visits]
     const uint16_t* entry_off;
     int32_t max_local, max_entries, max_owned, max_elem;

@@ -17,7 +17,7 @@ from .utils import triangle_gauss_points, interval_gauss_points
 
 NCONST = 32
 I_C, I_W, I_FB, I_TX, I_TY, I_NG1, I_XI1, I_W1 = 0, 6, 7, 13, 14, 15, 16, 24
-NEED_GX, NEED_GU, WITH_EDGES = 1, 2, 4
+NEED_GX, NEED_GU, WITH_EDGES, TILES_ONLY, HINT_NO_BODY, HINT_C_PS = 1, 2, 4, 16, 32, 64
 
 
 class _TriEnergyFn(torch.autograd.Function):
@@ -25,11 +25,11 @@ class _TriEnergyFn(torch.autograd.Function):
     launch as the energy and handed to autograd in backward (scaled on device by grad_output)."""
 
     @staticmethod
-    def forward(ctx, x_free, u_free, model, consts, with_edges, t_force, loss_obj):
+    def forward(ctx, x_free, u_free, model, consts, hints, with_edges, t_force, loss_obj):
         plan = model._plan()
         dt, dev = x_free.dtype, x_free.device
         need_gx, need_gu = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        flags = (NEED_GX if need_gx else 0) | (NEED_GU if need_gu else 0) | (WITH_EDGES if with_edges else 0)
+        flags = (NEED_GX if need_gx else 0) | (NEED_GU if need_gu else 0) | (WITH_EDGES if with_edges else 0) | hints
         xb, ub = model._fixed_pair()
         out = torch.empty(4, device=dev, dtype=dt)
         gx = torch.empty_like(x_free) if need_gx else None
@@ -72,7 +72,7 @@ class _TriEnergyFn(torch.autograd.Function):
                     go = go.to(g.dtype)
                 _lib.check(_lib.fn("hidenn_scale_inplace", g.dtype)(_lib.ptr(g), C.c_int64(g.numel()), _lib.ptr(go),
                                                                     _lib.stream_ptr()))
-        return gx, gu, None, None, None, None, None
+        return gx, gu, None, None, None, None, None, None
 
 
 class EnergyLoss2D:
@@ -128,10 +128,12 @@ class EnergyLoss2D:
             base[I_NG1] = float(self.ng1)
             base[I_XI1:I_XI1 + self.ng1] = self.xg_1d.to(device=dev, dtype=dt)
             base[I_W1:I_W1 + self.ng1] = self.wg_1d.to(device=dev, dtype=dt)
-            self._consts_cache = (key, base)
-        base = self._consts_cache[1]
+            # plane-stress form of C (loss.py:29-32) lets the kernel skip the zero couplings; checked once per rebuild
+            c_ps = bool((Cs[0, 2] == 0).item() and (Cs[1, 2] == 0).item())
+            self._consts_cache = (key, base, HINT_C_PS if c_ps else 0)
+        base, hint_c = self._consts_cache[1], self._consts_cache[2]
         if b_force is None:
-            return base
+            return base, hint_c | HINT_NO_BODY
         # b_force sees the *reference* Gauss points (reference loss.py:60,80; Q4) -> constant 3x2 load matrix
         xg = self.xg.to(device=dev, dtype=dt)
         wg = self.wg.to(device=dev, dtype=dt)
@@ -140,7 +142,7 @@ class EnergyLoss2D:
         Fb = torch.einsum("g,gk,gi->ki", wg, N, b)
         c = base.clone()
         c[I_FB:I_FB + 6] = Fb.reshape(-1)
-        return c
+        return c, hint_c
 
     def _scratch(self, plan, dev, dt):
         key = (id(plan), dev, dt)
@@ -211,8 +213,8 @@ class EnergyLoss2D:
         model._check_ready()
         if with_edges:
             model.N_edges            # AttributeError if the model has no neumann_edges (reference Q9)
-        consts = self._consts(model, b_force)
-        loss = _TriEnergyFn.apply(model.node_coords_free, model.u_free, model, consts, with_edges, t_force, self)
+        consts, hints = self._consts(model, b_force)
+        loss = _TriEnergyFn.apply(model.node_coords_free, model.u_free, model, consts, hints, with_edges, t_force, self)
         return loss
 
     def domain_energy(self, model, b_force: Optional[Callable[[torch.Tensor], torch.Tensor]] = None) -> torch.Tensor:

@@ -86,6 +86,10 @@ def plate_mesh(nx: int, ny: int, length: float = 2.0, height: float = 1.0,
     assert 0 <= c0 < c1 <= nx - 1
     hx, hy = length / (nx - 1), height / (ny - 1)
 
+    # build one extra cell column on each side so that hole-rim flags of interface nodes see the
+    # neighbouring strip's removed elements (keeps boundary masks identical to the global mesh)
+    own0, own1 = c0, c1
+    c0, c1 = max(c0 - 1, 0), min(c1 + 1, nx - 1)
     ixs = np.arange(c0, c1 + 1, dtype=np.int64)
     iys = np.arange(ny, dtype=np.int64)
     IX, IY = np.meshgrid(ixs, iys, indexing="ij")           # [ncol+1, ny]
@@ -138,8 +142,9 @@ def plate_mesh(nx: int, ny: int, length: float = 2.0, height: float = 1.0,
     bad = conn[~elem_ok].ravel()
     rim[bad] = True
     rim &= ~inside
-    conn = conn[elem_ok]
-    cell_of_elem = cell_of_elem[elem_ok]
+    own = (cx[cell_of_elem] >= own0) & (cx[cell_of_elem] < own1)
+    conn = conn[elem_ok & own]
+    cell_of_elem = cell_of_elem[elem_ok & own]
 
     used = np.zeros(x.size, dtype=bool)
     used[conn.ravel()] = True
@@ -188,7 +193,7 @@ def plate_mesh(nx: int, ny: int, length: float = 2.0, height: float = 1.0,
     return PlateMesh(coords, np.ascontiguousarray(conn), boundary, dirichlet, neumann,
                      neumann_edges.astype(np.int64), gid,
                      meta=dict(nx=nx, ny=ny, length=length, height=height, jitter=jitter, diag=diag,
-                               seed=seed, ordering=ordering, col_range=(c0, c1)))
+                               seed=seed, ordering=ordering, col_range=(own0, own1)))
 
 
 def plate_dims_for_elements(n_elems: int, aspect: float = 2.0, hole_fraction: float = 0.0745):

@@ -51,6 +51,8 @@ extern "C" {
 #define HIDENN_NEED_GU 2      /* write d loss / d u_free           */
 #define HIDENN_WITH_EDGES 4   /* include the Neumann edge term (src/loss.py:91-110) */
 #define HIDENN_TILES_ONLY 16  /* measurement aid: launch only the tile kernel (per-tile energies stay in scratch) */
+#define HIDENN_HINT_NO_BODY_FORCE 32   /* caller guarantees consts[HIDENN_TRI_FB..] == 0 (b_force=None): skips those terms */
+#define HIDENN_HINT_C_PLANE_STRESS 64  /* caller guarantees C02 == C12 == 0 (the matrix form of src/loss.py:29-32)      */
 
 const char* hidenn_last_error(void);
 int hidenn_version(void);

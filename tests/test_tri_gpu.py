@@ -230,7 +230,7 @@ def test_host_buffer_entry_point():
     g = gold("tri_f64_jitter")
     model = build(g)
     loss_fn = loss_of(g, torch.float64)
-    consts = loss_fn._consts(model, None).cpu()
+    consts = loss_fn._consts(model, None)[0].cpu()
     plan = model._plan()
     xb, ub = model._fixed_pair()
     xf = model.node_coords_free.detach().cpu().pin_memory()
