@@ -422,9 +422,9 @@ def main():
                        "halo_recompute": plan.info["elem_visits"] / max(1, ne_local), "setup_s": setup_s},
             "loss": loss_val,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": args.steps * (2 + 2 + (4 if world > 1 else 0)),
+            "gpu_launches": args.steps * (2 + 2 + (2 if world > 1 else 0)),
             "gpu_launches_note": "per step: tri_tile_kernel + tri_edge_finalize_kernel + 2 scale_inplace_kernel"
-                                 + (" + 4 halo pack/unpack" if world > 1 else ""),
+                                 + (" + halo pack_all + unpack_all (plus one copy and the NCCL all-reduce)" if world > 1 else ""),
         }
         if extra:
             line["extra"] = extra

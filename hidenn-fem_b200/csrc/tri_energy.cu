@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "tri_plan.h"
 
+#include <cstdlib>
+
 namespace hidenn {
 
 constexpr int kTileBlock = 256;
@@ -98,8 +100,8 @@ template <typename R, bool BODY> __device__ __forceinline__ TriConsts<R> load_co
 
 constexpr int kPre = 3;   // element packs prefetched per thread before the first barrier (kPre*256 >= typical tile)
 
-template <typename R, bool BODY, bool ISO>
-__global__ void __launch_bounds__(kTileBlock, 3)
+template <typename R, bool BODY, bool ISO, int MINB>
+__global__ void __launch_bounds__(kTileBlock, MINB)
 tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ x_free,
                 const typename Real2<R>::type* __restrict__ x_fixed, const typename Real2<R>::type* __restrict__ u_free,
                 const typename Real2<R>::type* __restrict__ u_fixed, const R* __restrict__ consts, const int flags,
@@ -107,7 +109,6 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
                 R* __restrict__ tile_energy) {
     using R2 = typename Real2<R>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const TileDesc td = P.tiles[blockIdx.x];
     // shared layout: node pairs xy | uv, fold partial pairs gu | gx (n_entries + 1 dump slot), reduce scratch
     R2* s_xy = reinterpret_cast<R2*>(smem_raw);
     R2* s_uv = s_xy + P.max_local;
@@ -115,39 +116,42 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
     R2* s_px = s_pu + (P.max_entries + 1);
     R* s_red = reinterpret_cast<R*>(s_px + (P.max_entries + 1));
     const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
 
-    // phase 1: issue every global load of the tile up front -- element packs and fold offsets into registers,
-    // node slots -> AoS pair gathers -> shared memory
+    // phase 1: every global load of the tile is issued up front.  The tile records have fixed strides, so the
+    // slot / pack / offset addresses depend only on blockIdx (no wait on the descriptor); padding entries are inert.
+    const int2* __restrict__ slots = P.t_slots + (size_t)tile * P.stride_local;
+    const unsigned long long* __restrict__ packs = P.elem_pack + (size_t)tile * P.stride_elem;
+    const uint32_t* __restrict__ offs = P.entry_off + (size_t)tile * P.stride_owned;
+    int2 myslot[2];
+    uint32_t myoff[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int i = tid + k * kTileBlock;
+        myslot[k] = i < P.stride_local ? __ldg(slots + i) : make_int2(-1, -1);
+        myoff[k] = i < P.stride_owned ? __ldg(offs + i) : 0u;
+    }
     unsigned long long wpre[kPre];
 #pragma unroll
     for (int k = 0; k < kPre; ++k) {
         const int i = tid + k * kTileBlock;
-        wpre[k] = i < td.n_elem ? __ldg(P.elem_pack + td.elem_off + i) : 0ull;
+        wpre[k] = i < P.stride_elem ? __ldg(packs + i) : 0ull;
     }
-    int2 myslot[2];
-    unsigned myoff[2][2];
+    const TileDesc td = P.tiles[tile];
+    const TriConsts<R> K = load_consts<R, BODY>(consts);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int i = tid + k * kTileBlock;
-        myslot[k] = make_int2(-1, -1);
-        myoff[k][0] = myoff[k][1] = 0;
         if (i < td.n_local) {
-            const int2 sl = __ldg(P.t_slots + td.node_off + i);
-            myslot[k] = sl;
-            s_xy[i] = load_slot<R2>(x_free, x_fixed, sl.x);
-            s_uv[i] = load_slot<R2>(u_free, u_fixed, sl.y);
-        }
-        if (i < td.n_owned) {
-            myoff[k][0] = __ldg(P.entry_off + td.off_off + i);
-            myoff[k][1] = __ldg(P.entry_off + td.off_off + i + 1);
+            s_xy[i] = load_slot<R2>(x_free, x_fixed, myslot[k].x);
+            s_uv[i] = load_slot<R2>(u_free, u_fixed, myslot[k].y);
         }
     }
     for (int i = tid + 2 * kTileBlock; i < td.n_local; i += kTileBlock) {      // tiles with more than 512 local nodes
-        const int2 sl = __ldg(P.t_slots + td.node_off + i);
+        const int2 sl = __ldg(slots + i);
         s_xy[i] = load_slot<R2>(x_free, x_fixed, sl.x);
         s_uv[i] = load_slot<R2>(u_free, u_fixed, sl.y);
     }
-    const TriConsts<R> K = load_consts<R, BODY>(consts);
     __syncthreads();
 
     // phase 2: elements -> energy + gradient partials stored at their precomputed fold slots
@@ -169,11 +173,12 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
 #pragma unroll
     for (int k = 0; k < kPre; ++k)
         if (tid + k * kTileBlock < td.n_elem) do_element(wpre[k]);
-    for (int i = tid + kPre * kTileBlock; i < td.n_elem; i += kTileBlock) do_element(__ldg(P.elem_pack + td.elem_off + i));
+    for (int i = tid + kPre * kTileBlock; i < td.n_elem; i += kTileBlock) do_element(__ldg(packs + i));
     __syncthreads();
 
     // phase 3: owned nodes fold their slot range in fixed order and store the final gradients
-    auto fold_node = [&](const unsigned b, const unsigned e, const int2 sl) {
+    auto fold_node = [&](const uint32_t oc, const int2 sl) {
+        const unsigned b = oc & 0xFFFFu, e = b + (oc >> 16);
         R ax = R(0), ay = R(0), bx = R(0), by = R(0);
         for (unsigned k = b; k < e; ++k) {
             const R2 u = s_pu[k], x = s_px[k];
@@ -184,9 +189,8 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
     };
 #pragma unroll
     for (int k = 0; k < 2; ++k)
-        if (tid + k * kTileBlock < td.n_owned) fold_node(myoff[k][0], myoff[k][1], myslot[k]);
-    for (int i = tid + 2 * kTileBlock; i < td.n_owned; i += kTileBlock)
-        fold_node(__ldg(P.entry_off + td.off_off + i), __ldg(P.entry_off + td.off_off + i + 1), __ldg(P.t_slots + td.node_off + i));
+        if (tid + k * kTileBlock < td.n_owned) fold_node(myoff[k], myslot[k]);
+    for (int i = tid + 2 * kTileBlock; i < td.n_owned; i += kTileBlock) fold_node(__ldg(offs + i), __ldg(slots + i));
 
     // tile energy (fixed-order block sum)
     const R tot = block_sum<R, kTileBlock>(e_acc, s_red);
@@ -208,8 +212,10 @@ tri_tile_energy_only_kernel(const TriPlanDev P, const typename Real2<R>::type* _
     R2* s_uv = s_xy + td.n_local;
     R* s_red = reinterpret_cast<R*>(s_uv + td.n_local);
     const int tid = threadIdx.x;
+    const int2* __restrict__ slots = P.t_slots + (size_t)blockIdx.x * P.stride_local;
+    const unsigned long long* __restrict__ packs = P.elem_pack + (size_t)blockIdx.x * P.stride_elem;
     for (int i = tid; i < td.n_local; i += kTileBlock) {
-        const int2 sl = __ldg(P.t_slots + td.node_off + i);
+        const int2 sl = __ldg(slots + i);
         s_xy[i] = load_slot<R2>(x_free, x_fixed, sl.x);
         s_uv[i] = load_slot<R2>(u_free, u_fixed, sl.y);
     }
@@ -218,7 +224,7 @@ tri_tile_energy_only_kernel(const TriPlanDev P, const typename Real2<R>::type* _
     R e_acc = R(0);
     constexpr unsigned LM = (1u << kLidBits) - 1u;
     for (int i = tid; i < td.n_elem; i += kTileBlock) {
-        const unsigned long long w = __ldg(P.elem_pack + td.elem_off + i);
+        const unsigned long long w = __ldg(packs + i);
         if (!((w >> kOwnerBit) & 1ull)) continue;
         const unsigned l0 = (unsigned)(w) & LM, l1 = (unsigned)(w >> kLidBits) & LM, l2 = (unsigned)(w >> (2 * kLidBits)) & LM;
         R e;
@@ -348,19 +354,43 @@ template <typename R> static size_t smem_for(const hidenn_tri_plan* p) {
     return (size_t)p->dev.max_local * 4 * sizeof(R) + (size_t)(p->dev.max_entries + 1) * 4 * sizeof(R) + 128;
 }
 
+template <typename R, bool BODY, bool ISO, int MINB>
+static int launch_tile_mb(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed, const R* consts,
+                          int flags, R* gx, R* gu, R* scratch, cudaStream_t stream, size_t smem) {
+    using R2 = typename Real2<R>::type;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_kernel<R, BODY, ISO, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_kernel<R, BODY, ISO, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = smem;
+    }
+    tri_tile_kernel<R, BODY, ISO, MINB><<<p->dev.n_tiles, kTileBlock, smem, stream>>>(
+        p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch);
+    return 0;
+}
+
+// resident CTAs per SM the tile kernel is compiled for: as many as the tile's shared memory allows
+// (227 KB per SM, 1 KB reserved per CTA), capped where the register budget would start to spill.
+static int pick_minb(size_t smem, int real_bytes) {
+    static const int env = [] { const char* e = getenv("HIDENN_TILE_MINB"); return e ? atoi(e) : 0; }();
+    int mb = (int)((227 * 1024) / (smem + 1024));
+    const int cap = real_bytes == 8 ? 4 : 6;
+    mb = mb < 2 ? 2 : (mb > cap ? cap : mb);
+    if (env >= 2 && env <= 6) mb = env;
+    return mb;
+}
+
 template <typename R, bool BODY, bool ISO>
 static int launch_tile(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed, const R* consts,
                        int flags, R* gx, R* gu, R* scratch, cudaStream_t stream) {
-    using R2 = typename Real2<R>::type;
     const size_t smem = smem_for<R>(p);
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_kernel<R, BODY, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    switch (pick_minb(smem, (int)sizeof(R))) {
+        case 2: return launch_tile_mb<R, BODY, ISO, 2>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
+        case 3: return launch_tile_mb<R, BODY, ISO, 3>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
+        case 4: return launch_tile_mb<R, BODY, ISO, 4>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
+        case 5: return launch_tile_mb<R, BODY, ISO, 5>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
+        default: return launch_tile_mb<R, BODY, ISO, 6>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
     }
-    tri_tile_kernel<R, BODY, ISO><<<p->dev.n_tiles, kTileBlock, smem, stream>>>(
-        p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch);
-    return 0;
 }
 
 template <typename R>

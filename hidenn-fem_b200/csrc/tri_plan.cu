@@ -78,7 +78,8 @@ struct TileBuild {
     int32_t n_owned = 0;
     std::vector<int32_t> elems;     // ascending global element id
     std::vector<unsigned long long> pack;
-    std::vector<uint16_t> off;      // n_owned+1
+    std::vector<uint32_t> off;      // n_owned: fold-slot start | count << 16
+    int32_t n_entries = 0;          // padded slot count (= dump slot index)
     int err = 0;
 };
 
@@ -220,15 +221,18 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
             halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
             B.nodes.insert(B.nodes.end(), halo.begin(), halo.end());
             if ((int64_t)B.nodes.size() > kMaxLocal) { B.err = 1; continue; }
-            B.off.resize(B.n_owned + 1);
+            B.off.resize(B.n_owned);
             int64_t acc = 0;
             for (int32_t l = 0; l < B.n_owned; ++l) {
-                B.off[l] = (uint16_t)acc;
-                acc += n2o[B.nodes[l] + 1] - n2o[B.nodes[l]];
+                const int64_t cnt = n2o[B.nodes[l] + 1] - n2o[B.nodes[l]];
+                B.off[l] = (uint32_t)acc | ((uint32_t)cnt << 16);
+                // odd stride between consecutive nodes' slot ranges: the 8 lanes of a quarter-warp then read
+                // 8 different 16-byte bank groups in the fold (an even stride such as 6 gives 2-way conflicts)
+                acc += cnt == 0 ? 0 : (cnt | 1);
                 if (acc > kMaxEntries) { B.err = 2; break; }
             }
             if (B.err) continue;
-            B.off[B.n_owned] = (uint16_t)acc;
+            B.n_entries = (int32_t)acc;
             B.pack.resize(B.elems.size());
             for (size_t i = 0; i < B.elems.size(); ++i) {
                 const int32_t e = B.elems[i];
@@ -240,7 +244,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
                     if (lid >= 0) {
                         const int32_t key = e * 4 + c;
                         for (int64_t k = n2o[n]; k < n2o[n + 1]; ++k)
-                            if (n2e[k] == key) { pos = (unsigned long long)(B.off[lid] + (k - n2o[n])); break; }
+                            if (n2e[k] == key) { pos = (unsigned long long)((B.off[lid] & 0xFFFFu) + (k - n2o[n])); break; }
                     } else {
                         auto it = std::lower_bound(B.nodes.begin() + B.n_owned, B.nodes.end(), n);
                         lid = (int32_t)(it - B.nodes.begin());
@@ -276,7 +280,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     for (auto& B : tb) {
         node_visits += (int64_t)B.nodes.size();
         elem_visits += (int64_t)B.elems.size();
-        off_total += B.n_owned + 1;
+        off_total += B.n_owned;
     }
     HIDENN_REQUIRE(node_visits < 2147483000LL && elem_visits < 2147483000LL, "plan_create: mesh too large for int32 tile offsets");
     p->tiles.resize(n_tiles);
@@ -293,7 +297,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
         d.elem_off = (int32_t)p->t_elem.size();
         d.n_elem = (int32_t)B.elems.size();
         d.off_off = (int32_t)p->entry_off.size();
-        d.n_entries = B.off.empty() ? 0 : B.off[B.n_owned];
+        d.n_entries = B.n_entries;
         p->tiles[t] = d;
         p->t_node.insert(p->t_node.end(), B.nodes.begin(), B.nodes.end());
         p->t_elem.insert(p->t_elem.end(), B.elems.begin(), B.elems.end());
@@ -310,8 +314,20 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     p->node_visits = node_visits;
     p->elem_visits = elem_visits;
 
-    std::vector<int2> t_slots(node_visits);
-    for (int64_t i = 0; i < node_visits; ++i) t_slots[i] = make_int2(p->xslot[p->t_node[i]], p->uslot[p->t_node[i]]);
+    // device layout: fixed-stride records per tile
+    const int32_t SL = (max_local + 1) & ~1, SE = (max_elem + 1) & ~1, SO = (max_owned + 3) & ~3;
+    std::vector<int2> t_slots((size_t)n_tiles * SL, make_int2(-1, -1));
+    std::vector<unsigned long long> d_pack((size_t)n_tiles * SE, 0ull);
+    std::vector<uint32_t> d_off((size_t)n_tiles * SO, 0u);
+    for (int64_t t = 0; t < n_tiles; ++t) {
+        const TileDesc& d = p->tiles[t];
+        for (int32_t i = 0; i < d.n_local; ++i) {
+            const int32_t n = p->t_node[d.node_off + i];
+            t_slots[(size_t)t * SL + i] = make_int2(p->xslot[n], p->uslot[n]);
+        }
+        std::copy(p->elem_pack.begin() + d.elem_off, p->elem_pack.begin() + d.elem_off + d.n_elem, d_pack.begin() + (size_t)t * SE);
+        std::copy(p->entry_off.begin() + d.off_off, p->entry_off.begin() + d.off_off + d.n_owned, d_off.begin() + (size_t)t * SO);
+    }
 
     // Neumann edges: slot quads + node-centric CSR (each edge node folded by one thread)
     p->edges32.resize(2 * Ned);
@@ -358,8 +374,9 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     int rc = 0;
     rc |= upload(pp, p->tiles, &D.tiles);
     rc |= upload(pp, t_slots, &D.t_slots);
-    rc |= upload(pp, p->elem_pack, &D.elem_pack);
-    rc |= upload(pp, p->entry_off, &D.entry_off);
+    rc |= upload(pp, d_pack, &D.elem_pack);
+    rc |= upload(pp, d_off, &D.entry_off);
+    D.stride_local = SL; D.stride_elem = SE; D.stride_owned = SO;
     rc |= upload(pp, e_slots, &D.e_slots);
     rc |= upload(pp, en_xslot, &D.en_xslot);
     rc |= upload(pp, en_uslot, &D.en_uslot);

@@ -13,7 +13,7 @@ struct TileDesc {          // 32 B
     int32_t n_local;
     int32_t elem_off;      // first entry in elem_pack
     int32_t n_elem;
-    int32_t off_off;       // first entry in entry_off (n_owned+1 values)
+    int32_t off_off;       // first entry in the compact host entry_off (n_owned values)
     int32_t n_entries;     // sum of owned valences = shared-memory partial slots
     int32_t pad;
 };
@@ -31,9 +31,11 @@ constexpr int kMaxValence = 255;
 struct TriPlanDev {
     const TileDesc* tiles;
     int32_t n_tiles;
-    const int2* t_slots;         // [node visits]: (xslot, uslot)
-    const unsigned long long* elem_pack;   // [element visits]
-    const uint16_t* entry_off;
+    // fixed-stride tile records (tile t starts at t*stride): every load address depends only on blockIdx
+    const int2* t_slots;                   // [n_tiles, stride_local]: (xslot, uslot) per local node, padded with (-1,-1)
+    const unsigned long long* elem_pack;   // [n_tiles, stride_elem], padded with 0
+    const uint32_t* entry_off;             // [n_tiles, stride_owned]: fold-slot start | count << 16 per owned node
+    int32_t stride_local, stride_elem, stride_owned;
     int32_t max_local, max_entries, max_owned, max_elem;
     // Neumann edges
     int32_t n_edges;
@@ -65,7 +67,7 @@ struct hidenn_tri_plan {
     std::vector<int32_t> t_node;            // global node id of every tile-local node
     std::vector<int32_t> t_elem;            // global element id of every tile element visit
     std::vector<unsigned long long> elem_pack;
-    std::vector<uint16_t> entry_off;
+    std::vector<uint32_t> entry_off;        // compact: start | count << 16 per owned node, tiles back to back
     std::vector<int32_t> xslot, uslot;
     std::vector<int32_t> conn32;
     std::vector<int64_t> n2e_off;

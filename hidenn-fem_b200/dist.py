@@ -37,7 +37,7 @@ class HaloPlan:
 
     @property
     def buffer_len(self):
-        return 1 + 4 * self.shared_gid.shape[0]
+        return 2 + 4 * self.shared_gid.shape[0]
 
 
 def shared_ids_from_candidates(cands: Sequence[np.ndarray]) -> np.ndarray:
@@ -128,7 +128,11 @@ def partition_elements(mesh: meshgen.PlateMesh, world: int, rank: int) -> meshge
 # device-side exchange
 # ------------------------------------------------------------------------------------------------
 class HaloExchange:
-    """Packs [loss, shared-node gradients] with the C-ABI pack kernels, all-reduces once (NCCL), unpacks."""
+    """[loss, shared-node gradients]: one pack kernel, one NCCL all-reduce, one unpack kernel per evaluation.
+
+    Message layout  [loss, 0 | gx pairs (S) | gu pairs (S)]  in ascending global node id (same on every rank).
+    `send` keeps zeros at the positions of shared nodes this rank does not hold (or holds as fixed), so the sum
+    over ranks is exactly the sum of the partial gradients."""
 
     def __init__(self, plan: HaloPlan, device, dtype, group=None):
         self.plan = plan
@@ -139,41 +143,25 @@ class HaloExchange:
         self.dtype = dtype
         S = plan.shared_gid.shape[0]
         self.S = S
-        self.buf = torch.zeros(1 + 4 * S, device=self.device, dtype=dtype)
-        t = lambda a, d: torch.from_numpy(np.ascontiguousarray(a)).to(self.device, d)
-        self.x_rows, self.u_rows = t(plan.x_rows, torch.int32), t(plan.u_rows, torch.int32)
-        # staging is dense per kind: gx pairs at [1, 1+2S), gu pairs at [1+2S, 1+4S); rows scatter by position
-        self.x_pos, self.u_pos = t(plan.x_pos, torch.int64), t(plan.u_pos, torch.int64)
-        self.stage_x = torch.empty(max(self.x_rows.numel(), 1), 2, device=self.device, dtype=dtype)
-        self.stage_u = torch.empty(max(self.u_rows.numel(), 1), 2, device=self.device, dtype=dtype)
+        self.send = torch.zeros(2 + 4 * S, device=self.device, dtype=dtype)
+        self.recv = torch.zeros_like(self.send)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
+        self.x_rows, self.x_pos = t(plan.x_rows), t(plan.x_pos)
+        self.u_rows, self.u_pos = t(plan.u_rows), t(plan.u_pos)
 
     def exchange(self, out, gx, gu):
         """out: device [4] (loss first); gx/gu: parameter-layout gradients or None. In place."""
         s = _lib.stream_ptr()
         dt = self.dtype
-        self.buf.zero_()
-        self.buf[0:1].copy_(out[0:1])
-        S = self.S
-        bx = self.buf[1:1 + 2 * S].view(S, 2)
-        bu = self.buf[1 + 2 * S:1 + 4 * S].view(S, 2)
-        if gx is not None and self.x_rows.numel():
-            _lib.check(_lib.fn("hidenn_halo_pack", dt)(_lib.ptr(gx), _lib.ptr(self.x_rows), C.c_int64(self.x_rows.numel()),
-                                                       _lib.ptr(self.stage_x), s))
-            bx[self.x_pos] = self.stage_x[:self.x_rows.numel()]
-        if gu is not None and self.u_rows.numel():
-            _lib.check(_lib.fn("hidenn_halo_pack", dt)(_lib.ptr(gu), _lib.ptr(self.u_rows), C.c_int64(self.u_rows.numel()),
-                                                       _lib.ptr(self.stage_u), s))
-            bu[self.u_pos] = self.stage_u[:self.u_rows.numel()]
-        dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
-        out[0:1].copy_(self.buf[0:1])
-        if gx is not None and self.x_rows.numel():
-            self.stage_x[:self.x_rows.numel()] = bx[self.x_pos]
-            _lib.check(_lib.fn("hidenn_halo_unpack", dt)(_lib.ptr(gx), _lib.ptr(self.x_rows), C.c_int64(self.x_rows.numel()),
-                                                         _lib.ptr(self.stage_x), s))
-        if gu is not None and self.u_rows.numel():
-            self.stage_u[:self.u_rows.numel()] = bu[self.u_pos]
-            _lib.check(_lib.fn("hidenn_halo_unpack", dt)(_lib.ptr(gu), _lib.ptr(self.u_rows), C.c_int64(self.u_rows.numel()),
-                                                         _lib.ptr(self.stage_u), s))
+        nx, nu = C.c_int64(self.x_rows.numel()), C.c_int64(self.u_rows.numel())
+        _lib.check(_lib.fn("hidenn_halo_pack_all", dt)(
+            _lib.ptr(gx), _lib.ptr(self.x_rows), _lib.ptr(self.x_pos), nx, _lib.ptr(gu), _lib.ptr(self.u_rows), _lib.ptr(self.u_pos), nu,
+            _lib.ptr(out), C.c_int64(self.S), _lib.ptr(self.send), s))
+        self.recv.copy_(self.send)
+        dist.all_reduce(self.recv, op=dist.ReduceOp.SUM, group=self.group)
+        _lib.check(_lib.fn("hidenn_halo_unpack_all", dt)(
+            _lib.ptr(gx), _lib.ptr(self.x_rows), _lib.ptr(self.x_pos), nx, _lib.ptr(gu), _lib.ptr(self.u_rows), _lib.ptr(self.u_pos), nu,
+            _lib.ptr(out), C.c_int64(self.S), _lib.ptr(self.recv), s))
 
 
 class DistributedEnergyLoss2D(EnergyLoss2D):

@@ -206,6 +206,23 @@ int hidenn_halo_unpack_f64(double* g, const int32_t* idx, int64_t n, const doubl
 int hidenn_halo_pack_f32(const float* g, const int32_t* idx, int64_t n, float* buf, void* stream);
 int hidenn_halo_unpack_f32(float* g, const int32_t* idx, int64_t n, const float* buf, void* stream);
 
+/* One-launch pack / unpack of the whole halo message  buf = [loss, 0 | gx pairs (S) | gu pairs (S)]:
+ *   pack:   buf[0] = *loss;  bufx[xpos[i]] = gx[xrows[i]];  bufu[upos[i]] = gu[urows[i]]   (other entries untouched)
+ *   unpack: *loss = buf[0];  gx[xrows[i]] = bufx[xpos[i]];  gu[urows[i]] = bufu[upos[i]]
+ * gx / gu may be NULL (frozen parameter).  S = number of shared nodes; xpos/upos index pairs. */
+int hidenn_halo_pack_all_f64(const double* gx, const int32_t* xrows, const int32_t* xpos, int64_t nx,
+                             const double* gu, const int32_t* urows, const int32_t* upos, int64_t nu,
+                             const double* loss, int64_t S, double* buf, void* stream);
+int hidenn_halo_unpack_all_f64(double* gx, const int32_t* xrows, const int32_t* xpos, int64_t nx,
+                               double* gu, const int32_t* urows, const int32_t* upos, int64_t nu,
+                               double* loss, int64_t S, const double* buf, void* stream);
+int hidenn_halo_pack_all_f32(const float* gx, const int32_t* xrows, const int32_t* xpos, int64_t nx,
+                             const float* gu, const int32_t* urows, const int32_t* upos, int64_t nu,
+                             const float* loss, int64_t S, float* buf, void* stream);
+int hidenn_halo_unpack_all_f32(float* gx, const int32_t* xrows, const int32_t* xpos, int64_t nx,
+                               float* gu, const int32_t* urows, const int32_t* upos, int64_t nu,
+                               float* loss, int64_t S, const float* buf, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,7 +67,7 @@ def main():
             o.step()
     eu2 = rel(model.u_free.detach(), gmodel.u_free.detach()[ru])
     ex2 = rel(model.node_coords_free.detach(), gmodel.node_coords_free.detach()[rx])
-    ok = ok and eu2 < 1e-7 and ex2 < 1e-9
+    ok = ok and eu2 < (1e-7 if dt == torch.float64 else 1e-4) and ex2 < (1e-9 if dt == torch.float64 else 1e-5)
     res = torch.tensor([el, ex, eu, eu2, ex2, 0.0 if ok else 1.0], device=dev, dtype=torch.float64)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     if rank == 0:

@@ -56,7 +56,7 @@ def _worker(rank, world, port, mode, q):
         S = shared.shape[0]
         buf = torch.zeros(plan.buffer_len, dtype=torch.float64)
         buf[0] = float(loss)
-        bx, bu = buf[1:1 + 2 * S].view(S, 2), buf[1 + 2 * S:].view(S, 2)
+        bx, bu = buf[2:2 + 2 * S].view(S, 2), buf[2 + 2 * S:].view(S, 2)
         bx[torch.from_numpy(plan.x_pos)] = torch.from_numpy(gx[plan.x_rows])
         bu[torch.from_numpy(plan.u_pos)] = torch.from_numpy(gu[plan.u_rows])
         dist.all_reduce(buf)
@@ -107,5 +107,5 @@ def test_halo_plan_indices():
     # node 1 (gid 3) has a fixed coordinate: no x row; node 2 (gid 7) has a fixed displacement: no u row
     assert list(p.x_pos) == [1, 2] and list(p.x_rows) == [3, 1]
     assert list(p.u_pos) == [0, 1] and list(p.u_rows) == [1, 3]
-    assert p.buffer_len == 1 + 4 * 4
+    assert p.buffer_len == 2 + 4 * 4
     assert list(hd.shared_ids_from_candidates([np.array([1, 2, 3]), np.array([3, 4]), np.array([4, 4, 9])])) == [3, 4]
