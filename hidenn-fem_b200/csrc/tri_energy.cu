@@ -178,9 +178,10 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
 
     // phase 3: owned nodes fold their slot range in fixed order and store the final gradients
     auto fold_node = [&](const uint32_t oc, const int2 sl) {
-        const unsigned b = oc & 0xFFFFu, e = b + (oc >> 16);
+        constexpr unsigned G = sizeof(R) == 8 ? 8u : 16u;     // slot k of a node sits G entries after slot k-1 (tri_plan.cu)
+        const unsigned b = oc & 0xFFFFu, e = b + (oc >> 16) * G;
         R ax = R(0), ay = R(0), bx = R(0), by = R(0);
-        for (unsigned k = b; k < e; ++k) {
+        for (unsigned k = b; k < e; k += G) {
             const R2 u = s_pu[k], x = s_px[k];
             ax += u.x; ay += u.y; bx += x.x; by += x.y;
         }

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstring>
+#include <cstdlib>
 #include <future>
 #include <memory>
 #include <numeric>
@@ -73,6 +74,7 @@ struct Rcb {
     }
 };
 
+
 struct TileBuild {
     std::vector<int32_t> nodes;     // owned (ascending) then halo (ascending)
     int32_t n_owned = 0;
@@ -82,6 +84,65 @@ struct TileBuild {
     int32_t n_entries = 0;          // padded slot count (= dump slot index)
     int err = 0;
 };
+
+// Lane assignment inside a tile.  Which thread handles which element is free (every fold slot is written exactly
+// once and read in slot order), so elements are greedily grouped such that the lanes that access shared memory
+// in the same pass -- 8 lanes for 16-byte pairs (FP64), 16 lanes for 8-byte pairs (FP32) -- hit different bank
+// groups in the 3 gathers and the 3 partial stores.  Random placement costs ~2.2 wavefronts per pass.
+static void reorder_for_banks(TileBuild& B, int real_bytes) {
+    const int E = (int)B.pack.size();
+    const int G = real_bytes == 8 ? 8 : 16;          // lanes per shared-memory pass = number of bank groups
+    if (E <= G) return;
+    constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
+    const unsigned dump = (unsigned)B.n_entries;
+    struct Item { uint16_t lid[3], pos[3]; };
+    std::vector<Item> it(E);
+    for (int i = 0; i < E; ++i) {
+        const unsigned long long w = B.pack[i];
+        for (int c = 0; c < 3; ++c) {
+            it[i].lid[c] = (uint16_t)((w >> (kLidBits * c)) & LM);
+            it[i].pos[c] = (uint16_t)((w >> (3 * kLidBits + kPosBits * c)) & PM);
+        }
+    }
+    std::vector<char> used(E, 0);
+    std::vector<int> ord;
+    ord.reserve(E);
+    static const int W = [] { const char* e = getenv("HIDENN_PLAN_WINDOW"); return e ? atoi(e) : 512; }();
+    if (W <= 0) return;
+    int head = 0;
+    while ((int)ord.size() < E) {
+        int cg[3][16] = {}, cp[3][16] = {};
+        int lidat[3][16];
+        for (int c = 0; c < 3; ++c) for (int b = 0; b < 16; ++b) lidat[c][b] = -1;
+        for (int slot = 0; slot < G && (int)ord.size() < E; ++slot) {
+            int best = -1, best_cost = 1 << 30, seen = 0;
+            for (int j = head; j < E && seen < W; ++j) {
+                if (used[j]) continue;
+                ++seen;
+                int cost = 0;
+                for (int c = 0; c < 3; ++c) {
+                    const int b = it[j].lid[c] % G;
+                    if (cg[c][b] > 0 && lidat[c][b] != (int)it[j].lid[c]) cost += cg[c][b];     // same address = broadcast
+                    if (it[j].pos[c] != dump) cost += cp[c][it[j].pos[c] % G];     // == lid % G for owned corners
+                }
+                if (cost < best_cost) { best_cost = cost; best = j; if (cost == 0) break; }
+            }
+            used[best] = 1;
+            ord.push_back(best);
+            for (int c = 0; c < 3; ++c) {
+                const int b = it[best].lid[c] % G;
+                if (lidat[c][b] != (int)it[best].lid[c]) { cg[c][b]++; lidat[c][b] = it[best].lid[c]; }
+                if (it[best].pos[c] != dump) cp[c][it[best].pos[c] % G]++;
+            }
+            while (head < E && used[head]) ++head;
+        }
+    }
+    std::vector<unsigned long long> np(E);
+    std::vector<int32_t> ne(E);
+    for (int i = 0; i < E; ++i) { np[i] = B.pack[ord[i]]; ne[i] = B.elems[ord[i]]; }
+    B.pack.swap(np);
+    B.elems.swap(ne);
+}
 
 int plan_ensure_generic(hidenn_tri_plan* p) {
     if (p->generic_uploaded) return 0;
@@ -195,22 +256,34 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     const int64_t* n2o = p->n2e_off.data();
     const int32_t* n2e = p->n2e_ent.data();
     auto build_range = [&](int64_t t0, int64_t t1) {
-        std::vector<int32_t> cand, halo;
+        std::vector<int32_t> cand, halo, owned_sorted, perm, lid_of;
+        const int G = real_bytes == 8 ? 8 : 16;
         for (int64_t t = t0; t < t1; ++t) {
             TileBuild& B = tb[t];
-            B.nodes.assign(order.begin() + tile_begin[t], order.begin() + tile_begin[t + 1]);
-            std::sort(B.nodes.begin(), B.nodes.end());
-            B.n_owned = (int32_t)B.nodes.size();
+            // owned nodes: looked up through an id-sorted list, numbered locally by descending valence so that
+            // every group of G consecutive local nodes has (nearly) equal valence -- see the slot layout below
+            owned_sorted.assign(order.begin() + tile_begin[t], order.begin() + tile_begin[t + 1]);
+            std::sort(owned_sorted.begin(), owned_sorted.end());
+            B.n_owned = (int32_t)owned_sorted.size();
+            perm.resize(B.n_owned);
+            std::iota(perm.begin(), perm.end(), 0);
+            std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) {
+                const int64_t va = n2o[owned_sorted[a] + 1] - n2o[owned_sorted[a]], vb = n2o[owned_sorted[b] + 1] - n2o[owned_sorted[b]];
+                return va > vb;
+            });
+            lid_of.resize(B.n_owned);
+            B.nodes.resize(B.n_owned);
+            for (int32_t l = 0; l < B.n_owned; ++l) { lid_of[perm[l]] = l; B.nodes[l] = owned_sorted[perm[l]]; }
             cand.clear();
-            for (int32_t n : B.nodes)
+            for (int32_t n : owned_sorted)
                 for (int64_t k = n2o[n]; k < n2o[n + 1]; ++k) cand.push_back(n2e[k] >> 2);
             std::sort(cand.begin(), cand.end());
             cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
             B.elems = cand;
             halo.clear();
             auto owned_id = [&](int32_t n) -> int32_t {
-                auto it = std::lower_bound(B.nodes.begin(), B.nodes.begin() + B.n_owned, n);
-                return (it != B.nodes.begin() + B.n_owned && *it == n) ? (int32_t)(it - B.nodes.begin()) : -1;
+                auto it = std::lower_bound(owned_sorted.begin(), owned_sorted.end(), n);
+                return (it != owned_sorted.end() && *it == n) ? lid_of[it - owned_sorted.begin()] : -1;
             };
             for (int32_t e : B.elems)
                 for (int c = 0; c < 3; ++c) {
@@ -221,14 +294,20 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
             halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
             B.nodes.insert(B.nodes.end(), halo.begin(), halo.end());
             if ((int64_t)B.nodes.size() > kMaxLocal) { B.err = 1; continue; }
+            // Fold-slot layout: local nodes in groups of G (the lanes one shared-memory pass serves: 8 x 16 B for FP64,
+            // 16 x 8 B for FP32).  Slot k of node l lives at  base[group] + k*G + (l % G): the G lanes that fold a group
+            // read one contiguous 128-byte row per step (conflict-free), and the bank group of any partial store is
+            // l % G -- the same as for the gather of that node, so the lane assignment below fixes both at once.
             B.off.resize(B.n_owned);
             int64_t acc = 0;
-            for (int32_t l = 0; l < B.n_owned; ++l) {
-                const int64_t cnt = n2o[B.nodes[l] + 1] - n2o[B.nodes[l]];
-                B.off[l] = (uint32_t)acc | ((uint32_t)cnt << 16);
-                // odd stride between consecutive nodes' slot ranges: the 8 lanes of a quarter-warp then read
-                // 8 different 16-byte bank groups in the fold (an even stride such as 6 gives 2-way conflicts)
-                acc += cnt == 0 ? 0 : (cnt | 1);
+            for (int32_t g0 = 0; g0 < B.n_owned; g0 += G) {
+                int64_t mx = 0;
+                for (int32_t l = g0; l < std::min(B.n_owned, g0 + G); ++l) mx = std::max<int64_t>(mx, n2o[B.nodes[l] + 1] - n2o[B.nodes[l]]);
+                for (int32_t l = g0; l < std::min(B.n_owned, g0 + G); ++l) {
+                    const int64_t cnt = n2o[B.nodes[l] + 1] - n2o[B.nodes[l]];
+                    B.off[l] = (uint32_t)(acc + (l - g0)) | ((uint32_t)cnt << 16);
+                }
+                acc += mx * G;
                 if (acc > kMaxEntries) { B.err = 2; break; }
             }
             if (B.err) continue;
@@ -244,7 +323,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
                     if (lid >= 0) {
                         const int32_t key = e * 4 + c;
                         for (int64_t k = n2o[n]; k < n2o[n + 1]; ++k)
-                            if (n2e[k] == key) { pos = (unsigned long long)((B.off[lid] & 0xFFFFu) + (k - n2o[n])); break; }
+                            if (n2e[k] == key) { pos = (unsigned long long)((B.off[lid] & 0xFFFFu) + (k - n2o[n]) * G); break; }
                     } else {
                         auto it = std::lower_bound(B.nodes.begin() + B.n_owned, B.nodes.end(), n);
                         lid = (int32_t)(it - B.nodes.begin());
@@ -255,6 +334,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
                 if (owned_id(c32[3 * (int64_t)e]) >= 0) w |= 1ull << kOwnerBit;
                 B.pack[i] = w;
             }
+            reorder_for_banks(B, real_bytes);
         }
     };
     {
@@ -446,5 +526,37 @@ extern "C" int hidenn_tri_plan_decode(const hidenn_tri_plan* p, int64_t* out_ele
             out_owner[v] = (uint8_t)((w >> kOwnerBit) & 1ull);
         }
     }
+    return 0;
+}
+
+// Simulated shared-memory passes of the tile kernel's gathers and partial stores for the current lane assignment
+// (model: one pass serves lanes whose 16-byte (FP64) / 8-byte (FP32) words fall in different bank groups; equal
+// addresses broadcast).  out[0] = gather passes, out[1] = ideal gather passes, out[2] = store passes, out[3] = ideal.
+extern "C" int hidenn_tri_plan_bank_stats(const hidenn_tri_plan* p, int real_bytes, int64_t* out4) {
+    HIDENN_REQUIRE(p && out4 && (real_bytes == 8 || real_bytes == 4), "plan_bank_stats: bad arguments");
+    const int G = real_bytes == 8 ? 8 : 16;
+    constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
+    int64_t gp = 0, gi = 0, sp = 0, si = 0;
+    for (const TileDesc& d : p->tiles) {
+        for (int32_t base = 0; base < d.n_elem; base += G) {
+            const int n = std::min<int32_t>(G, d.n_elem - base);
+            for (int c = 0; c < 3; ++c) {
+                int cnt[16] = {}, cntp[16] = {};
+                std::vector<unsigned> seen[16];
+                for (int j = 0; j < n; ++j) {
+                    const unsigned long long w = p->elem_pack[d.elem_off + base + j];
+                    const unsigned lid = (unsigned)(w >> (kLidBits * c)) & LM;
+                    const unsigned pos = (unsigned)(w >> (3 * kLidBits + kPosBits * c)) & PM;
+                    auto& sv = seen[lid % G];
+                    if (std::find(sv.begin(), sv.end(), lid) == sv.end()) { sv.push_back(lid); cnt[lid % G]++; }
+                    if ((int)pos != d.n_entries) cntp[pos % G]++; else cntp[pos % G] = std::max(cntp[pos % G], 1);
+                }
+                gp += 2 * *std::max_element(cnt, cnt + 16);       // xy and uv gathers
+                sp += 2 * *std::max_element(cntp, cntp + 16);     // gu and gx stores
+                gi += 2; si += 2;
+            }
+        }
+    }
+    out4[0] = gp; out4[1] = gi; out4[2] = sp; out4[3] = si;
     return 0;
 }

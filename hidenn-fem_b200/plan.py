@@ -76,6 +76,11 @@ class TriPlan:
                                                      ow.ctypes.data_as(C.c_void_p)))
         return el, nd, ow
 
+    def bank_stats(self, real_bytes=None):
+        out = (C.c_int64 * 4)()
+        _lib.check(_lib.lib().hidenn_tri_plan_bank_stats(self._h, C.c_int(real_bytes or self.real_bytes), out))
+        return dict(gather=int(out[0]), gather_ideal=int(out[1]), store=int(out[2]), store_ideal=int(out[3]))
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             _lib.lib().hidenn_tri_plan_destroy(self._h)

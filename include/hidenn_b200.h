@@ -97,6 +97,10 @@ int hidenn_tri_plan_slots(const hidenn_tri_plan* plan, int32_t* xslot_host, int3
  * out_elem [visits], out_nodes [visits,3], out_owner [visits] (1 = this visit adds the energy). */
 int hidenn_tri_plan_decode(const hidenn_tri_plan* plan, int64_t* out_elem, int64_t* out_nodes, uint8_t* out_owner);
 
+/* Host-side model of the tile kernel's shared-memory passes for the plan's lane assignment:
+ * out4 = {gather passes, ideal gather passes, partial-store passes, ideal store passes}. */
+int hidenn_tri_plan_bank_stats(const hidenn_tri_plan* plan, int real_bytes, int64_t* out4);
+
 /* ------------------------------------------------------------------------------------------
  * Fused energy + gradients:  EnergyLoss2D.__call__ (src/loss.py:113-116) =
  * domain_energy (src/loss.py:55-88) over PiecewiseLinearShapeNN2D.forward
