@@ -254,6 +254,71 @@ def time_e2e(model, loss_fn, steps, warmup):
     return t * 1e3, h2d, d2h, float(out[0])
 
 
+def time_loop(step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def bench_grid_paths(device, steps, warmup, peak, full_c3=False):
+    """Configs C2 (1D bar energy, 1 M elements, FP64) and C3 (structured Q1 L2 projection) of SURVEY §8(d):
+    one step = loss forward + backward through the drop-in API.  Informational lines next to the C4 headline."""
+    from hidenn_fem_b200.models import PiecewiseLinearShapeNN, StructuredShapeNN2D
+    from hidenn_fem_b200 import models_grid as mg
+    from hidenn_fem_b200.utils import interval_gauss_points
+    out = {}
+    # C2: examples/example3.py at 1M elements, ng=2, fused kernel with the built-in body force
+    N = 1_000_001
+    m1 = PiecewiseLinearShapeNN(torch.linspace(0, 10.0, N, dtype=torch.float64), r_adapt=True, u0=0.0, uN=0.0).double().to(device)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        m1.u.copy_((1e-2 * torch.randn(N - 2, generator=g, dtype=torch.float64)).to(device))
+    xi, wi = interval_gauss_points(2, device=device, dtype=torch.float64)
+
+    def step_c2():
+        m1.zero_grad(set_to_none=True)
+        mg.bar_energy_loss(m1, xi, wi, None, 175.0, b_builtin=True).backward()
+    ms = time_loop(step_c2, steps, warmup)
+    mg._bar_state.check(block=True)
+    out["C2_bar_1M_f64_fused"] = {"ms_per_step": ms, "evals_per_s": (N - 1) * 2 / (ms * 1e-3),
+                                  "hbm_frac_informational": 4 * 8 * (N - 1) / (ms * 1e-3) / 1e9 / peak,
+                                  "note": "32 MB working set is L2-resident: launch/latency-bound (8 small kernels)"}
+
+    def step_c2g():
+        m1.zero_grad(set_to_none=True)
+        mg.energy_loss_generic(m1, xi, wi, mg.example3_b_force, E=175.0).backward()
+    ms = time_loop(step_c2g, max(3, steps // 4), 2)
+    out["C2_bar_1M_f64_generic_double_backward"] = {"ms_per_step": ms, "evals_per_s": (N - 1) * 2 / (ms * 1e-3)}
+    del m1
+    # C3: examples/example2.py scaled up; full batch of tensor-product samples through the generic forward
+    Ng, Ms = (4097, 8192) if full_c3 else (1025, 2048)
+    gx = torch.linspace(0, 1, Ng, dtype=torch.float64)
+    m2 = StructuredShapeNN2D(gx, gx.clone(), r_adapt=True).double().to(device)
+    xs = torch.linspace(0, 1, Ms, dtype=torch.float64, device=device)
+    XX, YY = torch.meshgrid(xs, xs, indexing="ij")
+    x_train = torch.stack([XX.flatten(), YY.flatten()], dim=1)
+    u_true = torch.sin(2 * torch.pi * x_train[:, 0]) * torch.cos(2 * torch.pi * x_train[:, 1])
+    del XX, YY
+
+    def step_c3():
+        m2.zero_grad(set_to_none=True)
+        ((m2(x_train) - u_true) ** 2).mean().backward()
+    ms = time_loop(step_c3, max(2, steps // 5), 1)
+    M = x_train.shape[0]
+    out["C3_structured_l2_%dx%d_nodes_%d_samples_f64" % (Ng, Ng, M)] = {
+        "ms_per_step": ms, "evals_per_s": M / (ms * 1e-3),
+        "hbm_frac_informational": (3 * 8 * M + 2 * 8 * Ng * Ng) / (ms * 1e-3) / 1e9 / peak,
+        "note": "generic differentiable forward + deterministic sort-based fold (torch.sort dominates)"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_step_factory(n_elems, dtype):
     """The reference's CPU torch path restated in oracle/torch_port.py, same generator, bounded size."""
@@ -394,6 +459,14 @@ def main():
             ab = 12 * m2.connectivity.shape[0] + 2 * s2 * 2 * m2.node_coords.shape[0] + 2 * s2 * (p2.info["n_free_x"] + p2.info["n_free_u"])
             extra[tag] = {"ms_per_step": ms2, "kernel_ms": k2, "evals_per_s": m2.connectivity.shape[0] * NG / (ms2 * 1e-3),
                           "roofline_frac": ab / (k2 * 1e-3) / 1e9 / peak}
+
+    if args.extra and world == 1:
+        try:
+            del model, loss_fn
+            torch.cuda.empty_cache()
+            extra.update(bench_grid_paths(device, args.steps, args.warmup, peak, full_c3=True))
+        except Exception as e:      # the headline must survive a failure of the informational lines
+            extra["grid_paths_error"] = repr(e)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -98,6 +98,8 @@ template <typename R, bool BODY> __device__ __forceinline__ TriConsts<R> load_co
     return K;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 constexpr int kPre = 3;   // element packs prefetched per thread before the first barrier (kPre*256 >= typical tile)
 
 template <typename R, bool BODY, bool ISO, int MINB>
@@ -106,9 +108,11 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
                 const typename Real2<R>::type* __restrict__ x_fixed, const typename Real2<R>::type* __restrict__ u_free,
                 const typename Real2<R>::type* __restrict__ u_fixed, const R* __restrict__ consts, const int flags,
                 typename Real2<R>::type* __restrict__ gx_free, typename Real2<R>::type* __restrict__ gu_free,
-                R* __restrict__ tile_energy) {
+                R* __restrict__ tile_energy, const int pf_dist, long long* __restrict__ timing) {
     using R2 = typename Real2<R>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    long long tk0 = 0, tk1 = 0, tk2 = 0;
+    if (timing) tk0 = clock64();
     // shared layout: node pairs xy | uv, fold partial pairs gu | gx (n_entries + 1 dump slot), reduce scratch
     R2* s_xy = reinterpret_cast<R2*>(smem_raw);
     R2* s_uv = s_xy + P.max_local;
@@ -130,6 +134,25 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
         const int i = tid + k * kTileBlock;
         myslot[k] = i < P.stride_local ? __ldg(slots + i) : make_int2(-1, -1);
         myoff[k] = i < P.stride_owned ? __ldg(offs + i) : 0u;
+    }
+    // L2 prefetch for the tile that will run on this SM about one CTA lifetime from now (tile + pf_dist): its record
+    // arrays now, its node pairs at the end of this CTA (when the slots loaded here have arrived).  The dependent
+    // slot -> node-pair chain of that tile then hits L2 instead of DRAM; DRAM traffic is unchanged.
+    const int ptile = tile + pf_dist;
+    const bool pf = pf_dist > 0 && ptile < P.n_tiles;
+    int2 pslot[2] = {make_int2(-1, -1), make_int2(-1, -1)};
+    if (pf) {
+        const char* r0 = reinterpret_cast<const char*>(P.elem_pack + (size_t)ptile * P.stride_elem);
+        const char* r1 = reinterpret_cast<const char*>(P.entry_off + (size_t)ptile * P.stride_owned);
+        const int n0 = P.stride_elem * 8, n1 = P.stride_owned * 4;
+        for (int o = tid * 128; o < n0; o += kTileBlock * 128) prefetch_l2(r0 + o);
+        for (int o = tid * 128; o < n1; o += kTileBlock * 128) prefetch_l2(r1 + o);
+        const int2* ps = P.t_slots + (size_t)ptile * P.stride_local;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = tid + k * kTileBlock;
+            if (i < P.stride_local) pslot[k] = __ldg(ps + i);
+        }
     }
     unsigned long long wpre[kPre];
 #pragma unroll
@@ -153,6 +176,7 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
         s_uv[i] = load_slot<R2>(u_free, u_fixed, sl.y);
     }
     __syncthreads();
+    if (timing) tk1 = clock64();
 
     // phase 2: elements -> energy + gradient partials stored at their precomputed fold slots
     R e_acc = R(0);
@@ -175,6 +199,7 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
         if (tid + k * kTileBlock < td.n_elem) do_element(wpre[k]);
     for (int i = tid + kPre * kTileBlock; i < td.n_elem; i += kTileBlock) do_element(__ldg(packs + i));
     __syncthreads();
+    if (timing) tk2 = clock64();
 
     // phase 3: owned nodes fold their slot range in fixed order and store the final gradients
     auto fold_node = [&](const uint32_t oc, const int2 sl) {
@@ -193,9 +218,24 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
         if (tid + k * kTileBlock < td.n_owned) fold_node(myoff[k], myslot[k]);
     for (int i = tid + 2 * kTileBlock; i < td.n_owned; i += kTileBlock) fold_node(__ldg(offs + i), __ldg(slots + i));
 
+    if (pf) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            // padding slots are (-1,-1) = row 0 of the fixed buffers: harmless
+            prefetch_l2(pslot[k].x >= 0 ? (const void*)(x_free + pslot[k].x) : (const void*)(x_fixed + (~pslot[k].x)));
+            prefetch_l2(pslot[k].y >= 0 ? (const void*)(u_free + pslot[k].y) : (const void*)(u_fixed + (~pslot[k].y)));
+        }
+    }
+
     // tile energy (fixed-order block sum)
     const R tot = block_sum<R, kTileBlock>(e_acc, s_red);
     if (tid == 0) tile_energy[blockIdx.x] = tot;
+    if (timing && tid == 0) {      // debug aid (hidenn_debug_tile_timing): per-phase SM cycles of this CTA
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long* t = timing + 5 * (long long)blockIdx.x;
+        t[0] = tk0; t[1] = tk1; t[2] = tk2; t[3] = clock64(); t[4] = smid;
+    }
 }
 
 // Energy-only variant (torch.no_grad() evaluations, e.g. logging): no fold, no gradient traffic.
@@ -355,6 +395,14 @@ template <typename R> static size_t smem_for(const hidenn_tri_plan* p) {
     return (size_t)p->dev.max_local * 4 * sizeof(R) + (size_t)(p->dev.max_entries + 1) * 4 * sizeof(R) + 128;
 }
 
+static long long* g_tile_timing = nullptr;     // set by hidenn_debug_tile_timing (measurement aid, not thread safe)
+
+// tiles between a CTA and the one it prefetches for: the number of CTAs resident on the chip (one "wave")
+static int prefetch_distance(int minb) {
+    static const int env = [] { const char* e = getenv("HIDENN_TILE_PREFETCH"); return e ? atoi(e) : -1; }();
+    return env >= 0 ? env : 148 * minb;
+}
+
 template <typename R, bool BODY, bool ISO, int MINB>
 static int launch_tile_mb(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed, const R* consts,
                           int flags, R* gx, R* gu, R* scratch, cudaStream_t stream, size_t smem) {
@@ -366,7 +414,8 @@ static int launch_tile_mb(const hidenn_tri_plan* p, const R* x_free, const R* x_
         configured = smem;
     }
     tri_tile_kernel<R, BODY, ISO, MINB><<<p->dev.n_tiles, kTileBlock, smem, stream>>>(
-        p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch);
+        p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch,
+        prefetch_distance(MINB), g_tile_timing);
     return 0;
 }
 
@@ -375,7 +424,7 @@ static int launch_tile_mb(const hidenn_tri_plan* p, const R* x_free, const R* x_
 static int pick_minb(size_t smem, int real_bytes) {
     static const int env = [] { const char* e = getenv("HIDENN_TILE_MINB"); return e ? atoi(e) : 0; }();
     int mb = (int)((227 * 1024) / (smem + 1024));
-    const int cap = real_bytes == 8 ? 4 : 6;
+    const int cap = real_bytes == 8 ? 4 : 5;
     mb = mb < 2 ? 2 : (mb > cap ? cap : mb);
     if (env >= 2 && env <= 6) mb = env;
     return mb;
@@ -485,6 +534,11 @@ template <typename R> static int scale_launch(R* g, int64_t n, const R* s, void*
 }  // namespace hidenn
 
 using namespace hidenn;
+
+extern "C" int hidenn_debug_tile_timing(long long* dev_buf) {
+    hidenn::g_tile_timing = dev_buf;
+    return 0;
+}
 
 extern "C" int hidenn_tri_energy_f64(const hidenn_tri_plan* plan, const double* x_free, const double* x_fixed,
                                      const double* u_free, const double* u_fixed, const double* consts,
