@@ -162,6 +162,8 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
     }
     const TileDesc td = P.tiles[tile];
     const TriConsts<R> K = load_consts<R, BODY>(consts);
+    long long tk_desc = 0;
+    if (timing) tk_desc = clock64() + (td.n_local == -12345 ? 1 : 0) + (myslot[0].x == -12345 ? 1 : 0);   // after desc + slots arrive
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int i = tid + k * kTileBlock;
@@ -218,6 +220,8 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
         if (tid + k * kTileBlock < td.n_owned) fold_node(myoff[k], myslot[k]);
     for (int i = tid + 2 * kTileBlock; i < td.n_owned; i += kTileBlock) fold_node(__ldg(offs + i), __ldg(slots + i));
 
+    long long tk3 = 0;
+    if (timing) tk3 = clock64();
     if (pf) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -233,8 +237,191 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
     if (timing && tid == 0) {      // debug aid (hidenn_debug_tile_timing): per-phase SM cycles of this CTA
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        long long* t = timing + 5 * (long long)blockIdx.x;
-        t[0] = tk0; t[1] = tk1; t[2] = tk2; t[3] = clock64(); t[4] = smid;
+        long long* t = timing + 8 * (long long)blockIdx.x;
+        t[0] = tk0; t[1] = tk1; t[2] = tk2; t[3] = clock64(); t[4] = smid; t[5] = tk3; t[6] = tk_desc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent variant of the tile kernel: each CTA walks tiles blockIdx.x, +gridDim.x, ... and overlaps the
+// whole load chain of the NEXT tile with the element / fold phases of the current one:
+//   * node pairs of tile t+1 are gathered with cp.async (LDGSTS) into the second node buffer while tile t
+//     computes (their slots were loaded one iteration earlier);
+//   * packs / fold offsets of tile t+1 and the slots of tile t+2 are loaded into registers during the fold of
+//     tile t, when register pressure is low.
+// Two block barriers per tile; the tile-energy partials ride on the next barrier (double-buffered).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async_pair(void* smem_dst, const void* gsrc, const int bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (bytes == 16) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <typename R, bool BODY, bool ISO, int MINB>
+__global__ void __launch_bounds__(kTileBlock, MINB)
+tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ x_free,
+                           const typename Real2<R>::type* __restrict__ x_fixed, const typename Real2<R>::type* __restrict__ u_free,
+                           const typename Real2<R>::type* __restrict__ u_fixed, const R* __restrict__ consts, const int flags,
+                           typename Real2<R>::type* __restrict__ gx_free, typename Real2<R>::type* __restrict__ gu_free,
+                           R* __restrict__ tile_energy) {
+    using R2 = typename Real2<R>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // shared layout: 2 x (xy | uv) node buffers, fold partial pairs gu | gx (+ dump slot), 2 x 8 warp energy partials
+    R2* s_node = reinterpret_cast<R2*>(smem_raw);
+    const int nb = 2 * P.max_local;                       // pairs per node buffer
+    R2* s_pu = s_node + 2 * nb;
+    R2* s_px = s_pu + (P.max_entries + 1);
+    R* s_red = reinterpret_cast<R*>(s_px + (P.max_entries + 1));      // [2][8]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nct = gridDim.x;
+    int tile = blockIdx.x;
+    if (tile >= P.n_tiles) return;
+    constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
+    constexpr unsigned G = sizeof(R) == 8 ? 8u : 16u;
+    constexpr int PB = (int)sizeof(R2);
+
+    auto load_slots = [&](const int t, int2 (&sl)[2]) {
+        const int2* __restrict__ src = P.t_slots + (size_t)t * P.stride_local;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = tid + k * kTileBlock;
+            sl[k] = i < P.stride_local ? __ldg(src + i) : make_int2(0, 0);
+        }
+    };
+    auto issue_gathers = [&](const int t, const int2 (&sl)[2], R2* buf) {
+        R2* bxy = buf;
+        R2* buv = buf + P.max_local;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = tid + k * kTileBlock;
+            if (i < P.stride_local && i < P.max_local) {
+                cp_async_pair(bxy + i, sl[k].x >= 0 ? (const void*)(x_free + sl[k].x) : (const void*)(x_fixed + (~sl[k].x)), PB);
+                cp_async_pair(buv + i, sl[k].y >= 0 ? (const void*)(u_free + sl[k].y) : (const void*)(u_fixed + (~sl[k].y)), PB);
+            }
+        }
+        const int2* __restrict__ src = P.t_slots + (size_t)t * P.stride_local;
+        for (int i = tid + 2 * kTileBlock; i < P.max_local; i += kTileBlock) {     // tiles with more than 512 local nodes
+            const int2 s2 = __ldg(src + i);
+            cp_async_pair(bxy + i, s2.x >= 0 ? (const void*)(x_free + s2.x) : (const void*)(x_fixed + (~s2.x)), PB);
+            cp_async_pair(buv + i, s2.y >= 0 ? (const void*)(u_free + s2.y) : (const void*)(u_fixed + (~s2.y)), PB);
+        }
+    };
+    auto load_meta = [&](const int t, unsigned long long (&pk)[kPre], uint32_t (&of)[2]) {
+        const unsigned long long* __restrict__ packs = P.elem_pack + (size_t)t * P.stride_elem;
+        const uint32_t* __restrict__ offs = P.entry_off + (size_t)t * P.stride_owned;
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+            const int i = tid + k * kTileBlock;
+            pk[k] = i < P.stride_elem ? __ldg(packs + i) : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int i = tid + k * kTileBlock;
+            of[k] = i < P.stride_owned ? __ldg(offs + i) : 0u;
+        }
+    };
+
+    // prologue: first tile's slots -> gathers; second tile's slots; first tile's packs / offsets / descriptor
+    int2 slot_cur[2], slot_nxt[2];
+    unsigned long long pk[kPre];
+    uint32_t off[2];
+    load_slots(tile, slot_cur);
+    if (tile + nct < P.n_tiles) load_slots(tile + nct, slot_nxt);
+    else { slot_nxt[0] = slot_nxt[1] = make_int2(0, 0); }
+    load_meta(tile, pk, off);
+    TileDesc td = P.tiles[tile];
+    const TriConsts<R> K = load_consts<R, BODY>(consts);
+    issue_gathers(tile, slot_cur, s_node);
+    cp_async_wait_all();
+    __syncthreads();
+
+    int b = 0;
+    int prev_tile = -1;
+    for (;;) {
+        // node buffer b holds this tile; the partial buffer is free (the previous fold ended before the barrier)
+        if (tid == 0 && prev_tile >= 0) {        // energy of the previous tile, summed in fixed warp order
+            const R* r = s_red + (b ^ 1) * 8;
+            tile_energy[prev_tile] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        }
+        const int tnext = tile + nct;
+        const bool has_next = tnext < P.n_tiles;
+        if (has_next) issue_gathers(tnext, slot_nxt, s_node + (b ^ 1) * nb);      // lands during E + F of this tile
+
+        // E: elements -> energy + gradient partials at their fold slots
+        const R2* s_xy = s_node + b * nb;
+        const R2* s_uv = s_xy + P.max_local;
+        R e_acc = R(0);
+        auto do_element = [&](const unsigned long long w) {
+            const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
+            const unsigned l0 = lo & LM, l1 = (lo >> kLidBits) & LM, l2 = (lo >> (2 * kLidBits)) & LM;
+            const unsigned p0 = (unsigned)(w >> (3 * kLidBits)) & PM, p1 = (hi >> (3 * kLidBits + kPosBits - 32)) & PM,
+                           p2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
+            R e;
+            R2 gu[3], gx[3];
+            tri_element<R, BODY, ISO>(s_xy[l0], s_xy[l1], s_xy[l2], s_uv[l0], s_uv[l1], s_uv[l2], K, e, gu, gx);
+            e_acc += (hi >> 31) ? e : R(0);
+            s_pu[p0] = gu[0]; s_px[p0] = gx[0];
+            s_pu[p1] = gu[1]; s_px[p1] = gx[1];
+            s_pu[p2] = gu[2]; s_px[p2] = gx[2];
+        };
+#pragma unroll
+        for (int k = 0; k < kPre; ++k)
+            if (tid + k * kTileBlock < td.n_elem) do_element(pk[k]);
+        {
+            const unsigned long long* __restrict__ packs = P.elem_pack + (size_t)tile * P.stride_elem;
+            for (int i = tid + kPre * kTileBlock; i < td.n_elem; i += kTileBlock) do_element(__ldg(packs + i));
+        }
+        e_acc = warp_sum(e_acc);
+        if (lane == 0) s_red[b * 8 + wid] = e_acc;
+        __syncthreads();
+
+        // F: fold.  First put the next tile's metadata loads in flight (registers are cheap in this phase).
+        unsigned long long pk_n[kPre];
+        uint32_t off_n[2];
+        int2 slot_n2[2];
+        TileDesc td_n = td;
+        if (has_next) {
+            load_meta(tnext, pk_n, off_n);
+            td_n = P.tiles[tnext];
+            if (tnext + nct < P.n_tiles) load_slots(tnext + nct, slot_n2);
+            else { slot_n2[0] = slot_n2[1] = make_int2(0, 0); }
+        }
+        auto fold_node = [&](const uint32_t oc, const int2 sl) {
+            const unsigned fb = oc & 0xFFFFu, fe = fb + (oc >> 16) * G;
+            R ax = R(0), ay = R(0), bx = R(0), by = R(0);
+            for (unsigned k = fb; k < fe; k += G) {
+                const R2 u = s_pu[k], x = s_px[k];
+                ax += u.x; ay += u.y; bx += x.x; by += x.y;
+            }
+            if ((flags & HIDENN_NEED_GU) && sl.y >= 0) gu_free[sl.y] = mk2<R>(ax, ay);
+            if ((flags & HIDENN_NEED_GX) && sl.x >= 0) gx_free[sl.x] = mk2<R>(bx, by);
+        };
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (tid + k * kTileBlock < td.n_owned) fold_node(off[k], slot_cur[k]);
+        {
+            const uint32_t* __restrict__ offs = P.entry_off + (size_t)tile * P.stride_owned;
+            const int2* __restrict__ slots = P.t_slots + (size_t)tile * P.stride_local;
+            for (int i = tid + 2 * kTileBlock; i < td.n_owned; i += kTileBlock) fold_node(__ldg(offs + i), __ldg(slots + i));
+        }
+        prev_tile = tile;
+        if (!has_next) break;
+        // rotate the pipeline registers
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { slot_cur[k] = slot_nxt[k]; slot_nxt[k] = slot_n2[k]; off[k] = off_n[k]; }
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) pk[k] = pk_n[k];
+        td = td_n;
+        tile = tnext;
+        b ^= 1;
+        cp_async_wait_all();
+        __syncthreads();      // next tile's nodes visible; every fold read of the partial buffer is done
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const R* r = s_red + b * 8;
+        tile_energy[prev_tile] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
     }
 }
 
@@ -419,6 +606,23 @@ static int launch_tile_mb(const hidenn_tri_plan* p, const R* x_free, const R* x_
     return 0;
 }
 
+template <typename R, bool BODY, bool ISO, int MINB>
+static int launch_tile_persistent_mb(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed,
+                                     const R* consts, int flags, R* gx, R* gu, R* scratch, cudaStream_t stream, size_t smem) {
+    using R2 = typename Real2<R>::type;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_persistent_kernel<R, BODY, ISO, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_persistent_kernel<R, BODY, ISO, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = smem;
+    }
+    static const int n_sm = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+    const int grid = std::min(p->dev.n_tiles, n_sm * MINB);
+    tri_tile_persistent_kernel<R, BODY, ISO, MINB><<<grid, kTileBlock, smem, stream>>>(
+        p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch);
+    return 0;
+}
+
 // resident CTAs per SM the tile kernel is compiled for: as many as the tile's shared memory allows
 // (227 KB per SM, 1 KB reserved per CTA), capped where the register budget would start to spill.
 static int pick_minb(size_t smem, int real_bytes) {
@@ -430,9 +634,27 @@ static int pick_minb(size_t smem, int real_bytes) {
     return mb;
 }
 
+template <typename R> static size_t smem_persistent_for(const hidenn_tri_plan* p) {
+    return (size_t)p->dev.max_local * 8 * sizeof(R) + (size_t)(p->dev.max_entries + 1) * 4 * sizeof(R) + 16 * sizeof(R) + 64;
+}
+
+static bool use_persistent() {
+    static const int env = [] { const char* e = getenv("HIDENN_TILE_PERSISTENT"); return e ? atoi(e) : 1; }();
+    return env != 0;
+}
+
 template <typename R, bool BODY, bool ISO>
 static int launch_tile(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed, const R* consts,
                        int flags, R* gx, R* gu, R* scratch, cudaStream_t stream) {
+    if (use_persistent() && !g_tile_timing) {
+        const size_t smem = smem_persistent_for<R>(p);
+        switch (pick_minb(smem, (int)sizeof(R))) {
+            case 2: return launch_tile_persistent_mb<R, BODY, ISO, 2>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
+            case 3: return launch_tile_persistent_mb<R, BODY, ISO, 3>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
+            case 4: return launch_tile_persistent_mb<R, BODY, ISO, 4>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
+            default: return launch_tile_persistent_mb<R, BODY, ISO, 5>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
+        }
+    }
     const size_t smem = smem_for<R>(p);
     switch (pick_minb(smem, (int)sizeof(R))) {
         case 2: return launch_tile_mb<R, BODY, ISO, 2>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);

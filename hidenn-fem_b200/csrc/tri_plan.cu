@@ -396,7 +396,8 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
 
     // device layout: fixed-stride records per tile
     const int32_t SL = (max_local + 1) & ~1, SE = (max_elem + 1) & ~1, SO = (max_owned + 3) & ~3;
-    std::vector<int2> t_slots((size_t)n_tiles * SL, make_int2(-1, -1));
+    // padding slots must stay loadable: row 0 of the fixed buffer if it exists, else row 0 of the free Parameter
+    std::vector<int2> t_slots((size_t)n_tiles * SL, make_int2(p->n_fixed_x > 0 ? -1 : 0, p->n_fixed_u > 0 ? -1 : 0));
     std::vector<unsigned long long> d_pack((size_t)n_tiles * SE, 0ull);
     std::vector<uint32_t> d_off((size_t)n_tiles * SO, 0u);
     for (int64_t t = 0; t < n_tiles; ++t) {

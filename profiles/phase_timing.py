@@ -18,18 +18,20 @@ m, model, loss_fn, _ = bench.make_workload(a, 0, 1, dev, dt, a.ordering, a.elems
 plan = model._plan()
 for _ in range(3):
     model.zero_grad(); loss_fn(model).backward()
-buf = torch.zeros(plan.info["n_tiles"] * 5, dtype=torch.int64, device=dev)
+buf = torch.zeros(plan.info["n_tiles"] * 8, dtype=torch.int64, device=dev)
 L = _lib.lib()
 L.hidenn_debug_tile_timing(C.c_void_p(buf.data_ptr()))
 ms = bench.time_kernel(model, loss_fn, 5, 2)
 L.hidenn_debug_tile_timing(C.c_void_p(0))
 torch.cuda.synchronize()
-t = buf.cpu().numpy().reshape(-1, 5)
+t = buf.cpu().numpy().reshape(-1, 8)
 p1, p2, p3 = t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2]
 tot = t[:, 3] - t[:, 0]
 print(f"kernel {ms*1e3:.1f} us, tiles {len(t)}, elems/tile {plan.info['elem_visits']/len(t):.0f}")
-for name, v in (("stage (loads->smem)", p1), ("elements", p2), ("fold+store", p3), ("CTA total", tot)):
-    print(f"  {name:22s} mean {v.mean():8.0f} cyc  p10 {np.percentile(v,10):8.0f}  p50 {np.percentile(v,50):8.0f}  p90 {np.percentile(v,90):8.0f}  ({100*v.mean()/tot.mean():4.1f}%)")
+pa, pb, pc, pd = t[:, 6] - t[:, 0], t[:, 1] - t[:, 6], t[:, 5] - t[:, 2], t[:, 3] - t[:, 5]
+for name, v in (("stage (loads->smem)", p1), ("  .. desc+slots arrive", pa), ("  .. gathers+barrier", pb), ("elements", p2), ("fold+store", p3),
+                ("  .. fold loops+stores (thread 0)", pc), ("  .. prefetch+reduce+barrier", pd), ("CTA total", tot)):
+    print(f"  {name:34s} mean {v.mean():8.0f} cyc  p10 {np.percentile(v,10):8.0f}  p50 {np.percentile(v,50):8.0f}  p90 {np.percentile(v,90):8.0f}  ({100*v.mean()/tot.mean():4.1f}%)")
 # concurrency: per SM, sum of CTA lifetimes / wall span
 sm = t[:, 4]
 occ = []
