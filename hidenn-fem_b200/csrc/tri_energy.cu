@@ -352,6 +352,7 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
         const R2* s_xy = s_node + b * nb;
         const R2* s_uv = s_xy + P.max_local;
         R e_acc = R(0);
+        const unsigned dumpv = (unsigned)td.n_entries;
         auto do_element = [&](const unsigned long long w) {
             const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
             const unsigned l0 = lo & LM, l1 = (lo >> kLidBits) & LM, l2 = (lo >> (2 * kLidBits)) & LM;
@@ -361,9 +362,10 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
             R2 gu[3], gx[3];
             tri_element<R, BODY, ISO>(s_xy[l0], s_xy[l1], s_xy[l2], s_uv[l0], s_uv[l1], s_uv[l2], K, e, gu, gx);
             e_acc += (hi >> 31) ? e : R(0);
-            s_pu[p0] = gu[0]; s_px[p0] = gx[0];
-            s_pu[p1] = gu[1]; s_px[p1] = gx[1];
-            s_pu[p2] = gu[2]; s_px[p2] = gx[2];
+            // halo corners carry the tile's dump position: skip their stores (predicated, no branch)
+            if (p0 != dumpv) { s_pu[p0] = gu[0]; s_px[p0] = gx[0]; }
+            if (p1 != dumpv) { s_pu[p1] = gu[1]; s_px[p1] = gx[1]; }
+            if (p2 != dumpv) { s_pu[p2] = gu[2]; s_px[p2] = gx[2]; }
         };
 #pragma unroll
         for (int k = 0; k < kPre; ++k)
