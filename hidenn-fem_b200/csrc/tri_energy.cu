@@ -258,8 +258,8 @@ __device__ __forceinline__ void cp_async_pair(void* smem_dst, const void* gsrc, 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <typename R, bool BODY, bool ISO, int MINB>
-__global__ void __launch_bounds__(kTileBlock, MINB)
+template <typename R, bool BODY, bool ISO, int MINB, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, MINB)
 tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ x_free,
                            const typename Real2<R>::type* __restrict__ x_fixed, const typename Real2<R>::type* __restrict__ u_free,
                            const typename Real2<R>::type* __restrict__ u_fixed, const R* __restrict__ consts, const int flags,
@@ -272,7 +272,7 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
     const int nb = 2 * P.max_local;                       // pairs per node buffer
     R2* s_pu = s_node + 2 * nb;
     R2* s_px = s_pu + (P.max_entries + 1);
-    R* s_red = reinterpret_cast<R*>(s_px + (P.max_entries + 1));      // [2][8]
+    R* s_red = reinterpret_cast<R*>(s_px + (P.max_entries + 1));      // [2][16]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nct = gridDim.x;
     int tile = blockIdx.x;
@@ -280,12 +280,14 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
     constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
     constexpr unsigned G = sizeof(R) == 8 ? 8u : 16u;
     constexpr int PB = (int)sizeof(R2);
+    constexpr int NPRE = 768 / BLOCK;      // element packs held in registers per thread (768 >= typical tile)
+    constexpr int NW = BLOCK / 32;
 
     auto load_slots = [&](const int t, int2 (&sl)[2]) {
         const int2* __restrict__ src = P.t_slots + (size_t)t * P.stride_local;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const int i = tid + k * kTileBlock;
+            const int i = tid + k * BLOCK;
             sl[k] = i < P.stride_local ? __ldg(src + i) : make_int2(0, 0);
         }
     };
@@ -294,37 +296,37 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
         R2* buv = buf + P.max_local;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const int i = tid + k * kTileBlock;
+            const int i = tid + k * BLOCK;
             if (i < P.stride_local && i < P.max_local) {
                 cp_async_pair(bxy + i, sl[k].x >= 0 ? (const void*)(x_free + sl[k].x) : (const void*)(x_fixed + (~sl[k].x)), PB);
                 cp_async_pair(buv + i, sl[k].y >= 0 ? (const void*)(u_free + sl[k].y) : (const void*)(u_fixed + (~sl[k].y)), PB);
             }
         }
         const int2* __restrict__ src = P.t_slots + (size_t)t * P.stride_local;
-        for (int i = tid + 2 * kTileBlock; i < P.max_local; i += kTileBlock) {     // tiles with more than 512 local nodes
+        for (int i = tid + 2 * BLOCK; i < P.max_local; i += BLOCK) {     // tiles with more than 512 local nodes
             const int2 s2 = __ldg(src + i);
             cp_async_pair(bxy + i, s2.x >= 0 ? (const void*)(x_free + s2.x) : (const void*)(x_fixed + (~s2.x)), PB);
             cp_async_pair(buv + i, s2.y >= 0 ? (const void*)(u_free + s2.y) : (const void*)(u_fixed + (~s2.y)), PB);
         }
     };
-    auto load_meta = [&](const int t, unsigned long long (&pk)[kPre], uint32_t (&of)[2]) {
+    auto load_meta = [&](const int t, unsigned long long (&pk)[NPRE], uint32_t (&of)[2]) {
         const unsigned long long* __restrict__ packs = P.elem_pack + (size_t)t * P.stride_elem;
         const uint32_t* __restrict__ offs = P.entry_off + (size_t)t * P.stride_owned;
 #pragma unroll
-        for (int k = 0; k < kPre; ++k) {
-            const int i = tid + k * kTileBlock;
+        for (int k = 0; k < NPRE; ++k) {
+            const int i = tid + k * BLOCK;
             pk[k] = i < P.stride_elem ? __ldg(packs + i) : 0ull;
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const int i = tid + k * kTileBlock;
+            const int i = tid + k * BLOCK;
             of[k] = i < P.stride_owned ? __ldg(offs + i) : 0u;
         }
     };
 
     // prologue: first tile's slots -> gathers; second tile's slots; first tile's packs / offsets / descriptor
     int2 slot_cur[2], slot_nxt[2];
-    unsigned long long pk[kPre];
+    unsigned long long pk[NPRE];
     uint32_t off[2];
     load_slots(tile, slot_cur);
     if (tile + nct < P.n_tiles) load_slots(tile + nct, slot_nxt);
@@ -341,8 +343,11 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
     for (;;) {
         // node buffer b holds this tile; the partial buffer is free (the previous fold ended before the barrier)
         if (tid == 0 && prev_tile >= 0) {        // energy of the previous tile, summed in fixed warp order
-            const R* r = s_red + (b ^ 1) * 8;
-            tile_energy[prev_tile] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+            const R* r = s_red + (b ^ 1) * 16;
+            R acc = R(0);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) acc += r[w];
+            tile_energy[prev_tile] = acc;
         }
         const int tnext = tile + nct;
         const bool has_next = tnext < P.n_tiles;
@@ -368,18 +373,18 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
             if (p2 != dumpv) { s_pu[p2] = gu[2]; s_px[p2] = gx[2]; }
         };
 #pragma unroll
-        for (int k = 0; k < kPre; ++k)
-            if (tid + k * kTileBlock < td.n_elem) do_element(pk[k]);
+        for (int k = 0; k < NPRE; ++k)
+            if (tid + k * BLOCK < td.n_elem) do_element(pk[k]);
         {
             const unsigned long long* __restrict__ packs = P.elem_pack + (size_t)tile * P.stride_elem;
-            for (int i = tid + kPre * kTileBlock; i < td.n_elem; i += kTileBlock) do_element(__ldg(packs + i));
+            for (int i = tid + NPRE * BLOCK; i < td.n_elem; i += BLOCK) do_element(__ldg(packs + i));
         }
         e_acc = warp_sum(e_acc);
-        if (lane == 0) s_red[b * 8 + wid] = e_acc;
+        if (lane == 0) s_red[b * 16 + wid] = e_acc;
         __syncthreads();
 
         // F: fold.  First put the next tile's metadata loads in flight (registers are cheap in this phase).
-        unsigned long long pk_n[kPre];
+        unsigned long long pk_n[NPRE];
         uint32_t off_n[2];
         int2 slot_n2[2];
         TileDesc td_n = td;
@@ -401,11 +406,11 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
         };
 #pragma unroll
         for (int k = 0; k < 2; ++k)
-            if (tid + k * kTileBlock < td.n_owned) fold_node(off[k], slot_cur[k]);
+            if (tid + k * BLOCK < td.n_owned) fold_node(off[k], slot_cur[k]);
         {
             const uint32_t* __restrict__ offs = P.entry_off + (size_t)tile * P.stride_owned;
             const int2* __restrict__ slots = P.t_slots + (size_t)tile * P.stride_local;
-            for (int i = tid + 2 * kTileBlock; i < td.n_owned; i += kTileBlock) fold_node(__ldg(offs + i), __ldg(slots + i));
+            for (int i = tid + 2 * BLOCK; i < td.n_owned; i += BLOCK) fold_node(__ldg(offs + i), __ldg(slots + i));
         }
         prev_tile = tile;
         if (!has_next) break;
@@ -413,7 +418,7 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
 #pragma unroll
         for (int k = 0; k < 2; ++k) { slot_cur[k] = slot_nxt[k]; slot_nxt[k] = slot_n2[k]; off[k] = off_n[k]; }
 #pragma unroll
-        for (int k = 0; k < kPre; ++k) pk[k] = pk_n[k];
+        for (int k = 0; k < NPRE; ++k) pk[k] = pk_n[k];
         td = td_n;
         tile = tnext;
         b ^= 1;
@@ -422,8 +427,11 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
     }
     __syncthreads();
     if (tid == 0) {
-        const R* r = s_red + b * 8;
-        tile_energy[prev_tile] = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        const R* r = s_red + b * 16;
+        R acc = R(0);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) acc += r[w];
+        tile_energy[prev_tile] = acc;
     }
 }
 
@@ -608,19 +616,19 @@ static int launch_tile_mb(const hidenn_tri_plan* p, const R* x_free, const R* x_
     return 0;
 }
 
-template <typename R, bool BODY, bool ISO, int MINB>
+template <typename R, bool BODY, bool ISO, int MINB, int BLOCK>
 static int launch_tile_persistent_mb(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed,
                                      const R* consts, int flags, R* gx, R* gu, R* scratch, cudaStream_t stream, size_t smem) {
     using R2 = typename Real2<R>::type;
     static thread_local size_t configured = 0;
     if (smem > configured) {
-        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_persistent_kernel<R, BODY, ISO, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_persistent_kernel<R, BODY, ISO, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_persistent_kernel<R, BODY, ISO, MINB, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_persistent_kernel<R, BODY, ISO, MINB, BLOCK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = smem;
     }
     static const int n_sm = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
     const int grid = std::min(p->dev.n_tiles, n_sm * MINB);
-    tri_tile_persistent_kernel<R, BODY, ISO, MINB><<<grid, kTileBlock, smem, stream>>>(
+    tri_tile_persistent_kernel<R, BODY, ISO, MINB, BLOCK><<<grid, BLOCK, smem, stream>>>(
         p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch);
     return 0;
 }
@@ -637,7 +645,7 @@ static int pick_minb(size_t smem, int real_bytes) {
 }
 
 template <typename R> static size_t smem_persistent_for(const hidenn_tri_plan* p) {
-    return (size_t)p->dev.max_local * 8 * sizeof(R) + (size_t)(p->dev.max_entries + 1) * 4 * sizeof(R) + 16 * sizeof(R) + 64;
+    return (size_t)p->dev.max_local * 8 * sizeof(R) + (size_t)(p->dev.max_entries + 1) * 4 * sizeof(R) + 32 * sizeof(R) + 64;
 }
 
 static bool use_persistent() {
@@ -650,12 +658,21 @@ static int launch_tile(const hidenn_tri_plan* p, const R* x_free, const R* x_fix
                        int flags, R* gx, R* gu, R* scratch, cudaStream_t stream) {
     if (use_persistent() && !g_tile_timing) {
         const size_t smem = smem_persistent_for<R>(p);
-        switch (pick_minb(smem, (int)sizeof(R))) {
-            case 2: return launch_tile_persistent_mb<R, BODY, ISO, 2>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
-            case 3: return launch_tile_persistent_mb<R, BODY, ISO, 3>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
-            case 4: return launch_tile_persistent_mb<R, BODY, ISO, 4>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
-            default: return launch_tile_persistent_mb<R, BODY, ISO, 5>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
+        static const int blk = [] { const char* e = getenv("HIDENN_TILE_BLOCK"); return e ? atoi(e) : 384; }();
+        const int mb = pick_minb(smem, (int)sizeof(R));
+#define HIDENN_LAUNCH_P(MB, BL) \
+    return launch_tile_persistent_mb<R, BODY, ISO, MB, BL>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem)
+        if (blk == 384) {
+            if (mb <= 2) HIDENN_LAUNCH_P(2, 384);
+            HIDENN_LAUNCH_P(3, 384);
         }
+        switch (mb) {
+            case 2: HIDENN_LAUNCH_P(2, 256);
+            case 3: HIDENN_LAUNCH_P(3, 256);
+            case 4: HIDENN_LAUNCH_P(4, 256);
+            default: HIDENN_LAUNCH_P(5, 256);
+        }
+#undef HIDENN_LAUNCH_P
     }
     const size_t smem = smem_for<R>(p);
     switch (pick_minb(smem, (int)sizeof(R))) {
