@@ -658,7 +658,7 @@ static int launch_tile(const hidenn_tri_plan* p, const R* x_free, const R* x_fix
                        int flags, R* gx, R* gu, R* scratch, cudaStream_t stream) {
     if (use_persistent() && !g_tile_timing) {
         const size_t smem = smem_persistent_for<R>(p);
-        static const int blk = [] { const char* e = getenv("HIDENN_TILE_BLOCK"); return e ? atoi(e) : 384; }();
+        static const int blk = [] { const char* e = getenv("HIDENN_TILE_BLOCK"); return e ? atoi(e) : 256; }();
         const int mb = pick_minb(smem, (int)sizeof(R));
 #define HIDENN_LAUNCH_P(MB, BL) \
     return launch_tile_persistent_mb<R, BODY, ISO, MB, BL>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem)

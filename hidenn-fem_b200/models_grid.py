@@ -24,10 +24,21 @@ def _require_cuda(t, what):
     _lib.suffix(t.dtype)
 
 
+_scratch_cache = {}
+
+
 def _scratch_1d(n, like):
-    L = _lib.lib()
-    L.hidenn_1d_scratch_size.restype = C.c_int64
-    return torch.empty(int(L.hidenn_1d_scratch_size(c_i64(n))), device=like.device, dtype=like.dtype)
+    """Scan / reduction scratch (hidenn_1d_scratch_size), cached per size, device, dtype and stream."""
+    key = (n, like.device, like.dtype, torch.cuda.current_stream(like.device).cuda_stream)
+    t = _scratch_cache.get(key)
+    if t is None:
+        L = _lib.lib()
+        L.hidenn_1d_scratch_size.restype = C.c_int64
+        t = torch.empty(int(L.hidenn_1d_scratch_size(c_i64(n))), device=like.device, dtype=like.dtype)
+        if len(_scratch_cache) > 64:
+            _scratch_cache.clear()
+        _scratch_cache[key] = t
+    return t
 
 
 # ------------------------------------------------------------------------------------------------
@@ -234,8 +245,12 @@ class _BarEnergyFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, go):
         dg, du = ctx.saved_tensors
-        return (dg * go if dg is not None else None), ((du * go).to(ctx.udtype) if du is not None else None), \
-            None, None, None, None, None
+        if dg is None:
+            return None, None, None, None, None, None, None
+        g1 = go.reshape(1).to(dg.dtype).contiguous()
+        for t in (dg, du):       # grad_output applied on device; every block exits at once when it is 1
+            _lib.check(_lib.fn("hidenn_scale_inplace", t.dtype)(_lib.ptr(t), c_i64(t.numel()), _lib.ptr(g1), _lib.stream_ptr()))
+        return dg, du.to(ctx.udtype), None, None, None, None, None
 
 
 class _FlagState:
@@ -243,14 +258,18 @@ class _FlagState:
 
     def __init__(self):
         self.pending = []
+        self.free = []
 
     def note_flag(self, flag):
-        host = torch.empty(1, dtype=torch.int32).pin_memory()
+        if self.free:
+            host, ev = self.free.pop()
+        else:
+            host, ev = torch.empty(1, dtype=torch.int32).pin_memory(), torch.cuda.Event()
         host.copy_(flag, non_blocking=True)
-        ev = torch.cuda.Event()
         ev.record()
         self.pending.append((host, ev))
-        self.check(block=False)
+        if len(self.pending) > 4:
+            self.check(block=False)
 
     def check(self, block=True):
         keep = []
@@ -258,7 +277,9 @@ class _FlagState:
             if block:
                 ev.synchronize()
             if ev.query():
-                if int(host.item()) != 0:
+                bad = int(host[0]) != 0
+                self.free.append((host, ev))
+                if bad:
                     self.pending = []
                     raise RuntimeError("bar_energy_loss: a Gauss point fell outside its own element (degenerate grid); "
                                        "the fused path is invalid here -- use energy_loss_generic")
