@@ -389,6 +389,8 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=device)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
@@ -495,8 +497,8 @@ def main():
                        "halo_recompute": plan.info["elem_visits"] / max(1, ne_local), "setup_s": setup_s},
             "loss": loss_val,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": args.steps * (2 + 2 + (2 if world > 1 else 0)),
-            "gpu_launches_note": "per step: tri_tile_kernel + tri_edge_finalize_kernel + 2 scale_inplace_kernel"
+            "gpu_launches": args.steps * (2 + 1 + (2 if world > 1 else 0)),
+            "gpu_launches_note": "per step: tri_tile_persistent_kernel + tri_edge_finalize_kernel + scale_inplace2_kernel"
                                  + (" + halo pack_all + unpack_all (plus one copy and the NCCL all-reduce)" if world > 1 else ""),
         }
         if extra:

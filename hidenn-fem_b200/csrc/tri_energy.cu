@@ -479,7 +479,8 @@ tri_tile_energy_only_kernel(const TriPlanDev P, const typename Real2<R>::type* _
 // One CTA: the edge count is O(sqrt(Ne)).  Edge nodes are folded node-centrically (each node by one
 // thread, entries in ascending edge order) and *added* to the gradients the tile kernel stored.
 // ---------------------------------------------------------------------------------------------
-constexpr int kEdgeBlock = 1024;
+constexpr int kEdgeBlock = 256;
+constexpr int kEdgeMaxCtas = 64;
 
 template <typename R> struct EdgeEval {
     R ds, S;
@@ -513,6 +514,10 @@ __device__ __forceinline__ EdgeEval<R> edge_eval(const TriPlanDev& P, int e, con
     return E;
 }
 
+// Multi-CTA: edges / edge nodes / tile energies are strided over the whole grid; every CTA leaves fixed-order
+// FP64 partial sums in scratch, and the last CTA to finish (integer ticket) adds them in CTA order -> the result
+// does not depend on which CTA happens to be last.  fin = scratch region after the tile energies:
+// double part[2*kEdgeMaxCtas] | unsigned ticket (zero before the first launch, reset here).
 template <typename R>
 __global__ void __launch_bounds__(kEdgeBlock)
 tri_edge_finalize_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ x_free,
@@ -521,16 +526,19 @@ tri_edge_finalize_kernel(const TriPlanDev P, const typename Real2<R>::type* __re
                          const typename Real2<R>::type* __restrict__ u_fixed, const R* __restrict__ consts,
                          const R* __restrict__ t_table, const int flags, const R* __restrict__ tile_energy,
                          R* __restrict__ out, typename Real2<R>::type* __restrict__ gx_free,
-                         typename Real2<R>::type* __restrict__ gu_free, R* __restrict__ gt_out) {
+                         typename Real2<R>::type* __restrict__ gu_free, R* __restrict__ gt_out, double* __restrict__ part,
+                         unsigned* __restrict__ ticket) {
     using R2 = typename Real2<R>::type;
     __shared__ double s_red[kEdgeBlock / 32];
+    __shared__ unsigned s_last;
     const int tid = threadIdx.x;
+    const int gtid = blockIdx.x * kEdgeBlock + tid, gstride = gridDim.x * kEdgeBlock;
     const bool with_edges = (flags & HIDENN_WITH_EDGES) && P.n_edges > 0;
     const int ng1 = with_edges ? (int)consts[HIDENN_TRI_NG1] : 0;
 
     double e_edge = 0.0;
     if (with_edges) {
-        for (int e = tid; e < P.n_edges; e += kEdgeBlock) {
+        for (int e = gtid; e < P.n_edges; e += gstride) {
             const EdgeEval<R> E = edge_eval<R>(P, e, x_free, x_fixed, u_free, u_fixed, consts, t_table, ng1);
             e_edge += (double)(E.S * E.ds);
             if (gt_out) {   // d loss / d t_q = -w_q ds u_q
@@ -542,7 +550,7 @@ tri_edge_finalize_kernel(const TriPlanDev P, const typename Real2<R>::type* __re
             }
         }
         if (flags & (HIDENN_NEED_GX | HIDENN_NEED_GU)) {
-            for (int k = tid; k < P.n_enodes; k += kEdgeBlock) {
+            for (int k = gtid; k < P.n_enodes; k += gstride) {
                 R gux = R(0), guy = R(0), gxx = R(0), gxy = R(0);
                 for (int j = P.en_off[k]; j < P.en_off[k + 1]; ++j) {
                     const int ent = P.en_ent[j], e = ent >> 1, end = ent & 1;
@@ -569,16 +577,37 @@ tri_edge_finalize_kernel(const TriPlanDev P, const typename Real2<R>::type* __re
     }
     // domain energy: fixed-order strided + tree sum of the tile partials, accumulated in double
     double e_dom = 0.0;
-    for (int t = tid; t < P.n_tiles; t += kEdgeBlock) e_dom += (double)tile_energy[t];
+    for (int t = gtid; t < P.n_tiles; t += gstride) e_dom += (double)tile_energy[t];
     const double dom = block_sum<double, kEdgeBlock>(e_dom, s_red);
     __syncthreads();
     const double edg = block_sum<double, kEdgeBlock>(e_edge, s_red);
     if (tid == 0) {
-        out[0] = (R)(dom - edg);
-        out[1] = (R)dom;
-        out[2] = (R)edg;
-        out[3] = R(0);
+        part[2 * blockIdx.x] = dom;
+        part[2 * blockIdx.x + 1] = edg;
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
     }
+    __syncthreads();
+    if (s_last && tid == 0) {
+        __threadfence();
+        double d = 0.0, e = 0.0;
+        const volatile double* vp = part;
+        for (unsigned c = 0; c < gridDim.x; ++c) { d += vp[2 * c]; e += vp[2 * c + 1]; }
+        out[0] = (R)(d - e);
+        out[1] = (R)d;
+        out[2] = (R)e;
+        out[3] = R(0);
+        *ticket = 0u;
+    }
+}
+
+template <typename R>
+__global__ void scale_inplace2_kernel(R* __restrict__ g1, int64_t n1, R* __restrict__ g2, int64_t n2, const R* __restrict__ scale) {
+    const R s = __ldg(scale);
+    if (s == R(1)) return;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = i0; i < n1; i += st) g1[i] *= s;
+    for (int64_t i = i0; i < n2; i += st) g2[i] *= s;
 }
 
 template <typename R>
@@ -721,9 +750,17 @@ static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R*
         HIDENN_CUDA_OK(cudaGetLastError());
     }
     if (flags & HIDENN_TILES_ONLY) return 0;
-    tri_edge_finalize_kernel<R><<<1, kEdgeBlock, 0, stream>>>(p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free,
-                                                              (const R2*)u_fixed, consts, t_table, flags, scratch, out,
-                                                              (R2*)gx, (R2*)gu, gt);
+    {
+        // scratch layout: [0,n_tiles) tile energies | 8-byte aligned: double part[2*kEdgeMaxCtas] | unsigned ticket
+        const size_t off = ((size_t)(p->dev.n_tiles + 8) * sizeof(R) + 7) / 8 * 8;
+        double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + off);
+        unsigned* ticket = reinterpret_cast<unsigned*>(part + 2 * kEdgeMaxCtas);
+        const int work = std::max(std::max(p->dev.n_edges, p->dev.n_enodes), p->dev.n_tiles / 8);
+        const int grid = std::max(1, std::min(kEdgeMaxCtas, (work + kEdgeBlock - 1) / kEdgeBlock));
+        tri_edge_finalize_kernel<R><<<grid, kEdgeBlock, 0, stream>>>(p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free,
+                                                                      (const R2*)u_fixed, consts, t_table, flags, scratch, out,
+                                                                      (R2*)gx, (R2*)gu, gt, part, ticket);
+    }
     HIDENN_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -735,7 +772,7 @@ static int tri_energy_host(hidenn_tri_plan* p, const R* xf, const R* xb, const R
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     HIDENN_CUDA_OK(cudaSetDevice(p->device));
     const size_t nfx = 2 * (size_t)p->n_free_x, nbx = 2 * (size_t)p->n_fixed_x, nfu = 2 * (size_t)p->n_free_u, nbu = 2 * (size_t)p->n_fixed_u;
-    const size_t nsc = (size_t)p->dev.n_tiles + 8;
+    const size_t nsc = (size_t)p->dev.n_tiles + 8 + 280;
     auto al = [](size_t n) { return (n + 31) / 32 * 32; };
     const size_t total = al(nfx) * 2 + al(nbx) + al(nfu) * 2 + al(nbu) + al(HIDENN_TRI_NCONST) + al(4) + al(nsc);
     if (plan_ensure_arena(p, total * sizeof(R))) return 1;
@@ -749,6 +786,7 @@ static int tri_energy_host(hidenn_tri_plan* p, const R* xf, const R* xb, const R
     R* d_c = base; base += al(HIDENN_TRI_NCONST);
     R* d_out = base; base += al(4);
     R* d_sc = base;
+    HIDENN_CUDA_OK(cudaMemsetAsync(d_sc, 0, nsc * sizeof(R), stream));      // the finalize ticket must start at zero
     HIDENN_CUDA_OK(cudaMemcpyAsync(d_xf, xf, nfx * sizeof(R), cudaMemcpyHostToDevice, stream));
     if (nbx) HIDENN_CUDA_OK(cudaMemcpyAsync(d_xb, xb, nbx * sizeof(R), cudaMemcpyHostToDevice, stream));
     HIDENN_CUDA_OK(cudaMemcpyAsync(d_uf, uf, nfu * sizeof(R), cudaMemcpyHostToDevice, stream));
@@ -804,6 +842,22 @@ extern "C" int hidenn_tri_energy_host_f32(hidenn_tri_plan* plan, const float* a,
                                           const float* d, const float* k, int flags, float* out, float* gx, float* gu,
                                           void* stream) {
     return tri_energy_host<float>(plan, a, b, c, d, k, flags, out, gx, gu, stream);
+}
+template <typename R> static int scale2_launch(R* g1, int64_t n1, R* g2, int64_t n2, const R* s, void* stream_v) {
+    HIDENN_REQUIRE(s && (g1 || n1 == 0) && (g2 || n2 == 0), "scale_inplace2: NULL");
+    const int64_t n = std::max(n1, n2);
+    if (n <= 0) return 0;
+    const int block = 256;
+    const int grid = (int)std::min<int64_t>((n + block * 4 - 1) / (block * 4), 148 * 16);
+    scale_inplace2_kernel<R><<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(g1, n1, g2, n2, s);
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" int hidenn_scale_inplace2_f64(double* g1, int64_t n1, double* g2, int64_t n2, const double* s, void* stream) {
+    return scale2_launch<double>(g1, n1, g2, n2, s, stream);
+}
+extern "C" int hidenn_scale_inplace2_f32(float* g1, int64_t n1, float* g2, int64_t n2, const float* s, void* stream) {
+    return scale2_launch<float>(g1, n1, g2, n2, s, stream);
 }
 extern "C" int hidenn_scale_inplace_f64(double* g, int64_t n, const double* s, void* stream) { return scale_launch<double>(g, n, s, stream); }
 extern "C" int hidenn_scale_inplace_f32(float* g, int64_t n, const float* s, void* stream) { return scale_launch<float>(g, n, s, stream); }

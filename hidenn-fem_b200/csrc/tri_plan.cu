@@ -491,7 +491,7 @@ extern "C" int hidenn_tri_plan_info(const hidenn_tri_plan* p, int64_t* info) {
     info[2] = p->node_visits;
     info[3] = p->dev.max_local;
     info[4] = p->dev.max_entries;
-    info[5] = p->dev.n_tiles + 8;
+    info[5] = p->dev.n_tiles + 8 + 280;     // tile energies + finalize partials (64 x 2 doubles) + ticket
     info[6] = (int64_t)tile_smem_bytes(p, 8);
     info[7] = (int64_t)tile_smem_bytes(p, 4);
     info[8] = p->n_free_x;

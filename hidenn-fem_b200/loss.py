@@ -65,13 +65,14 @@ class _TriEnergyFn(torch.autograd.Function):
                                "gradient buffers to autograd without a copy -- evaluate the loss again instead")
         ctx.used = True
         gx, gu = ctx.saved_tensors
-        go = grad_out.reshape(1).contiguous()
-        for g in (gx, gu):
-            if g is not None:
-                if go.dtype != g.dtype:
-                    go = go.to(g.dtype)
-                _lib.check(_lib.fn("hidenn_scale_inplace", g.dtype)(_lib.ptr(g), C.c_int64(g.numel()), _lib.ptr(go),
-                                                                    _lib.stream_ptr()))
+        ref = gx if gx is not None else gu
+        if ref is not None:
+            go = grad_out.reshape(1).contiguous()
+            if go.dtype != ref.dtype:
+                go = go.to(ref.dtype)
+            _lib.check(_lib.fn("hidenn_scale_inplace2", ref.dtype)(
+                _lib.ptr(gx), C.c_int64(0 if gx is None else gx.numel()), _lib.ptr(gu), C.c_int64(0 if gu is None else gu.numel()),
+                _lib.ptr(go), _lib.stream_ptr()))
         return gx, gu, None, None, None, None, None, None
 
 
@@ -148,7 +149,7 @@ class EnergyLoss2D:
         key = (id(plan), dev, dt)
         s = self._scratch_cache.get(key)
         if s is None or s.numel() < plan.info["scratch"]:
-            s = torch.empty(plan.info["scratch"], device=dev, dtype=dt)
+            s = torch.zeros(plan.info["scratch"], device=dev, dtype=dt)     # the finalize ticket must start at zero
             self._scratch_cache[key] = s
         return s
 

@@ -119,7 +119,8 @@ int hidenn_tri_plan_bank_stats(const hidenn_tri_plan* plan, int real_bytes, int6
  *   out     dev [4]: loss, domain energy, edge energy, (unused)
  *   gx_free dev [Nfree,2], gu_free dev [Nufree,2]: overwritten (every row), not accumulated
  *   gt_out  dev [Ned,ng1,2] or NULL: d loss / d t_table (for tractions that depend on x)
- *   scratch dev [info[5]] reals
+ *   scratch dev [info[5]] reals, ZERO-INITIALISED before its first use (the kernels leave it reusable);
+ *           one evaluation in flight per scratch buffer
  * ------------------------------------------------------------------------------------------ */
 int hidenn_tri_energy_f64(const hidenn_tri_plan* plan,
                           const double* x_free, const double* x_fixed,
@@ -150,6 +151,8 @@ int hidenn_tri_energy_host_f32(hidenn_tri_plan* plan,
 
 /* g[i] *= *scale for i<n unless *scale == 1 (then every block exits at once): applies autograd's
  * grad_output to gradients computed in the forward launch without a host sync. */
+int hidenn_scale_inplace2_f64(double* g1, int64_t n1, double* g2, int64_t n2, const double* scale_dev, void* stream);
+int hidenn_scale_inplace2_f32(float* g1, int64_t n1, float* g2, int64_t n2, const float* scale_dev, void* stream);
 int hidenn_scale_inplace_f64(double* g, int64_t n, const double* scale_dev, void* stream);
 int hidenn_scale_inplace_f32(float* g, int64_t n, const float* scale_dev, void* stream);
 
