@@ -81,7 +81,14 @@ def ptr(t):
 
 
 def stream_ptr(device=None):
-    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """cudaStream_t of torch's current stream on the current device (raw handle, no Stream object)."""
+    if device is None:
+        idx = torch.cuda.current_device()
+    else:
+        idx = torch.device(device).index
+        if idx is None:
+            idx = torch.cuda.current_device()
+    return c_void_p(torch._C._cuda_getCurrentRawStream(idx))
 
 
 def suffix(dtype):
@@ -92,5 +99,13 @@ def suffix(dtype):
     raise HidennError(f"unsupported dtype {dtype}: the kernels are FP64 and FP32")
 
 
+_fn_cache = {}
+
+
 def fn(name, dtype):
-    return getattr(lib(), f"{name}_{suffix(dtype)}")
+    key = (name, dtype)
+    f = _fn_cache.get(key)
+    if f is None:
+        f = getattr(lib(), f"{name}_{suffix(dtype)}")
+        _fn_cache[key] = f
+    return f

@@ -205,7 +205,7 @@ tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ 
 
     // phase 3: owned nodes fold their slot range in fixed order and store the final gradients
     auto fold_node = [&](const uint32_t oc, const int2 sl) {
-        constexpr unsigned G = sizeof(R) == 8 ? 8u : 16u;     // slot k of a node sits G entries after slot k-1 (tri_plan.cu)
+        constexpr unsigned G = 8u;     // slot k of a node sits G entries after slot k-1 (tri_plan.cu)
         const unsigned b = oc & 0xFFFFu, e = b + (oc >> 16) * G;
         R ax = R(0), ay = R(0), bx = R(0), by = R(0);
         for (unsigned k = b; k < e; k += G) {
@@ -258,6 +258,44 @@ __device__ __forceinline__ void cp_async_pair(void* smem_dst, const void* gsrc, 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Shared-memory layouts of the persistent kernel.  FP64: node pairs xy | uv and partial pairs gu | gx as separate
+// 16-byte arrays.  FP32: one 16-byte record (x,y,ux,uy) per node and (gu.x,gu.y,gx.x,gx.y) per fold slot, so every
+// access is a single 128-bit pass of 8 lanes in both precisions.
+template <typename R> struct NodeBuf;
+template <> struct NodeBuf<double> {
+    double2* xy; double2* uv;
+    __device__ __forceinline__ NodeBuf(void* base, int max_local) : xy((double2*)base), uv((double2*)base + max_local) {}
+    __device__ __forceinline__ void load(unsigned l, double2& a, double2& b) const { a = xy[l]; b = uv[l]; }
+    __device__ __forceinline__ void* xy_ptr(int i) const { return xy + i; }
+    __device__ __forceinline__ void* uv_ptr(int i) const { return uv + i; }
+};
+template <> struct NodeBuf<float> {
+    float4* rec;
+    __device__ __forceinline__ NodeBuf(void* base, int) : rec((float4*)base) {}
+    __device__ __forceinline__ void load(unsigned l, float2& a, float2& b) const {
+        const float4 r = rec[l];
+        a = make_float2(r.x, r.y); b = make_float2(r.z, r.w);
+    }
+    __device__ __forceinline__ void* xy_ptr(int i) const { return reinterpret_cast<float2*>(rec + i); }
+    __device__ __forceinline__ void* uv_ptr(int i) const { return reinterpret_cast<float2*>(rec + i) + 1; }
+};
+template <typename R> struct PartBuf;
+template <> struct PartBuf<double> {
+    double2* pu; double2* px;
+    __device__ __forceinline__ PartBuf(void* base, int n) : pu((double2*)base), px((double2*)base + n) {}
+    __device__ __forceinline__ void store(unsigned p, double2 gu, double2 gx) const { pu[p] = gu; px[p] = gx; }
+    __device__ __forceinline__ void load(unsigned p, double2& gu, double2& gx) const { gu = pu[p]; gx = px[p]; }
+};
+template <> struct PartBuf<float> {
+    float4* rec;
+    __device__ __forceinline__ PartBuf(void* base, int) : rec((float4*)base) {}
+    __device__ __forceinline__ void store(unsigned p, float2 gu, float2 gx) const { rec[p] = make_float4(gu.x, gu.y, gx.x, gx.y); }
+    __device__ __forceinline__ void load(unsigned p, float2& gu, float2& gx) const {
+        const float4 r = rec[p];
+        gu = make_float2(r.x, r.y); gx = make_float2(r.z, r.w);
+    }
+};
+
 template <typename R, bool BODY, bool ISO, int MINB, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, MINB)
 tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ x_free,
@@ -270,15 +308,14 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
     // shared layout: 2 x (xy | uv) node buffers, fold partial pairs gu | gx (+ dump slot), 2 x 8 warp energy partials
     R2* s_node = reinterpret_cast<R2*>(smem_raw);
     const int nb = 2 * P.max_local;                       // pairs per node buffer
-    R2* s_pu = s_node + 2 * nb;
-    R2* s_px = s_pu + (P.max_entries + 1);
-    R* s_red = reinterpret_cast<R*>(s_px + (P.max_entries + 1));      // [2][16]
+    const PartBuf<R> part(s_node + 2 * nb, P.max_entries + 1);
+    R* s_red = reinterpret_cast<R*>(s_node + 2 * nb + 2 * (P.max_entries + 1));      // [2][16]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nct = gridDim.x;
     int tile = blockIdx.x;
     if (tile >= P.n_tiles) return;
     constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
-    constexpr unsigned G = sizeof(R) == 8 ? 8u : 16u;
+    constexpr unsigned G = 8u;
     constexpr int PB = (int)sizeof(R2);
     constexpr int NPRE = 768 / BLOCK;      // element packs held in registers per thread (768 >= typical tile)
     constexpr int NW = BLOCK / 32;
@@ -292,21 +329,20 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
         }
     };
     auto issue_gathers = [&](const int t, const int2 (&sl)[2], R2* buf) {
-        R2* bxy = buf;
-        R2* buv = buf + P.max_local;
+        const NodeBuf<R> nbuf(buf, P.max_local);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int i = tid + k * BLOCK;
             if (i < P.stride_local && i < P.max_local) {
-                cp_async_pair(bxy + i, sl[k].x >= 0 ? (const void*)(x_free + sl[k].x) : (const void*)(x_fixed + (~sl[k].x)), PB);
-                cp_async_pair(buv + i, sl[k].y >= 0 ? (const void*)(u_free + sl[k].y) : (const void*)(u_fixed + (~sl[k].y)), PB);
+                cp_async_pair(nbuf.xy_ptr(i), sl[k].x >= 0 ? (const void*)(x_free + sl[k].x) : (const void*)(x_fixed + (~sl[k].x)), PB);
+                cp_async_pair(nbuf.uv_ptr(i), sl[k].y >= 0 ? (const void*)(u_free + sl[k].y) : (const void*)(u_fixed + (~sl[k].y)), PB);
             }
         }
         const int2* __restrict__ src = P.t_slots + (size_t)t * P.stride_local;
         for (int i = tid + 2 * BLOCK; i < P.max_local; i += BLOCK) {     // tiles with more than 512 local nodes
             const int2 s2 = __ldg(src + i);
-            cp_async_pair(bxy + i, s2.x >= 0 ? (const void*)(x_free + s2.x) : (const void*)(x_fixed + (~s2.x)), PB);
-            cp_async_pair(buv + i, s2.y >= 0 ? (const void*)(u_free + s2.y) : (const void*)(u_fixed + (~s2.y)), PB);
+            cp_async_pair(nbuf.xy_ptr(i), s2.x >= 0 ? (const void*)(x_free + s2.x) : (const void*)(x_fixed + (~s2.x)), PB);
+            cp_async_pair(nbuf.uv_ptr(i), s2.y >= 0 ? (const void*)(u_free + s2.y) : (const void*)(u_fixed + (~s2.y)), PB);
         }
     };
     auto load_meta = [&](const int t, unsigned long long (&pk)[NPRE], uint32_t (&of)[2]) {
@@ -354,8 +390,7 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
         if (has_next) issue_gathers(tnext, slot_nxt, s_node + (b ^ 1) * nb);      // lands during E + F of this tile
 
         // E: elements -> energy + gradient partials at their fold slots
-        const R2* s_xy = s_node + b * nb;
-        const R2* s_uv = s_xy + P.max_local;
+        const NodeBuf<R> nodes(s_node + b * nb, P.max_local);
         R e_acc = R(0);
         const unsigned dumpv = (unsigned)td.n_entries;
         auto do_element = [&](const unsigned long long w) {
@@ -364,13 +399,14 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
             const unsigned p0 = (unsigned)(w >> (3 * kLidBits)) & PM, p1 = (hi >> (3 * kLidBits + kPosBits - 32)) & PM,
                            p2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
             R e;
-            R2 gu[3], gx[3];
-            tri_element<R, BODY, ISO>(s_xy[l0], s_xy[l1], s_xy[l2], s_uv[l0], s_uv[l1], s_uv[l2], K, e, gu, gx);
+            R2 gu[3], gx[3], v0, v1, v2, U0, U1, U2;
+            nodes.load(l0, v0, U0); nodes.load(l1, v1, U1); nodes.load(l2, v2, U2);
+            tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx);
             e_acc += (hi >> 31) ? e : R(0);
             // halo corners carry the tile's dump position: skip their stores (predicated, no branch)
-            if (p0 != dumpv) { s_pu[p0] = gu[0]; s_px[p0] = gx[0]; }
-            if (p1 != dumpv) { s_pu[p1] = gu[1]; s_px[p1] = gx[1]; }
-            if (p2 != dumpv) { s_pu[p2] = gu[2]; s_px[p2] = gx[2]; }
+            if (p0 != dumpv) part.store(p0, gu[0], gx[0]);
+            if (p1 != dumpv) part.store(p1, gu[1], gx[1]);
+            if (p2 != dumpv) part.store(p2, gu[2], gx[2]);
         };
 #pragma unroll
         for (int k = 0; k < NPRE; ++k)
@@ -398,7 +434,8 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
             const unsigned fb = oc & 0xFFFFu, fe = fb + (oc >> 16) * G;
             R ax = R(0), ay = R(0), bx = R(0), by = R(0);
             for (unsigned k = fb; k < fe; k += G) {
-                const R2 u = s_pu[k], x = s_px[k];
+                R2 u, x;
+                part.load(k, u, x);
                 ax += u.x; ay += u.y; bx += x.x; by += x.y;
             }
             if ((flags & HIDENN_NEED_GU) && sl.y >= 0) gu_free[sl.y] = mk2<R>(ax, ay);

@@ -91,7 +91,8 @@ struct TileBuild {
 // groups in the 3 gathers and the 3 partial stores.  Random placement costs ~2.2 wavefronts per pass.
 static void reorder_for_banks(TileBuild& B, int real_bytes) {
     const int E = (int)B.pack.size();
-    const int G = real_bytes == 8 ? 8 : 16;          // lanes per shared-memory pass = number of bank groups
+    (void)real_bytes;
+    const int G = 8;          // lanes per 128-bit shared-memory pass = number of 16-byte bank groups (both precisions)
     if (E <= G) return;
     constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
     const unsigned dump = (unsigned)B.n_entries;
@@ -257,7 +258,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     const int32_t* n2e = p->n2e_ent.data();
     auto build_range = [&](int64_t t0, int64_t t1) {
         std::vector<int32_t> cand, halo, owned_sorted, perm, lid_of;
-        const int G = real_bytes == 8 ? 8 : 16;
+        const int G = 8;
         for (int64_t t = t0; t < t1; ++t) {
             TileBuild& B = tb[t];
             // owned nodes: looked up through an id-sorted list, numbered locally by descending valence so that
@@ -535,7 +536,8 @@ extern "C" int hidenn_tri_plan_decode(const hidenn_tri_plan* p, int64_t* out_ele
 // addresses broadcast).  out[0] = gather passes, out[1] = ideal gather passes, out[2] = store passes, out[3] = ideal.
 extern "C" int hidenn_tri_plan_bank_stats(const hidenn_tri_plan* p, int real_bytes, int64_t* out4) {
     HIDENN_REQUIRE(p && out4 && (real_bytes == 8 || real_bytes == 4), "plan_bank_stats: bad arguments");
-    const int G = real_bytes == 8 ? 8 : 16;
+    (void)real_bytes;
+    const int G = 8;
     constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
     int64_t gp = 0, gi = 0, sp = 0, si = 0;
     for (const TileDesc& d : p->tiles) {

@@ -253,3 +253,32 @@ def test_cpu_tensor_raises():
     loss_fn = loss_of(g, torch.float64)
     with pytest.raises(_lib.HidennError, match="no CPU fallback"):
         loss_fn(model)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_large_tiles_strip_mesh(dtype):
+    """Two-node-wide strip (valence <= 4): tiles reach > 512 local nodes / > 768 element visits, which exercises the
+    tail loops of the tile kernels that ordinary meshes never enter."""
+    from hidenn_fem_b200 import meshgen
+    m = meshgen.plate_mesh(4001, 2, jitter=0.0, diag="random", seed=3, ordering="natural", holes=())
+    rng = np.random.default_rng(5)
+    npdt = np.float64 if dtype == torch.float64 else np.float32
+    coords = (m.node_coords + 0.2 * (2.0 / 4000) * rng.standard_normal(m.node_coords.shape) * (~m.dirichlet_mask)[:, None]).astype(npdt)
+    bmask = m.dirichlet_mask.copy()
+    g = dict(node_coords=coords, connectivity=m.connectivity, boundary_mask=bmask, dirichlet_mask=m.dirichlet_mask,
+             neumann_edges=m.neumann_edges, u_fixed=np.asarray(0.0), gauss_order=4, gauss_order_1d=2,
+             node_coords_free=coords[~bmask], node_coords_fixed=coords[bmask],
+             u_free=(1e-3 * rng.standard_normal((int((~m.dirichlet_mask).sum()), 2))).astype(npdt))
+    for tn in (640, 2048):
+        model = build(g, tile_nodes=tn)
+        info = model._plan().info
+        if tn == 640:
+            assert info["max_local"] > 512 and info["max_elem"] > 768, info
+        loss_fn = loss_of(g, dtype)
+        loss = loss_fn(model)
+        loss.backward()
+        lo, gx, gu = tri_oracle(dict(g), "default", dtype=np.float64)
+        tol = TOL[dtype]
+        assert abs(loss.item() - float(lo)) <= tol * abs(float(lo))
+        assert relmax(model.node_coords_free.grad.cpu().numpy(), gx) < tol
+        assert relmax(model.u_free.grad.cpu().numpy(), gu) < tol
