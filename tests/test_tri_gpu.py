@@ -257,8 +257,8 @@ def test_cpu_tensor_raises():
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_large_tiles_strip_mesh(dtype):
-    """Two-node-wide strip (valence <= 4): tiles reach > 512 local nodes / > 768 element visits, which exercises the
-    tail loops of the tile kernels that ordinary meshes never enter."""
+    """Two-node-wide strip (valence <= 4): tiles reach > 512 local nodes, which exercises the tail loops of the tile
+    kernels that ordinary meshes never enter."""
     from hidenn_fem_b200 import meshgen
     m = meshgen.plate_mesh(4001, 2, jitter=0.0, diag="random", seed=3, ordering="natural", holes=())
     rng = np.random.default_rng(5)
@@ -273,7 +273,7 @@ def test_large_tiles_strip_mesh(dtype):
         model = build(g, tile_nodes=tn)
         info = model._plan().info
         if tn == 640:
-            assert info["max_local"] > 512 and info["max_elem"] > 768, info
+            assert info["max_local"] > 512, info      # exercises the > 2 nodes-per-thread staging / fold loops
         loss_fn = loss_of(g, dtype)
         loss = loss_fn(model)
         loss.backward()
