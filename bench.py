@@ -427,7 +427,7 @@ def main():
     alg_bytes = 12 * ne_local + 2 * sz * (2 * nn_local) + 2 * sz * (nfree_x + nfree_u)
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "tri_tile_kernel<%s>" % ("double" if sz == 8 else "float"),
+                "traffic": None, "kernel": "tri_tile_persistent_kernel<%s>" % ("double" if sz == 8 else "float"),
                 "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_element": alg_bytes / ne_local, "peak_source": peak_src}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")

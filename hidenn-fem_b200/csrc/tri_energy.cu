@@ -724,15 +724,10 @@ static int launch_tile(const hidenn_tri_plan* p, const R* x_free, const R* x_fix
                        int flags, R* gx, R* gu, R* scratch, cudaStream_t stream) {
     if (use_persistent() && !g_tile_timing) {
         const size_t smem = smem_persistent_for<R>(p);
-        static const int blk = [] { const char* e = getenv("HIDENN_TILE_BLOCK"); return e ? atoi(e) : 256; }();
         const int mb = pick_minb(smem, (int)sizeof(R));
 #define HIDENN_LAUNCH_P(MB, BL) \
     return launch_tile_persistent_mb<R, BODY, ISO, MB, BL>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem)
-        if (blk == 384) {
-            if (mb <= 2) HIDENN_LAUNCH_P(2, 384);
-            HIDENN_LAUNCH_P(3, 384);
-        }
-        switch (mb) {
+        switch (mb) {      // 384-thread CTAs were measured slower (profiles/README.md) and are not instantiated
             case 2: HIDENN_LAUNCH_P(2, 256);
             case 3: HIDENN_LAUNCH_P(3, 256);
             case 4: HIDENN_LAUNCH_P(4, 256);
@@ -740,14 +735,8 @@ static int launch_tile(const hidenn_tri_plan* p, const R* x_free, const R* x_fix
         }
 #undef HIDENN_LAUNCH_P
     }
-    const size_t smem = smem_for<R>(p);
-    switch (pick_minb(smem, (int)sizeof(R))) {
-        case 2: return launch_tile_mb<R, BODY, ISO, 2>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
-        case 3: return launch_tile_mb<R, BODY, ISO, 3>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
-        case 4: return launch_tile_mb<R, BODY, ISO, 4>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
-        case 5: return launch_tile_mb<R, BODY, ISO, 5>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
-        default: return launch_tile_mb<R, BODY, ISO, 6>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem);
-    }
+    // non-persistent variant (A/B runs, per-phase timing aid): one configuration, 3 CTAs per SM
+    return launch_tile_mb<R, BODY, ISO, 3>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem_for<R>(p));
 }
 
 template <typename R>
