@@ -98,152 +98,10 @@ template <typename R, bool BODY> __device__ __forceinline__ TriConsts<R> load_co
     return K;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-constexpr int kPre = 3;   // element packs prefetched per thread before the first barrier (kPre*256 >= typical tile)
-
-template <typename R, bool BODY, bool ISO, int MINB>
-__global__ void __launch_bounds__(kTileBlock, MINB)
-tri_tile_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ x_free,
-                const typename Real2<R>::type* __restrict__ x_fixed, const typename Real2<R>::type* __restrict__ u_free,
-                const typename Real2<R>::type* __restrict__ u_fixed, const R* __restrict__ consts, const int flags,
-                typename Real2<R>::type* __restrict__ gx_free, typename Real2<R>::type* __restrict__ gu_free,
-                R* __restrict__ tile_energy, const int pf_dist, long long* __restrict__ timing) {
-    using R2 = typename Real2<R>::type;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    long long tk0 = 0, tk1 = 0, tk2 = 0;
-    if (timing) tk0 = clock64();
-    // shared layout: node pairs xy | uv, fold partial pairs gu | gx (n_entries + 1 dump slot), reduce scratch
-    R2* s_xy = reinterpret_cast<R2*>(smem_raw);
-    R2* s_uv = s_xy + P.max_local;
-    R2* s_pu = s_uv + P.max_local;
-    R2* s_px = s_pu + (P.max_entries + 1);
-    R* s_red = reinterpret_cast<R*>(s_px + (P.max_entries + 1));
-    const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
-
-    // phase 1: every global load of the tile is issued up front.  The tile records have fixed strides, so the
-    // slot / pack / offset addresses depend only on blockIdx (no wait on the descriptor); padding entries are inert.
-    const int2* __restrict__ slots = P.t_slots + (size_t)tile * P.stride_local;
-    const unsigned long long* __restrict__ packs = P.elem_pack + (size_t)tile * P.stride_elem;
-    const uint32_t* __restrict__ offs = P.entry_off + (size_t)tile * P.stride_owned;
-    int2 myslot[2];
-    uint32_t myoff[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int i = tid + k * kTileBlock;
-        myslot[k] = i < P.stride_local ? __ldg(slots + i) : make_int2(-1, -1);
-        myoff[k] = i < P.stride_owned ? __ldg(offs + i) : 0u;
-    }
-    // L2 prefetch for the tile that will run on this SM about one CTA lifetime from now (tile + pf_dist): its record
-    // arrays now, its node pairs at the end of this CTA (when the slots loaded here have arrived).  The dependent
-    // slot -> node-pair chain of that tile then hits L2 instead of DRAM; DRAM traffic is unchanged.
-    const int ptile = tile + pf_dist;
-    const bool pf = pf_dist > 0 && ptile < P.n_tiles;
-    int2 pslot[2] = {make_int2(-1, -1), make_int2(-1, -1)};
-    if (pf) {
-        const char* r0 = reinterpret_cast<const char*>(P.elem_pack + (size_t)ptile * P.stride_elem);
-        const char* r1 = reinterpret_cast<const char*>(P.entry_off + (size_t)ptile * P.stride_owned);
-        const int n0 = P.stride_elem * 8, n1 = P.stride_owned * 4;
-        for (int o = tid * 128; o < n0; o += kTileBlock * 128) prefetch_l2(r0 + o);
-        for (int o = tid * 128; o < n1; o += kTileBlock * 128) prefetch_l2(r1 + o);
-        const int2* ps = P.t_slots + (size_t)ptile * P.stride_local;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int i = tid + k * kTileBlock;
-            if (i < P.stride_local) pslot[k] = __ldg(ps + i);
-        }
-    }
-    unsigned long long wpre[kPre];
-#pragma unroll
-    for (int k = 0; k < kPre; ++k) {
-        const int i = tid + k * kTileBlock;
-        wpre[k] = i < P.stride_elem ? __ldg(packs + i) : 0ull;
-    }
-    const TileDesc td = P.tiles[tile];
-    const TriConsts<R> K = load_consts<R, BODY>(consts);
-    long long tk_desc = 0;
-    if (timing) tk_desc = clock64() + (td.n_local == -12345 ? 1 : 0) + (myslot[0].x == -12345 ? 1 : 0);   // after desc + slots arrive
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int i = tid + k * kTileBlock;
-        if (i < td.n_local) {
-            s_xy[i] = load_slot<R2>(x_free, x_fixed, myslot[k].x);
-            s_uv[i] = load_slot<R2>(u_free, u_fixed, myslot[k].y);
-        }
-    }
-    for (int i = tid + 2 * kTileBlock; i < td.n_local; i += kTileBlock) {      // tiles with more than 512 local nodes
-        const int2 sl = __ldg(slots + i);
-        s_xy[i] = load_slot<R2>(x_free, x_fixed, sl.x);
-        s_uv[i] = load_slot<R2>(u_free, u_fixed, sl.y);
-    }
-    __syncthreads();
-    if (timing) tk1 = clock64();
-
-    // phase 2: elements -> energy + gradient partials stored at their precomputed fold slots
-    R e_acc = R(0);
-    constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
-    auto do_element = [&](const unsigned long long w) {
-        const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
-        const unsigned l0 = lo & LM, l1 = (lo >> kLidBits) & LM, l2 = (lo >> (2 * kLidBits)) & LM;
-        const unsigned p0 = (unsigned)(w >> (3 * kLidBits)) & PM, p1 = (hi >> (3 * kLidBits + kPosBits - 32)) & PM,
-                       p2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
-        R e;
-        R2 gu[3], gx[3];
-        tri_element<R, BODY, ISO>(s_xy[l0], s_xy[l1], s_xy[l2], s_uv[l0], s_uv[l1], s_uv[l2], K, e, gu, gx);
-        e_acc += (hi >> 31) ? e : R(0);
-        s_pu[p0] = gu[0]; s_px[p0] = gx[0];
-        s_pu[p1] = gu[1]; s_px[p1] = gx[1];
-        s_pu[p2] = gu[2]; s_px[p2] = gx[2];
-    };
-#pragma unroll
-    for (int k = 0; k < kPre; ++k)
-        if (tid + k * kTileBlock < td.n_elem) do_element(wpre[k]);
-    for (int i = tid + kPre * kTileBlock; i < td.n_elem; i += kTileBlock) do_element(__ldg(packs + i));
-    __syncthreads();
-    if (timing) tk2 = clock64();
-
-    // phase 3: owned nodes fold their slot range in fixed order and store the final gradients
-    auto fold_node = [&](const uint32_t oc, const int2 sl) {
-        constexpr unsigned G = 8u;     // slot k of a node sits G entries after slot k-1 (tri_plan.cu)
-        const unsigned b = oc & 0xFFFFu, e = b + (oc >> 16) * G;
-        R ax = R(0), ay = R(0), bx = R(0), by = R(0);
-        for (unsigned k = b; k < e; k += G) {
-            const R2 u = s_pu[k], x = s_px[k];
-            ax += u.x; ay += u.y; bx += x.x; by += x.y;
-        }
-        if ((flags & HIDENN_NEED_GU) && sl.y >= 0) gu_free[sl.y] = mk2<R>(ax, ay);
-        if ((flags & HIDENN_NEED_GX) && sl.x >= 0) gx_free[sl.x] = mk2<R>(bx, by);
-    };
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-        if (tid + k * kTileBlock < td.n_owned) fold_node(myoff[k], myslot[k]);
-    for (int i = tid + 2 * kTileBlock; i < td.n_owned; i += kTileBlock) fold_node(__ldg(offs + i), __ldg(slots + i));
-
-    long long tk3 = 0;
-    if (timing) tk3 = clock64();
-    if (pf) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            // padding slots are (-1,-1) = row 0 of the fixed buffers: harmless
-            prefetch_l2(pslot[k].x >= 0 ? (const void*)(x_free + pslot[k].x) : (const void*)(x_fixed + (~pslot[k].x)));
-            prefetch_l2(pslot[k].y >= 0 ? (const void*)(u_free + pslot[k].y) : (const void*)(u_fixed + (~pslot[k].y)));
-        }
-    }
-
-    // tile energy (fixed-order block sum)
-    const R tot = block_sum<R, kTileBlock>(e_acc, s_red);
-    if (tid == 0) tile_energy[blockIdx.x] = tot;
-    if (timing && tid == 0) {      // debug aid (hidenn_debug_tile_timing): per-phase SM cycles of this CTA
-        unsigned smid;
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        long long* t = timing + 8 * (long long)blockIdx.x;
-        t[0] = tk0; t[1] = tk1; t[2] = tk2; t[3] = clock64(); t[4] = smid; t[5] = tk3; t[6] = tk_desc;
-    }
-}
+constexpr int kPre = 3;
 
 // ---------------------------------------------------------------------------------------------
-// Persistent variant of the tile kernel: each CTA walks tiles blockIdx.x, +gridDim.x, ... and overlaps the
+// The tile kernel is persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ... and overlaps the
 // whole load chain of the NEXT tile with the element / fold phases of the current one:
 //   * node pairs of tile t+1 are gathered with cp.async (LDGSTS) into the second node buffer while tile t
 //     computes (their slots were loaded one iteration earlier);
@@ -302,14 +160,16 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
                            const typename Real2<R>::type* __restrict__ x_fixed, const typename Real2<R>::type* __restrict__ u_free,
                            const typename Real2<R>::type* __restrict__ u_fixed, const R* __restrict__ consts, const int flags,
                            typename Real2<R>::type* __restrict__ gx_free, typename Real2<R>::type* __restrict__ gu_free,
-                           R* __restrict__ tile_energy) {
+                           R* __restrict__ tile_energy, long long* __restrict__ timing) {
     using R2 = typename Real2<R>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // shared layout: 2 x (xy | uv) node buffers, fold partial pairs gu | gx (+ dump slot), 2 x 8 warp energy partials
+    // shared layout: 2 x (xy | uv) node buffers, fold partial pairs gu | gx (+ dump slot), output staging (gu | gx per
+    // owned node), 2 x 16 warp energy partials
     R2* s_node = reinterpret_cast<R2*>(smem_raw);
     const int nb = 2 * P.max_local;                       // pairs per node buffer
     const PartBuf<R> part(s_node + 2 * nb, P.max_entries + 1);
-    R* s_red = reinterpret_cast<R*>(s_node + 2 * nb + 2 * (P.max_entries + 1));      // [2][16]
+    const PartBuf<R> outb(s_node + 2 * nb + 2 * (P.max_entries + 1), P.max_owned);
+    R* s_red = reinterpret_cast<R*>(s_node + 2 * nb + 2 * (P.max_entries + 1) + 2 * P.max_owned);      // [2][16]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nct = gridDim.x;
     int tile = blockIdx.x;
@@ -320,29 +180,57 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
     constexpr int NPRE = 768 / BLOCK;      // element packs held in registers per thread (768 >= typical tile)
     constexpr int NW = BLOCK / 32;
 
-    auto load_slots = [&](const int t, int2 (&sl)[2]) {
+    // node records come in memory order: record j of a tile is (slots, local id = shared-memory position)
+    auto load_slots = [&](const int t, int2 (&sl)[2], unsigned (&ld)[2]) {
         const int2* __restrict__ src = P.t_slots + (size_t)t * P.stride_local;
+        const uint16_t* __restrict__ lsrc = P.t_lid + (size_t)t * P.stride_local;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int i = tid + k * BLOCK;
             sl[k] = i < P.stride_local ? __ldg(src + i) : make_int2(0, 0);
+            ld[k] = i < P.stride_local ? (unsigned)__ldg(lsrc + i) : 0xFFFFu;
         }
     };
-    auto issue_gathers = [&](const int t, const int2 (&sl)[2], R2* buf) {
+    auto issue_gathers = [&](const int t, const int2 (&sl)[2], const unsigned (&ld)[2], R2* buf) {
         const NodeBuf<R> nbuf(buf, P.max_local);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const int i = tid + k * BLOCK;
-            if (i < P.stride_local && i < P.max_local) {
-                cp_async_pair(nbuf.xy_ptr(i), sl[k].x >= 0 ? (const void*)(x_free + sl[k].x) : (const void*)(x_fixed + (~sl[k].x)), PB);
-                cp_async_pair(nbuf.uv_ptr(i), sl[k].y >= 0 ? (const void*)(u_free + sl[k].y) : (const void*)(u_fixed + (~sl[k].y)), PB);
+            if (ld[k] != 0xFFFFu) {      // consecutive lanes read consecutive Parameter rows; the record lands at its local id
+                cp_async_pair(nbuf.xy_ptr(ld[k]), sl[k].x >= 0 ? (const void*)(x_free + sl[k].x) : (const void*)(x_fixed + (~sl[k].x)), PB);
+                cp_async_pair(nbuf.uv_ptr(ld[k]), sl[k].y >= 0 ? (const void*)(u_free + sl[k].y) : (const void*)(u_fixed + (~sl[k].y)), PB);
             }
         }
         const int2* __restrict__ src = P.t_slots + (size_t)t * P.stride_local;
-        for (int i = tid + 2 * BLOCK; i < P.max_local; i += BLOCK) {     // tiles with more than 512 local nodes
+        const uint16_t* __restrict__ lsrc = P.t_lid + (size_t)t * P.stride_local;
+        for (int i = tid + 2 * BLOCK; i < P.stride_local; i += BLOCK) {     // tiles with more than 2*BLOCK local nodes
+            const unsigned l2 = __ldg(lsrc + i);
+            if (l2 == 0xFFFFu) continue;
             const int2 s2 = __ldg(src + i);
-            cp_async_pair(nbuf.xy_ptr(i), s2.x >= 0 ? (const void*)(x_free + s2.x) : (const void*)(x_fixed + (~s2.x)), PB);
-            cp_async_pair(nbuf.uv_ptr(i), s2.y >= 0 ? (const void*)(u_free + s2.y) : (const void*)(u_fixed + (~s2.y)), PB);
+            cp_async_pair(nbuf.xy_ptr(l2), s2.x >= 0 ? (const void*)(x_free + s2.x) : (const void*)(x_fixed + (~s2.x)), PB);
+            cp_async_pair(nbuf.uv_ptr(l2), s2.y >= 0 ? (const void*)(u_free + s2.y) : (const void*)(u_fixed + (~s2.y)), PB);
+        }
+    };
+    // final gradient stores of a finished tile: records in memory order, values from the output staging buffer
+    auto flush_outputs = [&](const int t, const int n_owned, const int2 (&sl)[2], const unsigned (&ld)[2]) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (ld[k] < (unsigned)n_owned) {
+                R2 gu, gx;
+                outb.load(ld[k], gu, gx);
+                if ((flags & HIDENN_NEED_GU) && sl[k].y >= 0) gu_free[sl[k].y] = gu;
+                if ((flags & HIDENN_NEED_GX) && sl[k].x >= 0) gx_free[sl[k].x] = gx;
+            }
+        }
+        const int2* __restrict__ src = P.t_slots + (size_t)t * P.stride_local;
+        const uint16_t* __restrict__ lsrc = P.t_lid + (size_t)t * P.stride_local;
+        for (int i = tid + 2 * BLOCK; i < P.stride_local; i += BLOCK) {
+            const unsigned l2 = __ldg(lsrc + i);
+            if (l2 >= (unsigned)n_owned) continue;
+            const int2 s2 = __ldg(src + i);
+            R2 gu, gx;
+            outb.load(l2, gu, gx);
+            if ((flags & HIDENN_NEED_GU) && s2.y >= 0) gu_free[s2.y] = gu;
+            if ((flags & HIDENN_NEED_GX) && s2.x >= 0) gx_free[s2.x] = gx;
         }
     };
     auto load_meta = [&](const int t, unsigned long long (&pk)[NPRE], uint32_t (&of)[2]) {
@@ -362,20 +250,23 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
 
     // prologue: first tile's slots -> gathers; second tile's slots; first tile's packs / offsets / descriptor
     int2 slot_cur[2], slot_nxt[2];
+    unsigned lid_cur[2], lid_nxt[2];
     unsigned long long pk[NPRE];
     uint32_t off[2];
-    load_slots(tile, slot_cur);
-    if (tile + nct < P.n_tiles) load_slots(tile + nct, slot_nxt);
-    else { slot_nxt[0] = slot_nxt[1] = make_int2(0, 0); }
+    load_slots(tile, slot_cur, lid_cur);
+    if (tile + nct < P.n_tiles) load_slots(tile + nct, slot_nxt, lid_nxt);
+    else { slot_nxt[0] = slot_nxt[1] = make_int2(0, 0); lid_nxt[0] = lid_nxt[1] = 0xFFFFu; }
     load_meta(tile, pk, off);
     TileDesc td = P.tiles[tile];
     const TriConsts<R> K = load_consts<R, BODY>(consts);
-    issue_gathers(tile, slot_cur, s_node);
+    issue_gathers(tile, slot_cur, lid_cur, s_node);
     cp_async_wait_all();
     __syncthreads();
 
     int b = 0;
-    int prev_tile = -1;
+    int prev_tile = -1, prev_owned = 0;
+    int2 slot_prev[2] = {make_int2(0, 0), make_int2(0, 0)};
+    unsigned lid_prev[2] = {0xFFFFu, 0xFFFFu};
     for (;;) {
         // node buffer b holds this tile; the partial buffer is free (the previous fold ended before the barrier)
         if (tid == 0 && prev_tile >= 0) {        // energy of the previous tile, summed in fixed warp order
@@ -385,9 +276,12 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
             for (int w = 0; w < NW; ++w) acc += r[w];
             tile_energy[prev_tile] = acc;
         }
+        long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
+        if (timing) tk0 = clock64();
         const int tnext = tile + nct;
         const bool has_next = tnext < P.n_tiles;
-        if (has_next) issue_gathers(tnext, slot_nxt, s_node + (b ^ 1) * nb);      // lands during E + F of this tile
+        if (has_next) issue_gathers(tnext, slot_nxt, lid_nxt, s_node + (b ^ 1) * nb);      // lands during E + F of this tile
+        if (prev_tile >= 0) flush_outputs(prev_tile, prev_owned, slot_prev, lid_prev);      // coalesced stores of the previous tile
 
         // E: elements -> energy + gradient partials at their fold slots
         const NodeBuf<R> nodes(s_node + b * nb, P.max_local);
@@ -417,20 +311,24 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
         }
         e_acc = warp_sum(e_acc);
         if (lane == 0) s_red[b * 16 + wid] = e_acc;
+        if (timing) tk1 = clock64();
         __syncthreads();
+        if (timing) tk2 = clock64();
 
         // F: fold.  First put the next tile's metadata loads in flight (registers are cheap in this phase).
         unsigned long long pk_n[NPRE];
         uint32_t off_n[2];
         int2 slot_n2[2];
+        unsigned lid_n2[2];
         TileDesc td_n = td;
         if (has_next) {
             load_meta(tnext, pk_n, off_n);
             td_n = P.tiles[tnext];
-            if (tnext + nct < P.n_tiles) load_slots(tnext + nct, slot_n2);
-            else { slot_n2[0] = slot_n2[1] = make_int2(0, 0); }
+            if (tnext + nct < P.n_tiles) load_slots(tnext + nct, slot_n2, lid_n2);
+            else { slot_n2[0] = slot_n2[1] = make_int2(0, 0); lid_n2[0] = lid_n2[1] = 0xFFFFu; }
         }
-        auto fold_node = [&](const uint32_t oc, const int2 sl) {
+        // thread l folds owned node l (its slot rows are conflict-free) into the output staging buffer
+        auto fold_node = [&](const uint32_t oc, const int l) {
             const unsigned fb = oc & 0xFFFFu, fe = fb + (oc >> 16) * G;
             R ax = R(0), ay = R(0), bx = R(0), by = R(0);
             for (unsigned k = fb; k < fe; k += G) {
@@ -438,31 +336,46 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
                 part.load(k, u, x);
                 ax += u.x; ay += u.y; bx += x.x; by += x.y;
             }
-            if ((flags & HIDENN_NEED_GU) && sl.y >= 0) gu_free[sl.y] = mk2<R>(ax, ay);
-            if ((flags & HIDENN_NEED_GX) && sl.x >= 0) gx_free[sl.x] = mk2<R>(bx, by);
+            outb.store(l, mk2<R>(ax, ay), mk2<R>(bx, by));
         };
 #pragma unroll
         for (int k = 0; k < 2; ++k)
-            if (tid + k * BLOCK < td.n_owned) fold_node(off[k], slot_cur[k]);
+            if (tid + k * BLOCK < td.n_owned) fold_node(off[k], tid + k * BLOCK);
         {
             const uint32_t* __restrict__ offs = P.entry_off + (size_t)tile * P.stride_owned;
-            const int2* __restrict__ slots = P.t_slots + (size_t)tile * P.stride_local;
-            for (int i = tid + 2 * BLOCK; i < td.n_owned; i += BLOCK) fold_node(__ldg(offs + i), __ldg(slots + i));
+            for (int i = tid + 2 * BLOCK; i < td.n_owned; i += BLOCK) fold_node(__ldg(offs + i), i);
+        }
+        if (timing) tk3 = clock64();
+        if (timing && (tid == 0 || tid == BLOCK - 1)) {     // per-tile phase clocks of the first and last warp (debug aid)
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            long long* tt = timing + 16 * (long long)tile + (tid == 0 ? 0 : 8);
+            tt[0] = tk0; tt[1] = tk1; tt[2] = tk2; tt[3] = tk3; tt[4] = smid;
         }
         prev_tile = tile;
+        prev_owned = td.n_owned;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) { slot_prev[k] = slot_cur[k]; lid_prev[k] = lid_cur[k]; }
         if (!has_next) break;
         // rotate the pipeline registers
 #pragma unroll
-        for (int k = 0; k < 2; ++k) { slot_cur[k] = slot_nxt[k]; slot_nxt[k] = slot_n2[k]; off[k] = off_n[k]; }
+        for (int k = 0; k < 2; ++k) {
+            slot_cur[k] = slot_nxt[k]; slot_nxt[k] = slot_n2[k]; off[k] = off_n[k];
+            lid_cur[k] = lid_nxt[k]; lid_nxt[k] = lid_n2[k];
+        }
 #pragma unroll
         for (int k = 0; k < NPRE; ++k) pk[k] = pk_n[k];
         td = td_n;
         tile = tnext;
         b ^= 1;
+        if (timing && (tid == 0 || tid == BLOCK - 1)) timing[16 * (long long)prev_tile + (tid == 0 ? 5 : 13)] = clock64();
         cp_async_wait_all();
-        __syncthreads();      // next tile's nodes visible; every fold read of the partial buffer is done
+        if (timing && (tid == 0 || tid == BLOCK - 1)) timing[16 * (long long)prev_tile + (tid == 0 ? 6 : 14)] = clock64();
+        __syncthreads();      // next tile's nodes visible; fold reads of the partials and staging writes are done
+        if (timing && (tid == 0 || tid == BLOCK - 1)) timing[16 * (long long)prev_tile + (tid == 0 ? 7 : 15)] = clock64();
     }
     __syncthreads();
+    flush_outputs(prev_tile, prev_owned, slot_prev, lid_prev);
     if (tid == 0) {
         const R* r = s_red + b * 16;
         R acc = R(0);
@@ -488,11 +401,13 @@ tri_tile_energy_only_kernel(const TriPlanDev P, const typename Real2<R>::type* _
     R* s_red = reinterpret_cast<R*>(s_uv + td.n_local);
     const int tid = threadIdx.x;
     const int2* __restrict__ slots = P.t_slots + (size_t)blockIdx.x * P.stride_local;
+    const uint16_t* __restrict__ lids = P.t_lid + (size_t)blockIdx.x * P.stride_local;
     const unsigned long long* __restrict__ packs = P.elem_pack + (size_t)blockIdx.x * P.stride_elem;
-    for (int i = tid; i < td.n_local; i += kTileBlock) {
+    for (int i = tid; i < td.n_local; i += kTileBlock) {      // records in memory order land at their local id
         const int2 sl = __ldg(slots + i);
-        s_xy[i] = load_slot<R2>(x_free, x_fixed, sl.x);
-        s_uv[i] = load_slot<R2>(u_free, u_fixed, sl.y);
+        const unsigned l = __ldg(lids + i);
+        s_xy[l] = load_slot<R2>(x_free, x_fixed, sl.x);
+        s_uv[l] = load_slot<R2>(u_free, u_fixed, sl.y);
     }
     const TriConsts<R> K = load_consts<R, true>(consts);
     __syncthreads();
@@ -654,33 +569,11 @@ __global__ void scale_inplace_kernel(R* __restrict__ g, int64_t n, const R* __re
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) g[i] *= s;
 }
 
-template <typename R> static size_t smem_for(const hidenn_tri_plan* p) {
+template <typename R> [[maybe_unused]] static size_t smem_for(const hidenn_tri_plan* p) {
     return (size_t)p->dev.max_local * 4 * sizeof(R) + (size_t)(p->dev.max_entries + 1) * 4 * sizeof(R) + 128;
 }
 
 static long long* g_tile_timing = nullptr;     // set by hidenn_debug_tile_timing (measurement aid, not thread safe)
-
-// tiles between a CTA and the one it prefetches for: the number of CTAs resident on the chip (one "wave")
-static int prefetch_distance(int minb) {
-    static const int env = [] { const char* e = getenv("HIDENN_TILE_PREFETCH"); return e ? atoi(e) : -1; }();
-    return env >= 0 ? env : 148 * minb;
-}
-
-template <typename R, bool BODY, bool ISO, int MINB>
-static int launch_tile_mb(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed, const R* consts,
-                          int flags, R* gx, R* gu, R* scratch, cudaStream_t stream, size_t smem) {
-    using R2 = typename Real2<R>::type;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_kernel<R, BODY, ISO, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_kernel<R, BODY, ISO, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = smem;
-    }
-    tri_tile_kernel<R, BODY, ISO, MINB><<<p->dev.n_tiles, kTileBlock, smem, stream>>>(
-        p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch,
-        prefetch_distance(MINB), g_tile_timing);
-    return 0;
-}
 
 template <typename R, bool BODY, bool ISO, int MINB, int BLOCK>
 static int launch_tile_persistent_mb(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed,
@@ -695,7 +588,8 @@ static int launch_tile_persistent_mb(const hidenn_tri_plan* p, const R* x_free, 
     static const int n_sm = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
     const int grid = std::min(p->dev.n_tiles, n_sm * MINB);
     tri_tile_persistent_kernel<R, BODY, ISO, MINB, BLOCK><<<grid, BLOCK, smem, stream>>>(
-        p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch);
+        p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch,
+        g_tile_timing);
     return 0;
 }
 
@@ -711,32 +605,23 @@ static int pick_minb(size_t smem, int real_bytes) {
 }
 
 template <typename R> static size_t smem_persistent_for(const hidenn_tri_plan* p) {
-    return (size_t)p->dev.max_local * 8 * sizeof(R) + (size_t)(p->dev.max_entries + 1) * 4 * sizeof(R) + 32 * sizeof(R) + 64;
-}
-
-static bool use_persistent() {
-    static const int env = [] { const char* e = getenv("HIDENN_TILE_PERSISTENT"); return e ? atoi(e) : 1; }();
-    return env != 0;
+    return (size_t)p->dev.max_local * 8 * sizeof(R) + (size_t)(p->dev.max_entries + 1) * 4 * sizeof(R) +
+           (size_t)p->dev.max_owned * 4 * sizeof(R) + 32 * sizeof(R) + 64;
 }
 
 template <typename R, bool BODY, bool ISO>
 static int launch_tile(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed, const R* consts,
                        int flags, R* gx, R* gu, R* scratch, cudaStream_t stream) {
-    if (use_persistent() && !g_tile_timing) {
-        const size_t smem = smem_persistent_for<R>(p);
-        const int mb = pick_minb(smem, (int)sizeof(R));
+    const size_t smem = smem_persistent_for<R>(p);
 #define HIDENN_LAUNCH_P(MB, BL) \
     return launch_tile_persistent_mb<R, BODY, ISO, MB, BL>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem)
-        switch (mb) {      // 384-thread CTAs were measured slower (profiles/README.md) and are not instantiated
-            case 2: HIDENN_LAUNCH_P(2, 256);
-            case 3: HIDENN_LAUNCH_P(3, 256);
-            case 4: HIDENN_LAUNCH_P(4, 256);
-            default: HIDENN_LAUNCH_P(5, 256);
-        }
-#undef HIDENN_LAUNCH_P
+    switch (pick_minb(smem, (int)sizeof(R))) {      // 384- and 128-thread CTAs were measured no faster (profiles/README.md)
+        case 2: HIDENN_LAUNCH_P(2, 256);
+        case 3: HIDENN_LAUNCH_P(3, 256);
+        case 4: HIDENN_LAUNCH_P(4, 256);
+        default: HIDENN_LAUNCH_P(5, 256);
     }
-    // non-persistent variant (A/B runs, per-phase timing aid): one configuration, 3 CTAs per SM
-    return launch_tile_mb<R, BODY, ISO, 3>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem_for<R>(p));
+#undef HIDENN_LAUNCH_P
 }
 
 template <typename R>

@@ -399,14 +399,25 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     const int32_t SL = (max_local + 1) & ~1, SE = (max_elem + 1) & ~1, SO = (max_owned + 3) & ~3;
     // padding slots must stay loadable: row 0 of the fixed buffer if it exists, else row 0 of the free Parameter
     std::vector<int2> t_slots((size_t)n_tiles * SL, make_int2(p->n_fixed_x > 0 ? -1 : 0, p->n_fixed_u > 0 ? -1 : 0));
+    std::vector<uint16_t> t_lid((size_t)n_tiles * SL, (uint16_t)0xFFFF);
     std::vector<unsigned long long> d_pack((size_t)n_tiles * SE, 0ull);
     std::vector<uint32_t> d_off((size_t)n_tiles * SO, 0u);
+    {
+        std::vector<std::pair<int32_t, int32_t>> byid;
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            const TileDesc& d = p->tiles[t];
+            byid.resize(d.n_local);
+            for (int32_t i = 0; i < d.n_local; ++i) byid[i] = {p->t_node[d.node_off + i], i};
+            std::sort(byid.begin(), byid.end());                 // memory order
+            for (int32_t j = 0; j < d.n_local; ++j) {
+                const int32_t n = byid[j].first;
+                t_slots[(size_t)t * SL + j] = make_int2(p->xslot[n], p->uslot[n]);
+                t_lid[(size_t)t * SL + j] = (uint16_t)byid[j].second;
+            }
+        }
+    }
     for (int64_t t = 0; t < n_tiles; ++t) {
         const TileDesc& d = p->tiles[t];
-        for (int32_t i = 0; i < d.n_local; ++i) {
-            const int32_t n = p->t_node[d.node_off + i];
-            t_slots[(size_t)t * SL + i] = make_int2(p->xslot[n], p->uslot[n]);
-        }
         std::copy(p->elem_pack.begin() + d.elem_off, p->elem_pack.begin() + d.elem_off + d.n_elem, d_pack.begin() + (size_t)t * SE);
         std::copy(p->entry_off.begin() + d.off_off, p->entry_off.begin() + d.off_off + d.n_owned, d_off.begin() + (size_t)t * SO);
     }
@@ -456,6 +467,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     int rc = 0;
     rc |= upload(pp, p->tiles, &D.tiles);
     rc |= upload(pp, t_slots, &D.t_slots);
+    rc |= upload(pp, t_lid, &D.t_lid);
     rc |= upload(pp, d_pack, &D.elem_pack);
     rc |= upload(pp, d_off, &D.entry_off);
     D.stride_local = SL; D.stride_elem = SE; D.stride_owned = SO;

@@ -32,7 +32,11 @@ struct TriPlanDev {
     const TileDesc* tiles;
     int32_t n_tiles;
     // fixed-stride tile records (tile t starts at t*stride): every load address depends only on blockIdx
-    const int2* t_slots;                   // [n_tiles, stride_local]: (xslot, uslot) per local node, padded with (-1,-1)
+    // node records are listed in MEMORY order (ascending node id = ascending Parameter row): the staging gathers
+    // and the final gradient stores of a warp then touch consecutive 16-byte pairs; t_lid gives the tile-local id
+    // (shared-memory position; owned nodes < n_owned) of each record
+    const int2* t_slots;                   // [n_tiles, stride_local]: (xslot, uslot), padded with a loadable row
+    const uint16_t* t_lid;                 // [n_tiles, stride_local]: local id, padding = 0xFFFF
     const unsigned long long* elem_pack;   // [n_tiles, stride_elem], padded with 0
     const uint32_t* entry_off;             // [n_tiles, stride_owned]: fold-slot start | count << 16 per owned node
     int32_t stride_local, stride_elem, stride_owned;

@@ -98,8 +98,7 @@ int hidenn_tri_plan_slots(const hidenn_tri_plan* plan, int32_t* xslot_host, int3
 int hidenn_tri_plan_decode(const hidenn_tri_plan* plan, int64_t* out_elem, int64_t* out_nodes, uint8_t* out_owner);
 
 /* Measurement aid: when dev_buf != NULL every tile CTA of later hidenn_tri_energy_* launches records
- * clock64 at {start, after staging, after elements, end}, its SM id, {after fold, after slots arrive} into
- * dev_buf[8*tile + 0..6] (thread 0 of the CTA). */
+ * phase clocks into dev_buf[16*tile ..] (see profiles/phase_timing.py for the layout of the kernel variant in use). */
 int hidenn_debug_tile_timing(long long* dev_buf);
 
 /* Host-side model of the tile kernel's shared-memory passes for the plan's lane assignment:

@@ -1,5 +1,8 @@
-"""Per-phase cycle breakdown of the tile kernel (clock64 inside the kernel, hidenn_debug_tile_timing).
-    python profiles/phase_timing.py [--elems N] [--dtype f64|f32] [--tile-nodes T] [--ordering morton]"""
+"""Per-phase cycle breakdown of the persistent tile kernel (clock64 inside the kernel, hidenn_debug_tile_timing).
+    python profiles/phase_timing.py [--elems N] [--dtype f64|f32] [--tile-nodes T] [--ordering morton]
+Layout per tile (16 int64): thread 0 -> [0..7], thread 255 -> [8..15]:
+  0 tile start (after the barrier), 1 elements done (before barrier), 2 after barrier, 3 fold+stores done, 4 smid,
+  5 after rotate, 6 after cp.async.wait_all, 7 after the closing barrier."""
 import argparse, ctypes as C, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -18,25 +21,23 @@ m, model, loss_fn, _ = bench.make_workload(a, 0, 1, dev, dt, a.ordering, a.elems
 plan = model._plan()
 for _ in range(3):
     model.zero_grad(); loss_fn(model).backward()
-buf = torch.zeros(plan.info["n_tiles"] * 8, dtype=torch.int64, device=dev)
+buf = torch.zeros(plan.info["n_tiles"] * 16, dtype=torch.int64, device=dev)
 L = _lib.lib()
 L.hidenn_debug_tile_timing(C.c_void_p(buf.data_ptr()))
 ms = bench.time_kernel(model, loss_fn, 5, 2)
 L.hidenn_debug_tile_timing(C.c_void_p(0))
 torch.cuda.synchronize()
-t = buf.cpu().numpy().reshape(-1, 8)
-p1, p2, p3 = t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2]
-tot = t[:, 3] - t[:, 0]
-print(f"kernel {ms*1e3:.1f} us, tiles {len(t)}, elems/tile {plan.info['elem_visits']/len(t):.0f}")
-pa, pb, pc, pd = t[:, 6] - t[:, 0], t[:, 1] - t[:, 6], t[:, 5] - t[:, 2], t[:, 3] - t[:, 5]
-for name, v in (("stage (loads->smem)", p1), ("  .. desc+slots arrive", pa), ("  .. gathers+barrier", pb), ("elements", p2), ("fold+store", p3),
-                ("  .. fold loops+stores (thread 0)", pc), ("  .. prefetch+reduce+barrier", pd), ("CTA total", tot)):
-    print(f"  {name:34s} mean {v.mean():8.0f} cyc  p10 {np.percentile(v,10):8.0f}  p50 {np.percentile(v,50):8.0f}  p90 {np.percentile(v,90):8.0f}  ({100*v.mean()/tot.mean():4.1f}%)")
-# concurrency: per SM, sum of CTA lifetimes / wall span
-sm = t[:, 4]
-occ = []
-for s_ in np.unique(sm)[:8]:
-    sel = sm == s_
-    span = t[sel, 3].max() - t[sel, 0].min()
-    occ.append(tot[sel].sum() / span)
-print("  mean resident CTAs per SM (first 8 SMs):", np.round(occ, 2))
+t = buf.cpu().numpy().reshape(-1, 16)
+t = t[(t[:, 7] > 0) & (t[:, 15] > 0)]          # tiles that are not the last of their CTA
+print(f"kernel {ms*1e3:.1f} us, tiles {plan.info['n_tiles']}, elems/tile {plan.info['elem_visits']/plan.info['n_tiles']:.0f}")
+def row(name, v, tot):
+    print(f"  {name:44s} mean {v.mean():8.0f} cyc  p10 {np.percentile(v,10):8.0f}  p50 {np.percentile(v,50):8.0f}  p90 {np.percentile(v,90):8.0f}  ({100*v.mean()/tot:4.1f}%)")
+for w, o in (("warp 0", 0), ("warp 7", 8)):
+    tot = (t[:, o + 7] - t[:, o + 0]).mean()
+    print(f" {w}: per-tile loop {tot:.0f} cycles")
+    row("E: gathers issue + elements", t[:, o + 1] - t[:, o + 0], tot)
+    row("   wait at barrier B2", t[:, o + 2] - t[:, o + 1], tot)
+    row("F: metadata loads + fold + stores", t[:, o + 3] - t[:, o + 2], tot)
+    row("   rotate (waits for the metadata loads)", t[:, o + 5] - t[:, o + 3], tot)
+    row("   cp.async.wait_all", t[:, o + 6] - t[:, o + 5], tot)
+    row("   wait at barrier B1", t[:, o + 7] - t[:, o + 6], tot)
