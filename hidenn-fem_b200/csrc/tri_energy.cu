@@ -98,7 +98,7 @@ template <typename R, bool BODY> __device__ __forceinline__ TriConsts<R> load_co
     return K;
 }
 
-constexpr int kPre = 3;
+
 
 // ---------------------------------------------------------------------------------------------
 // The tile kernel is persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ... and overlaps the

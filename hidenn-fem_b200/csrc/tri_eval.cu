@@ -180,11 +180,15 @@ __global__ void halo_unpack_kernel(typename Real2<R>::type* __restrict__ g, cons
 template <typename R, bool PACK>
 __global__ void halo_all_kernel(typename Real2<R>::type* gx, const int32_t* __restrict__ xrows, const int32_t* __restrict__ xpos, int64_t nx,
                                 typename Real2<R>::type* gu, const int32_t* __restrict__ urows, const int32_t* __restrict__ upos, int64_t nu,
-                                R* loss, int64_t S, R* buf) {
+                                R* loss, int64_t S, R* buf, R* zero_other) {
     using R2 = typename Real2<R>::type;
     R2* bx = reinterpret_cast<R2*>(buf) + 1;
     R2* bu = bx + S;
     const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if (PACK && zero_other) {
+        R2* z = reinterpret_cast<R2*>(zero_other);
+        for (int64_t i = i0; i < 1 + 2 * S; i += stride) z[i] = mk2<R>(R(0), R(0));
+    }
     if (i0 == 0) {
         if (PACK) { buf[0] = *loss; buf[1] = R(0); } else *loss = buf[0];
     }
@@ -200,13 +204,13 @@ __global__ void halo_all_kernel(typename Real2<R>::type* gx, const int32_t* __re
 
 template <typename R, bool PACK>
 static int halo_all(R* gx, const int32_t* xrows, const int32_t* xpos, int64_t nx, R* gu, const int32_t* urows, const int32_t* upos,
-                    int64_t nu, R* loss, int64_t S, R* buf, void* s) {
+                    int64_t nu, R* loss, int64_t S, R* buf, R* zero_other, void* s) {
     using R2 = typename Real2<R>::type;
     HIDENN_REQUIRE(loss && buf, "halo_pack_all/unpack_all: NULL loss or buffer");
     HIDENN_REQUIRE((nx == 0 || !gx || (xrows && xpos)) && (nu == 0 || !gu || (urows && upos)), "halo_pack_all/unpack_all: NULL index arrays");
-    const int64_t n = nx > nu ? nx : nu;
+    const int64_t n = std::max<int64_t>(std::max(nx, nu), zero_other ? 1 + 2 * S : 0);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 8));
-    halo_all_kernel<R, PACK><<<grid, 256, 0, (cudaStream_t)s>>>((R2*)gx, xrows, xpos, nx, (R2*)gu, urows, upos, nu, loss, S, buf);
+    halo_all_kernel<R, PACK><<<grid, 256, 0, (cudaStream_t)s>>>((R2*)gx, xrows, xpos, nx, (R2*)gu, urows, upos, nu, loss, S, buf, zero_other);
     HIDENN_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -335,12 +339,13 @@ using namespace hidenn;
 #define HIDENN_HALO_ALL_API(SUF, T)                                                                                              \
     extern "C" int hidenn_halo_pack_all_##SUF(const T* gx, const int32_t* xr, const int32_t* xp, int64_t nx, const T* gu,          \
                                               const int32_t* ur, const int32_t* up, int64_t nu, const T* loss, int64_t S, T* buf,  \
-                                              void* s) {                                                                          \
-        return halo_all<T, true>(const_cast<T*>(gx), xr, xp, nx, const_cast<T*>(gu), ur, up, nu, const_cast<T*>(loss), S, buf, s); \
+                                              T* zero_other, void* s) {                                                           \
+        return halo_all<T, true>(const_cast<T*>(gx), xr, xp, nx, const_cast<T*>(gu), ur, up, nu, const_cast<T*>(loss), S, buf,     \
+                                 zero_other, s);                                                                                  \
     }                                                                                                                             \
     extern "C" int hidenn_halo_unpack_all_##SUF(T* gx, const int32_t* xr, const int32_t* xp, int64_t nx, T* gu, const int32_t* ur, \
                                                 const int32_t* up, int64_t nu, T* loss, int64_t S, const T* buf, void* s) {        \
-        return halo_all<T, false>(gx, xr, xp, nx, gu, ur, up, nu, loss, S, const_cast<T*>(buf), s);                                \
+        return halo_all<T, false>(gx, xr, xp, nx, gu, ur, up, nu, loss, S, const_cast<T*>(buf), nullptr, s);                                \
     }
 HIDENN_HALO_ALL_API(f64, double)
 HIDENN_HALO_ALL_API(f32, float)

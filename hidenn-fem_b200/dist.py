@@ -131,8 +131,8 @@ class HaloExchange:
     """[loss, shared-node gradients]: one pack kernel, one NCCL all-reduce, one unpack kernel per evaluation.
 
     Message layout  [loss, 0 | gx pairs (S) | gu pairs (S)]  in ascending global node id (same on every rank).
-    `send` keeps zeros at the positions of shared nodes this rank does not hold (or holds as fixed), so the sum
-    over ranks is exactly the sum of the partial gradients."""
+    The message buffer holds zeros at the positions of shared nodes this rank does not hold (or holds as fixed),
+    so the in-place sum over ranks is exactly the sum of the partial gradients."""
 
     def __init__(self, plan: HaloPlan, device, dtype, group=None):
         self.plan = plan
@@ -143,8 +143,9 @@ class HaloExchange:
         self.dtype = dtype
         S = plan.shared_gid.shape[0]
         self.S = S
-        self.send = torch.zeros(2 + 4 * S, device=self.device, dtype=dtype)
-        self.recv = torch.zeros_like(self.send)
+        # two alternating message buffers: the pack kernel of one step clears the buffer of the next step
+        self.bufs = [torch.zeros(2 + 4 * S, device=self.device, dtype=dtype) for _ in range(2)]
+        self.parity = 0
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)
         self.x_rows, self.x_pos = t(plan.x_rows), t(plan.x_pos)
         self.u_rows, self.u_pos = t(plan.u_rows), t(plan.u_pos)
@@ -154,14 +155,15 @@ class HaloExchange:
         s = _lib.stream_ptr()
         dt = self.dtype
         nx, nu = C.c_int64(self.x_rows.numel()), C.c_int64(self.u_rows.numel())
+        buf, other = self.bufs[self.parity], self.bufs[self.parity ^ 1]
+        self.parity ^= 1
         _lib.check(_lib.fn("hidenn_halo_pack_all", dt)(
             _lib.ptr(gx), _lib.ptr(self.x_rows), _lib.ptr(self.x_pos), nx, _lib.ptr(gu), _lib.ptr(self.u_rows), _lib.ptr(self.u_pos), nu,
-            _lib.ptr(out), C.c_int64(self.S), _lib.ptr(self.send), s))
-        self.recv.copy_(self.send)
-        dist.all_reduce(self.recv, op=dist.ReduceOp.SUM, group=self.group)
+            _lib.ptr(out), C.c_int64(self.S), _lib.ptr(buf), _lib.ptr(other), s))
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
         _lib.check(_lib.fn("hidenn_halo_unpack_all", dt)(
             _lib.ptr(gx), _lib.ptr(self.x_rows), _lib.ptr(self.x_pos), nx, _lib.ptr(gu), _lib.ptr(self.u_rows), _lib.ptr(self.u_pos), nu,
-            _lib.ptr(out), C.c_int64(self.S), _lib.ptr(self.recv), s))
+            _lib.ptr(out), C.c_int64(self.S), _lib.ptr(buf), s))
 
 
 class DistributedEnergyLoss2D(EnergyLoss2D):

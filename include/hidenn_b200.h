@@ -220,16 +220,18 @@ int hidenn_halo_unpack_f32(float* g, const int32_t* idx, int64_t n, const float*
 /* One-launch pack / unpack of the whole halo message  buf = [loss, 0 | gx pairs (S) | gu pairs (S)]:
  *   pack:   buf[0] = *loss;  bufx[xpos[i]] = gx[xrows[i]];  bufu[upos[i]] = gu[urows[i]]   (other entries untouched)
  *   unpack: *loss = buf[0];  gx[xrows[i]] = bufx[xpos[i]];  gu[urows[i]] = bufu[upos[i]]
- * gx / gu may be NULL (frozen parameter).  S = number of shared nodes; xpos/upos index pairs. */
+ * gx / gu may be NULL (frozen parameter).  S = number of shared nodes; xpos/upos index pairs.
+ * pack also clears `zero_other` (another message buffer of the same size, or NULL): with two alternating buffers the
+ * in-place all-reduce never needs a separate copy or memset. */
 int hidenn_halo_pack_all_f64(const double* gx, const int32_t* xrows, const int32_t* xpos, int64_t nx,
                              const double* gu, const int32_t* urows, const int32_t* upos, int64_t nu,
-                             const double* loss, int64_t S, double* buf, void* stream);
+                             const double* loss, int64_t S, double* buf, double* zero_other, void* stream);
 int hidenn_halo_unpack_all_f64(double* gx, const int32_t* xrows, const int32_t* xpos, int64_t nx,
                                double* gu, const int32_t* urows, const int32_t* upos, int64_t nu,
                                double* loss, int64_t S, const double* buf, void* stream);
 int hidenn_halo_pack_all_f32(const float* gx, const int32_t* xrows, const int32_t* xpos, int64_t nx,
                              const float* gu, const int32_t* urows, const int32_t* upos, int64_t nu,
-                             const float* loss, int64_t S, float* buf, void* stream);
+                             const float* loss, int64_t S, float* buf, float* zero_other, void* stream);
 int hidenn_halo_unpack_all_f32(float* gx, const int32_t* xrows, const int32_t* xpos, int64_t nx,
                                float* gu, const int32_t* urows, const int32_t* upos, int64_t nu,
                                float* loss, int64_t S, const float* buf, void* stream);
