@@ -385,275 +385,6 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Warp-specialised variant (one 640-thread CTA per SM): three teams work on three different tiles at once,
-//   L (4 warps)  stages tile i+2 (cp.async gathers, records in memory order) and flushes the gradients of tile i,
-//   E (12 warps) computes the elements of tile i+1 .. into partial buffer (i+1)&1,
-//   F (4 warps)  folds tile i from partial buffer i&1 into the output staging buffer,
-// handing buffers over with named barriers (bar.arrive / bar.sync).  Per-tile time is bounded by the slowest team
-// instead of the sum of the phases.  Same arithmetic, same fold order, same results as the persistent kernel.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bar_sync_n(const int id, const int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive_n(const int id, const int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-constexpr int kWsE = 384, kWsF = 192, kWsS = 64, kWsW = 64, kWsBlock = kWsE + kWsF + kWsS + kWsW;     // 22 warps
-constexpr int kWsNodeBufs = 3;
-enum : int { BAR_NODES_FULL = 1, BAR_NODES_FREE = 4, BAR_PART_FULL = 7, BAR_PART_FREE = 9, BAR_OUT_FULL = 11, BAR_OUT_FREE = 13 };
-
-template <typename R, bool BODY, bool ISO>
-__global__ void __launch_bounds__(kWsBlock, 1)
-tri_tile_ws_kernel(const TriPlanDev P, const typename Real2<R>::type* __restrict__ x_free,
-                   const typename Real2<R>::type* __restrict__ x_fixed, const typename Real2<R>::type* __restrict__ u_free,
-                   const typename Real2<R>::type* __restrict__ u_fixed, const R* __restrict__ consts, const int flags,
-                   typename Real2<R>::type* __restrict__ gx_free, typename Real2<R>::type* __restrict__ gu_free,
-                   R* __restrict__ tile_energy) {
-    using R2 = typename Real2<R>::type;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // shared layout: 3 node-record buffers | 2 fold-partial buffers (+ dump slot) | 2 output staging buffers | warp energies
-    R2* s_node = reinterpret_cast<R2*>(smem_raw);
-    const int nb = 2 * P.max_local, np = 2 * (P.max_entries + 1), no = 2 * P.max_owned;       // pairs per buffer
-    R2* s_part = s_node + kWsNodeBufs * nb;
-    R2* s_out = s_part + 2 * np;
-    R* s_red = reinterpret_cast<R*>(s_out + 2 * no);                                          // [2][16]
-    const int tid = threadIdx.x;
-    const int nct = gridDim.x;
-    const int i_count = (P.n_tiles - (int)blockIdx.x + nct - 1) / nct;                        // tiles of this CTA (>= 1)
-    constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
-    constexpr unsigned G = 8u;
-    constexpr int PB = (int)sizeof(R2);
-    constexpr int NN_ALL = kWsE + kWsS, NP_ALL = kWsE + kWsF, NO_ALL = kWsF + kWsW;            // barrier populations
-
-    if (tid < kWsE) {
-        // ------------------------------------------------------------------ E team (12 warps): elements
-        constexpr int NPRE = 2;
-        const int lane = tid & 31, wid = tid >> 5;
-        const TriConsts<R> K = load_consts<R, BODY>(consts);
-        unsigned long long pk[NPRE];
-        int tile = blockIdx.x;
-        {
-            const unsigned long long* __restrict__ packs = P.elem_pack + (size_t)tile * P.stride_elem;
-#pragma unroll
-            for (int k = 0; k < NPRE; ++k) pk[k] = (tid + k * kWsE) < P.stride_elem ? __ldg(packs + tid + k * kWsE) : 0ull;
-        }
-        TileDesc td = P.tiles[tile];
-        int nbuf = 0;
-        for (int i = 0; i < i_count; ++i, tile += nct) {
-            const int b = i & 1;
-            bar_sync_n(BAR_NODES_FULL + nbuf, NN_ALL);
-            if (i >= 2) bar_sync_n(BAR_PART_FREE + b, NP_ALL);
-            unsigned long long pk_n[NPRE] = {0ull, 0ull};
-            TileDesc td_n = td;
-            if (i + 1 < i_count) {
-                const unsigned long long* __restrict__ packs = P.elem_pack + (size_t)(tile + nct) * P.stride_elem;
-#pragma unroll
-                for (int k = 0; k < NPRE; ++k) pk_n[k] = (tid + k * kWsE) < P.stride_elem ? __ldg(packs + tid + k * kWsE) : 0ull;
-                td_n = P.tiles[tile + nct];
-            }
-            const NodeBuf<R> nodes(s_node + nbuf * nb, P.max_local);
-            const PartBuf<R> part(s_part + b * np, P.max_entries + 1);
-            const unsigned dumpv = (unsigned)td.n_entries;
-            R e_acc = R(0);
-            auto do_element = [&](const unsigned long long w) {
-                const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
-                const unsigned l0 = lo & LM, l1 = (lo >> kLidBits) & LM, l2 = (lo >> (2 * kLidBits)) & LM;
-                const unsigned p0 = (unsigned)(w >> (3 * kLidBits)) & PM, p1 = (hi >> (3 * kLidBits + kPosBits - 32)) & PM,
-                               p2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
-                R e;
-                R2 gu[3], gx[3], v0, v1, v2, U0, U1, U2;
-                nodes.load(l0, v0, U0); nodes.load(l1, v1, U1); nodes.load(l2, v2, U2);
-                tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx);
-                e_acc += (hi >> 31) ? e : R(0);
-                if (p0 != dumpv) part.store(p0, gu[0], gx[0]);
-                if (p1 != dumpv) part.store(p1, gu[1], gx[1]);
-                if (p2 != dumpv) part.store(p2, gu[2], gx[2]);
-            };
-#pragma unroll
-            for (int k = 0; k < NPRE; ++k)
-                if (tid + k * kWsE < td.n_elem) do_element(pk[k]);
-            {
-                const unsigned long long* __restrict__ packs = P.elem_pack + (size_t)tile * P.stride_elem;
-                for (int j = tid + NPRE * kWsE; j < td.n_elem; j += kWsE) do_element(__ldg(packs + j));
-            }
-            e_acc = warp_sum(e_acc);
-            if (lane == 0) s_red[b * 16 + wid] = e_acc;
-            __threadfence_block();
-            bar_arrive_n(BAR_PART_FULL + b, NP_ALL);                                    // partials + energies of tile i complete
-            if (i + kWsNodeBufs < i_count) bar_arrive_n(BAR_NODES_FREE + nbuf, NN_ALL);  // node buffer may be restaged
-#pragma unroll
-            for (int k = 0; k < NPRE; ++k) pk[k] = pk_n[k];
-            td = td_n;
-            nbuf = nbuf == kWsNodeBufs - 1 ? 0 : nbuf + 1;
-        }
-    } else if (tid < kWsE + kWsF) {
-        // ------------------------------------------------------------------ F team (6 warps): fold
-        constexpr int NF = 2;                                               // owned nodes per thread held in registers
-        const int ft = tid - kWsE;
-        int tile = blockIdx.x;
-        uint32_t off[NF];
-        {
-            const uint32_t* __restrict__ offs = P.entry_off + (size_t)tile * P.stride_owned;
-#pragma unroll
-            for (int k = 0; k < NF; ++k) off[k] = (ft + k * kWsF) < P.stride_owned ? __ldg(offs + ft + k * kWsF) : 0u;
-        }
-        int n_owned = P.tiles[tile].n_owned;
-        for (int i = 0; i < i_count; ++i, tile += nct) {
-            const int b = i & 1;
-            uint32_t off_n[NF] = {0u, 0u};
-            int n_owned_n = 0;
-            if (i + 1 < i_count) {
-                const uint32_t* __restrict__ offs = P.entry_off + (size_t)(tile + nct) * P.stride_owned;
-#pragma unroll
-                for (int k = 0; k < NF; ++k) off_n[k] = (ft + k * kWsF) < P.stride_owned ? __ldg(offs + ft + k * kWsF) : 0u;
-                n_owned_n = P.tiles[tile + nct].n_owned;
-            }
-            bar_sync_n(BAR_PART_FULL + b, NP_ALL);
-            const PartBuf<R> part(s_part + b * np, P.max_entries + 1);
-            const PartBuf<R> outb(s_out + b * no, P.max_owned);
-            R2 ru[NF], rx[NF];
-            auto fold_node = [&](const uint32_t oc, R2& su, R2& sx) {
-                const unsigned fb = oc & 0xFFFFu, fe = fb + (oc >> 16) * G;
-                R ax = R(0), ay = R(0), bx = R(0), by = R(0);
-                for (unsigned k = fb; k < fe; k += G) {
-                    R2 u, x;
-                    part.load(k, u, x);
-                    ax += u.x; ay += u.y; bx += x.x; by += x.y;
-                }
-                su = mk2<R>(ax, ay); sx = mk2<R>(bx, by);
-            };
-#pragma unroll
-            for (int k = 0; k < NF; ++k)
-                if (ft + k * kWsF < n_owned) fold_node(off[k], ru[k], rx[k]);
-            if (ft == 0) {                                                   // tile energy, warps in fixed order
-                const R* r = s_red + b * 16;
-                R acc = R(0);
-#pragma unroll
-                for (int w = 0; w < kWsE / 32; ++w) acc += r[w];
-                tile_energy[tile] = acc;
-            }
-            if (i >= 2) bar_sync_n(BAR_OUT_FREE + b, NO_ALL);                // staging buffer b was flushed (tile i-2)
-#pragma unroll
-            for (int k = 0; k < NF; ++k)
-                if (ft + k * kWsF < n_owned) outb.store(ft + k * kWsF, ru[k], rx[k]);
-            {
-                const uint32_t* __restrict__ offs = P.entry_off + (size_t)tile * P.stride_owned;
-                for (int l = ft + NF * kWsF; l < n_owned; l += kWsF) {       // tiles with more than 384 owned nodes
-                    R2 su, sx;
-                    fold_node(__ldg(offs + l), su, sx);
-                    outb.store(l, su, sx);
-                }
-            }
-            __threadfence_block();
-            if (i + 2 < i_count) bar_arrive_n(BAR_PART_FREE + b, NP_ALL);    // partial buffer b may be overwritten
-            bar_arrive_n(BAR_OUT_FULL + b, NO_ALL);
-#pragma unroll
-            for (int k = 0; k < NF; ++k) off[k] = off_n[k];
-            n_owned = n_owned_n;
-        }
-    } else {
-        // ------------------------------------------------------------------ S team (2 warps): staging;  W team (2 warps): gradient flush
-        constexpr int NL = 8;                                               // node records per thread held in registers (512 per tile)
-        const bool is_stage = tid < kWsE + kWsF + kWsS;
-        const int lt = is_stage ? tid - kWsE - kWsF : tid - kWsE - kWsF - kWsS;
-        constexpr int TS = 64;
-        auto load_recs = [&](const int t, int2 (&sl)[NL], unsigned (&ld)[NL]) {
-            const int2* __restrict__ src = P.t_slots + (size_t)t * P.stride_local;
-            const uint16_t* __restrict__ lsrc = P.t_lid + (size_t)t * P.stride_local;
-#pragma unroll
-            for (int k = 0; k < NL; ++k) {
-                const int j = lt + k * TS;
-                sl[k] = j < P.stride_local ? __ldg(src + j) : make_int2(0, 0);
-                ld[k] = j < P.stride_local ? (unsigned)__ldg(lsrc + j) : 0xFFFFu;
-            }
-        };
-        if (is_stage) {
-            auto issue_gathers = [&](const int t, const int2 (&sl)[NL], const unsigned (&ld)[NL], R2* buf) {
-                const NodeBuf<R> nbuf(buf, P.max_local);
-#pragma unroll
-                for (int k = 0; k < NL; ++k) {
-                    if (ld[k] != 0xFFFFu) {
-                        cp_async_pair(nbuf.xy_ptr(ld[k]), sl[k].x >= 0 ? (const void*)(x_free + sl[k].x) : (const void*)(x_fixed + (~sl[k].x)), PB);
-                        cp_async_pair(nbuf.uv_ptr(ld[k]), sl[k].y >= 0 ? (const void*)(u_free + sl[k].y) : (const void*)(u_fixed + (~sl[k].y)), PB);
-                    }
-                }
-                const int2* __restrict__ src = P.t_slots + (size_t)t * P.stride_local;
-                const uint16_t* __restrict__ lsrc = P.t_lid + (size_t)t * P.stride_local;
-                for (int j = lt + NL * TS; j < P.stride_local; j += TS) {   // tiles with more than 512 local nodes
-                    const unsigned l2 = __ldg(lsrc + j);
-                    if (l2 == 0xFFFFu) continue;
-                    const int2 s2 = __ldg(src + j);
-                    cp_async_pair(nbuf.xy_ptr(l2), s2.x >= 0 ? (const void*)(x_free + s2.x) : (const void*)(x_fixed + (~s2.x)), PB);
-                    cp_async_pair(nbuf.uv_ptr(l2), s2.y >= 0 ? (const void*)(u_free + s2.y) : (const void*)(u_fixed + (~s2.y)), PB);
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            };
-            // tile j is staged into buffer j % 3 as soon as E released it (tile j-3); its arrival is announced one
-            // iteration later, after the next tile's gathers are already in flight
-            int2 sl[NL], sl_n[NL];
-            unsigned ld[NL], ld_n[NL];
-            int tile = blockIdx.x;
-            load_recs(tile, sl, ld);
-            int nbuf = 0, pbuf = 0;
-            for (int j = 0; j < i_count; ++j, tile += nct) {
-                if (j >= kWsNodeBufs) bar_sync_n(BAR_NODES_FREE + nbuf, NN_ALL);
-                issue_gathers(tile, sl, ld, s_node + nbuf * nb);
-                if (j + 1 < i_count) load_recs(tile + nct, sl_n, ld_n);
-                if (j >= 1) {
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");        // tile j-1 has landed
-                    __threadfence_block();
-                    bar_arrive_n(BAR_NODES_FULL + pbuf, NN_ALL);
-                }
-                pbuf = nbuf;
-                nbuf = nbuf == kWsNodeBufs - 1 ? 0 : nbuf + 1;
-#pragma unroll
-                for (int k = 0; k < NL; ++k) { sl[k] = sl_n[k]; ld[k] = ld_n[k]; }
-            }
-            cp_async_wait_all();
-            __threadfence_block();
-            bar_arrive_n(BAR_NODES_FULL + pbuf, NN_ALL);
-        } else {
-            // flush tile i: records in memory order -> consecutive lanes store consecutive Parameter rows
-            int2 fs[NL], fs_n[NL];
-            unsigned fl[NL], fl_n[NL];
-            int tile = blockIdx.x;
-            load_recs(tile, fs, fl);
-            int n_owned = P.tiles[tile].n_owned;
-            for (int i = 0; i < i_count; ++i, tile += nct) {
-                const int b = i & 1;
-                int n_owned_n = 0;
-                if (i + 1 < i_count) { load_recs(tile + nct, fs_n, fl_n); n_owned_n = P.tiles[tile + nct].n_owned; }
-                bar_sync_n(BAR_OUT_FULL + b, NO_ALL);
-                const PartBuf<R> outb(s_out + b * no, P.max_owned);
-#pragma unroll
-                for (int k = 0; k < NL; ++k) {
-                    if (fl[k] < (unsigned)n_owned) {
-                        R2 gu, gx;
-                        outb.load(fl[k], gu, gx);
-                        if ((flags & HIDENN_NEED_GU) && fs[k].y >= 0) gu_free[fs[k].y] = gu;
-                        if ((flags & HIDENN_NEED_GX) && fs[k].x >= 0) gx_free[fs[k].x] = gx;
-                    }
-                }
-                {
-                    const int2* __restrict__ src = P.t_slots + (size_t)tile * P.stride_local;
-                    const uint16_t* __restrict__ lsrc = P.t_lid + (size_t)tile * P.stride_local;
-                    for (int j = lt + NL * TS; j < P.stride_local; j += TS) {
-                        const unsigned l2 = __ldg(lsrc + j);
-                        if (l2 >= (unsigned)n_owned) continue;
-                        const int2 s2 = __ldg(src + j);
-                        R2 gu, gx;
-                        outb.load(l2, gu, gx);
-                        if ((flags & HIDENN_NEED_GU) && s2.y >= 0) gu_free[s2.y] = gu;
-                        if ((flags & HIDENN_NEED_GX) && s2.x >= 0) gx_free[s2.x] = gx;
-                    }
-                }
-                if (i + 2 < i_count) bar_arrive_n(BAR_OUT_FREE + b, NO_ALL);     // staging buffer b may be rewritten (tile i+2)
-#pragma unroll
-                for (int k = 0; k < NL; ++k) { fs[k] = fs_n[k]; fl[k] = fl_n[k]; }
-                n_owned = n_owned_n;
-            }
-        }
-    }
-}
-
 // Energy-only variant (torch.no_grad() evaluations, e.g. logging): no fold, no gradient traffic.
 template <typename R>
 __global__ void __launch_bounds__(kTileBlock)
@@ -878,35 +609,9 @@ template <typename R> static size_t smem_persistent_for(const hidenn_tri_plan* p
            (size_t)p->dev.max_owned * 4 * sizeof(R) + 32 * sizeof(R) + 64;
 }
 
-template <typename R> static size_t smem_ws_for(const hidenn_tri_plan* p) {
-    return (size_t)kWsNodeBufs * p->dev.max_local * 4 * sizeof(R) +
-           2 * ((size_t)(p->dev.max_entries + 1) * 4 * sizeof(R) + (size_t)p->dev.max_owned * 4 * sizeof(R)) + 32 * sizeof(R) + 64;
-}
-
-template <typename R, bool BODY, bool ISO>
-static int launch_tile_ws(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed, const R* consts,
-                          int flags, R* gx, R* gu, R* scratch, cudaStream_t stream, size_t smem) {
-    using R2 = typename Real2<R>::type;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_ws_kernel<R, BODY, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    static const int n_sm = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
-    const int grid = std::min(p->dev.n_tiles, n_sm);
-    tri_tile_ws_kernel<R, BODY, ISO><<<grid, kWsBlock, smem, stream>>>(
-        p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch);
-    return 0;
-}
-
 template <typename R, bool BODY, bool ISO>
 static int launch_tile(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed, const R* consts,
                        int flags, R* gx, R* gu, R* scratch, cudaStream_t stream) {
-    static const int ws = [] { const char* e = getenv("HIDENN_TILE_WS"); return e ? atoi(e) : 0; }();
-    if (ws && !g_tile_timing) {
-        const size_t smem_ws = smem_ws_for<R>(p);
-        if (smem_ws <= 227 * 1024) return launch_tile_ws<R, BODY, ISO>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem_ws);
-    }
     const size_t smem = smem_persistent_for<R>(p);
 #define HIDENN_LAUNCH_P(MB, BL) \
     return launch_tile_persistent_mb<R, BODY, ISO, MB, BL>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem)
