@@ -36,6 +36,12 @@ __device__ __forceinline__ double fast_rcp(double x) {
 __device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
 
 // BODY: a body force table is present (Fb != 0).  ISO: C has the plane-stress form c02 = c12 = 0.
+//
+// Division-free chain: with adj = [[d,-b],[-c,a]] (J^-1 = adj/det) every quantity is a numerator times a power of
+// 1/det:  G = Gt/det,  eps = et/det,  sigma = st/det,  psi = pt/det^2,  |det| W psi = k1 pt  with k1 = W/|det|,
+// |det| W P J^-1 = k1 Mt,  and  dE/dJ = k2 (pt adj' - Mt^T Gt)  with k2 = k1/det.  The reciprocal (MUFU seed + 2
+// Newton steps, 7 dependent operations) is needed only for the three final scalings, so it overlaps the ~40
+// numerator operations instead of heading the dependency chain; the FP64 count drops from ~85 to ~68 per element.
 template <typename R, bool BODY, bool ISO>
 __device__ __forceinline__ void tri_element(const typename Real2<R>::type v0, const typename Real2<R>::type v1,
                                             const typename Real2<R>::type v2, const typename Real2<R>::type U0,
@@ -45,10 +51,10 @@ __device__ __forceinline__ void tri_element(const typename Real2<R>::type v0, co
     const R a = v0.x - v2.x, b = v1.x - v2.x, c = v0.y - v2.y, d = v1.y - v2.y;
     const R det = a * d - b * c;
     const R inv = fast_rcp(det);
-    const R j00 = d * inv, j01 = -b * inv, j10 = -c * inv, j11 = a * inv;     // J^-1 (reference uses J^-1, not J^-T)
     const R p0 = U0.x - U2.x, p1 = U1.x - U2.x, q0 = U0.y - U2.y, q1 = U1.y - U2.y;
-    const R G00 = p0 * j00 + p1 * j01, G01 = p0 * j10 + p1 * j11;
-    const R G10 = q0 * j00 + q1 * j01, G11 = q0 * j10 + q1 * j11;
+    // Gt = dU . adj^T   (the reference's J^-1 quirk: G = dU . J^-T)
+    const R G00 = p0 * d - p1 * b, G01 = p1 * a - p0 * c;
+    const R G10 = q0 * d - q1 * b, G11 = q1 * a - q0 * c;
     const R e0 = G00, e1 = G11, e2 = G01 + G10;
     R s0, s1, s2;
     if (ISO) {
@@ -60,29 +66,32 @@ __device__ __forceinline__ void tri_element(const typename Real2<R>::type v0, co
         s1 = K.c01 * e0 + K.c11 * e1 + K.c12 * e2;
         s2 = K.c02 * e0 + K.c12 * e1 + K.c22 * e2;
     }
-    const R psi = R(0.5) * (e0 * s0 + e1 * s1 + e2 * s2);
-    R dens = K.W * psi;
-    if (BODY) dens -= U0.x * K.fb[0] + U0.y * K.fb[1] + U1.x * K.fb[2] + U1.y * K.fb[3] + U2.x * K.fb[4] + U2.y * K.fb[5];
-    const R A = fabs(det);
-    energy = A * dens;
-    const R AW = A * K.W;
-    // M = AW * P * Jinv  (P = d psi / d G = [[s0,s2],[s2,s1]])
-    const R t0 = AW * s0, t1 = AW * s1, t2 = AW * s2;
-    const R M00 = t0 * j00 + t2 * j10, M01 = t0 * j01 + t2 * j11;
-    const R M10 = t2 * j00 + t1 * j10, M11 = t2 * j01 + t1 * j11;
+    const R pt = R(0.5) * (e0 * s0 + e1 * s1 + e2 * s2);
+    // Mt = St . adj   (St = [[s0,s2],[s2,s1]])
+    const R M00 = s0 * d - s2 * c, M01 = s2 * a - s0 * b;
+    const R M10 = s2 * d - s1 * c, M11 = s1 * a - s2 * b;
+    // Nt = pt adj' - Mt^T Gt
+    const R N00 = pt * d - (M00 * G00 + M10 * G10), N01 = -(pt * c) - (M00 * G01 + M10 * G11);
+    const R N10 = -(pt * b) - (M01 * G00 + M11 * G10), N11 = pt * a - (M01 * G01 + M11 * G11);
+    const R k1 = K.W * fabs(inv);
+    const R k2 = k1 * inv;
+    energy = k1 * pt;
+    R g00 = k1 * M00, g10 = k1 * M10, g01 = k1 * M01, g11 = k1 * M11;
+    R D00 = k2 * N00, D01 = k2 * N01, D10 = k2 * N10, D11 = k2 * N11;
     if (BODY) {
-        gu[0] = mk2<R>(M00 - A * K.fb[0], M10 - A * K.fb[1]);
-        gu[1] = mk2<R>(M01 - A * K.fb[2], M11 - A * K.fb[3]);
-        gu[2] = mk2<R>(-(M00 + M01) - A * K.fb[4], -(M10 + M11) - A * K.fb[5]);
+        const R A = fabs(det);
+        const R bw = U0.x * K.fb[0] + U0.y * K.fb[1] + U1.x * K.fb[2] + U1.y * K.fb[3] + U2.x * K.fb[4] + U2.y * K.fb[5];
+        energy -= A * bw;
+        const R sb = det < R(0) ? bw : -bw;            // d(-|det| bw)/dJ = -sign(det) bw adj'
+        D00 += sb * d; D01 -= sb * c; D10 -= sb * b; D11 += sb * a;
+        gu[0] = mk2<R>(g00 - A * K.fb[0], g10 - A * K.fb[1]);
+        gu[1] = mk2<R>(g01 - A * K.fb[2], g11 - A * K.fb[3]);
+        gu[2] = mk2<R>(-(g00 + g01) - A * K.fb[4], -(g10 + g11) - A * K.fb[5]);
     } else {
-        gu[0] = mk2<R>(M00, M10);
-        gu[1] = mk2<R>(M01, M11);
-        gu[2] = mk2<R>(-(M00 + M01), -(M10 + M11));
+        gu[0] = mk2<R>(g00, g10);
+        gu[1] = mk2<R>(g01, g11);
+        gu[2] = mk2<R>(-(g00 + g01), -(g10 + g11));
     }
-    // dE/dJ = s*adj(J)^T-like term * dens  -  M^T G
-    const R sd = det < R(0) ? -dens : dens;
-    const R D00 = sd * d - (M00 * G00 + M10 * G10), D01 = -sd * c - (M00 * G01 + M10 * G11);
-    const R D10 = -sd * b - (M01 * G00 + M11 * G10), D11 = sd * a - (M01 * G01 + M11 * G11);
     gx[0] = mk2<R>(D00, D10);
     gx[1] = mk2<R>(D01, D11);
     gx[2] = mk2<R>(-(D00 + D01), -(D10 + D11));
