@@ -195,7 +195,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     HIDENN_REQUIRE(Ne >= 0 && Nn > 0 && Nn < (int64_t)2147483000 && Ne < (int64_t)500000000, "plan_create: sizes out of range");
     HIDENN_REQUIRE(real_bytes == 8 || real_bytes == 4, "plan_create: real_bytes must be 8 or 4");
     HIDENN_REQUIRE(Ned == 0 || edges != nullptr, "plan_create: edges NULL");
-    if (tile_nodes <= 0) tile_nodes = 288;
+    if (tile_nodes <= 0) tile_nodes = 330;      // largest tile whose fold slots fit the 11-bit position fields at valence ~6
     HIDENN_REQUIRE(tile_nodes >= 8 && tile_nodes <= 2048, "plan_create: tile_nodes must be in [8,2048]");
 
     for (int64_t i = 0; i < 3 * Ne; ++i)
