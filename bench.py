@@ -251,7 +251,18 @@ def time_e2e(model, loss_fn, steps, warmup):
     for _ in range(n):
         call()          # synchronous: returns when loss and gradients are in host memory
     t = (time.perf_counter() - t0) / n
-    return t * 1e3, h2d, d2h, float(out[0])
+    loss = float(out[0])
+    # same call with the three-stream pipeline switched off (copies and kernels back to back), for comparison
+    os.environ["HIDENN_HOST_CHUNKS"] = "1"
+    try:
+        call()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            call()
+        t_serial = (time.perf_counter() - t0) / 3
+    finally:
+        del os.environ["HIDENN_HOST_CHUNKS"]
+    return t * 1e3, h2d, d2h, loss, t_serial * 1e3
 
 
 def time_loop(step, steps, warmup):
@@ -315,7 +326,7 @@ def bench_grid_paths(device, steps, warmup, peak, full_c3=False):
     out["C3_structured_l2_%dx%d_nodes_%d_samples_f64" % (Ng, Ng, M)] = {
         "ms_per_step": ms, "evals_per_s": M / (ms * 1e-3),
         "hbm_frac_informational": (3 * 8 * M + 2 * 8 * Ng * Ng) / (ms * 1e-3) / 1e9 / peak,
-        "note": "generic differentiable forward + deterministic sort-based fold (torch.sort dominates)"}
+        "note": "shared-memory-staged lookup forward + sort-free deterministic binning + fused cell fold backward"}
     return out
 
 
@@ -439,9 +450,10 @@ def main():
 
     e2e = None
     if not args.no_e2e and world == 1:
-        ms_e2e, h2d, d2h, l_e2e = time_e2e(model, loss_fn, args.steps, args.warmup)
+        ms_e2e, h2d, d2h, l_e2e, ms_serial = time_e2e(model, loss_fn, args.steps, args.warmup)
         e2e = {"value": ne_local * NG / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": ms_e2e, "api": "hidenn_tri_energy_host_%s (pinned host buffers)" % args.dtype,
+               "ms_per_step": ms_e2e, "ms_per_step_unpipelined": ms_serial,
+               "api": "hidenn_tri_energy_host_%s (pinned host buffers; rows in / tiles / gradient rows out overlapped on 3 streams)" % args.dtype,
                "loss_matches_resident": bool(abs(l_e2e - loss_val) <= 1e-9 * abs(loss_val))}
     elif world > 1:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,

@@ -2,6 +2,7 @@
 // the deterministic cell / node / grid-line folds.  Reference: /root/reference/src/models.py:180-212.
 #include "../../include/hidenn_b200_grid.h"
 #include "common.cuh"
+#include <algorithm>
 
 namespace hidenn {
 
@@ -14,6 +15,44 @@ template <typename R> __device__ __forceinline__ int lookup_line(const R* __rest
     int64_t e = lo - 1;
     e = e < 0 ? 0 : (e > N - 2 ? N - 2 : e);
     return (int)e;
+}
+
+template <typename R> __device__ __forceinline__ int lookup_line_smem(const R* grid, int N, R x) {
+    int lo = 0, hi = N;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (grid[mid] < x) lo = mid + 1; else hi = mid;
+    }
+    const int e = lo - 1;
+    return e < 0 ? 0 : (e > N - 2 ? N - 2 : e);
+}
+
+// both grid lines staged in shared memory (used when they fit): the two binary searches then cost LDS latency only
+template <typename R>
+__global__ void __launch_bounds__(256)
+q1_fwd_smem_kernel(const R* __restrict__ gx, int Nx, const R* __restrict__ gy, int Ny, const R* __restrict__ uf,
+                   const typename Real2<R>::type* __restrict__ x, int64_t M, R* __restrict__ u, int32_t* __restrict__ ixo,
+                   int32_t* __restrict__ iyo) {
+    extern __shared__ __align__(16) unsigned char q1_smem[];
+    R* sx = reinterpret_cast<R*>(q1_smem);
+    R* sy = sx + Nx;
+    for (int i = threadIdx.x; i < Nx; i += 256) sx[i] = gx[i];
+    for (int i = threadIdx.x; i < Ny; i += 256) sy[i] = gy[i];
+    __syncthreads();
+    for (int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x; m < M; m += (int64_t)gridDim.x * 256) {
+        const typename Real2<R>::type p = x[m];
+        const int ix = lookup_line_smem<R>(sx, Nx, p.x), iy = lookup_line_smem<R>(sy, Ny, p.y);
+        const R u00 = __ldg(uf + (int64_t)ix * Ny + iy), u10 = __ldg(uf + (int64_t)(ix + 1) * Ny + iy);
+        const R u01 = __ldg(uf + (int64_t)ix * Ny + iy + 1), u11 = __ldg(uf + (int64_t)(ix + 1) * Ny + iy + 1);
+        const R x0 = sx[ix], x1 = sx[ix + 1], y0 = sy[iy], y1 = sy[iy + 1];
+        R hx = x1 - x0, hy = y1 - y0;
+        hx = hx < R(1e-10) ? R(1e-10) : hx;
+        hy = hy < R(1e-10) ? R(1e-10) : hy;
+        const R N1x = (x1 - p.x) / hx, N2x = (p.x - x0) / hx, N1y = (y1 - p.y) / hy, N2y = (p.y - y0) / hy;
+        u[m] = N1x * N1y * u00 + N2x * N1y * u10 + N1x * N2y * u01 + N2x * N2y * u11;
+        if (ixo) ixo[m] = ix;
+        if (iyo) iyo[m] = iy;
+    }
 }
 
 template <typename R>
@@ -37,6 +76,84 @@ q1_fwd_kernel(const R* __restrict__ gx, int64_t Nx, const R* __restrict__ gy, in
     }
 }
 
+// VJP pieces of one sample in cell (ix,iy): o[0..3] = d u00,u10,u01,u11; o[4..5] = d gx_i, gx_{i+1}; o[6..7] = d gy_j, gy_{j+1}
+template <typename R>
+__device__ __forceinline__ void q1_row(const R x0, const R x1, const R y0, const R y1, const R u00, const R u10, const R u01,
+                                       const R u11, const typename Real2<R>::type p, const R rv, R (&o)[8]) {
+    const R hxr = x1 - x0, hyr = y1 - y0;
+    const bool ax = hxr >= R(1e-10), ay = hyr >= R(1e-10);
+    const R ihx = R(1) / (ax ? hxr : R(1e-10)), ihy = R(1) / (ay ? hyr : R(1e-10));
+    const R N1x = (x1 - p.x) * ihx, N2x = (p.x - x0) * ihx, N1y = (y1 - p.y) * ihy, N2y = (p.y - y0) * ihy;
+    o[0] = rv * N1x * N1y; o[1] = rv * N2x * N1y; o[2] = rv * N1x * N2y; o[3] = rv * N2x * N2y;
+    const R A = N1y * u00 + N2y * u01, B = N1y * u10 + N2y * u11;
+    const R numx = A * (x1 - p.x) + B * (p.x - x0);
+    const R qx = ax ? numx * ihx * ihx : R(0);
+    o[4] = rv * (-B * ihx + qx);
+    o[5] = rv * (A * ihx - qx);
+    const R Cc = N1x * u00 + N2x * u10, D = N1x * u01 + N2x * u11;
+    const R numy = Cc * (y1 - p.y) + D * (p.y - y0);
+    const R qy = ay ? numy * ihy * ihy : R(0);
+    o[6] = rv * (-D * ihy + qy);
+    o[7] = rv * (Cc * ihy - qy);
+}
+
+__global__ void __launch_bounds__(256) q1_bin_count_kernel(const int32_t* __restrict__ ix, const int32_t* __restrict__ iy, int64_t M,
+                                                            int64_t cy, int32_t* __restrict__ cnt) {
+    for (int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x; m < M; m += (int64_t)gridDim.x * 256)
+        atomicAdd(cnt + (int64_t)ix[m] * cy + iy[m], 1);
+}
+
+__global__ void __launch_bounds__(256) q1_bin_scatter_kernel(const int32_t* __restrict__ ix, const int32_t* __restrict__ iy, int64_t M,
+                                                              int64_t cy, const int32_t* __restrict__ seg, int32_t* __restrict__ cursor,
+                                                              int32_t* __restrict__ order) {
+    for (int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x; m < M; m += (int64_t)gridDim.x * 256) {
+        const int64_t c = (int64_t)ix[m] * cy + iy[m];
+        order[seg[c] + atomicAdd(cursor + c, 1)] = (int32_t)m;
+    }
+}
+
+// canonical order inside every cell: ascending sample id (insertion sort; cells hold a handful of samples)
+__global__ void __launch_bounds__(256) q1_bin_sort_kernel(int64_t ncell, const int32_t* __restrict__ seg, int32_t* __restrict__ order) {
+    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < ncell; c += (int64_t)gridDim.x * 256) {
+        const int32_t b = seg[c], e = seg[c + 1];
+        for (int32_t i = b + 1; i < e; ++i) {
+            const int32_t v = order[i];
+            int32_t j = i - 1;
+            while (j >= b && order[j] > v) { order[j + 1] = order[j]; --j; }
+            order[j + 1] = v;
+        }
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+q1_fused_cells_kernel(const R* __restrict__ gx, const R* __restrict__ gy, int64_t Nx, int64_t Ny, const R* __restrict__ uf,
+                      const typename Real2<R>::type* __restrict__ x, const R* __restrict__ r, const int32_t* __restrict__ seg,
+                      const int32_t* __restrict__ order, R* __restrict__ cell_tmp) {
+    const int64_t cy = Ny - 1, ncell = (Nx - 1) * cy;
+    for (int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x; c < ncell; c += (int64_t)gridDim.x * 256) {
+        R a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = R(0);
+        const int32_t b = seg[c], e = seg[c + 1];
+        if (e > b) {
+            const int64_t i = c / cy, j = c % cy;
+            const R x0 = __ldg(gx + i), x1 = __ldg(gx + i + 1), y0 = __ldg(gy + j), y1 = __ldg(gy + j + 1);
+            const R u00 = __ldg(uf + i * Ny + j), u10 = __ldg(uf + (i + 1) * Ny + j);
+            const R u01 = __ldg(uf + i * Ny + j + 1), u11 = __ldg(uf + (i + 1) * Ny + j + 1);
+            for (int32_t q = b; q < e; ++q) {
+                const int32_t m = order[q];
+                R o[8];
+                q1_row<R>(x0, x1, y0, y1, u00, u10, u01, u11, x[m], r[m], o);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] += o[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cell_tmp[8 * c + k] = a[k];
+    }
+}
+
 template <typename R>
 __global__ void __launch_bounds__(256)
 q1_bwd_kernel(const R* __restrict__ gx, const R* __restrict__ gy, int64_t Ny, const R* __restrict__ uf,
@@ -46,25 +163,12 @@ q1_bwd_kernel(const R* __restrict__ gx, const R* __restrict__ gy, int64_t Ny, co
         const typename Real2<R>::type p = x[m];
         const int ix = ixs[m], iy = iys[m];
         const R x0 = __ldg(gx + ix), x1 = __ldg(gx + ix + 1), y0 = __ldg(gy + iy), y1 = __ldg(gy + iy + 1);
-        const R hxr = x1 - x0, hyr = y1 - y0;
-        const bool ax = hxr >= R(1e-10), ay = hyr >= R(1e-10);
-        const R ihx = R(1) / (ax ? hxr : R(1e-10)), ihy = R(1) / (ay ? hyr : R(1e-10));
-        const R N1x = (x1 - p.x) * ihx, N2x = (p.x - x0) * ihx, N1y = (y1 - p.y) * ihy, N2y = (p.y - y0) * ihy;
         const R u00 = __ldg(uf + (int64_t)ix * Ny + iy), u10 = __ldg(uf + (int64_t)(ix + 1) * Ny + iy);
         const R u01 = __ldg(uf + (int64_t)ix * Ny + iy + 1), u11 = __ldg(uf + (int64_t)(ix + 1) * Ny + iy + 1);
-        const R rv = r[m];
-        R* o = rows + 8 * m;
-        o[0] = rv * N1x * N1y; o[1] = rv * N2x * N1y; o[2] = rv * N1x * N2y; o[3] = rv * N2x * N2y;
-        const R A = N1y * u00 + N2y * u01, B = N1y * u10 + N2y * u11;       // u = A N1x + B N2x
-        const R numx = A * (x1 - p.x) + B * (p.x - x0);
-        const R qx = ax ? numx * ihx * ihx : R(0);
-        o[4] = rv * (-B * ihx + qx);
-        o[5] = rv * (A * ihx - qx);
-        const R Cc = N1x * u00 + N2x * u10, D = N1x * u01 + N2x * u11;      // u = C N1y + D N2y
-        const R numy = Cc * (y1 - p.y) + D * (p.y - y0);
-        const R qy = ay ? numy * ihy * ihy : R(0);
-        o[6] = rv * (-D * ihy + qy);
-        o[7] = rv * (Cc * ihy - qy);
+        R o[8];
+        q1_row<R>(x0, x1, y0, y1, u00, u10, u01, u11, p, r[m], o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rows[8 * m + k] = o[k];
     }
 }
 
@@ -135,7 +239,20 @@ static int q1_fwd(const R* gx, int64_t Nx, const R* gy, int64_t Ny, const R* uf,
     HIDENN_REQUIRE(Nx >= 2 && Ny >= 2, "q1_interp_fwd: both grids need at least 2 nodes");
     if (M <= 0) return 0;
     HIDENN_REQUIRE(gx && gy && uf && x && u, "q1_interp_fwd: NULL");
-    q1_fwd_kernel<R><<<grid_for(M), 256, 0, (cudaStream_t)s>>>(gx, Nx, gy, Ny, uf, (const typename Real2<R>::type*)x, M, u, ix, iy);
+    const size_t lines = (size_t)(Nx + Ny) * sizeof(R);
+    if (lines <= 100 * 1024 && M >= 65536) {
+        // persistent-ish grid: every CTA stages the lines once and strides over the samples
+        HIDENN_CUDA_OK(cudaFuncSetAttribute(q1_fwd_smem_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (lines + 1024)));
+        const int64_t want = (M + 255) / 256;
+        const int grid = (int)std::min<int64_t>(want, (int64_t)sms * per_sm);
+        q1_fwd_smem_kernel<R><<<grid, 256, lines, (cudaStream_t)s>>>(gx, (int)Nx, gy, (int)Ny, uf, (const typename Real2<R>::type*)x, M, u, ix, iy);
+    } else {
+        q1_fwd_kernel<R><<<grid_for(M), 256, 0, (cudaStream_t)s>>>(gx, Nx, gy, Ny, uf, (const typename Real2<R>::type*)x, M, u, ix, iy);
+    }
     HIDENN_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -163,9 +280,51 @@ static int q1_fold(const R* rows, const int64_t* order, const int64_t* seg, int6
     return 0;
 }
 
+template <typename R>
+static int q1_bwd_fused(const R* gx, int64_t Nx, const R* gy, int64_t Ny, const R* uf, const R* x, const R* r, int64_t M, const int32_t* seg,
+                        const int32_t* order, R* cell_tmp, R* du, R* dgx, R* dgy, void* s) {
+    HIDENN_REQUIRE(Nx >= 2 && Ny >= 2 && gx && gy && uf && seg && cell_tmp && du && dgx && dgy, "q1_bwd_fused: bad arguments");
+    HIDENN_REQUIRE(M == 0 || (x && r && order), "q1_bwd_fused: NULL sample arrays");
+    cudaStream_t st = (cudaStream_t)s;
+    const int64_t ncell = (Nx - 1) * (Ny - 1);
+    q1_fused_cells_kernel<R><<<grid_for(ncell), 256, 0, st>>>(gx, gy, Nx, Ny, uf, (const typename Real2<R>::type*)x, r, seg, order, cell_tmp);
+    q1_fold_nodes_kernel<R><<<grid_for(Nx * Ny), 256, 0, st>>>(cell_tmp, Nx, Ny, du);
+    q1_fold_lines_kernel<R><<<(int)(Nx + Ny), 256, 0, st>>>(cell_tmp, Nx, Ny, dgx, dgy);
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace hidenn
 
 using namespace hidenn;
+
+extern "C" int hidenn_q1_bin_count(const int32_t* ix, const int32_t* iy, int64_t M, int64_t Ny, int32_t* cnt, void* s) {
+    if (M <= 0) return 0;
+    HIDENN_REQUIRE(ix && iy && cnt && Ny >= 2, "q1_bin_count: bad arguments");
+    q1_bin_count_kernel<<<grid_for(M), 256, 0, (cudaStream_t)s>>>(ix, iy, M, Ny - 1, cnt);
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" int hidenn_q1_bin_scatter(const int32_t* ix, const int32_t* iy, int64_t M, int64_t Nx, int64_t Ny, const int32_t* seg,
+                                     int32_t* cursor, int32_t* order, void* s) {
+    HIDENN_REQUIRE(Nx >= 2 && Ny >= 2 && seg, "q1_bin_scatter: bad arguments");
+    if (M <= 0) return 0;
+    HIDENN_REQUIRE(ix && iy && cursor && order, "q1_bin_scatter: NULL");
+    q1_bin_scatter_kernel<<<grid_for(M), 256, 0, (cudaStream_t)s>>>(ix, iy, M, Ny - 1, seg, cursor, order);
+    q1_bin_sort_kernel<<<grid_for((Nx - 1) * (Ny - 1)), 256, 0, (cudaStream_t)s>>>((Nx - 1) * (Ny - 1), seg, order);
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+extern "C" int hidenn_q1_bwd_fused_f64(const double* gx, int64_t Nx, const double* gy, int64_t Ny, const double* uf, const double* x,
+                                       const double* r, int64_t M, const int32_t* seg, const int32_t* order, double* tmp, double* du,
+                                       double* dgx, double* dgy, void* s) {
+    return q1_bwd_fused<double>(gx, Nx, gy, Ny, uf, x, r, M, seg, order, tmp, du, dgx, dgy, s);
+}
+extern "C" int hidenn_q1_bwd_fused_f32(const float* gx, int64_t Nx, const float* gy, int64_t Ny, const float* uf, const float* x,
+                                       const float* r, int64_t M, const int32_t* seg, const int32_t* order, float* tmp, float* du,
+                                       float* dgx, float* dgy, void* s) {
+    return q1_bwd_fused<float>(gx, Nx, gy, Ny, uf, x, r, M, seg, order, tmp, du, dgx, dgy, s);
+}
 
 #define HIDENN_Q1_API(SUF, T)                                                                                                       \
     extern "C" int hidenn_q1_interp_fwd_##SUF(const T* gx, int64_t Nx, const T* gy, int64_t Ny, const T* uf, const T* x, int64_t M,  \

@@ -181,7 +181,7 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
     R* s_red = reinterpret_cast<R*>(s_node + 2 * nb + 2 * (P.max_entries + 1) + 2 * P.max_owned);      // [2][16]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nct = gridDim.x;
-    int tile = blockIdx.x;
+    int tile = P.tile_begin + blockIdx.x;
     if (tile >= P.n_tiles) return;
     constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
     constexpr unsigned G = 8u;
@@ -488,7 +488,7 @@ tri_edge_finalize_kernel(const TriPlanDev P, const typename Real2<R>::type* __re
                          const R* __restrict__ t_table, const int flags, const R* __restrict__ tile_energy,
                          R* __restrict__ out, typename Real2<R>::type* __restrict__ gx_free,
                          typename Real2<R>::type* __restrict__ gu_free, R* __restrict__ gt_out, double* __restrict__ part,
-                         unsigned* __restrict__ ticket) {
+                         unsigned* __restrict__ ticket, typename Real2<R>::type* __restrict__ en_final) {
     using R2 = typename Real2<R>::type;
     __shared__ double s_red[kEdgeBlock / 32];
     __shared__ unsigned s_last;
@@ -531,8 +531,15 @@ tri_edge_finalize_kernel(const TriPlanDev P, const typename Real2<R>::type* __re
                     gxx += sg * E.dir.x; gxy += sg * E.dir.y;
                 }
                 const int xs = P.en_xslot[k], us = P.en_uslot[k];
-                if ((flags & HIDENN_NEED_GU) && us >= 0) { R2 g = gu_free[us]; g.x += gux; g.y += guy; gu_free[us] = g; }
-                if ((flags & HIDENN_NEED_GX) && xs >= 0) { R2 g = gx_free[xs]; g.x += gxx; g.y += gxy; gx_free[xs] = g; }
+                // en_final (host-buffer pipeline): final rows of the edge nodes, compact, so the host can patch them in
+                if ((flags & HIDENN_NEED_GU) && us >= 0) {
+                    R2 g = gu_free[us]; g.x += gux; g.y += guy; gu_free[us] = g;
+                    if (en_final) en_final[k] = g;
+                }
+                if ((flags & HIDENN_NEED_GX) && xs >= 0) {
+                    R2 g = gx_free[xs]; g.x += gxx; g.y += gxy; gx_free[xs] = g;
+                    if (en_final) en_final[P.n_enodes + k] = g;
+                }
             }
         }
     }
@@ -586,7 +593,8 @@ static long long* g_tile_timing = nullptr;     // set by hidenn_debug_tile_timin
 
 template <typename R, bool BODY, bool ISO, int MINB, int BLOCK>
 static int launch_tile_persistent_mb(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed,
-                                     const R* consts, int flags, R* gx, R* gu, R* scratch, cudaStream_t stream, size_t smem) {
+                                     const R* consts, int flags, R* gx, R* gu, R* scratch, cudaStream_t stream, size_t smem,
+                                     int tile_begin, int tile_end) {
     using R2 = typename Real2<R>::type;
     static thread_local size_t configured = 0;
     if (smem > configured) {
@@ -595,9 +603,12 @@ static int launch_tile_persistent_mb(const hidenn_tri_plan* p, const R* x_free, 
         configured = smem;
     }
     static const int n_sm = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
-    const int grid = std::min(p->dev.n_tiles, n_sm * MINB);
+    TriPlanDev P = p->dev;
+    P.tile_begin = tile_begin;
+    P.n_tiles = tile_end;
+    const int grid = std::min(tile_end - tile_begin, n_sm * MINB);
     tri_tile_persistent_kernel<R, BODY, ISO, MINB, BLOCK><<<grid, BLOCK, smem, stream>>>(
-        p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch,
+        P, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch,
         g_tile_timing);
     return 0;
 }
@@ -620,10 +631,11 @@ template <typename R> static size_t smem_persistent_for(const hidenn_tri_plan* p
 
 template <typename R, bool BODY, bool ISO>
 static int launch_tile(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed, const R* consts,
-                       int flags, R* gx, R* gu, R* scratch, cudaStream_t stream) {
+                       int flags, R* gx, R* gu, R* scratch, cudaStream_t stream, int tile_begin, int tile_end) {
     const size_t smem = smem_persistent_for<R>(p);
 #define HIDENN_LAUNCH_P(MB, BL) \
-    return launch_tile_persistent_mb<R, BODY, ISO, MB, BL>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem)
+    return launch_tile_persistent_mb<R, BODY, ISO, MB, BL>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, smem, \
+                                                           tile_begin, tile_end)
     switch (pick_minb(smem, (int)sizeof(R))) {      // 384- and 128-thread CTAs were measured no faster (profiles/README.md)
         case 2: HIDENN_LAUNCH_P(2, 256);
         case 3: HIDENN_LAUNCH_P(3, 256);
@@ -633,10 +645,13 @@ static int launch_tile(const hidenn_tri_plan* p, const R* x_free, const R* x_fix
 #undef HIDENN_LAUNCH_P
 }
 
+// kFinalizeOnly (internal): skip the tile kernels (the host-buffer pipeline has launched them range by range)
+constexpr int kFinalizeOnly = 1 << 30;
+
 template <typename R>
 static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed,
                              const R* consts, const R* t_table, int flags, R* out, R* gx, R* gu, R* gt, R* scratch,
-                             void* stream_v) {
+                             void* stream_v, int tile_begin = 0, int tile_end = -1, R* en_final = nullptr) {
     using R2 = typename Real2<R>::type;
     HIDENN_REQUIRE(p != nullptr, "tri_energy: plan is NULL");
     HIDENN_REQUIRE(p->device >= 0, "tri_energy: host-only plan (device=-1) cannot run kernels; there is no CPU fallback");
@@ -647,14 +662,17 @@ static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R*
     HIDENN_REQUIRE(!(flags & HIDENN_NEED_GU) || gu, "tri_energy: gu_free NULL");
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     const bool grad = flags & (HIDENN_NEED_GX | HIDENN_NEED_GU);
-    if (p->dev.n_tiles > 0) {
+    if (tile_end < 0) tile_end = p->dev.n_tiles;
+    if (tile_end > tile_begin && !(flags & kFinalizeOnly)) {
         if (grad) {
             const bool body = !(flags & HIDENN_HINT_NO_BODY_FORCE), iso = (flags & HIDENN_HINT_C_PLANE_STRESS) != 0;
             int rc;
-            if (body && iso) rc = launch_tile<R, true, true>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream);
-            else if (body) rc = launch_tile<R, true, false>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream);
-            else if (iso) rc = launch_tile<R, false, true>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream);
-            else rc = launch_tile<R, false, false>(p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream);
+#define HIDENN_TILE_ARGS p, x_free, x_fixed, u_free, u_fixed, consts, flags, gx, gu, scratch, stream, tile_begin, tile_end
+            if (body && iso) rc = launch_tile<R, true, true>(HIDENN_TILE_ARGS);
+            else if (body) rc = launch_tile<R, true, false>(HIDENN_TILE_ARGS);
+            else if (iso) rc = launch_tile<R, false, true>(HIDENN_TILE_ARGS);
+            else rc = launch_tile<R, false, false>(HIDENN_TILE_ARGS);
+#undef HIDENN_TILE_ARGS
             if (rc) return rc;
         } else {
             const size_t smem = (size_t)p->dev.max_local * 4 * sizeof(R) + 64 * 8;
@@ -679,22 +697,28 @@ static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R*
         const int grid = std::max(1, std::min(kEdgeMaxCtas, (work + kEdgeBlock - 1) / kEdgeBlock));
         tri_edge_finalize_kernel<R><<<grid, kEdgeBlock, 0, stream>>>(p->dev, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free,
                                                                       (const R2*)u_fixed, consts, t_table, flags, scratch, out,
-                                                                      (R2*)gx, (R2*)gu, gt, part, ticket);
+                                                                      (R2*)gx, (R2*)gu, gt, part, ticket, (R2*)en_final);
     }
     HIDENN_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
+// Host-buffer entry point.  Large meshes are pipelined over the caller's stream and two copy streams (see tri_plan.h): while the tile kernels of
+// chunk c run, the Parameter rows of chunk c+1 travel host->device and the finished gradient rows of chunk c-1 travel
+// device->host, so the two PCIe directions overlap instead of adding up.  Rows touched by the Neumann edge term are
+// patched from a compact buffer the finalize kernel fills.  Results are bit-identical to the resident entry point.
 template <typename R>
 static int tri_energy_host(hidenn_tri_plan* p, const R* xf, const R* xb, const R* uf, const R* ub, const R* consts_h, int flags,
                            R* out_h, R* gx_h, R* gu_h, void* stream_v) {
     HIDENN_REQUIRE(p != nullptr && p->device >= 0, "tri_energy_host: needs a device plan");
+    HIDENN_REQUIRE(xf && uf && consts_h && out_h, "tri_energy_host: NULL argument");
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
     HIDENN_CUDA_OK(cudaSetDevice(p->device));
     const size_t nfx = 2 * (size_t)p->n_free_x, nbx = 2 * (size_t)p->n_fixed_x, nfu = 2 * (size_t)p->n_free_u, nbu = 2 * (size_t)p->n_fixed_u;
     const size_t nsc = (size_t)p->dev.n_tiles + 8 + 280;
+    const size_t nen = 4 * (size_t)p->dev.n_enodes;
     auto al = [](size_t n) { return (n + 31) / 32 * 32; };
-    const size_t total = al(nfx) * 2 + al(nbx) + al(nfu) * 2 + al(nbu) + al(HIDENN_TRI_NCONST) + al(4) + al(nsc);
+    const size_t total = al(nfx) * 2 + al(nbx) + al(nfu) * 2 + al(nbu) + al(HIDENN_TRI_NCONST) + al(4) + al(nsc) + al(nen);
     if (plan_ensure_arena(p, total * sizeof(R))) return 1;
     R* base = reinterpret_cast<R*>(p->arena);
     R* d_xf = base; base += al(nfx);
@@ -705,18 +729,118 @@ static int tri_energy_host(hidenn_tri_plan* p, const R* xf, const R* xb, const R
     R* d_gu = base; base += al(nfu);
     R* d_c = base; base += al(HIDENN_TRI_NCONST);
     R* d_out = base; base += al(4);
-    R* d_sc = base;
+    R* d_sc = base; base += al(nsc);
+    R* d_en = base;
+    const bool want_gx = (flags & HIDENN_NEED_GX) && gx_h, want_gu = (flags & HIDENN_NEED_GU) && gu_h;
+    const int n_tiles = p->dev.n_tiles;
+    int chunks = 1;
+    if ((want_gx || want_gu) && n_tiles >= 512 && (nfx + nfu) * sizeof(R) >= ((size_t)8 << 20)) chunks = std::min(8, n_tiles / 256);
+    if (const char* e = getenv("HIDENN_HOST_CHUNKS")) chunks = std::max(1, std::min(atoi(e), std::max(1, n_tiles)));
+
     HIDENN_CUDA_OK(cudaMemsetAsync(d_sc, 0, nsc * sizeof(R), stream));      // the finalize ticket must start at zero
-    HIDENN_CUDA_OK(cudaMemcpyAsync(d_xf, xf, nfx * sizeof(R), cudaMemcpyHostToDevice, stream));
-    if (nbx) HIDENN_CUDA_OK(cudaMemcpyAsync(d_xb, xb, nbx * sizeof(R), cudaMemcpyHostToDevice, stream));
-    HIDENN_CUDA_OK(cudaMemcpyAsync(d_uf, uf, nfu * sizeof(R), cudaMemcpyHostToDevice, stream));
-    if (nbu) HIDENN_CUDA_OK(cudaMemcpyAsync(d_ub, ub, nbu * sizeof(R), cudaMemcpyHostToDevice, stream));
-    HIDENN_CUDA_OK(cudaMemcpyAsync(d_c, consts_h, HIDENN_TRI_NCONST * sizeof(R), cudaMemcpyHostToDevice, stream));
-    if (tri_energy_launch<R>(p, d_xf, d_xb, d_uf, d_ub, d_c, nullptr, flags, d_out, d_gx, d_gu, nullptr, d_sc, stream_v)) return 1;
+    if (chunks <= 1) {
+        HIDENN_CUDA_OK(cudaMemcpyAsync(d_xf, xf, nfx * sizeof(R), cudaMemcpyHostToDevice, stream));
+        if (nbx) HIDENN_CUDA_OK(cudaMemcpyAsync(d_xb, xb, nbx * sizeof(R), cudaMemcpyHostToDevice, stream));
+        HIDENN_CUDA_OK(cudaMemcpyAsync(d_uf, uf, nfu * sizeof(R), cudaMemcpyHostToDevice, stream));
+        if (nbu) HIDENN_CUDA_OK(cudaMemcpyAsync(d_ub, ub, nbu * sizeof(R), cudaMemcpyHostToDevice, stream));
+        HIDENN_CUDA_OK(cudaMemcpyAsync(d_c, consts_h, HIDENN_TRI_NCONST * sizeof(R), cudaMemcpyHostToDevice, stream));
+        if (tri_energy_launch<R>(p, d_xf, d_xb, d_uf, d_ub, d_c, nullptr, flags, d_out, d_gx, d_gu, nullptr, d_sc, stream_v)) return 1;
+        HIDENN_CUDA_OK(cudaMemcpyAsync(out_h, d_out, 4 * sizeof(R), cudaMemcpyDeviceToHost, stream));
+        if (want_gx) HIDENN_CUDA_OK(cudaMemcpyAsync(gx_h, d_gx, nfx * sizeof(R), cudaMemcpyDeviceToHost, stream));
+        if (want_gu) HIDENN_CUDA_OK(cudaMemcpyAsync(gu_h, d_gu, nfu * sizeof(R), cudaMemcpyDeviceToHost, stream));
+        HIDENN_CUDA_OK(cudaStreamSynchronize(stream));
+        return 0;
+    }
+
+    // side streams: one per PCIe direction (two per direction measured slower: same-direction transfers only
+    // interleave, profiles/README.md)
+    for (void*& st : p->pipe_streams)
+        if (!st) {
+            cudaStream_t a;
+            HIDENN_CUDA_OK(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+            st = a;
+        }
+    while (p->pipe_events.size() < (size_t)(3 * chunks + 1)) {
+        cudaEvent_t e;
+        HIDENN_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        p->pipe_events.push_back(e);
+    }
+    cudaStream_t s_inx = (cudaStream_t)p->pipe_streams[0], s_inu = s_inx;
+    cudaStream_t s_outx = (cudaStream_t)p->pipe_streams[1], s_outu = s_outx;
+    auto ev = [&](int i) { return (cudaEvent_t)p->pipe_events[i]; };
+    // the side streams start after whatever the caller queued on `stream` (and after the scratch memset)
+    HIDENN_CUDA_OK(cudaEventRecord(ev(3 * chunks), stream));
+    for (void* st : p->pipe_streams) HIDENN_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)st, ev(3 * chunks), 0));
+    HIDENN_CUDA_OK(cudaMemcpyAsync(d_c, consts_h, HIDENN_TRI_NCONST * sizeof(R), cudaMemcpyHostToDevice, s_inx));
+    if (nbx) HIDENN_CUDA_OK(cudaMemcpyAsync(d_xb, xb, nbx * sizeof(R), cudaMemcpyHostToDevice, s_inx));
+    if (nbu) HIDENN_CUDA_OK(cudaMemcpyAsync(d_ub, ub, nbu * sizeof(R), cudaMemcpyHostToDevice, s_inu));
+    // block -> chunk assignment: a block travels in with the chunk of the first tile that reads it and out with the
+    // chunk of the last tile that writes it (blocks no tile touches ride with the last chunk)
+    std::vector<int> tbound(chunks + 1);
+    for (int c = 0; c <= chunks; ++c) tbound[c] = (int)((int64_t)n_tiles * c / chunks);
+    auto chunk_of = [&](int32_t tile) {
+        if (tile < 0 || tile >= n_tiles) return chunks - 1;
+        int c = (int)std::min<int64_t>(chunks - 1, (int64_t)tile * chunks / n_tiles);
+        while (tile < tbound[c]) --c;
+        while (tile >= tbound[c + 1]) ++c;
+        return c;
+    };
+    // copy the blocks whose key tile lies in chunk c, merging neighbouring blocks into one transfer
+    auto copy_blocks = [&](const std::vector<int32_t>& key, int c, int32_t rows_per_block, size_t n_rows, R* dst, const R* src,
+                           cudaMemcpyKind kind, cudaStream_t s) -> int {
+        int b = 0;
+        while (b < kPipeBlocks) {
+            if ((size_t)b * rows_per_block >= n_rows) break;
+            if (chunk_of(key[b]) != c) { ++b; continue; }
+            int e = b + 1;
+            while (e < kPipeBlocks && (size_t)e * rows_per_block < n_rows && chunk_of(key[e]) == c) ++e;
+            const size_t r0 = (size_t)b * rows_per_block, r1 = std::min(n_rows, (size_t)e * rows_per_block);
+            HIDENN_CUDA_OK(cudaMemcpyAsync(dst + 2 * r0, src + 2 * r0, 2 * (r1 - r0) * sizeof(R), kind, s));
+            b = e;
+        }
+        return 0;
+    };
+    for (int c = 0; c < chunks; ++c) {
+        const int t0 = tbound[c], t1 = tbound[c + 1];
+        if (copy_blocks(p->first_need_x, c, p->pipe_rows_x, (size_t)p->n_free_x, d_xf, xf, cudaMemcpyHostToDevice, s_inx)) return 1;
+        if (copy_blocks(p->first_need_u, c, p->pipe_rows_u, (size_t)p->n_free_u, d_uf, uf, cudaMemcpyHostToDevice, s_inu)) return 1;
+        HIDENN_CUDA_OK(cudaEventRecord(ev(3 * c), s_inx));
+        HIDENN_CUDA_OK(cudaEventRecord(ev(3 * c + 1), s_inu));
+        HIDENN_CUDA_OK(cudaStreamWaitEvent(stream, ev(3 * c), 0));
+        HIDENN_CUDA_OK(cudaStreamWaitEvent(stream, ev(3 * c + 1), 0));
+        if (t1 > t0 &&
+            tri_energy_launch<R>(p, d_xf, d_xb, d_uf, d_ub, d_c, nullptr, flags | HIDENN_TILES_ONLY, d_out, d_gx, d_gu, nullptr, d_sc,
+                                 stream_v, t0, t1))
+            return 1;
+        HIDENN_CUDA_OK(cudaEventRecord(ev(3 * c + 2), stream));
+        if (want_gx) {
+            HIDENN_CUDA_OK(cudaStreamWaitEvent(s_outx, ev(3 * c + 2), 0));
+            if (copy_blocks(p->last_own_x, c, p->pipe_rows_x, (size_t)p->n_free_x, gx_h, d_gx, cudaMemcpyDeviceToHost, s_outx)) return 1;
+        }
+        if (want_gu) {
+            HIDENN_CUDA_OK(cudaStreamWaitEvent(s_outu, ev(3 * c + 2), 0));
+            if (copy_blocks(p->last_own_u, c, p->pipe_rows_u, (size_t)p->n_free_u, gu_h, d_gu, cudaMemcpyDeviceToHost, s_outu)) return 1;
+        }
+    }
+    // edge term + reduction; the edge-node rows it updates are fetched compactly and patched in below
+    if (tri_energy_launch<R>(p, d_xf, d_xb, d_uf, d_ub, d_c, nullptr, flags | kFinalizeOnly, d_out, d_gx, d_gu, nullptr, d_sc, stream_v, 0, -1,
+                             d_en))
+        return 1;
+    const bool edges = (flags & HIDENN_WITH_EDGES) && p->dev.n_edges > 0 && (want_gx || want_gu);
+    std::vector<R> en_h(edges ? nen : 0);
     HIDENN_CUDA_OK(cudaMemcpyAsync(out_h, d_out, 4 * sizeof(R), cudaMemcpyDeviceToHost, stream));
-    if ((flags & HIDENN_NEED_GX) && gx_h) HIDENN_CUDA_OK(cudaMemcpyAsync(gx_h, d_gx, nfx * sizeof(R), cudaMemcpyDeviceToHost, stream));
-    if ((flags & HIDENN_NEED_GU) && gu_h) HIDENN_CUDA_OK(cudaMemcpyAsync(gu_h, d_gu, nfu * sizeof(R), cudaMemcpyDeviceToHost, stream));
+    if (edges) HIDENN_CUDA_OK(cudaMemcpyAsync(en_h.data(), d_en, nen * sizeof(R), cudaMemcpyDeviceToHost, stream));
     HIDENN_CUDA_OK(cudaStreamSynchronize(stream));
+    HIDENN_CUDA_OK(cudaStreamSynchronize(s_outx));
+    HIDENN_CUDA_OK(cudaStreamSynchronize(s_outu));
+    if (edges) {
+        const size_t ne = (size_t)p->dev.n_enodes;
+        for (size_t k = 0; k < ne; ++k) {
+            const int32_t us = p->en_uslot_h[k], xs = p->en_xslot_h[k];
+            if (want_gu && us >= 0) { gu_h[2 * (size_t)us] = en_h[2 * k]; gu_h[2 * (size_t)us + 1] = en_h[2 * k + 1]; }
+            if (want_gx && xs >= 0) { gx_h[2 * (size_t)xs] = en_h[2 * (ne + k)]; gx_h[2 * (size_t)xs + 1] = en_h[2 * (ne + k) + 1]; }
+        }
+    }
     return 0;
 }
 

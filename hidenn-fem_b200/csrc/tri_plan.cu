@@ -9,6 +9,9 @@
 // ~tile_nodes owned nodes; a tile visits every element incident to an owned node ("owner computes",
 // halo elements recomputed), so each nodal gradient is folded and written by exactly one CTA in a
 // fixed order: deterministic, no float atomics, no second pass.
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include "../../include/hidenn_b200.h"
 #include "common.cuh"
 #include "tri_plan.h"
@@ -369,8 +372,18 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     p->t_elem.reserve(elem_visits);
     p->elem_pack.reserve(elem_visits);
     p->entry_off.reserve(off_total);
+    // tiles are laid out by ascending smallest owned node id (= ascending Parameter rows): neighbouring CTAs then work
+    // on neighbouring memory, and the host-buffer entry point can stream rows in and gradients out chunk by chunk
+    std::vector<int64_t> tord(n_tiles);
+    std::iota(tord.begin(), tord.end(), 0);
+    {
+        std::vector<int32_t> key(n_tiles, INT32_MAX);
+        for (int64_t t = 0; t < n_tiles; ++t)
+            for (int32_t l = 0; l < tb[t].n_owned; ++l) key[t] = std::min(key[t], tb[t].nodes[l]);
+        std::stable_sort(tord.begin(), tord.end(), [&](int64_t a, int64_t b) { return key[a] < key[b]; });
+    }
     for (int64_t t = 0; t < n_tiles; ++t) {
-        TileBuild& B = tb[t];
+        TileBuild& B = tb[tord[t]];
         TileDesc d{};
         d.node_off = (int32_t)p->t_node.size();
         d.n_owned = B.n_owned;
@@ -415,11 +428,59 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
                 t_lid[(size_t)t * SL + j] = (uint16_t)byid[j].second;
             }
         }
+        if (getenv("HIDENN_PLAN_RUNSTATS")) {       // debug: contiguous-row runs per tile (bulk-copy feasibility)
+            int64_t rx = 0, ru = 0, ro = 0, nl = 0, no = 0;
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                const TileDesc& d = p->tiles[t];
+                int2 prev = make_int2(INT32_MIN, INT32_MIN);
+                int prev_ox = INT32_MIN, prev_ou = INT32_MIN;
+                for (int32_t j = 0; j < d.n_local; ++j) {
+                    const int2 c = t_slots[(size_t)t * SL + j];
+                    if (!(c.x == prev.x + 1 && c.x > 0) && !(c.x < 0 && c.x == prev.x - 1)) ++rx;
+                    if (!(c.y == prev.y + 1 && c.y > 0) && !(c.y < 0 && c.y == prev.y - 1)) ++ru;
+                    prev = c;
+                    if (t_lid[(size_t)t * SL + j] < d.n_owned) {
+                        if (c.x >= 0) { if (c.x != prev_ox + 1) ++ro; prev_ox = c.x; }
+                        if (c.y >= 0) { if (c.y != prev_ou + 1) ++ro; prev_ou = c.y; }
+                        ++no;
+                    }
+                }
+                nl += d.n_local;
+            }
+            fprintf(stderr, "[plan runstats] tiles %lld  local/tile %.1f owned/tile %.1f  x-runs/tile %.1f u-runs/tile %.1f out-runs/tile %.1f\n",
+                    (long long)n_tiles, (double)nl / n_tiles, (double)no / n_tiles, (double)rx / n_tiles, (double)ru / n_tiles, (double)ro / n_tiles);
+        }
     }
     for (int64_t t = 0; t < n_tiles; ++t) {
         const TileDesc& d = p->tiles[t];
         std::copy(p->elem_pack.begin() + d.elem_off, p->elem_pack.begin() + d.elem_off + d.n_elem, d_pack.begin() + (size_t)t * SE);
         std::copy(p->entry_off.begin() + d.off_off, p->entry_off.begin() + d.off_off + d.n_owned, d_off.begin() + (size_t)t * SO);
+    }
+
+    // block tables of the host-buffer pipeline (see tri_plan.h)
+    {
+        auto rows_per_block = [](int64_t n) { return (int32_t)std::max<int64_t>(16, ((n + kPipeBlocks - 1) / kPipeBlocks + 15) / 16 * 16); };
+        p->pipe_rows_x = rows_per_block(p->n_free_x);
+        p->pipe_rows_u = rows_per_block(p->n_free_u);
+        p->first_need_x.assign(kPipeBlocks, INT32_MAX); p->first_need_u.assign(kPipeBlocks, INT32_MAX);
+        p->last_own_x.assign(kPipeBlocks, -1); p->last_own_u.assign(kPipeBlocks, -1);
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            const TileDesc& d = p->tiles[t];
+            for (int32_t i = 0; i < d.n_local; ++i) {
+                const int32_t n = p->t_node[d.node_off + i];
+                const int32_t xs = p->xslot[n], us = p->uslot[n];
+                if (xs >= 0) {
+                    const int32_t b = xs / p->pipe_rows_x;
+                    p->first_need_x[b] = std::min(p->first_need_x[b], (int32_t)t);
+                    if (i < d.n_owned) p->last_own_x[b] = (int32_t)t;
+                }
+                if (us >= 0) {
+                    const int32_t b = us / p->pipe_rows_u;
+                    p->first_need_u[b] = std::min(p->first_need_u[b], (int32_t)t);
+                    if (i < d.n_owned) p->last_own_u[b] = (int32_t)t;
+                }
+            }
+        }
     }
 
     // Neumann edges: slot quads + node-centric CSR (each edge node folded by one thread)
@@ -445,6 +506,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
         for (int64_t i = 0; i < 2 * Ned; ++i) en_ent[cur[en_id(p->edges32[i])]++] = (int32_t)i;   // edge*2+end, ascending
     }
 
+    p->en_xslot_h = en_xslot; p->en_uslot_h = en_uslot;
     // upload (device == -1: host-only plan for index tests, no compute possible)
     TriPlanDev& D0 = p->dev;
     D0.n_tiles = (int32_t)n_tiles;
@@ -489,6 +551,9 @@ extern "C" void hidenn_tri_plan_destroy(hidenn_tri_plan* p) {
     if (p->device >= 0) cudaSetDevice(p->device);
     for (void* q : p->dev_allocs) cudaFree(q);
     if (p->arena) cudaFree(p->arena);
+    for (void* e : p->pipe_events) cudaEventDestroy((cudaEvent_t)e);
+    for (void* st : p->pipe_streams)
+        if (st) cudaStreamDestroy((cudaStream_t)st);
     delete p;
 }
 
@@ -546,6 +611,26 @@ extern "C" int hidenn_tri_plan_decode(const hidenn_tri_plan* p, int64_t* out_ele
 // Simulated shared-memory passes of the tile kernel's gathers and partial stores for the current lane assignment
 // (model: one pass serves lanes whose 16-byte (FP64) / 8-byte (FP32) words fall in different bank groups; equal
 // addresses broadcast).  out[0] = gather passes, out[1] = ideal gather passes, out[2] = store passes, out[3] = ideal.
+extern "C" int hidenn_tri_plan_tiles(const hidenn_tri_plan* p, int64_t* node_off, int32_t* n_owned, int32_t* nodes) {
+    HIDENN_REQUIRE(p && node_off && n_owned && nodes, "plan_tiles: NULL");
+    const size_t nt = p->tiles.size();
+    for (size_t t = 0; t < nt; ++t) { node_off[t] = p->tiles[t].node_off; n_owned[t] = p->tiles[t].n_owned; }
+    node_off[nt] = (int64_t)p->t_node.size();
+    std::copy(p->t_node.begin(), p->t_node.end(), nodes);
+    return 0;
+}
+
+extern "C" int hidenn_tri_plan_pipeline(const hidenn_tri_plan* p, int32_t* rows2, int32_t* first_need_x, int32_t* last_own_x,
+                                        int32_t* first_need_u, int32_t* last_own_u) {
+    HIDENN_REQUIRE(p && rows2 && first_need_x && last_own_x && first_need_u && last_own_u, "plan_pipeline: NULL");
+    rows2[0] = p->pipe_rows_x; rows2[1] = p->pipe_rows_u;
+    std::copy(p->first_need_x.begin(), p->first_need_x.end(), first_need_x);
+    std::copy(p->last_own_x.begin(), p->last_own_x.end(), last_own_x);
+    std::copy(p->first_need_u.begin(), p->first_need_u.end(), first_need_u);
+    std::copy(p->last_own_u.begin(), p->last_own_u.end(), last_own_u);
+    return 0;
+}
+
 extern "C" int hidenn_tri_plan_bank_stats(const hidenn_tri_plan* p, int real_bytes, int64_t* out4) {
     HIDENN_REQUIRE(p && out4 && (real_bytes == 8 || real_bytes == 4), "plan_bank_stats: bad arguments");
     (void)real_bytes;

@@ -27,10 +27,12 @@ constexpr int kOwnerBit = 63;
 constexpr int kMaxLocal = (1 << kLidBits) - 1;       // local ids 0..1022
 constexpr int kMaxEntries = (1 << kPosBits) - 1;     // fold slots 0..2046 + dump slot <= 2047
 constexpr int kMaxValence = 255;
+constexpr int kPipeBlocks = 64;
 
 struct TriPlanDev {
     const TileDesc* tiles;
-    int32_t n_tiles;
+    int32_t n_tiles;                       // a tile launch walks tiles [tile_begin, n_tiles)
+    int32_t tile_begin;
     // fixed-stride tile records (tile t starts at t*stride): every load address depends only on blockIdx
     // node records are listed in MEMORY order (ascending node id = ascending Parameter row): the staging gathers
     // and the final gradient stores of a warp then touch consecutive 16-byte pairs; t_lid gives the tile-local id
@@ -84,6 +86,16 @@ struct hidenn_tri_plan {
     // arena for the host-buffer entry points
     void* arena = nullptr;
     size_t arena_bytes = 0;
+    // Host-buffer pipeline (tri_energy_host).  Tiles are listed by ascending smallest owned node id and the Parameter
+    // rows are cut into kPipeBlocks blocks; first_need_*[b] is the first tile that reads a row of block b, last_own_*[b]
+    // the last tile that writes one.  A chunk of tiles then needs the blocks whose first_need falls in it (sent
+    // host->device just before) and completes the blocks whose last_own falls in it (fetched device->host right after),
+    // so on side streams the copies of chunk c+1 and c-1 overlap the kernels of chunk c in both PCIe directions.
+    int32_t pipe_rows_x = 0, pipe_rows_u = 0;                                    // rows per block
+    std::vector<int32_t> first_need_x, last_own_x, first_need_u, last_own_u;     // [kPipeBlocks]
+    std::vector<int32_t> en_xslot_h, en_uslot_h;              // host copies of the Neumann edge-node rows
+    void* pipe_streams[2] = {nullptr, nullptr};               // cudaStream_t: rows in, gradient rows out
+    std::vector<void*> pipe_events;                           // cudaEvent_t
 };
 
 namespace hidenn {

@@ -358,20 +358,24 @@ class _Q1InterpFn(torch.autograd.Function):
         dt, dev = gx.dtype, gx.device
         M = xs.shape[0]
         Nx, Ny = gx.shape[0], gy.shape[0]
-        rows = torch.empty(M, 8, device=dev, dtype=dt)
         s = _lib.stream_ptr()
-        _lib.check(_lib.fn("hidenn_q1_interp_bwd", dt)(_lib.ptr(gx), c_i64(Nx), _lib.ptr(gy), c_i64(Ny), _lib.ptr(uf), _lib.ptr(xs),
-                                                       _lib.ptr(ix), _lib.ptr(iy), _lib.ptr(r.to(dt).contiguous()), c_i64(M),
-                                                       _lib.ptr(rows), s))
+        L = _lib.lib()
         ncell = (Nx - 1) * (Ny - 1)
-        cell = ix.to(torch.int64) * (Ny - 1) + iy.to(torch.int64)
-        sorted_c, order = torch.sort(cell, stable=True)
-        seg = torch.searchsorted(sorted_c, torch.arange(ncell + 1, device=dev, dtype=torch.int64))
+        # sort-free deterministic binning: integer histogram -> prefix -> scatter -> per-cell ascending sample id
+        count = torch.zeros(ncell, device=dev, dtype=torch.int32)
+        _lib.check(L.hidenn_q1_bin_count(_lib.ptr(ix), _lib.ptr(iy), c_i64(M), c_i64(Ny), _lib.ptr(count), s))
+        seg = torch.zeros(ncell + 1, device=dev, dtype=torch.int32)
+        torch.cumsum(count, 0, dtype=torch.int32, out=seg[1:])
+        count.zero_()
+        order = torch.empty(max(M, 1), device=dev, dtype=torch.int32)
+        _lib.check(L.hidenn_q1_bin_scatter(_lib.ptr(ix), _lib.ptr(iy), c_i64(M), c_i64(Nx), c_i64(Ny), _lib.ptr(seg),
+                                           _lib.ptr(count), _lib.ptr(order), s))
         tmp = torch.empty(ncell, 8, device=dev, dtype=dt)
         du = torch.empty(Nx, Ny, device=dev, dtype=dt)
         dgx = torch.empty(Nx, device=dev, dtype=dt)
         dgy = torch.empty(Ny, device=dev, dtype=dt)
-        _lib.check(_lib.fn("hidenn_q1_fold_rows", dt)(_lib.ptr(rows), _lib.ptr(order), _lib.ptr(seg), c_i64(Nx), c_i64(Ny),
+        _lib.check(_lib.fn("hidenn_q1_bwd_fused", dt)(_lib.ptr(gx), c_i64(Nx), _lib.ptr(gy), c_i64(Ny), _lib.ptr(uf), _lib.ptr(xs),
+                                                      _lib.ptr(r.to(dt).contiguous()), c_i64(M), _lib.ptr(seg), _lib.ptr(order),
                                                       _lib.ptr(tmp), _lib.ptr(du), _lib.ptr(dgx), _lib.ptr(dgy), s))
         return dgx, dgy, du.to(ctx.udtype), None
 

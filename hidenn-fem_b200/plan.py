@@ -76,6 +76,23 @@ class TriPlan:
                                                      ow.ctypes.data_as(C.c_void_p)))
         return el, nd, ow
 
+    def tiles(self):
+        """(node_off [n_tiles+1], n_owned [n_tiles], nodes [node_visits]): tile membership, owned nodes first."""
+        nt = self.info["n_tiles"]
+        off = np.empty(nt + 1, np.int64)
+        own = np.empty(nt, np.int32)
+        nodes = np.empty(self.info["node_visits"], np.int32)
+        _lib.check(_lib.lib().hidenn_tri_plan_tiles(self._h, off.ctypes.data_as(C.c_void_p), own.ctypes.data_as(C.c_void_p),
+                                                    nodes.ctypes.data_as(C.c_void_p)))
+        return off, own, nodes
+
+    def pipeline(self):
+        """Row-block tables of the host-buffer pipeline: dict(rows_x, rows_u, first_need_x, last_own_x, first_need_u, last_own_u)."""
+        rows = np.empty(2, np.int32)
+        t = [np.empty(64, np.int32) for _ in range(4)]
+        _lib.check(_lib.lib().hidenn_tri_plan_pipeline(self._h, rows.ctypes.data_as(C.c_void_p), *[a.ctypes.data_as(C.c_void_p) for a in t]))
+        return dict(rows_x=int(rows[0]), rows_u=int(rows[1]), first_need_x=t[0], last_own_x=t[1], first_need_u=t[2], last_own_u=t[3])
+
     def bank_stats(self, real_bytes=None):
         out = (C.c_int64 * 4)()
         _lib.check(_lib.lib().hidenn_tri_plan_bank_stats(self._h, C.c_int(real_bytes or self.real_bytes), out))

@@ -105,6 +105,15 @@ int hidenn_debug_tile_timing(long long* dev_buf);
  * out4 = {gather passes, ideal gather passes, partial-store passes, ideal store passes}. */
 int hidenn_tri_plan_bank_stats(const hidenn_tri_plan* plan, int real_bytes, int64_t* out4);
 
+/* Tile membership (tests): node_off [n_tiles+1] into nodes [info[2] = node_visits] (global node ids, owned nodes of a
+ * tile first), n_owned [n_tiles].  Tiles are listed by ascending smallest owned node id. */
+int hidenn_tri_plan_tiles(const hidenn_tri_plan* plan, int64_t* node_off, int32_t* n_owned, int32_t* nodes);
+/* Row-block tables of the host-buffer pipeline (hidenn_tri_energy_host_*): the free rows are cut into 64 blocks of
+ * rows2[0] (node_coords_free) / rows2[1] (u_free) rows; first_need[b] = first tile reading a row of block b
+ * (INT32_MAX: none), last_own[b] = last tile writing one (-1: none).  Each array has 64 entries. */
+int hidenn_tri_plan_pipeline(const hidenn_tri_plan* plan, int32_t* rows2, int32_t* first_need_x, int32_t* last_own_x,
+                             int32_t* first_need_u, int32_t* last_own_u);
+
 /* ------------------------------------------------------------------------------------------
  * Fused energy + gradients:  EnergyLoss2D.__call__ (src/loss.py:113-116) =
  * domain_energy (src/loss.py:55-88) over PiecewiseLinearShapeNN2D.forward

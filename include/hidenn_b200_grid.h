@@ -86,6 +86,23 @@ int hidenn_q1_fold_rows_f64(const double* rows, const int64_t* order, const int6
 int hidenn_q1_fold_rows_f32(const float* rows, const int64_t* order, const int64_t* seg, int64_t Nx, int64_t Ny,
                             float* cell_tmp, float* du_full, float* dgx, float* dgy, void* stream);
 
+/* Sort-free deterministic cell binning for the structured backward:
+ *   count:   cell_count[c] += 1 for every sample (integer atomics; cell_count dev [ncell] int32, zeroed by the caller)
+ *   scatter: order[seg[c] + k] = sample ids of cell c (seg dev [ncell+1] int32 = exclusive prefix of the counts,
+ *            cursor dev [ncell] int32 zeroed by the caller), then every cell's ids are sorted ascending in place,
+ *            so the summation order of the fold is the sample index order -- independent of the atomics' arrival order. */
+int hidenn_q1_bin_count(const int32_t* ix, const int32_t* iy, int64_t M, int64_t Ny, int32_t* cell_count, void* stream);
+int hidenn_q1_bin_scatter(const int32_t* ix, const int32_t* iy, int64_t M, int64_t Nx, int64_t Ny, const int32_t* seg,
+                          int32_t* cursor, int32_t* order, void* stream);
+/* Fused structured backward: per cell, the VJP pieces of its samples (recomputed from x, r; never materialised) are
+ * summed in `order`, then folded to nodes / grid lines exactly like hidenn_q1_fold_rows. */
+int hidenn_q1_bwd_fused_f64(const double* gx, int64_t Nx, const double* gy, int64_t Ny, const double* u_full,
+                            const double* x, const double* r, int64_t M, const int32_t* seg, const int32_t* order,
+                            double* cell_tmp, double* du_full, double* dgx, double* dgy, void* stream);
+int hidenn_q1_bwd_fused_f32(const float* gx, int64_t Nx, const float* gy, int64_t Ny, const float* u_full,
+                            const float* x, const float* r, int64_t M, const int32_t* seg, const int32_t* order,
+                            float* cell_tmp, float* du_full, float* dgx, float* dgy, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -219,3 +219,92 @@ def test_structured_lookup_and_large_vs_oracle():
     model.zero_grad()
     ((model(T(x)) - T(ut)) ** 2).mean().backward()
     assert torch.equal(g1, model.u.grad)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_structured_fused_backward_matches_row_fold(dt):
+    """Sort-free binning + fused cell fold vs materialised rows + stable sort + fold: the permutation is bit-exact
+    (ascending sample id inside a cell), the sums agree to rounding (the fused kernel contracts a += r*(...) into FMAs)
+    and are bit-identical run to run although the scatter uses integer atomics.  Includes cells with thousands of samples."""
+    import ctypes as C
+    from hidenn_fem_b200 import _lib
+    rng = np.random.default_rng(11)
+    Nx, Ny, M = 65, 49, 120_000
+    gx = T(np.sort(rng.random(Nx)), dtype=dt)
+    gy = T(np.sort(rng.random(Ny)), dtype=dt)
+    uf = T(rng.standard_normal((Nx, Ny)), dtype=dt)
+    xs = rng.random((M, 2))
+    xs[:5000] = 0.5 + 1e-4 * rng.standard_normal((5000, 2))          # a few cells hold thousands of samples
+    x = T(xs, dtype=dt)
+    r = T(rng.standard_normal(M), dtype=dt)
+    L, s, i64 = _lib.lib(), _lib.stream_ptr(), C.c_int64
+    u = torch.empty(M, device="cuda", dtype=dt)
+    ix = torch.empty(M, device="cuda", dtype=torch.int32)
+    iy = torch.empty_like(ix)
+    _lib.check(_lib.fn("hidenn_q1_interp_fwd", dt)(_lib.ptr(gx), i64(Nx), _lib.ptr(gy), i64(Ny), _lib.ptr(uf), _lib.ptr(x), i64(M),
+                                                   _lib.ptr(u), _lib.ptr(ix), _lib.ptr(iy), s))
+    ncell = (Nx - 1) * (Ny - 1)
+    # (a) rows + stable sort
+    rows = torch.empty(M, 8, device="cuda", dtype=dt)
+    _lib.check(_lib.fn("hidenn_q1_interp_bwd", dt)(_lib.ptr(gx), i64(Nx), _lib.ptr(gy), i64(Ny), _lib.ptr(uf), _lib.ptr(x),
+                                                   _lib.ptr(ix), _lib.ptr(iy), _lib.ptr(r), i64(M), _lib.ptr(rows), s))
+    cell = ix.long() * (Ny - 1) + iy.long()
+    _, order64 = torch.sort(cell, stable=True)
+    seg64 = torch.zeros(ncell + 1, device="cuda", dtype=torch.int64)
+    seg64[1:] = torch.cumsum(torch.bincount(cell, minlength=ncell), 0)
+    outs = []
+    for _ in range(2):
+        outs.append((torch.empty(ncell, 8, device="cuda", dtype=dt), torch.empty(Nx, Ny, device="cuda", dtype=dt),
+                     torch.empty(Nx, device="cuda", dtype=dt), torch.empty(Ny, device="cuda", dtype=dt)))
+    t, du, dgx, dgy = outs[0]
+    _lib.check(_lib.fn("hidenn_q1_fold_rows", dt)(_lib.ptr(rows), _lib.ptr(order64), _lib.ptr(seg64), i64(Nx), i64(Ny), _lib.ptr(t),
+                                                  _lib.ptr(du), _lib.ptr(dgx), _lib.ptr(dgy), s))
+    # (b) histogram + scatter + per-cell canonical order + fused fold
+    cnt = torch.zeros(ncell, device="cuda", dtype=torch.int32)
+    _lib.check(L.hidenn_q1_bin_count(_lib.ptr(ix), _lib.ptr(iy), i64(M), i64(Ny), _lib.ptr(cnt), s))
+    assert torch.equal(cnt.long(), torch.bincount(cell, minlength=ncell))
+    seg = torch.zeros(ncell + 1, device="cuda", dtype=torch.int32)
+    seg[1:] = torch.cumsum(cnt, 0).int()
+    cnt.zero_()
+    order = torch.empty(M, device="cuda", dtype=torch.int32)
+    _lib.check(L.hidenn_q1_bin_scatter(_lib.ptr(ix), _lib.ptr(iy), i64(M), i64(Nx), i64(Ny), _lib.ptr(seg), _lib.ptr(cnt),
+                                       _lib.ptr(order), s))
+    assert torch.equal(order.long(), order64)                        # index work: bit-exact with the stable sort
+    t2, du2, dgx2, dgy2 = outs[1]
+    _lib.check(_lib.fn("hidenn_q1_bwd_fused", dt)(_lib.ptr(gx), i64(Nx), _lib.ptr(gy), i64(Ny), _lib.ptr(uf), _lib.ptr(x), _lib.ptr(r),
+                                                  i64(M), _lib.ptr(seg), _lib.ptr(order), _lib.ptr(t2), _lib.ptr(du2), _lib.ptr(dgx2),
+                                                  _lib.ptr(dgy2), s))
+    tol = 1e-12 if dt == torch.float64 else 2e-5
+    for a, b in ((du, du2), (dgx, dgx2), (dgy, dgy2)):
+        assert relmax(b.cpu().numpy(), a.cpu().numpy()) < tol
+    # run-to-run: redo the (atomic) scatter and the fold
+    cnt.zero_()
+    order_b = torch.empty_like(order)
+    _lib.check(L.hidenn_q1_bin_scatter(_lib.ptr(ix), _lib.ptr(iy), i64(M), i64(Nx), i64(Ny), _lib.ptr(seg), _lib.ptr(cnt),
+                                       _lib.ptr(order_b), s))
+    t3, du3, dgx3, dgy3 = (torch.empty_like(v) for v in outs[1])
+    _lib.check(_lib.fn("hidenn_q1_bwd_fused", dt)(_lib.ptr(gx), i64(Nx), _lib.ptr(gy), i64(Ny), _lib.ptr(uf), _lib.ptr(x), _lib.ptr(r),
+                                                  i64(M), _lib.ptr(seg), _lib.ptr(order_b), _lib.ptr(t3), _lib.ptr(du3), _lib.ptr(dgx3),
+                                                  _lib.ptr(dgy3), s))
+    torch.cuda.synchronize()
+    assert torch.equal(order, order_b)
+    assert torch.equal(du2, du3) and torch.equal(dgx2, dgx3) and torch.equal(dgy2, dgy3)
+
+
+def test_structured_forward_smem_and_global_lookup_agree():
+    """The shared-memory-staged forward (grid lines fit in smem, M >= 65536) and the global-memory one give the same bits."""
+    from hidenn_fem_b200.models import StructuredShapeNN2D
+    rng = np.random.default_rng(5)
+    Nx, Ny = 1025, 513
+    model = StructuredShapeNN2D(torch.linspace(0, 2, Nx, dtype=torch.float64), torch.linspace(0, 1, Ny, dtype=torch.float64),
+                                r_adapt=True).double().cuda()
+    with torch.no_grad():
+        model.u.copy_(T(rng.standard_normal((Nx, Ny))) if model.u.dim() == 2 else T(rng.standard_normal(model.u.shape)))
+    x = T(rng.random((100_000, 2)) * np.array([2.2, 1.1]) - 0.05)
+    with torch.no_grad():
+        big = model(x)                       # smem path
+        small = torch.cat([model(x[i:i + 50_000 // 2]) for i in range(0, 100_000, 25_000)])   # < 65536 -> global path
+    assert torch.equal(big, small)
+    gxx, gyy = (a.detach().cpu().numpy() for a in model.grid)
+    po, _, _ = cf.q1_interp(gxx, gyy, model.u.detach().cpu().numpy().reshape(Nx, Ny), x.cpu().numpy())
+    assert relmax(big.cpu().numpy(), po) < 1e-12

@@ -130,3 +130,35 @@ def test_plan_lane_assignment_reduces_bank_passes(real_bytes):
     st = p.bank_stats()
     assert st["gather"] / st["gather_ideal"] < (1.5 if real_bytes == 8 else 1.9)
     assert st["store"] / st["store_ideal"] < (1.5 if real_bytes == 8 else 1.9)
+
+
+@pytest.mark.parametrize("ordering", ["morton", "natural", "random"])
+def test_pipeline_block_tables_cover_every_tile(ordering):
+    """Host-buffer pipeline invariants (include/hidenn_b200.h, hidenn_tri_plan_pipeline): every free row a tile reads lies
+    in a block whose first_need <= tile, every row it writes in a block whose last_own >= tile, every node is owned by
+    exactly one tile, and tiles are listed by ascending smallest owned node id."""
+    from hidenn_fem_b200 import meshgen
+    from hidenn_fem_b200.plan import TriPlan
+    m = meshgen.plate_mesh(101, 51, jitter=0.2, diag="random", seed=1, ordering=ordering)
+    bmask = m.boundary_mask & ~m.neumann_mask
+    plan = TriPlan(m.connectivity, m.node_coords.shape[0], m.node_coords, bmask, m.dirichlet_mask, m.neumann_edges,
+                   tile_nodes=64, device=-1)
+    off, n_owned, nodes = plan.tiles()
+    xs, us = plan.slots()
+    T = plan.pipeline()
+    nt = plan.info["n_tiles"]
+    owner_count = np.zeros(m.node_coords.shape[0], np.int64)
+    mins = []
+    for t in range(nt):
+        loc = nodes[off[t]:off[t + 1]]
+        own = loc[:n_owned[t]]
+        owner_count[own] += 1
+        mins.append(own.min())
+        for slots, rows, need, last in ((xs, T["rows_x"], T["first_need_x"], T["last_own_x"]),
+                                        (us, T["rows_u"], T["first_need_u"], T["last_own_u"])):
+            r = slots[loc]
+            assert (need[r[r >= 0] // rows] <= t).all()
+            ro = slots[own]
+            assert (last[ro[ro >= 0] // rows] >= t).all()
+    assert (owner_count == 1).all()
+    assert mins == sorted(mins)
