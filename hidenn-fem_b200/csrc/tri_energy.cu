@@ -181,7 +181,7 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
     R* s_red = reinterpret_cast<R*>(s_node + 2 * nb + 2 * (P.max_entries + 1) + 2 * P.max_owned);      // [2][16]
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int nct = gridDim.x;
-    int tile = P.tile_begin + blockIdx.x;
+    int tile = blockIdx.x;
     if (tile >= P.n_tiles) return;
     constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
     constexpr unsigned G = 8u;
@@ -603,13 +603,19 @@ static int launch_tile_persistent_mb(const hidenn_tri_plan* p, const R* x_free, 
         configured = smem;
     }
     static const int n_sm = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+    // a tile range [tile_begin, tile_end) is run by shifting the fixed-stride record pointers: the kernel itself always
+    // walks tiles 0 .. n_tiles-1 of the view it is given
     TriPlanDev P = p->dev;
-    P.tile_begin = tile_begin;
-    P.n_tiles = tile_end;
-    const int grid = std::min(tile_end - tile_begin, n_sm * MINB);
+    P.tiles += tile_begin;
+    P.t_slots += (size_t)tile_begin * P.stride_local;
+    P.t_lid += (size_t)tile_begin * P.stride_local;
+    P.elem_pack += (size_t)tile_begin * P.stride_elem;
+    P.entry_off += (size_t)tile_begin * P.stride_owned;
+    P.n_tiles = tile_end - tile_begin;
+    const int grid = std::min(P.n_tiles, n_sm * MINB);
     tri_tile_persistent_kernel<R, BODY, ISO, MINB, BLOCK><<<grid, BLOCK, smem, stream>>>(
-        P, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu, scratch,
-        g_tile_timing);
+        P, (const R2*)x_free, (const R2*)x_fixed, (const R2*)u_free, (const R2*)u_fixed, consts, flags, (R2*)gx, (R2*)gu,
+        scratch + tile_begin, g_tile_timing ? g_tile_timing + 16 * (long long)tile_begin : nullptr);
     return 0;
 }
 

@@ -380,7 +380,8 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
         std::vector<int32_t> key(n_tiles, INT32_MAX);
         for (int64_t t = 0; t < n_tiles; ++t)
             for (int32_t l = 0; l < tb[t].n_owned; ++l) key[t] = std::min(key[t], tb[t].nodes[l]);
-        std::stable_sort(tord.begin(), tord.end(), [&](int64_t a, int64_t b) { return key[a] < key[b]; });
+        if (!getenv("HIDENN_PLAN_RCB_ORDER"))      // debug: keep the recursive-bisection order
+            std::stable_sort(tord.begin(), tord.end(), [&](int64_t a, int64_t b) { return key[a] < key[b]; });
     }
     for (int64_t t = 0; t < n_tiles; ++t) {
         TileBuild& B = tb[tord[t]];

@@ -31,8 +31,7 @@ constexpr int kPipeBlocks = 64;
 
 struct TriPlanDev {
     const TileDesc* tiles;
-    int32_t n_tiles;                       // a tile launch walks tiles [tile_begin, n_tiles)
-    int32_t tile_begin;
+    int32_t n_tiles;
     // fixed-stride tile records (tile t starts at t*stride): every load address depends only on blockIdx
     // node records are listed in MEMORY order (ascending node id = ascending Parameter row): the staging gathers
     // and the final gradient stores of a warp then touch consecutive 16-byte pairs; t_lid gives the tile-local id
