@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--cpu-sample-elems", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph replay of the step")
+    ap.add_argument("--watchdog-s", type=int, default=1500, help="dump all thread stacks and exit if the run takes longer")
     ap.add_argument("--extra", action="store_true", help="also time the random-ordering and FP32 variants (N=1)")
     return ap.parse_args()
 
@@ -161,14 +163,19 @@ def make_workload(args, rank, world, device, dtype, ordering, n_elems_per_gpu, t
     return m, model, loss_fn, (nx, ny)
 
 
-def time_steps(model, loss_fn, steps, warmup, world):
+def time_steps(model, loss_fn, steps, warmup, world, graph=True):
     import torch.distributed as dist
 
-    def step():
-        model.zero_grad(set_to_none=True)
-        loss = loss_fn(model)
-        loss.backward()
-        return loss
+    if graph:
+        # public API: hidenn_fem_b200.graph.GraphedEnergyStep == zero_grad + loss_fn(model) + backward, replayed
+        from hidenn_fem_b200.graph import GraphedEnergyStep
+        step = GraphedEnergyStep(model, loss_fn)
+    else:
+        def step():
+            model.zero_grad(set_to_none=True)
+            loss = loss_fn(model)
+            loss.backward()
+            return loss
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
@@ -388,9 +395,16 @@ def run_reference(args):
 
 def main():
     args = parse()
+    if args.watchdog_s > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog_s, exit=True)      # a hung collective must not hold the GPU box
     if args.impl == "reference":
         run_reference(args)
         return
+    # stdout carries exactly one JSON line: anything libraries print (NCCL's version banner, warnings) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -400,8 +414,6 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=device)
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
@@ -416,7 +428,7 @@ def main():
 
     sampler = ClockSampler(physical_index(local))
     sampler.start()
-    ms_step, loss_val = time_steps(model, loss_fn, args.steps, args.warmup, world)
+    ms_step, loss_val = time_steps(model, loss_fn, args.steps, args.warmup, world, graph=not args.no_graph)
     clocks = sampler.stop()
     ms_kernel = time_kernel(model, loss_fn, args.steps, args.warmup)
 
@@ -466,7 +478,7 @@ def main():
             del model, loss_fn
             torch.cuda.empty_cache()
             m2, model, loss_fn, _ = make_workload(args, 0, 1, device, dt2, ordr, args.elems, args.tile_nodes)
-            ms2, _ = time_steps(model, loss_fn, args.steps, args.warmup, 1)
+            ms2, _ = time_steps(model, loss_fn, args.steps, args.warmup, 1, graph=not args.no_graph)
             k2 = time_kernel(model, loss_fn, args.steps, args.warmup)
             s2 = 8 if dt2 == torch.float64 else 4
             p2 = model._plan()
@@ -504,6 +516,7 @@ def main():
                                    "(fwd+bwd, r-adaptive), unstructured triangles (jitter 0.25, hashed diagonals), gauss_order=4",
                        "elements_total": ne_total, "nodes_total": nn_total, "elements_per_gpu": ne_local,
                        "grid_nodes": list(dims), "ordering": args.ordering, "partition": "column strips + halo nodes" if world > 1 else "none",
+                       "launch": "eager" if args.no_graph else "CUDA-graph replay of zero_grad+loss+backward (hidenn_fem_b200.graph.GraphedEnergyStep)",
                        "l2_policy": "inputs+outputs+plan per launch (> 400 MB) exceed the 126 MB L2; no flush needed",
                        "tile_nodes": plan.info["max_local"], "n_tiles": plan.info["n_tiles"],
                        "halo_recompute": plan.info["elem_visits"] / max(1, ne_local), "setup_s": setup_s},
@@ -515,7 +528,8 @@ def main():
         }
         if extra:
             line["extra"] = extra
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

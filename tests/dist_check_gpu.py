@@ -20,6 +20,8 @@ import bench  # noqa: E402
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(150, exit=True)      # a hung collective must not hold the box
     ap = argparse.ArgumentParser()
     ap.add_argument("--elems", type=int, default=400_000)
     ap.add_argument("--dtype", default="f64")
@@ -68,6 +70,13 @@ def main():
     eu2 = rel(model.u_free.detach(), gmodel.u_free.detach()[ru])
     ex2 = rel(model.node_coords_free.detach(), gmodel.node_coords_free.detach()[rx])
     ok = ok and eu2 < (1e-7 if dt == torch.float64 else 1e-4) and ex2 < (1e-9 if dt == torch.float64 else 1e-5)
+    # CUDA-graph replay of the rank-local step + eager halo exchange: same bits as the eager step, twice in a row
+    from hidenn_fem_b200.graph import GraphedEnergyStep
+    l_e, gx_e, gu_e = evaluate(model, loss_fn)
+    step = GraphedEnergyStep(model, loss_fn)
+    for _ in range(2):
+        l_g = step()
+        ok = ok and l_g.item() == l_e and torch.equal(model.node_coords_free.grad, gx_e) and torch.equal(model.u_free.grad, gu_e)
     res = torch.tensor([el, ex, eu, eu2, ex2, 0.0 if ok else 1.0], device=dev, dtype=torch.float64)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     if rank == 0:

@@ -316,3 +316,26 @@ def test_large_tiles_strip_mesh(dtype):
         assert abs(loss.item() - float(lo)) <= tol * abs(float(lo))
         assert relmax(model.node_coords_free.grad.cpu().numpy(), gx) < tol
         assert relmax(model.u_free.grad.cpu().numpy(), gu) < tol
+
+
+def test_graphed_step_matches_eager_and_tracks_parameter_updates():
+    """hidenn_fem_b200.graph.GraphedEnergyStep: the replayed step returns the same bits as the eager calls, and sees
+    in-place parameter updates (an Adam loop on the replayed step follows the eager trajectory exactly)."""
+    from hidenn_fem_b200.graph import GraphedEnergyStep
+    g = _mesh_case(60_000, torch.float64, "morton", u_scale=1e-3)
+    m_eager, m_graph = build(g), build(g)
+    loss_fn = loss_of(g, torch.float64)
+    step = GraphedEnergyStep(m_graph, loss_fn)
+    opt_e = torch.optim.Adam(m_eager.parameters(), lr=1e-6)
+    opt_g = torch.optim.Adam(m_graph.parameters(), lr=1e-6)
+    for _ in range(4):
+        opt_e.zero_grad()
+        le = loss_fn(m_eager)
+        le.backward()
+        lg = step()
+        assert lg.item() == le.item()
+        assert torch.equal(m_graph.u_free.grad, m_eager.u_free.grad)
+        assert torch.equal(m_graph.node_coords_free.grad, m_eager.node_coords_free.grad)
+        opt_e.step()
+        opt_g.step()
+    assert torch.equal(m_graph.u_free, m_eager.u_free)
