@@ -260,7 +260,9 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     const int64_t* n2o = p->n2e_off.data();
     const int32_t* n2e = p->n2e_ent.data();
     auto build_range = [&](int64_t t0, int64_t t1) {
-        std::vector<int32_t> cand, halo, owned_sorted, perm, lid_of;
+        std::vector<int32_t> cand, halo, owned_sorted, perm, lid_of, halo_lid, pool_of;
+        std::vector<std::pair<int32_t, int32_t>> pools;
+        std::vector<std::vector<int32_t>> free_res;
         const int G = 8;
         for (int64_t t = t0; t < t1; ++t) {
             TileBuild& B = tb[t];
@@ -296,8 +298,51 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
                 }
             std::sort(halo.begin(), halo.end());
             halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
-            B.nodes.insert(B.nodes.end(), halo.begin(), halo.end());
-            if ((int64_t)B.nodes.size() > kMaxLocal) { B.err = 1; continue; }
+            const int32_t n_halo = (int32_t)halo.size(), n_local = B.n_owned + n_halo;
+            if (n_local > kMaxLocal) { B.err = 1; continue; }
+            // Local ids within a valence class (and among the halo nodes) are free.  The node records are staged and
+            // the gradients flushed in MEMORY order, 8 consecutive records per 128-byte shared-memory pass, each
+            // landing at / read from its local id: choose the ids so that the 8 records of a pass have 8 different
+            // ids mod 8 (different bank groups) wherever the class still has such an id free.
+            {
+                pools.clear();
+                pool_of.assign(B.n_owned, 0);
+                for (int32_t l = 0; l < B.n_owned;) {             // classes = runs of equal valence in the sorted order
+                    const int64_t v = n2o[owned_sorted[perm[l]] + 1] - n2o[owned_sorted[perm[l]]];
+                    int32_t e = l;
+                    while (e < B.n_owned && n2o[owned_sorted[perm[e]] + 1] - n2o[owned_sorted[perm[e]]] == v) { pool_of[perm[e]] = (int32_t)pools.size(); ++e; }
+                    pools.push_back({l, e});
+                    l = e;
+                }
+                pools.push_back({B.n_owned, n_local});              // halo pool
+                free_res.assign(pools.size() * 8, std::vector<int32_t>());
+                for (size_t q = 0; q < pools.size(); ++q)
+                    for (int32_t l = pools[q].second - 1; l >= pools[q].first; --l) free_res[q * 8 + (l & 7)].push_back(l);   // pop_back = lowest id
+                halo_lid.assign(n_halo, 0);
+                B.nodes.assign(n_local, 0);
+                int32_t io = 0, ih = 0, j = 0;
+                unsigned used = 0;
+                while (io < B.n_owned || ih < n_halo) {
+                    const bool take_owned = ih >= n_halo || (io < B.n_owned && owned_sorted[io] < halo[ih]);
+                    const size_t q = take_owned ? (size_t)pool_of[io] : pools.size() - 1;
+                    if ((j & 7) == 0) used = 0;
+                    int best = -1;
+                    size_t best_free = 0;
+                    for (int r = 0; r < 8; ++r) {                   // unused residue with the most ids left in this class
+                        const size_t nf = free_res[q * 8 + r].size();
+                        if (nf > best_free && !((used >> r) & 1u)) { best = r; best_free = nf; }
+                    }
+                    if (best < 0)                                   // class exhausted for the free residues: accept a conflict
+                        for (int r = 0; r < 8; ++r)
+                            if (free_res[q * 8 + r].size() > best_free) { best = r; best_free = free_res[q * 8 + r].size(); }
+                    const int32_t l = free_res[q * 8 + best].back();
+                    free_res[q * 8 + best].pop_back();
+                    used |= 1u << best;
+                    if (take_owned) { lid_of[io] = l; B.nodes[l] = owned_sorted[io]; ++io; }
+                    else { halo_lid[ih] = l; B.nodes[l] = halo[ih]; ++ih; }
+                    ++j;
+                }
+            }
             // Fold-slot layout: local nodes in groups of G (the lanes one shared-memory pass serves: 8 x 16 B for FP64,
             // 16 x 8 B for FP32).  Slot k of node l lives at  base[group] + k*G + (l % G): the G lanes that fold a group
             // read one contiguous 128-byte row per step (conflict-free), and the bank group of any partial store is
@@ -329,8 +374,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
                         for (int64_t k = n2o[n]; k < n2o[n + 1]; ++k)
                             if (n2e[k] == key) { pos = (unsigned long long)((B.off[lid] & 0xFFFFu) + (k - n2o[n]) * G); break; }
                     } else {
-                        auto it = std::lower_bound(B.nodes.begin() + B.n_owned, B.nodes.end(), n);
-                        lid = (int32_t)(it - B.nodes.begin());
+                        lid = halo_lid[std::lower_bound(halo.begin(), halo.end(), n) - halo.begin()];
                     }
                     w |= (unsigned long long)lid << (kLidBits * c);
                     w |= pos << (3 * kLidBits + kPosBits * c);
@@ -629,6 +673,27 @@ extern "C" int hidenn_tri_plan_pipeline(const hidenn_tri_plan* p, int32_t* rows2
     std::copy(p->last_own_x.begin(), p->last_own_x.end(), last_own_x);
     std::copy(p->first_need_u.begin(), p->first_need_u.end(), first_need_u);
     std::copy(p->last_own_u.begin(), p->last_own_u.end(), last_own_u);
+    return 0;
+}
+
+extern "C" int hidenn_tri_plan_stage_stats(const hidenn_tri_plan* p, int64_t* out2) {
+    HIDENN_REQUIRE(p && out2, "plan_stage_stats: NULL");
+    // shared-memory passes of the staging writes / flush reads: 8 consecutive memory-order records per pass
+    std::vector<int32_t> byid;
+    int64_t passes = 0, ideal = 0;
+    for (const TileDesc& d : p->tiles) {
+        byid.resize(d.n_local);
+        std::vector<std::pair<int32_t, int32_t>> rec(d.n_local);
+        for (int32_t i = 0; i < d.n_local; ++i) rec[i] = {p->t_node[d.node_off + i], i};
+        std::sort(rec.begin(), rec.end());
+        for (int32_t j0 = 0; j0 < d.n_local; j0 += 8) {
+            int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+            for (int32_t j = j0; j < std::min(d.n_local, j0 + 8); ++j) mx = std::max(mx, ++cnt[rec[j].second & 7]);
+            passes += mx;
+            ideal += 1;
+        }
+    }
+    out2[0] = passes; out2[1] = ideal;
     return 0;
 }
 

@@ -98,6 +98,11 @@ class TriPlan:
         _lib.check(_lib.lib().hidenn_tri_plan_bank_stats(self._h, C.c_int(real_bytes or self.real_bytes), out))
         return dict(gather=int(out[0]), gather_ideal=int(out[1]), store=int(out[2]), store_ideal=int(out[3]))
 
+    def stage_stats(self):
+        out = (C.c_int64 * 2)()
+        _lib.check(_lib.lib().hidenn_tri_plan_stage_stats(self._h, out))
+        return dict(passes=int(out[0]), ideal=int(out[1]))
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             _lib.lib().hidenn_tri_plan_destroy(self._h)

@@ -104,6 +104,9 @@ int hidenn_debug_tile_timing(long long* dev_buf);
 /* Host-side model of the tile kernel's shared-memory passes for the plan's lane assignment:
  * out4 = {gather passes, ideal gather passes, partial-store passes, ideal store passes}. */
 int hidenn_tri_plan_bank_stats(const hidenn_tri_plan* plan, int real_bytes, int64_t* out4);
+/* Same model for the node staging / gradient flush (8 consecutive memory-order records per pass, each at its local id):
+ * out2 = {passes, ideal passes}. */
+int hidenn_tri_plan_stage_stats(const hidenn_tri_plan* plan, int64_t* out2);
 
 /* Tile membership (tests): node_off [n_tiles+1] into nodes [info[2] = node_visits] (global node ids, owned nodes of a
  * tile first), n_owned [n_tiles].  Tiles are listed by ascending smallest owned node id. */

@@ -162,3 +162,16 @@ def test_pipeline_block_tables_cover_every_tile(ordering):
             assert (last[ro[ro >= 0] // rows] >= t).all()
     assert (owner_count == 1).all()
     assert mins == sorted(mins)
+
+
+def test_staging_passes_near_ideal():
+    """Local ids are chosen so that the 8 memory-order records of one staging / flush pass land in 8 different bank
+    groups (include/hidenn_b200.h, hidenn_tri_plan_stage_stats): random ids would need ~2.5 passes per ideal pass."""
+    from hidenn_fem_b200 import meshgen
+    from hidenn_fem_b200.plan import TriPlan
+    for ordering in ("morton", "random"):
+        m = meshgen.plate_mesh(301, 151, jitter=0.25, diag="random", seed=0, ordering=ordering)
+        plan = TriPlan(m.connectivity, m.node_coords.shape[0], m.node_coords, m.boundary_mask & ~m.neumann_mask,
+                       m.dirichlet_mask, m.neumann_edges, device=-1)
+        st = plan.stage_stats()
+        assert st["passes"] <= 1.15 * st["ideal"], st
