@@ -47,6 +47,23 @@ def shared_ids_from_candidates(cands: Sequence[np.ndarray]) -> np.ndarray:
     return ids[cnt >= 2]
 
 
+def shared_owner_from_candidates(cands: Sequence[np.ndarray], shared_gid: np.ndarray) -> np.ndarray:
+    """Owner rank of every shared node = the lowest rank whose candidate list holds it ([S] int64)."""
+    owner = np.full(shared_gid.shape, len(cands), np.int64)
+    for r in range(len(cands) - 1, -1, -1):
+        owner[np.isin(shared_gid, cands[r])] = r
+    return owner
+
+
+def owner_weights(plan: "HaloPlan", shared_owner: np.ndarray, rank: int, n_free_x: int, n_free_u: int):
+    """Per-row weights for global reductions over sharded Parameters (optim.ShardedLBFGS): 1 for the rows this rank
+    owns, 0 for its copies of shared rows owned by a lower rank.  Returns (wx [n_free_x], wu [n_free_u]) float64."""
+    wx, wu = np.ones(n_free_x), np.ones(n_free_u)
+    wx[plan.x_rows[shared_owner[plan.x_pos] != rank]] = 0.0
+    wu[plan.u_rows[shared_owner[plan.u_pos] != rank]] = 0.0
+    return wx, wu
+
+
 def build_halo_plan(global_node_id: np.ndarray, free_mask: np.ndarray, u_free_mask: np.ndarray,
                     shared_gid: np.ndarray) -> HaloPlan:
     order = np.argsort(global_node_id, kind="stable")
@@ -185,4 +202,10 @@ def setup_strip_halo(mesh: meshgen.PlateMesh, boundary_mask: np.ndarray, dirichl
     cands = gather_candidates(strip_candidates(mesh), group)
     shared = shared_ids_from_candidates(cands)
     plan = build_halo_plan(mesh.global_node_id, ~boundary_mask, ~dirichlet_mask, shared)
-    return HaloExchange(plan, device, dtype, group)
+    halo = HaloExchange(plan, device, dtype, group)
+    rank = dist.get_rank(group)
+    wx, wu = owner_weights(plan, shared_owner_from_candidates(cands, shared), rank, int((~boundary_mask).sum()),
+                           int((~dirichlet_mask).sum()))
+    # row weights for optim.ShardedLBFGS(model.parameters(), weights=halo.row_weights): [node_coords_free, u_free] order
+    halo.row_weights = [torch.from_numpy(wx).to(halo.device, dtype), torch.from_numpy(wu).to(halo.device, dtype)]
+    return halo

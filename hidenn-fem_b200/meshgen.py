@@ -210,3 +210,28 @@ def invert_some_elements(conn: np.ndarray, fraction: float, seed: int = 0) -> np
     pick = _hash_u01(np.arange(conn.shape[0]) + (1 << 41), seed) < fraction
     out[pick, 0], out[pick, 1] = conn[pick, 1], conn[pick, 0]
     return out
+
+
+def reorder_for_locality(node_coords: np.ndarray, connectivity: np.ndarray, boundary_mask: np.ndarray,
+                         dirichlet_mask: np.ndarray, neumann_edges: Optional[np.ndarray] = None, bits: int = 20):
+    """Mesh ingestion helper for meshes with arbitrary numbering (gmsh / meshzoo output, the 6-tuple of
+    /root/reference/src/mesh.py:125-153, 252-276): renumber the nodes along a Z (Morton) curve of their coordinates
+    and list the elements by their smallest new node id.  The fused kernels are correct for any numbering but read
+    Parameter rows through 32-byte sectors, so a numbering without locality runs ~3.5x slower (profiles/README.md).
+
+    Returns (node_coords, connectivity, boundary_mask, dirichlet_mask, neumann_edges, new_to_old, elem_new_to_old):
+    `new_to_old[i]` is the original index of new node i (to map results back: u_old[new_to_old] = u_new); corner
+    order inside every element is kept (the reference's results depend on it)."""
+    xy = np.asarray(node_coords, dtype=np.float64)
+    conn = np.asarray(connectivity, dtype=np.int64)
+    lo, hi = xy.min(0), xy.max(0)
+    span = np.where(hi > lo, hi - lo, 1.0)
+    q = np.minimum(((xy - lo) / span * ((1 << bits) - 1)).astype(np.uint64), np.uint64((1 << bits) - 1))
+    new_to_old = np.argsort(morton2(q[:, 0], q[:, 1]), kind="stable")
+    old_to_new = np.empty_like(new_to_old)
+    old_to_new[new_to_old] = np.arange(new_to_old.size)
+    conn_new = old_to_new[conn]
+    elem_order = np.argsort(conn_new.min(1), kind="stable")
+    edges = None if neumann_edges is None else old_to_new[np.asarray(neumann_edges, dtype=np.int64)]
+    return (np.asarray(node_coords)[new_to_old], conn_new[elem_order], np.asarray(boundary_mask)[new_to_old],
+            np.asarray(dirichlet_mask)[new_to_old], edges, new_to_old, elem_order)

@@ -77,6 +77,22 @@ def main():
     for _ in range(2):
         l_g = step()
         ok = ok and l_g.item() == l_e and torch.equal(model.node_coords_free.grad, gx_e) and torch.equal(model.u_free.grad, gu_e)
+    # sharded L-BFGS (global inner products through the owner weights) vs the stock optimiser on one GPU
+    from hidenn_fem_b200.optim import ShardedLBFGS
+    ob = ShardedLBFGS(model.parameters(), max_iter=6, history_size=6, weights=loss_fn.halo.row_weights)
+    og = torch.optim.LBFGS(gmodel.parameters(), max_iter=6, history_size=6)
+    lb, lg = [], []
+    for _ in range(2):
+        def c1():
+            ob.zero_grad(); l = loss_fn(model); l.backward(); return l
+        def c2():
+            og.zero_grad(); l = gloss_fn(gmodel); l.backward(); return l
+        lb.append(float(ob.step(c1).detach())); lg.append(float(og.step(c2).detach()))
+    eu3 = rel(model.u_free.detach(), gmodel.u_free.detach()[ru])
+    el3 = max(abs(a - b) / abs(b) for a, b in zip(lb, lg))
+    ok = ok and eu3 < (1e-6 if dt == torch.float64 else 1e-2) and el3 < (1e-8 if dt == torch.float64 else 1e-3)
+    if rank == 0:
+        print("sharded LBFGS vs single-GPU LBFGS: losses %s vs %s (rel %.2e), u rel %.2e" % (lb, lg, el3, eu3))
     res = torch.tensor([el, ex, eu, eu2, ex2, 0.0 if ok else 1.0], device=dev, dtype=torch.float64)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     if rank == 0:

@@ -109,3 +109,124 @@ def test_halo_plan_indices():
     assert list(p.u_pos) == [0, 1] and list(p.u_rows) == [1, 3]
     assert p.buffer_len == 2 + 4 * 4
     assert list(hd.shared_ids_from_candidates([np.array([1, 2, 3]), np.array([3, 4]), np.array([4, 4, 9])])) == [3, 4]
+
+
+def _lbfgs_worker(rank, world, port, q):
+    """ShardedLBFGS on the real strip partition: the local energy / gradients come from the numpy oracle, the halo
+    sums from the same index plan the CUDA pack kernels use; compared with torch.optim.LBFGS on the global mesh."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from hidenn_fem_b200 import meshgen, dist as hd
+        from hidenn_fem_b200.optim import ShardedLBFGS
+        nx, ny = 21, 11
+        kw = dict(jitter=0.2, diag="random", seed=0, ordering="morton")
+        xg, wg = cf.triangle_gauss_points(4)
+        xi1, w1 = cf.interval_gauss_points(2)
+        Cm = cf.plane_stress_C(E=1.0, nu=0.3)
+
+        class OracleLoss(torch.autograd.Function):          # numpy closed form behind autograd (CPU test only)
+            @staticmethod
+            def forward(ctx, u_free, m, umask, exchange):
+                U = np.zeros((m.node_coords.shape[0], 2)); U[umask] = u_free.detach().numpy()
+                t_q = np.tile(np.array([1e-3, 0.0]), (m.neumann_edges.shape[0], xi1.shape[0], 1))
+                loss, dX, dU = cf.tri_energy_full(m.node_coords, U, m.connectivity, Cm, xg, wg, None, m.neumann_edges, xi1, w1,
+                                                  t_q=t_q)
+                loss, gu = exchange(float(loss), dU[umask])
+                ctx.gu = torch.from_numpy(gu)
+                return torch.tensor(loss, dtype=torch.float64)
+
+            @staticmethod
+            def backward(ctx, go):
+                return ctx.gu * go, None, None, None
+
+        def train(m, exchange, weights, group_on):
+            umask = ~m.dirichlet_mask
+            u = torch.nn.Parameter(torch.zeros(int(umask.sum()), 2, dtype=torch.float64))
+            opt = (ShardedLBFGS([u], max_iter=8, history_size=5, weights=weights) if group_on
+                   else torch.optim.LBFGS([u], max_iter=8, history_size=5))
+            losses = []
+
+            def closure():
+                opt.zero_grad()
+                l = OracleLoss.apply(u, m, umask, exchange)
+                l.backward()
+                return l
+            for _ in range(3):
+                losses.append(float(opt.step(closure)))
+            return losses, u.detach().numpy(), umask
+
+        m = hd.strip_mesh(nx, ny, rank, world, **kw)
+        cands = hd.gather_candidates(hd.strip_candidates(m))
+        shared = hd.shared_ids_from_candidates(cands)
+        plan = hd.build_halo_plan(m.global_node_id, ~m.boundary_mask, ~m.dirichlet_mask, shared)
+        S = shared.shape[0]
+        _, wu = hd.owner_weights(plan, hd.shared_owner_from_candidates(cands, shared), rank, int((~m.boundary_mask).sum()),
+                                 int((~m.dirichlet_mask).sum()))
+
+        def exchange(loss, gu):
+            buf = torch.zeros(1 + 2 * S, dtype=torch.float64)
+            buf[0] = loss
+            bu = buf[1:].view(S, 2)
+            bu[torch.from_numpy(plan.u_pos)] = torch.from_numpy(gu[plan.u_rows])
+            dist.all_reduce(buf)
+            gu = gu.copy()
+            gu[plan.u_rows] = bu[torch.from_numpy(plan.u_pos)].numpy()
+            return float(buf[0]), gu
+
+        ls, u_loc, umask = train(m, exchange, [torch.from_numpy(wu)], True)
+        glob = meshgen.plate_mesh(nx, ny, **kw)
+        lg, u_glob, gum = train(glob, lambda l, g: (l, g), None, False)
+        pos = {g: i for i, g in enumerate(glob.global_node_id)}
+        loc = np.array([pos[g] for g in m.global_node_id])
+        full = np.zeros((glob.node_coords.shape[0], 2)); full[gum] = u_glob
+        q.put((rank, relmax(np.array(ls), np.array(lg)), relmax(u_loc, full[loc][umask]), float(wu.sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_lbfgs_follows_global_lbfgs():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_lbfgs_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, el, eu, nw in res:
+        assert el < 1e-9 and eu < 1e-7, (rank, el, eu)
+    # every free displacement row is owned exactly once across ranks
+    from hidenn_fem_b200 import meshgen
+    glob = meshgen.plate_mesh(21, 11, jitter=0.2, diag="random", seed=0, ordering="morton")
+    assert sum(r[3] for r in res) == float((~glob.dirichlet_mask).sum())
+
+
+def test_sharded_lbfgs_equals_torch_lbfgs_single_process():
+    from hidenn_fem_b200.optim import ShardedLBFGS
+    torch.manual_seed(0)
+    n = 120
+    A = torch.randn(n, n, dtype=torch.float64)
+    A = A @ A.T / n + torch.eye(n, dtype=torch.float64)
+    b = torch.randn(n, dtype=torch.float64)
+
+    def run(cls, **kw):
+        x = torch.nn.Parameter(torch.zeros(n, dtype=torch.float64))
+        y = torch.nn.Parameter(torch.ones(5, 2, dtype=torch.float64))
+        opt = cls([x, y], **kw)
+
+        def closure():
+            opt.zero_grad()
+            l = 0.5 * x @ A @ x - b @ x + (y ** 4).sum() + y.sum() * x[:3].sum()
+            l.backward()
+            return l
+        ls = [float(opt.step(closure).detach()) for _ in range(5)]
+        return np.array(ls), x.detach().numpy(), y.detach().numpy()
+
+    for kw in (dict(), dict(lr=0.5, max_iter=7, history_size=3)):
+        l1, x1, y1 = run(torch.optim.LBFGS, **kw)
+        l2, x2, y2 = run(ShardedLBFGS, **kw)
+        assert relmax(l2, l1) < 1e-10 and relmax(x2, x1) < 1e-8 and relmax(y2, y1) < 1e-8
