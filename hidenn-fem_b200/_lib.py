@@ -12,7 +12,7 @@ import re
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhidenn_b200.so")
+LIB_PATH = os.environ.get("HIDENN_LIB") or os.path.join(HERE, "libhidenn_b200.so")      # HIDENN_LIB: A/B builds (profiles/)
 HEADERS = [os.path.join(os.path.dirname(HERE), "include", h) for h in ("hidenn_b200.h", "hidenn_b200_grid.h")]
 
 _lib = None
