@@ -339,3 +339,64 @@ def test_graphed_step_matches_eager_and_tracks_parameter_updates():
         opt_e.step()
         opt_g.step()
     assert torch.equal(m_graph.u_free, m_eager.u_free)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_full_size_properties_10m_elements(dtype):
+    """BASELINE config C4 at full size (10 M triangles, the bench workload), checked through properties that need no
+    oracle run: determinism, exact 2x scaling of u (domain energy x4, edge energy x2, bit for bit), Euler's identity
+    <dE/du, u> = 2 E_dom - E_edge, rigid-translation invariance, and a central-difference directional derivative."""
+    from hidenn_fem_b200 import meshgen
+    g = _mesh_case(10_000_000, dtype, "morton", u_scale=1e-3)
+    model = build(g)
+    loss_fn = loss_of(g, dtype)
+    f64 = dtype == torch.float64
+
+    def evaluate():
+        model.zero_grad(set_to_none=True)
+        l = loss_fn(model)
+        l.backward()
+        parts = loss_fn.last_parts.clone()
+        return parts, model.node_coords_free.grad.clone(), model.u_free.grad.clone()
+
+    p0, gx0, gu0 = evaluate()
+    p1, gx1, gu1 = evaluate()
+    assert torch.equal(p0, p1) and torch.equal(gx0, gx1) and torch.equal(gu0, gu1)            # determinism
+    assert torch.isfinite(p0).all() and torch.isfinite(gx0).all() and torch.isfinite(gu0).all()
+    assert abs(p0[0].item() - (p0[1].item() - p0[2].item())) <= (1e-12 if f64 else 2e-7) * abs(p0[1].item())
+
+    # Euler: E_dom is quadratic and E_edge linear in u (u_fixed = 0)
+    lhs = (gu0.double() * model.u_free.detach().double()).sum().item()
+    rhs = 2.0 * p0[1].item() - p0[2].item()
+    assert abs(lhs - rhs) <= (1e-10 if f64 else 2e-4) * max(abs(p0[1].item()), abs(rhs))
+
+    # u -> 2u is exact in floating point: every product scales by a power of two
+    with torch.no_grad():
+        model.u_free.mul_(2.0)
+    p2, gx2, gu2 = evaluate()
+    assert p2[1].item() == 4.0 * p0[1].item() and p2[2].item() == 2.0 * p0[2].item()
+    with torch.no_grad():
+        model.u_free.mul_(0.5)
+
+    # central difference along the gradient direction in u (exact for a quadratic up to rounding); the step is sized
+    # so that the two energies differ by ~20 % and FP32 cancellation stays harmless
+    v = gu0
+    g2 = (gu0.double() ** 2).sum().item()
+    h = 0.1 * abs(p0[1].item()) / g2
+    vals = []
+    for sgn in (1.0, -1.0):
+        with torch.no_grad():
+            saved = model.u_free.detach().clone()
+            model.u_free.add_(v, alpha=sgn * h)
+            vals.append(loss_fn(model).item())
+            model.u_free.copy_(saved)
+    fd = (vals[0] - vals[1]) / (2 * h)
+    assert abs(fd - g2) <= (1e-8 if f64 else 1e-3) * g2
+
+    # rigid translation of every node (free and fixed): J and hence the energy do not change
+    pa = evaluate()[0]
+    with torch.no_grad():
+        model.node_coords_free.add_(torch.tensor([0.25, -0.5], device="cuda", dtype=dtype))
+        model.node_coords_fixed.add_(torch.tensor([0.25, -0.5], device="cuda", dtype=dtype))
+        pb = loss_fn(model)
+    assert abs(pb.item() - pa[0].item()) <= (1e-9 if f64 else 1e-3) * abs(pa[1].item())
