@@ -308,3 +308,44 @@ def test_structured_forward_smem_and_global_lookup_agree():
     gxx, gyy = (a.detach().cpu().numpy() for a in model.grid)
     po, _, _ = cf.q1_interp(gxx, gyy, model.u.detach().cpu().numpy().reshape(Nx, Ny), x.cpu().numpy())
     assert relmax(big.cpu().numpy(), po) < 1e-12
+
+
+def test_structured_full_size_properties():
+    """BASELINE config C3 at full size (4097 x 4097 nodes, 2^26 samples, FP64) through oracle-free properties:
+    a bilinear field is reproduced, u -> 2u scales prediction and gradients exactly, the nodal gradients of an MSE
+    loss add up to the sum of the residual weights (partition of unity), and the step is bit-reproducible."""
+    from hidenn_fem_b200.models import StructuredShapeNN2D
+    Nx = Ny = 4097
+    M = 1 << 26
+    g1 = torch.linspace(0, 1, Nx, dtype=torch.float64)
+    model = StructuredShapeNN2D(g1, g1.clone(), r_adapt=True).double().cuda()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    with torch.no_grad():
+        model.increments_x.add_(0.3 * (torch.rand(Nx - 1, device="cuda", dtype=torch.float64, generator=gen) - 0.5) * model.increments_x.abs())
+        model.increments_y.add_(0.3 * (torch.rand(Ny - 1, device="cuda", dtype=torch.float64, generator=gen) - 0.5) * model.increments_y.abs())
+    x = torch.rand(M, 2, device="cuda", dtype=torch.float64, generator=gen)
+    gx, gy = (a.detach() for a in model.grid)
+    bil = lambda X, Y: 0.3 + 1.7 * X - 0.9 * Y + 2.3 * X * Y
+    with torch.no_grad():
+        model.u.copy_(bil(gx[:, None], gy[None, :]))
+        pred = model(x)
+    assert (pred - bil(x[:, 0], x[:, 1])).abs().max().item() < 1e-12            # bilinear reproduction
+
+    target = torch.sin(6.0 * x[:, 0]) * torch.cos(4.0 * x[:, 1])
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        p = model(x)
+        loss = ((p - target) ** 2).mean()
+        loss.backward()
+        return p.detach(), loss.item(), model.u.grad.clone(), model.increments_x.grad.clone()
+
+    p1, l1, du1, dix1 = step()
+    p2, l2, du2, dix2 = step()
+    assert l1 == l2 and torch.equal(du1, du2) and torch.equal(dix1, dix2)          # deterministic (integer atomics only)
+    r = 2.0 * (p1 - target) / M
+    assert abs(du1.sum().item() - r.sum().item()) <= 1e-10 * r.abs().sum().item()  # partition of unity
+    with torch.no_grad():
+        model.u.mul_(2.0)
+        p3 = model(x)
+    assert torch.equal(p3, 2.0 * p1)                                               # exact power-of-two scaling
