@@ -17,31 +17,61 @@ template <typename R> __device__ __forceinline__ int lookup_line(const R* __rest
     return (int)e;
 }
 
-template <typename R> __device__ __forceinline__ int lookup_line_smem(const R* grid, int N, R x) {
-    int lo = 0, hi = N;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (grid[mid] < x) lo = mid + 1; else hi = mid;
+// clamp(searchsorted_left(grid, x) - 1, 0, N-2), bit-exact, but starting from the position a uniform grid would give:
+// r-adaptive grids stay close to uniform, so a few neighbour comparisons replace the ~log2(N) dependent loads of a
+// bisection (which remains the fallback when the guess is more than 4 lines off).  inv = (N-1) / (grid[N-1] - grid[0]).
+template <typename R> __device__ __forceinline__ int lookup_line_smem(const R* grid, int N, R x, R g0, R inv) {
+    const R t = (x - g0) * inv;
+    int lo = t >= R(0) ? (t < (R)(N - 1) ? (int)t : N - 1) : 0;       // NaN -> 0, like the bisection
+    if (lo > 0 && grid[lo - 1] >= x) {                                // first index with grid[i] >= x lies to the left
+        int steps = 0;
+        do { --lo; } while (lo > 0 && grid[lo - 1] >= x && ++steps < 4);
+        if (lo > 0 && grid[lo - 1] >= x) {
+            int a = 0, b = lo;
+            while (a < b) { const int mid = (a + b) >> 1; if (grid[mid] < x) a = mid + 1; else b = mid; }
+            lo = a;
+        }
+    } else {
+        int steps = 0;
+        while (lo < N && grid[lo] < x && steps < 4) { ++lo; ++steps; }
+        if (lo < N && grid[lo] < x) {
+            int a = lo + 1, b = N;
+            while (a < b) { const int mid = (a + b) >> 1; if (grid[mid] < x) a = mid + 1; else b = mid; }
+            lo = a;
+        }
     }
     const int e = lo - 1;
     return e < 0 ? 0 : (e > N - 2 ? N - 2 : e);
 }
 
-// both grid lines staged in shared memory (used when they fit): the two binary searches then cost LDS latency only
-template <typename R>
+// both grid lines staged in shared memory (used when they fit): the two binary searches then cost LDS latency only.
+// L2 = true: fused L2-projection loss -- writes the residual weight 2 (u_h - target) / M instead of u_h and leaves
+// the CTA's sum of squared residuals (fixed order: per-thread strided sum, warp tree, warp order) in partial[blockIdx.x].
+template <typename R, bool L2, bool SMEM>
 __global__ void __launch_bounds__(256)
 q1_fwd_smem_kernel(const R* __restrict__ gx, int Nx, const R* __restrict__ gy, int Ny, const R* __restrict__ uf,
-                   const typename Real2<R>::type* __restrict__ x, int64_t M, R* __restrict__ u, int32_t* __restrict__ ixo,
-                   int32_t* __restrict__ iyo) {
+                   const typename Real2<R>::type* __restrict__ x, const R* __restrict__ target, int64_t M, R* __restrict__ u,
+                   int32_t* __restrict__ ixo, int32_t* __restrict__ iyo, R* __restrict__ partial) {
     extern __shared__ __align__(16) unsigned char q1_smem[];
-    R* sx = reinterpret_cast<R*>(q1_smem);
-    R* sy = sx + Nx;
-    for (int i = threadIdx.x; i < Nx; i += 256) sx[i] = gx[i];
-    for (int i = threadIdx.x; i < Ny; i += 256) sy[i] = gy[i];
-    __syncthreads();
+    __shared__ R s_red[8];
+    const R* sx = gx;
+    const R* sy = gy;
+    if (SMEM) {
+        R* wx = reinterpret_cast<R*>(q1_smem);
+        R* wy = wx + Nx;
+        for (int i = threadIdx.x; i < Nx; i += 256) wx[i] = gx[i];
+        for (int i = threadIdx.x; i < Ny; i += 256) wy[i] = gy[i];
+        __syncthreads();
+        sx = wx; sy = wy;
+    }
+    const R scale = R(2) / (R)M;
+    const R gx0 = sx[0], gy0 = sy[0];
+    const R spanx = sx[Nx - 1] - gx0, spany = sy[Ny - 1] - gy0;
+    const R invx = spanx > R(0) ? (R)(Nx - 1) / spanx : R(0), invy = spany > R(0) ? (R)(Ny - 1) / spany : R(0);
+    R acc = R(0);
     for (int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x; m < M; m += (int64_t)gridDim.x * 256) {
         const typename Real2<R>::type p = x[m];
-        const int ix = lookup_line_smem<R>(sx, Nx, p.x), iy = lookup_line_smem<R>(sy, Ny, p.y);
+        const int ix = lookup_line_smem<R>(sx, Nx, p.x, gx0, invx), iy = lookup_line_smem<R>(sy, Ny, p.y, gy0, invy);
         const R u00 = __ldg(uf + (int64_t)ix * Ny + iy), u10 = __ldg(uf + (int64_t)(ix + 1) * Ny + iy);
         const R u01 = __ldg(uf + (int64_t)ix * Ny + iy + 1), u11 = __ldg(uf + (int64_t)(ix + 1) * Ny + iy + 1);
         const R x0 = sx[ix], x1 = sx[ix + 1], y0 = sy[iy], y1 = sy[iy + 1];
@@ -49,31 +79,30 @@ q1_fwd_smem_kernel(const R* __restrict__ gx, int Nx, const R* __restrict__ gy, i
         hx = hx < R(1e-10) ? R(1e-10) : hx;
         hy = hy < R(1e-10) ? R(1e-10) : hy;
         const R N1x = (x1 - p.x) / hx, N2x = (p.x - x0) / hx, N1y = (y1 - p.y) / hy, N2y = (p.y - y0) / hy;
-        u[m] = N1x * N1y * u00 + N2x * N1y * u10 + N1x * N2y * u01 + N2x * N2y * u11;
+        const R uh = N1x * N1y * u00 + N2x * N1y * u10 + N1x * N2y * u01 + N2x * N2y * u11;
+        if (L2) {
+            const R d = uh - target[m];
+            acc += d * d;
+            u[m] = scale * d;
+        } else {
+            u[m] = uh;
+        }
         if (ixo) ixo[m] = ix;
         if (iyo) iyo[m] = iy;
+    }
+    if (L2) {
+        const R tot = block_sum<R, 256>(acc, s_red);
+        if (threadIdx.x == 0) partial[blockIdx.x] = tot;
     }
 }
 
 template <typename R>
-__global__ void __launch_bounds__(256)
-q1_fwd_kernel(const R* __restrict__ gx, int64_t Nx, const R* __restrict__ gy, int64_t Ny, const R* __restrict__ uf,
-              const typename Real2<R>::type* __restrict__ x, int64_t M, R* __restrict__ u, int32_t* __restrict__ ixo,
-              int32_t* __restrict__ iyo) {
-    for (int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x; m < M; m += (int64_t)gridDim.x * 256) {
-        const typename Real2<R>::type p = x[m];
-        const int ix = lookup_line<R>(gx, Nx, p.x), iy = lookup_line<R>(gy, Ny, p.y);
-        const R x0 = __ldg(gx + ix), x1 = __ldg(gx + ix + 1), y0 = __ldg(gy + iy), y1 = __ldg(gy + iy + 1);
-        R hx = x1 - x0, hy = y1 - y0;
-        hx = hx < R(1e-10) ? R(1e-10) : hx;
-        hy = hy < R(1e-10) ? R(1e-10) : hy;
-        const R N1x = (x1 - p.x) / hx, N2x = (p.x - x0) / hx, N1y = (y1 - p.y) / hy, N2y = (p.y - y0) / hy;
-        const R u00 = __ldg(uf + (int64_t)ix * Ny + iy), u10 = __ldg(uf + (int64_t)(ix + 1) * Ny + iy);
-        const R u01 = __ldg(uf + (int64_t)ix * Ny + iy + 1), u11 = __ldg(uf + (int64_t)(ix + 1) * Ny + iy + 1);
-        u[m] = N1x * N1y * u00 + N2x * N1y * u10 + N1x * N2y * u01 + N2x * N2y * u11;
-        if (ixo) ixo[m] = ix;
-        if (iyo) iyo[m] = iy;
-    }
+__global__ void __launch_bounds__(256) q1_l2_finish_kernel(const R* __restrict__ partial, int n, int64_t M, R* __restrict__ loss) {
+    __shared__ double s_red[8];
+    double a = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) a += (double)partial[i];
+    const double tot = block_sum<double, 256>(a, s_red);
+    if (threadIdx.x == 0) loss[0] = (R)(tot / (double)M);
 }
 
 // VJP pieces of one sample in cell (ix,iy): o[0..3] = d u00,u10,u01,u11; o[4..5] = d gx_i, gx_{i+1}; o[6..7] = d gy_j, gy_{j+1}
@@ -234,25 +263,51 @@ __global__ void __launch_bounds__(256) q1_fold_lines_kernel(const R* __restrict_
 
 static inline int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 32)); }
 
+constexpr int kQ1L2MaxCtas = 148 * 8;
+
+// grid: every CTA stages the lines once (when they fit in 100 KB) and strides over the samples
+template <typename R, bool L2>
+static int q1_fwd_launch(const R* gx, int64_t Nx, const R* gy, int64_t Ny, const R* uf, const R* x, const R* target, int64_t M, R* out,
+                         int32_t* ix, int32_t* iy, R* partial, cudaStream_t st, int* grid_out = nullptr) {
+    using R2 = typename Real2<R>::type;
+    HIDENN_REQUIRE(Nx < (1LL << 31) && Ny < (1LL << 31), "q1 forward: grid lines longer than 2^31");
+    const size_t lines = (size_t)(Nx + Ny) * sizeof(R);
+    const bool smem = lines <= 100 * 1024 && M >= 65536;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = smem ? (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (lines + 1024))) : 8;
+    const int64_t want = (M + 255) / 256;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, std::min<int64_t>((int64_t)sms * per_sm, kQ1L2MaxCtas)));
+    if (grid_out) *grid_out = grid;
+    if (smem) {
+        HIDENN_CUDA_OK(cudaFuncSetAttribute(q1_fwd_smem_kernel<R, L2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        q1_fwd_smem_kernel<R, L2, true><<<grid, 256, lines, st>>>(gx, (int)Nx, gy, (int)Ny, uf, (const R2*)x, target, M, out, ix, iy, partial);
+    } else {
+        q1_fwd_smem_kernel<R, L2, false><<<grid, 256, 0, st>>>(gx, (int)Nx, gy, (int)Ny, uf, (const R2*)x, target, M, out, ix, iy, partial);
+    }
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename R>
+static int q1_l2_fwd(const R* gx, int64_t Nx, const R* gy, int64_t Ny, const R* uf, const R* x, const R* target, int64_t M, R* r, int32_t* ix,
+                     int32_t* iy, R* partial, R* loss, void* s) {
+    HIDENN_REQUIRE(Nx >= 2 && Ny >= 2 && M > 0, "q1_l2_fwd: needs M > 0 samples and grids of at least 2 nodes");
+    HIDENN_REQUIRE(gx && gy && uf && x && target && r && ix && iy && partial && loss, "q1_l2_fwd: NULL");
+    int grid = 0;
+    if (q1_fwd_launch<R, true>(gx, Nx, gy, Ny, uf, x, target, M, r, ix, iy, partial, (cudaStream_t)s, &grid)) return 1;
+    q1_l2_finish_kernel<R><<<1, 256, 0, (cudaStream_t)s>>>(partial, grid, M, loss);
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template <typename R>
 static int q1_fwd(const R* gx, int64_t Nx, const R* gy, int64_t Ny, const R* uf, const R* x, int64_t M, R* u, int32_t* ix, int32_t* iy, void* s) {
     HIDENN_REQUIRE(Nx >= 2 && Ny >= 2, "q1_interp_fwd: both grids need at least 2 nodes");
     if (M <= 0) return 0;
     HIDENN_REQUIRE(gx && gy && uf && x && u, "q1_interp_fwd: NULL");
-    const size_t lines = (size_t)(Nx + Ny) * sizeof(R);
-    if (lines <= 100 * 1024 && M >= 65536) {
-        // persistent-ish grid: every CTA stages the lines once and strides over the samples
-        HIDENN_CUDA_OK(cudaFuncSetAttribute(q1_fwd_smem_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (lines + 1024)));
-        const int64_t want = (M + 255) / 256;
-        const int grid = (int)std::min<int64_t>(want, (int64_t)sms * per_sm);
-        q1_fwd_smem_kernel<R><<<grid, 256, lines, (cudaStream_t)s>>>(gx, (int)Nx, gy, (int)Ny, uf, (const typename Real2<R>::type*)x, M, u, ix, iy);
-    } else {
-        q1_fwd_kernel<R><<<grid_for(M), 256, 0, (cudaStream_t)s>>>(gx, Nx, gy, Ny, uf, (const typename Real2<R>::type*)x, M, u, ix, iy);
-    }
+    if (q1_fwd_launch<R, false>(gx, Nx, gy, Ny, uf, x, nullptr, M, u, ix, iy, nullptr, (cudaStream_t)s)) return 1;
     HIDENN_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -297,6 +352,16 @@ static int q1_bwd_fused(const R* gx, int64_t Nx, const R* gy, int64_t Ny, const 
 }  // namespace hidenn
 
 using namespace hidenn;
+
+extern "C" int64_t hidenn_q1_l2_partials(void) { return kQ1L2MaxCtas; }
+extern "C" int hidenn_q1_l2_fwd_f64(const double* gx, int64_t Nx, const double* gy, int64_t Ny, const double* uf, const double* x,
+                                    const double* t, int64_t M, double* r, int32_t* ix, int32_t* iy, double* partial, double* loss, void* s) {
+    return q1_l2_fwd<double>(gx, Nx, gy, Ny, uf, x, t, M, r, ix, iy, partial, loss, s);
+}
+extern "C" int hidenn_q1_l2_fwd_f32(const float* gx, int64_t Nx, const float* gy, int64_t Ny, const float* uf, const float* x,
+                                    const float* t, int64_t M, float* r, int32_t* ix, int32_t* iy, float* partial, float* loss, void* s) {
+    return q1_l2_fwd<float>(gx, Nx, gy, Ny, uf, x, t, M, r, ix, iy, partial, loss, s);
+}
 
 extern "C" int hidenn_q1_bin_count(const int32_t* ix, const int32_t* iy, int64_t M, int64_t Ny, int32_t* cnt, void* s) {
     if (M <= 0) return 0;

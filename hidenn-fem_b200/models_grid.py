@@ -334,6 +334,80 @@ def example3_b_force(x):
 # ------------------------------------------------------------------------------------------------
 # structured Q1 model (models.py:93-212)
 # ------------------------------------------------------------------------------------------------
+def _q1_backward(gx, gy, uf, xs, ix, iy, r):
+    """VJP of the structured interpolation for cotangent r [M]: sort-free deterministic binning (integer histogram ->
+    prefix -> scatter -> per-cell ascending sample id) + fused per-cell fold + node / grid-line folds."""
+    dt, dev = gx.dtype, gx.device
+    M, Nx, Ny = xs.shape[0], gx.shape[0], gy.shape[0]
+    s = _lib.stream_ptr()
+    L = _lib.lib()
+    ncell = (Nx - 1) * (Ny - 1)
+    count = torch.zeros(ncell, device=dev, dtype=torch.int32)
+    _lib.check(L.hidenn_q1_bin_count(_lib.ptr(ix), _lib.ptr(iy), c_i64(M), c_i64(Ny), _lib.ptr(count), s))
+    seg = torch.zeros(ncell + 1, device=dev, dtype=torch.int32)
+    torch.cumsum(count, 0, dtype=torch.int32, out=seg[1:])
+    count.zero_()
+    order = torch.empty(max(M, 1), device=dev, dtype=torch.int32)
+    _lib.check(L.hidenn_q1_bin_scatter(_lib.ptr(ix), _lib.ptr(iy), c_i64(M), c_i64(Nx), c_i64(Ny), _lib.ptr(seg),
+                                       _lib.ptr(count), _lib.ptr(order), s))
+    tmp = torch.empty(ncell, 8, device=dev, dtype=dt)
+    du = torch.empty(Nx, Ny, device=dev, dtype=dt)
+    dgx = torch.empty(Nx, device=dev, dtype=dt)
+    dgy = torch.empty(Ny, device=dev, dtype=dt)
+    _lib.check(_lib.fn("hidenn_q1_bwd_fused", dt)(_lib.ptr(gx), c_i64(Nx), _lib.ptr(gy), c_i64(Ny), _lib.ptr(uf), _lib.ptr(xs),
+                                                  _lib.ptr(r), c_i64(M), _lib.ptr(seg), _lib.ptr(order),
+                                                  _lib.ptr(tmp), _lib.ptr(du), _lib.ptr(dgx), _lib.ptr(dgy), s))
+    return dgx, dgy, du
+
+
+class _Q1L2Fn(torch.autograd.Function):
+    """mean((model(x) - target)^2) in one forward pass (lookups, interpolation, residual weights, loss) and the fused
+    structured backward on the residual weights."""
+
+    @staticmethod
+    def forward(ctx, gx, gy, u_full, x, target):
+        _require_cuda(gx, "l2_projection_loss")
+        dt, dev = gx.dtype, gx.device
+        gxc, gyc, uf = gx.contiguous(), gy.to(dt).contiguous(), u_full.to(dt).contiguous()
+        xs, tg = x.to(dt).contiguous(), target.to(dt).contiguous().reshape(-1)
+        M = xs.shape[0]
+        if tg.shape[0] != M:
+            raise ValueError("l2_projection_loss: target must have one value per sample")
+        r = torch.empty(M, device=dev, dtype=dt)
+        ix = torch.empty(M, device=dev, dtype=torch.int32)
+        iy = torch.empty(M, device=dev, dtype=torch.int32)
+        partial = torch.empty(int(_lib.lib().hidenn_q1_l2_partials()), device=dev, dtype=dt)
+        loss = torch.empty(1, device=dev, dtype=dt)
+        _lib.check(_lib.fn("hidenn_q1_l2_fwd", dt)(_lib.ptr(gxc), c_i64(gxc.shape[0]), _lib.ptr(gyc), c_i64(gyc.shape[0]), _lib.ptr(uf),
+                                                   _lib.ptr(xs), _lib.ptr(tg), c_i64(M), _lib.ptr(r), _lib.ptr(ix), _lib.ptr(iy),
+                                                   _lib.ptr(partial), _lib.ptr(loss), _lib.stream_ptr()))
+        ctx.save_for_backward(gxc, gyc, uf, xs, ix, iy, r)
+        ctx.udtype = u_full.dtype
+        ctx.used = False
+        return loss[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        if ctx.used:
+            raise RuntimeError("l2_projection_loss: backward called twice on the same loss (the residual buffer is scaled in "
+                               "place); evaluate the loss again instead")
+        ctx.used = True
+        gx, gy, uf, xs, ix, iy, r = ctx.saved_tensors
+        dt = gx.dtype
+        scale = go.reshape(1).to(dt).contiguous()
+        _lib.check(_lib.fn("hidenn_scale_inplace", dt)(_lib.ptr(r), c_i64(r.numel()), _lib.ptr(scale), _lib.stream_ptr()))   # exits at once if 1
+        dgx, dgy, du = _q1_backward(gx, gy, uf, xs, ix, iy, r)
+        return dgx, dgy, du.to(ctx.udtype), None, None
+
+
+def l2_projection_loss(model, x, u_true):
+    """Fused drop-in for `((model(x) - u_true) ** 2).mean()` of examples/example2.py:45-46 on the structured model
+    (one forward pass instead of interpolation + three elementwise passes; same deterministic backward)."""
+    gx, gy = model.grid
+    return _Q1L2Fn.apply(gx, gy, model.u_full, x, u_true)
+
+
 class _Q1InterpFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gx, gy, u_full, x):
@@ -358,25 +432,7 @@ class _Q1InterpFn(torch.autograd.Function):
         dt, dev = gx.dtype, gx.device
         M = xs.shape[0]
         Nx, Ny = gx.shape[0], gy.shape[0]
-        s = _lib.stream_ptr()
-        L = _lib.lib()
-        ncell = (Nx - 1) * (Ny - 1)
-        # sort-free deterministic binning: integer histogram -> prefix -> scatter -> per-cell ascending sample id
-        count = torch.zeros(ncell, device=dev, dtype=torch.int32)
-        _lib.check(L.hidenn_q1_bin_count(_lib.ptr(ix), _lib.ptr(iy), c_i64(M), c_i64(Ny), _lib.ptr(count), s))
-        seg = torch.zeros(ncell + 1, device=dev, dtype=torch.int32)
-        torch.cumsum(count, 0, dtype=torch.int32, out=seg[1:])
-        count.zero_()
-        order = torch.empty(max(M, 1), device=dev, dtype=torch.int32)
-        _lib.check(L.hidenn_q1_bin_scatter(_lib.ptr(ix), _lib.ptr(iy), c_i64(M), c_i64(Nx), c_i64(Ny), _lib.ptr(seg),
-                                           _lib.ptr(count), _lib.ptr(order), s))
-        tmp = torch.empty(ncell, 8, device=dev, dtype=dt)
-        du = torch.empty(Nx, Ny, device=dev, dtype=dt)
-        dgx = torch.empty(Nx, device=dev, dtype=dt)
-        dgy = torch.empty(Ny, device=dev, dtype=dt)
-        _lib.check(_lib.fn("hidenn_q1_bwd_fused", dt)(_lib.ptr(gx), c_i64(Nx), _lib.ptr(gy), c_i64(Ny), _lib.ptr(uf), _lib.ptr(xs),
-                                                      _lib.ptr(r.to(dt).contiguous()), c_i64(M), _lib.ptr(seg), _lib.ptr(order),
-                                                      _lib.ptr(tmp), _lib.ptr(du), _lib.ptr(dgx), _lib.ptr(dgy), s))
+        dgx, dgy, du = _q1_backward(gx, gy, uf, xs, ix, iy, r.to(dt).contiguous())
         return dgx, dgy, du.to(ctx.udtype), None
 
 

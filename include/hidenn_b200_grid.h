@@ -103,6 +103,20 @@ int hidenn_q1_bwd_fused_f32(const float* gx, int64_t Nx, const float* gy, int64_
                             const float* x, const float* r, int64_t M, const int32_t* seg, const int32_t* order,
                             float* cell_tmp, float* du_full, float* dgx, float* dgy, void* stream);
 
+/* Fused structured L2-projection loss  mean((model(x) - target)^2)  (examples/example2.py:45-46; example1.py:37-38 for
+ * the same expression): one pass computes the lookups, the interpolation, the residual weights
+ *   r[m] = 2 (u_h(x_m) - target[m]) / M        (dev [M], = d loss / d u_h)
+ * and per-CTA partial sums of the squared residuals; a second one-CTA kernel adds the partials in CTA order ->
+ * loss dev [1].  partial dev [hidenn_q1_l2_partials()] reals.  The backward is hidenn_q1_bwd_fused_* on r
+ * (scaled by autograd's grad_output through hidenn_scale_inplace_*). */
+int64_t hidenn_q1_l2_partials(void);
+int hidenn_q1_l2_fwd_f64(const double* gx, int64_t Nx, const double* gy, int64_t Ny, const double* u_full, const double* x,
+                         const double* target, int64_t M, double* r, int32_t* ix, int32_t* iy, double* partial, double* loss,
+                         void* stream);
+int hidenn_q1_l2_fwd_f32(const float* gx, int64_t Nx, const float* gy, int64_t Ny, const float* u_full, const float* x,
+                         const float* target, int64_t M, float* r, int32_t* ix, int32_t* iy, float* partial, float* loss,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

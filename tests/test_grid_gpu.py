@@ -349,3 +349,35 @@ def test_structured_full_size_properties():
         model.u.mul_(2.0)
         p3 = model(x)
     assert torch.equal(p3, 2.0 * p1)                                               # exact power-of-two scaling
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_fused_l2_projection_loss_matches_generic_expression(dt):
+    """models_grid.l2_projection_loss == ((model(x) - u_true) ** 2).mean() (examples/example2.py:45-46): loss and the
+    gradients w.r.t. nodal values and both increment vectors, plus bit-reproducibility and grad_output scaling."""
+    from hidenn_fem_b200.models import StructuredShapeNN2D
+    from hidenn_fem_b200.models_grid import l2_projection_loss
+    rng = np.random.default_rng(2)
+    Nx, Ny, M = 129, 97, 150_000
+    mk = lambda: StructuredShapeNN2D(torch.linspace(0, 1, Nx, dtype=dt), torch.linspace(0, 2, Ny, dtype=dt), r_adapt=True).to(dt).cuda()
+    a, b = mk(), mk()
+    with torch.no_grad():
+        for m in (a, b):
+            m.u.copy_(T(rng.standard_normal((Nx, Ny)), dtype=dt) if m is a else a.u)
+            m.increments_x.copy_(a.increments_x * (1 if m is a else 1))
+        pert = T(1.0 + 0.2 * rng.standard_normal(Nx - 1), dtype=dt)
+        a.increments_x.mul_(pert); b.increments_x.mul_(pert)
+    x = T(rng.random((M, 2)) * np.array([1.0, 2.0]), dtype=dt)
+    ut = torch.sin(5 * x[:, 0]) * torch.cos(3 * x[:, 1])
+    la = 3.0 * l2_projection_loss(a, x, ut)
+    la.backward()
+    lb = 3.0 * ((b(x) - ut) ** 2).mean()
+    lb.backward()
+    tol = 1e-11 if dt == torch.float64 else 2e-4
+    assert abs(la.item() - lb.item()) <= tol * abs(lb.item())
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert relmax(pa.grad.cpu().numpy(), pb.grad.cpu().numpy()) < tol
+    g1 = [p.grad.clone() for p in a.parameters()]
+    a.zero_grad()
+    (3.0 * l2_projection_loss(a, x, ut)).backward()
+    assert all(torch.equal(u, p.grad) for u, p in zip(g1, a.parameters()))
