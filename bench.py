@@ -141,8 +141,13 @@ def make_workload(args, rank, world, device, dtype, ordering, n_elems_per_gpu, t
     from hidenn_fem_b200.loss import EnergyLoss2D
     nx, ny = meshgen.plate_dims_for_elements(n_elems_per_gpu * world)
     splits = balanced_splits(nx, ny, world, meshgen.DEFAULT_HOLES)
-    m = meshgen.plate_mesh(nx, ny, jitter=0.25, diag="random", seed=0, ordering=ordering,
+    reorder = ordering == "random+reorder"       # randomly numbered mesh passed through the ingestion helper
+    m = meshgen.plate_mesh(nx, ny, jitter=0.25, diag="random", seed=0, ordering="random" if reorder else ordering,
                            col_range=(splits[rank], splits[rank + 1]))
+    if reorder:
+        xy, conn, bm, dm, ed, n2o, _ = meshgen.reorder_for_locality(m.node_coords, m.connectivity, m.boundary_mask, m.dirichlet_mask,
+                                                                    m.neumann_edges)
+        m = meshgen.PlateMesh(xy, conn, bm, dm, m.neumann_mask[n2o], ed, m.global_node_id[n2o], meta=m.meta)
     T = torch.tensor
     torch.manual_seed(0)
     model = PiecewiseLinearShapeNN2D(T(m.node_coords, dtype=dtype), T(m.connectivity), T(m.boundary_mask),
@@ -483,8 +488,9 @@ def main():
 
     extra = {}
     if args.extra and world == 1:
-        for tag, dt2, ordr in (("f64_random_numbering", torch.float64, "random"), ("f32_morton", torch.float32, "morton"),
-                               ("f64_natural", torch.float64, "natural")):
+        for tag, dt2, ordr in (("f64_random_numbering", torch.float64, "random"),
+                               ("f64_random_numbering_after_reorder_for_locality", torch.float64, "random+reorder"),
+                               ("f32_morton", torch.float32, "morton"), ("f64_natural", torch.float64, "natural")):
             del model, loss_fn
             torch.cuda.empty_cache()
             m2, model, loss_fn, _ = make_workload(args, 0, 1, device, dt2, ordr, args.elems, args.tile_nodes)
