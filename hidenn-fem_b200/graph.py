@@ -53,11 +53,18 @@ class GraphedEnergyStep:
             if self._halo is not None:
                 loss_fn.halo = self._halo
         self.loss = loss.detach()                     # view of _parts[0]: the exchange completes it in place
-        self._gx = getattr(model, "node_coords_free", None)
-        self._gu = getattr(model, "u_free", None)
+        # the gradient tensors the graph writes; re-attached on every call so that an optimizer.zero_grad() in between
+        # (set_to_none=True is torch's default) cannot detach the parameters from them
+        self._static = [(p, p.grad) for p in model.parameters() if p.grad is not None]
+        gx = getattr(model, "node_coords_free", None)
+        gu = getattr(model, "u_free", None)
+        self._gx = None if gx is None else gx.grad
+        self._gu = None if gu is None else gu.grad
 
     def __call__(self):
         self.graph.replay()
+        for p, g in self._static:
+            p.grad = g
         if self._halo is not None:
-            self._halo.exchange(self._parts, None if self._gx is None else self._gx.grad, None if self._gu is None else self._gu.grad)
+            self._halo.exchange(self._parts, self._gx, self._gu)
         return self.loss

@@ -332,6 +332,7 @@ def test_graphed_step_matches_eager_and_tracks_parameter_updates():
         opt_e.zero_grad()
         le = loss_fn(m_eager)
         le.backward()
+        opt_g.zero_grad()                    # set_to_none=True: the replay must re-attach its gradient buffers
         lg = step()
         assert lg.item() == le.item()
         assert torch.equal(m_graph.u_free.grad, m_eager.u_free.grad)
