@@ -314,6 +314,14 @@ def bench_grid_paths(device, steps, warmup, peak, full_c3=False):
                                   "hbm_frac_informational": 4 * 8 * (N - 1) / (ms * 1e-3) / 1e9 / peak,
                                   "note": "32 MB working set is L2-resident: launch/latency-bound (8 small kernels)"}
 
+    from hidenn_fem_b200.graph import GraphedStep
+    g2 = GraphedStep(m1, lambda: mg.bar_energy_loss(m1, xi, wi, None, 175.0, b_builtin=True))
+    ms = time_loop(lambda: g2(), steps, warmup)
+    mg._bar_state.check(block=True)
+    out["C2_bar_1M_f64_fused_graph_replay"] = {"ms_per_step": ms, "evals_per_s": (N - 1) * 2 / (ms * 1e-3),
+                                               "hbm_frac_informational": 4 * 8 * (N - 1) / (ms * 1e-3) / 1e9 / peak}
+    del g2
+
     def step_c2g():
         m1.zero_grad(set_to_none=True)
         mg.energy_loss_generic(m1, xi, wi, mg.example3_b_force, E=175.0).backward()

@@ -13,58 +13,76 @@ from __future__ import annotations
 import torch
 
 
-class GraphedEnergyStep:
-    """step = GraphedEnergyStep(model, loss_fn);  loss = step()  ==  zero_grad(); loss = loss_fn(model); loss.backward()
+class GraphedStep:
+    """step = GraphedStep(model, fn);  loss = step()  ==  model.zero_grad(); loss = fn(); loss.backward()
 
-    `loss_fn_args` are forwarded to the loss (b_force / t_force callables must be capture-safe: no host syncs).
-    After each call `p.grad` of every trainable parameter holds the fresh gradient (same tensors every time) and the
-    returned 0-dim tensor the loss.  Gradient accumulation across calls is not available in this mode."""
+    `fn` is any capture-safe closure over the model's parameters built from this package's losses
+    (`lambda: loss_fn(model)`, `lambda: bar_energy_loss(model, xi, wi, None, E, b_builtin=True)`,
+    `lambda: l2_projection_loss(model, x, u)`): no host synchronisation, fixed shapes.  After each call `p.grad` of
+    every trainable parameter holds the fresh gradient (same tensors every time) and the returned 0-dim tensor the
+    loss.  Gradient accumulation across calls is not available in this mode."""
 
-    def __init__(self, model, loss_fn, *loss_fn_args, warmup: int = 3, **loss_fn_kw):
+    def __init__(self, model, fn, warmup: int = 3):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
-            raise RuntimeError("GraphedEnergyStep needs CUDA parameters (no CPU fallback)")
-        self.model, self.loss_fn = model, loss_fn
-        self._halo = getattr(loss_fn, "halo", None)
+            raise RuntimeError("GraphedStep needs CUDA parameters (no CPU fallback)")
+        self.model = model
 
         def one():
-            loss = loss_fn(model, *loss_fn_args, **loss_fn_kw)
+            loss = fn()
             loss.backward()
             return loss
 
-        if self._halo is not None:
-            loss_fn.halo = None           # the graph holds the rank-local part; the exchange follows each replay
-        try:
-            # warm-up on a side stream (constant tables, scratch, plan upload), as capture requires
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                for _ in range(max(1, warmup)):
-                    model.zero_grad(set_to_none=True)
-                    one()
-            torch.cuda.current_stream(dev).wait_stream(side)
-            torch.cuda.synchronize(dev)
-            model.zero_grad(set_to_none=True)
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                loss = one()
-            self._parts = loss_fn.last_parts          # [loss, domain, edge, 0] written by the finalize kernel
-        finally:
-            if self._halo is not None:
-                loss_fn.halo = self._halo
-        self.loss = loss.detach()                     # view of _parts[0]: the exchange completes it in place
+        # warm-up on a side stream (constant tables, scratch, plan upload), as capture requires
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                model.zero_grad(set_to_none=True)
+                one()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        model.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            loss = one()
+        self.loss = loss.detach()
         # the gradient tensors the graph writes; re-attached on every call so that an optimizer.zero_grad() in between
         # (set_to_none=True is torch's default) cannot detach the parameters from them
         self._static = [(p, p.grad) for p in model.parameters() if p.grad is not None]
+
+    def __call__(self):
+        self.graph.replay()
+        for p, g in self._static:
+            p.grad = g
+        return self.loss
+
+
+class GraphedEnergyStep(GraphedStep):
+    """step = GraphedEnergyStep(model, loss_fn);  loss = step()  ==  zero_grad(); loss = loss_fn(model); loss.backward()
+
+    `loss_fn_args` are forwarded to the loss (b_force / t_force callables must be capture-safe: no host syncs).
+    With a distributed loss (dist.DistributedEnergyLoss2D) the graph holds the rank-local part and the halo exchange
+    (pack, NCCL all-reduce, unpack) runs eagerly after every replay."""
+
+    def __init__(self, model, loss_fn, *loss_fn_args, warmup: int = 3, **loss_fn_kw):
+        self.loss_fn = loss_fn
+        self._halo = getattr(loss_fn, "halo", None)
+        if self._halo is not None:
+            loss_fn.halo = None           # the graph holds the rank-local part; the exchange follows each replay
+        try:
+            super().__init__(model, lambda: loss_fn(model, *loss_fn_args, **loss_fn_kw), warmup=warmup)
+            self._parts = loss_fn.last_parts          # [loss, domain, edge, 0] written by the finalize kernel;
+        finally:                                      # self.loss is a view of _parts[0]: the exchange completes it in place
+            if self._halo is not None:
+                loss_fn.halo = self._halo
         gx = getattr(model, "node_coords_free", None)
         gu = getattr(model, "u_free", None)
         self._gx = None if gx is None else gx.grad
         self._gu = None if gu is None else gu.grad
 
     def __call__(self):
-        self.graph.replay()
-        for p, g in self._static:
-            p.grad = g
+        super().__call__()
         if self._halo is not None:
             self._halo.exchange(self._parts, self._gx, self._gu)
         return self.loss

@@ -259,8 +259,16 @@ class _FlagState:
     def __init__(self):
         self.pending = []
         self.free = []
+        self.captured = []
 
     def note_flag(self, flag):
+        if torch.cuda.is_current_stream_capturing():
+            # graph.GraphedStep: the copy becomes a node of the graph; check() reads the pinned word after replays
+            host = torch.empty(1, dtype=torch.int32).pin_memory()
+            host.zero_()
+            host.copy_(flag, non_blocking=True)
+            self.captured.append(host)
+            return
         if self.free:
             host, ev = self.free.pop()
         else:
@@ -272,6 +280,12 @@ class _FlagState:
             self.check(block=False)
 
     def check(self, block=True):
+        if self.captured:
+            if block:
+                torch.cuda.synchronize()
+            if any(int(h[0]) != 0 for h in self.captured):
+                raise RuntimeError("bar_energy_loss: a Gauss point fell outside its own element (degenerate grid); "
+                                   "the fused path is invalid here -- use energy_loss_generic")
         keep = []
         for host, ev in self.pending:
             if block:

@@ -381,3 +381,32 @@ def test_fused_l2_projection_loss_matches_generic_expression(dt):
     a.zero_grad()
     (3.0 * l2_projection_loss(a, x, ut)).backward()
     assert all(torch.equal(u, p.grad) for u, p in zip(g1, a.parameters()))
+
+
+def test_graphed_step_on_the_bar_energy():
+    """graph.GraphedStep around the fused 1D bar energy: same bits as the eager step, follows in-place updates."""
+    from hidenn_fem_b200.graph import GraphedStep
+    from hidenn_fem_b200.models import PiecewiseLinearShapeNN
+    from hidenn_fem_b200 import models_grid as mg
+    from hidenn_fem_b200.utils import interval_gauss_points
+    N = 20_001
+    mk = lambda: PiecewiseLinearShapeNN(torch.linspace(0, 10.0, N, dtype=torch.float64), r_adapt=True, u0=0.0, uN=0.0).double().cuda()
+    a, b = mk(), mk()
+    xi, wi = interval_gauss_points(2, device="cuda", dtype=torch.float64)
+    with torch.no_grad():
+        a.u.normal_(0, 1e-2)
+        b.u.copy_(a.u)
+    step = GraphedStep(b, lambda: mg.bar_energy_loss(b, xi, wi, None, 175.0, b_builtin=True))
+    for _ in range(3):
+        a.zero_grad()
+        la = mg.bar_energy_loss(a, xi, wi, None, 175.0, b_builtin=True)
+        la.backward()
+        lb = step()
+        assert la.item() == lb.item()
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            assert torch.equal(pa.grad, pb.grad)
+        with torch.no_grad():
+            for pa, pb in zip(a.parameters(), b.parameters()):
+                pa.sub_(1e-4 * pa.grad)
+                pb.sub_(1e-4 * pb.grad)
+    mg._bar_state.check(block=True)
