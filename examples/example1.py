@@ -2,6 +2,9 @@
 import torch
 import torch.optim as optim
 
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))      # run from anywhere
 from hidenn_fem_b200.models import PiecewiseLinearShapeNN
 
 device = torch.device("cuda")

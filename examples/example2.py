@@ -3,6 +3,9 @@ class (the reference script itself raises TypeError because its structured class
 import torch
 import torch.optim as optim
 
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))      # run from anywhere
 from hidenn_fem_b200.models import PiecewiseLinearShapeNN2D
 
 device = torch.device("cuda")

@@ -6,6 +6,9 @@ import sys
 import torch
 import torch.optim as optim
 
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))      # run from anywhere
 from hidenn_fem_b200.models import PiecewiseLinearShapeNN
 from hidenn_fem_b200.models_grid import bar_energy_loss, energy_loss_generic, example3_b_force as b_force
 from hidenn_fem_b200.utils import interval_gauss_points

@@ -8,6 +8,9 @@ import argparse
 import numpy as np
 import torch
 
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))      # run from anywhere
 from hidenn_fem_b200 import meshgen
 from hidenn_fem_b200.models import PiecewiseLinearShapeNN2D
 from hidenn_fem_b200.loss import EnergyLoss2D
