@@ -30,6 +30,8 @@ import torch
 
 NG = 4
 METRIC = "element-quadrature evals/s (fwd+bwd)"
+WORKLOAD = ("C4 examples/example4.py 2D plate linear elasticity, EnergyLoss2D energy+gradient (fwd+bwd, r-adaptive), "
+            "unstructured triangles (jitter 0.25, hashed diagonals), gauss_order=4")
 UNIT = "evals/s"
 
 
@@ -408,8 +410,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
         "warmup": max(1, min(args.warmup, 2)), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "C4 2D plate linear elasticity energy+gradient (EnergyLoss2D fwd+bwd, r-adaptive), CPU sample",
-                   "elements": ne, "gauss_points": NG},
+        "config": {"workload": WORKLOAD, "elements_total": args.elems, "sample_elements": ne, "gauss_points": NG,
+                   "note": "CPU arm: every step is a bounded sample of the workload (same generator, scaled down)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -536,8 +538,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
-            "config": {"workload": "C4 examples/example4.py 2D plate linear elasticity, EnergyLoss2D energy+gradient "
-                                   "(fwd+bwd, r-adaptive), unstructured triangles (jitter 0.25, hashed diagonals), gauss_order=4",
+            "config": {"workload": WORKLOAD,
                        "elements_total": ne_total, "nodes_total": nn_total, "elements_per_gpu": ne_local,
                        "grid_nodes": list(dims), "ordering": args.ordering, "partition": "column strips + halo nodes" if world > 1 else "none",
                        "launch": "eager" if args.no_graph else "CUDA-graph replay of zero_grad+loss+backward (hidenn_fem_b200.graph.GraphedEnergyStep)",
