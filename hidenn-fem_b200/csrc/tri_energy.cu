@@ -740,8 +740,9 @@ static int tri_energy_host(hidenn_tri_plan* p, const R* xf, const R* xb, const R
     const bool want_gx = (flags & HIDENN_NEED_GX) && gx_h, want_gu = (flags & HIDENN_NEED_GU) && gu_h;
     const int n_tiles = p->dev.n_tiles;
     int chunks = 1;
-    if ((want_gx || want_gu) && n_tiles >= 512 && (nfx + nfu) * sizeof(R) >= ((size_t)8 << 20)) chunks = std::min(8, n_tiles / 256);
+    if ((flags & (HIDENN_NEED_GX | HIDENN_NEED_GU)) && n_tiles >= 512 && (nfx + nfu) * sizeof(R) >= ((size_t)8 << 20)) chunks = std::min(8, n_tiles / 256);
     if (const char* e = getenv("HIDENN_HOST_CHUNKS")) chunks = std::max(1, std::min(atoi(e), std::max(1, n_tiles)));
+    if (!(flags & (HIDENN_NEED_GX | HIDENN_NEED_GU))) chunks = 1;      // the energy-only kernel runs all tiles in one launch
 
     HIDENN_CUDA_OK(cudaMemsetAsync(d_sc, 0, nsc * sizeof(R), stream));      // the finalize ticket must start at zero
     if (chunks <= 1) {
