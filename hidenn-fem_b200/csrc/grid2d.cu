@@ -179,7 +179,7 @@ q1_fused_cells_kernel(const R* __restrict__ gx, const R* __restrict__ gy, int64_
             }
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) cell_tmp[8 * c + k] = a[k];
+        for (int k = 0; k < 8; ++k) cell_tmp[(int64_t)k * ncell + c] = a[k];
     }
 }
 
@@ -215,50 +215,69 @@ q1_fold_cells_kernel(const R* __restrict__ rows, const int64_t* __restrict__ ord
             for (int k = 0; k < 8; ++k) a[k] += rows[8 * m + k];
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) cell_tmp[8 * c + k] = a[k];
+        for (int k = 0; k < 8; ++k) cell_tmp[(int64_t)k * ncell + c] = a[k];      // [8, ncell]: every consumer reads one plane contiguously
     }
 }
 
 template <typename R>
 __global__ void __launch_bounds__(256)
 q1_fold_nodes_kernel(const R* __restrict__ cell_tmp, int64_t Nx, int64_t Ny, R* __restrict__ du) {
-    const int64_t total = Nx * Ny, cy = Ny - 1;
+    const int64_t total = Nx * Ny, cy = Ny - 1, ncell = (Nx - 1) * cy;
     for (int64_t n = (int64_t)blockIdx.x * 256 + threadIdx.x; n < total; n += (int64_t)gridDim.x * 256) {
         const int64_t i = n / Ny, j = n % Ny;
         R a = R(0);
-        if (i < Nx - 1 && j < Ny - 1) a += cell_tmp[8 * (i * cy + j) + 0];
-        if (i > 0 && j < Ny - 1) a += cell_tmp[8 * ((i - 1) * cy + j) + 1];
-        if (i < Nx - 1 && j > 0) a += cell_tmp[8 * (i * cy + j - 1) + 2];
-        if (i > 0 && j > 0) a += cell_tmp[8 * ((i - 1) * cy + j - 1) + 3];
+        if (i < Nx - 1 && j < Ny - 1) a += cell_tmp[0 * ncell + i * cy + j];
+        if (i > 0 && j < Ny - 1) a += cell_tmp[1 * ncell + (i - 1) * cy + j];
+        if (i < Nx - 1 && j > 0) a += cell_tmp[2 * ncell + i * cy + j - 1];
+        if (i > 0 && j > 0) a += cell_tmp[3 * ncell + (i - 1) * cy + j - 1];
         du[n] = a;
     }
 }
 
-// one block per grid line: fixed-order strided partial sums + block tree
+// x lines: one block per line, the cells of a line are contiguous in planes 4 / 5; fixed-order strided sums + block tree
 template <typename R>
-__global__ void __launch_bounds__(256) q1_fold_lines_kernel(const R* __restrict__ cell_tmp, int64_t Nx, int64_t Ny, R* __restrict__ dgx,
-                                                             R* __restrict__ dgy) {
+__global__ void __launch_bounds__(256) q1_fold_xlines_kernel(const R* __restrict__ cell_tmp, int64_t Nx, int64_t Ny, R* __restrict__ dgx) {
     __shared__ R s_red[8];
-    const int64_t cy = Ny - 1, cx = Nx - 1;
-    const int64_t line = blockIdx.x;
+    const int64_t cy = Ny - 1, cx = Nx - 1, ncell = cx * cy;
+    const int64_t i = blockIdx.x;
     R a = R(0);
-    if (line < Nx) {
-        const int64_t i = line;
-        for (int64_t j = threadIdx.x; j < cy; j += 256) {
-            if (i < cx) a += cell_tmp[8 * (i * cy + j) + 4];
-            if (i > 0) a += cell_tmp[8 * ((i - 1) * cy + j) + 5];
-        }
-    } else {
-        const int64_t j = line - Nx;
-        for (int64_t i = threadIdx.x; i < cx; i += 256) {
-            if (j < cy) a += cell_tmp[8 * (i * cy + j) + 6];
-            if (j > 0) a += cell_tmp[8 * (i * cy + j - 1) + 7];
-        }
+    for (int64_t j = threadIdx.x; j < cy; j += 256) {
+        if (i < cx) a += cell_tmp[4 * ncell + i * cy + j];
+        if (i > 0) a += cell_tmp[5 * ncell + (i - 1) * cy + j];
     }
     const R tot = block_sum<R, 256>(a, s_red);
-    if (threadIdx.x == 0) {
-        if (line < Nx) dgx[line] = tot; else dgy[line - Nx] = tot;
+    if (threadIdx.x == 0) dgx[i] = tot;
+}
+
+// y lines: a block owns 32 neighbouring lines (threadIdx.x) and walks the cell rows 8 at a time (threadIdx.y), so every
+// warp reads 32 consecutive values of planes 6 / 7; per-thread sums in ascending row order, then the 8 row groups in order
+template <typename R>
+__global__ void __launch_bounds__(256) q1_fold_ylines_kernel(const R* __restrict__ cell_tmp, int64_t Nx, int64_t Ny, R* __restrict__ dgy) {
+    __shared__ R s_part[8][33];
+    const int64_t cy = Ny - 1, cx = Nx - 1, ncell = cx * cy;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t j = (int64_t)blockIdx.x * 32 + tx;
+    R a = R(0);
+    if (j < Ny) {
+        for (int64_t i = ty; i < cx; i += 8) {
+            if (j < cy) a += cell_tmp[6 * ncell + i * cy + j];
+            if (j > 0) a += cell_tmp[7 * ncell + i * cy + j - 1];
+        }
     }
+    s_part[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && j < Ny) {
+        R tot = R(0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot += s_part[k][tx];
+        dgy[j] = tot;
+    }
+}
+
+template <typename R>
+static void q1_fold_lines(const R* cell_tmp, int64_t Nx, int64_t Ny, R* dgx, R* dgy, cudaStream_t st) {
+    q1_fold_xlines_kernel<R><<<(int)Nx, 256, 0, st>>>(cell_tmp, Nx, Ny, dgx);
+    q1_fold_ylines_kernel<R><<<(int)((Ny + 31) / 32), 256, 0, st>>>(cell_tmp, Nx, Ny, dgy);
 }
 
 static inline int grid_for(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, 148 * 32)); }
@@ -330,7 +349,7 @@ static int q1_fold(const R* rows, const int64_t* order, const int64_t* seg, int6
     const int64_t ncell = (Nx - 1) * (Ny - 1);
     q1_fold_cells_kernel<R><<<grid_for(ncell), 256, 0, st>>>(rows, order, seg, ncell, cell_tmp);
     q1_fold_nodes_kernel<R><<<grid_for(Nx * Ny), 256, 0, st>>>(cell_tmp, Nx, Ny, du);
-    q1_fold_lines_kernel<R><<<(int)(Nx + Ny), 256, 0, st>>>(cell_tmp, Nx, Ny, dgx, dgy);
+    q1_fold_lines<R>(cell_tmp, Nx, Ny, dgx, dgy, st);
     HIDENN_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -344,7 +363,7 @@ static int q1_bwd_fused(const R* gx, int64_t Nx, const R* gy, int64_t Ny, const 
     const int64_t ncell = (Nx - 1) * (Ny - 1);
     q1_fused_cells_kernel<R><<<grid_for(ncell), 256, 0, st>>>(gx, gy, Nx, Ny, uf, (const typename Real2<R>::type*)x, r, seg, order, cell_tmp);
     q1_fold_nodes_kernel<R><<<grid_for(Nx * Ny), 256, 0, st>>>(cell_tmp, Nx, Ny, du);
-    q1_fold_lines_kernel<R><<<(int)(Nx + Ny), 256, 0, st>>>(cell_tmp, Nx, Ny, dgx, dgy);
+    q1_fold_lines<R>(cell_tmp, Nx, Ny, dgx, dgy, st);
     HIDENN_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -79,7 +79,7 @@ int hidenn_q1_interp_bwd_f64(const double* gx, int64_t Nx, const double* gy, int
 int hidenn_q1_interp_bwd_f32(const float* gx, int64_t Nx, const float* gy, int64_t Ny, const float* u_full,
                              const float* x, const int32_t* ix, const int32_t* iy, const float* r, int64_t M,
                              float* rows, void* stream);
-/* deterministic fold: rows grouped by cell (ix*(Ny-1)+iy) through order/seg [ncell+1]; cell_tmp dev [ncell,8];
+/* deterministic fold: rows grouped by cell (ix*(Ny-1)+iy) through order/seg [ncell+1]; cell_tmp dev 8*ncell reals (scratch);
  * du_full dev [Nx,Ny]; dgx dev [Nx], dgy dev [Ny] */
 int hidenn_q1_fold_rows_f64(const double* rows, const int64_t* order, const int64_t* seg, int64_t Nx, int64_t Ny,
                             double* cell_tmp, double* du_full, double* dgx, double* dgy, void* stream);
