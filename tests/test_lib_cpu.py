@@ -1,6 +1,7 @@
 """CPU: the C-ABI library loads, exports every declared symbol, and its integer plan data is bit-exact.
 No compute entry point is called here (there is no GPU and no CPU fallback)."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -191,3 +192,27 @@ def test_reorder_for_locality_is_a_consistent_renumbering():
     # locality: mean |id difference| inside an element drops by an order of magnitude
     spread = lambda c: np.abs(c - c[:, [1, 2, 0]]).mean()
     assert spread(conn) < 0.1 * spread(m.connectivity)
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the product arm): exactly one JSON line on
+    stdout with the contract keys, the same metric / unit / workload name as the product arm, and zero GPU launches."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--cpu-sample-elems", "20000"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    sys.path.insert(0, root)
+    import bench
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT
+    assert d["config"]["workload"] == bench.WORKLOAD and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
