@@ -410,3 +410,38 @@ def test_graphed_step_on_the_bar_energy():
                 pa.sub_(1e-4 * pa.grad)
                 pb.sub_(1e-4 * pb.grad)
     mg._bar_state.check(block=True)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("M", [5_000, 200_000])
+def test_structured_lookup_indices_bit_exact(dt, M):
+    """ix / iy of the structured forward == clamp(searchsorted(grid, x) - 1, 0, N-2) (src/models.py:183-186), for the
+    shared-memory (large M) and global (small M) variants, on grids far from uniform (geometric grading: the uniform
+    guess is wrong by hundreds of lines, so the bisection fallback runs), with repeated grid values, points exactly
+    on nodes, outside the domain and at +-inf."""
+    import ctypes as C
+    from hidenn_fem_b200 import _lib
+    rng = np.random.default_rng(7)
+    Nx, Ny = 1500, 700
+    gx = np.cumsum(1.012 ** np.arange(Nx))
+    gx = (gx - gx[0]) / (gx[-1] - gx[0])
+    gy = np.sort(rng.random(Ny)) * 3.0 - 1.0
+    gy[100:104] = gy[100]                                      # repeated nodes
+    gy[0], gy[-1] = -1.0, 2.0
+    gxt, gyt = T(gx, dtype=dt), T(gy, dtype=dt)
+    gx, gy = gxt.cpu().numpy(), gyt.cpu().numpy()             # the values the kernel sees
+    x = np.stack([rng.random(M) * 1.2 - 0.1, rng.random(M) * 3.4 - 1.2], 1).astype(gx.dtype)
+    k = M // 4
+    x[:k, 0] = gx[rng.integers(0, Nx, k)]                      # exactly on nodes
+    x[:k, 1] = gy[rng.integers(0, Ny, k)]
+    x[k:k + 4] = np.array([[-np.inf, np.inf], [np.inf, -np.inf], [gx[0], gy[-1]], [gx[-1], gy[0]]], dtype=gx.dtype)
+    xt = T(x, dtype=dt)
+    uf = T(rng.standard_normal((Nx, Ny)), dtype=dt)
+    u = torch.empty(M, device="cuda", dtype=dt)
+    ix = torch.empty(M, device="cuda", dtype=torch.int32)
+    iy = torch.empty_like(ix)
+    _lib.check(_lib.fn("hidenn_q1_interp_fwd", dt)(_lib.ptr(gxt), C.c_int64(Nx), _lib.ptr(gyt), C.c_int64(Ny), _lib.ptr(uf), _lib.ptr(xt),
+                                                   C.c_int64(M), _lib.ptr(u), _lib.ptr(ix), _lib.ptr(iy), _lib.stream_ptr()))
+    ex = torch.clamp(torch.searchsorted(gxt, xt[:, 0].contiguous()) - 1, 0, Nx - 2)
+    ey = torch.clamp(torch.searchsorted(gyt, xt[:, 1].contiguous()) - 1, 0, Ny - 2)
+    assert torch.equal(ix.long(), ex) and torch.equal(iy.long(), ey)
