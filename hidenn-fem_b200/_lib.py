@@ -101,6 +101,36 @@ def suffix(dtype):
     raise HidennError(f"unsupported dtype {dtype}: the kernels are FP64 and FP32")
 
 
+class _NullRange:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class _NvtxRange:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *a):
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
+_NVTX = bool(os.environ.get("HIDENN_NVTX"))
+_null_range = _NullRange()
+
+
+def nvtx(name):
+    """NVTX range around a fused call when HIDENN_NVTX=1 (tracing hook of SURVEY §5); free otherwise."""
+    return _NvtxRange(name) if _NVTX else _null_range
+
+
 _fn_cache = {}
 
 

@@ -44,14 +44,16 @@ class _TriEnergyFn(torch.autograd.Function):
             t_table = t_live.detach().to(dt).contiguous()
             if t_live.requires_grad and need_gx:
                 gt = torch.empty_like(t_table)
-        _lib.check(_lib.fn("hidenn_tri_energy", dt)(
-            plan.handle, _lib.ptr(x_free), _lib.ptr(xb), _lib.ptr(u_free), _lib.ptr(ub), _lib.ptr(consts), _lib.ptr(t_table),
-            C.c_int(flags), _lib.ptr(out), _lib.ptr(gx), _lib.ptr(gu), _lib.ptr(gt), _lib.ptr(scratch), _lib.stream_ptr()))
+        with _lib.nvtx("hidenn.tri_energy"):
+            _lib.check(_lib.fn("hidenn_tri_energy", dt)(
+                plan.handle, _lib.ptr(x_free), _lib.ptr(xb), _lib.ptr(u_free), _lib.ptr(ub), _lib.ptr(consts), _lib.ptr(t_table),
+                C.c_int(flags), _lib.ptr(out), _lib.ptr(gx), _lib.ptr(gu), _lib.ptr(gt), _lib.ptr(scratch), _lib.stream_ptr()))
         if gt is not None:
             # chain d loss/d t_q through the user's traction to the edge end points (last line)
             (gxq,) = torch.autograd.grad(t_live, xq, gt.reshape(t_live.shape))
             loss_obj._scatter_edge_point_grads(model, gxq, gx)
-        loss_obj._post_forward(model, out, gx, gu)      # multi-GPU halo all-reduce hook (dist.py); no-op on one GPU
+        with _lib.nvtx("hidenn.halo_exchange"):
+            loss_obj._post_forward(model, out, gx, gu)  # multi-GPU halo all-reduce hook (dist.py); no-op on one GPU
         ctx.save_for_backward(gx if need_gx else None, gu if need_gu else None)
         ctx.used = False
         loss_obj.last_parts = out

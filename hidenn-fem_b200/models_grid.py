@@ -411,7 +411,8 @@ class _Q1L2Fn(torch.autograd.Function):
         dt = gx.dtype
         scale = go.reshape(1).to(dt).contiguous()
         _lib.check(_lib.fn("hidenn_scale_inplace", dt)(_lib.ptr(r), c_i64(r.numel()), _lib.ptr(scale), _lib.stream_ptr()))   # exits at once if 1
-        dgx, dgy, du = _q1_backward(gx, gy, uf, xs, ix, iy, r)
+        with _lib.nvtx("hidenn.q1_backward"):
+            dgx, dgy, du = _q1_backward(gx, gy, uf, xs, ix, iy, r)
         return dgx, dgy, du.to(ctx.udtype), None, None
 
 
