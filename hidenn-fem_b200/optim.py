@@ -8,6 +8,11 @@ stopping tests in the same order) with every reduction routed through `weights` 
 copies owned elsewhere) and one all-reduce; since the halo exchange leaves bit-identical gradients on every copy and
 all step coefficients are global scalars, the copies of a shared row stay bit-identical on all ranks.
 With `weights=None` and no process group it is a drop-in for the stock optimiser on one GPU.
+
+Two forms of the same iteration: the textbook two-loop recursion (one all-reduce per inner product, 2·history + 5 per
+iteration) and the vector-free form (default when distributed): the inner products of the new (s, y, g) with all stored
+pairs travel in ONE all-reduce, the recursion runs on the (2m+1)² Gram matrix on the host, and the direction is one
+linear combination of the stored vectors -- two passes over the history instead of four, two collectives per iteration.
 """
 from __future__ import annotations
 
@@ -20,7 +25,7 @@ import torch.distributed as dist
 class ShardedLBFGS(torch.optim.Optimizer):
     def __init__(self, params: Iterable[torch.Tensor], lr: float = 1.0, max_iter: int = 20, max_eval: Optional[int] = None,
                  tolerance_grad: float = 1e-7, tolerance_change: float = 1e-9, history_size: int = 100,
-                 weights: Optional[Sequence[Optional[torch.Tensor]]] = None, group=None):
+                 weights: Optional[Sequence[Optional[torch.Tensor]]] = None, group=None, vector_free: Optional[bool] = None):
         if max_eval is None:
             max_eval = max_iter * 5 // 4
         defaults = dict(lr=lr, max_iter=max_iter, max_eval=max_eval, tolerance_grad=tolerance_grad,
@@ -31,6 +36,9 @@ class ShardedLBFGS(torch.optim.Optimizer):
         self._params = self.param_groups[0]["params"]
         self._group = group
         self._distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        # vector-free form (Chen et al., "Large-scale L-BFGS using MapReduce", 2014): all inner products of an iteration
+        # travel in ONE all-reduce and the two-loop recursion runs on the (2m+1)^2 Gram matrix; default when distributed
+        self._vector_free = self._distributed if vector_free is None else bool(vector_free)
         self._w = None
         if weights is not None:
             if len(weights) != len(self._params):
@@ -83,6 +91,8 @@ class ShardedLBFGS(torch.optim.Optimizer):
     # -- one optimiser step (up to max_iter inner iterations, like the stock LBFGS) ----------------
     @torch.no_grad()
     def step(self, closure: Callable[[], torch.Tensor]):
+        if self._vector_free:
+            return self._step_vector_free(closure)
         g0 = self.param_groups[0]
         lr, max_iter, max_eval = g0["lr"], g0["max_iter"], g0["max_eval"]
         tol_g, tol_x, hist = g0["tolerance_grad"], g0["tolerance_change"], g0["history_size"]
@@ -154,4 +164,145 @@ class ShardedLBFGS(torch.optim.Optimizer):
                 break
 
         st.update(d=d, t=t, ys_hist=ys_hist, s_hist=s_hist, rho=rho, g_prev=g_prev, h_diag=h_diag, loss_prev=loss_prev)
+        return first_loss
+
+
+    # -- vector-free variant -------------------------------------------------------------------------
+    def _reduce_vec(self, t: torch.Tensor, op) -> torch.Tensor:
+        t = t.to(torch.float64).contiguous()
+        if self._distributed:
+            dist.all_reduce(t, op=op, group=self._group)
+        return t.cpu()
+
+    @torch.no_grad()
+    def _step_vector_free(self, closure: Callable[[], torch.Tensor]):
+        """Same iteration as `step`, but per inner iteration: one SUM all-reduce of 3(2k+1)+9 inner products (new s, y, g
+        against the stored pairs and themselves), the two-loop recursion on the Gram matrix (host, scalars only), the
+        direction as one linear combination of the stored vectors, and one MAX all-reduce for the two stopping norms."""
+        import numpy as np
+        g0 = self.param_groups[0]
+        lr, max_iter, max_eval = g0["lr"], g0["max_iter"], g0["max_eval"]
+        tol_g, tol_x, hist = g0["tolerance_grad"], g0["tolerance_change"], g0["history_size"]
+        closure = torch.enable_grad()(closure)
+        st = self.state[self._params[0]]
+        st.setdefault("func_evals", 0)
+        st.setdefault("n_iter", 0)
+
+        first_loss = closure()
+        loss = float(first_loss)
+        evals = 1
+        st["func_evals"] += 1
+        g = self._flat_grad()
+        if self._abs_max(g) <= tol_g:
+            return first_loss
+        n = g.numel()
+        w = self._w
+
+        S, Y = st.get("vf_S"), st.get("vf_Y")                  # [hist, n] ring storage, logical order kept in `order`
+        if S is None:
+            S = torch.empty(hist, n, device=g.device, dtype=g.dtype)
+            Y = torch.empty(hist, n, device=g.device, dtype=g.dtype)
+        order = st.get("vf_order", [])                         # physical rows of the stored pairs, oldest first
+        G = st.get("vf_G", np.zeros((0, 0)))                   # Gram of [s_0..s_{k-1}, y_0..y_{k-1}] (logical order)
+        d, t = st.get("d"), st.get("t")
+        g_prev, h_diag, loss_prev = st.get("g_prev"), st.get("h_diag", 1.0), st.get("loss_prev")
+
+        it = 0
+        while it < max_iter:
+            it += 1
+            st["n_iter"] += 1
+            if st["n_iter"] == 1:
+                d = g.neg()
+                order, G, h_diag = [], np.zeros((0, 0)), 1.0
+                gtd = -self._dot(g, g)
+            else:
+                y = g - g_prev
+                s = d * t
+                k = len(order)
+                V = torch.stack([s, y, g])                      # [3, n]
+                Vw = V * w if w is not None else V
+                parts = [V @ Vw.t()]                            # 3 x 3
+                if k:
+                    idx = torch.tensor(order, device=g.device)
+                    parts += [S[idx] @ Vw.t(), Y[idx] @ Vw.t()]   # k x 3 each
+                red = self._reduce_vec(torch.cat([p.reshape(-1) for p in parts]), dist.ReduceOp.SUM).numpy()
+                self_d = red[:9].reshape(3, 3)
+                sh = red[9:9 + 3 * k].reshape(k, 3) if k else np.zeros((0, 3))
+                yh = red[9 + 3 * k:].reshape(k, 3) if k else np.zeros((0, 3))
+                ys = self_d[0, 1]
+                sg = sh[:, 2].copy()
+                yg = yh[:, 2].copy()
+                if ys > 1e-10:                                  # accept the pair: extend (or rotate) the Gram matrix
+                    if k == hist:
+                        keep = [i for i in range(2 * k) if i not in (0, k)]
+                        G = G[np.ix_(keep, keep)]
+                        row = order.pop(0)
+                        sh, yh, sg, yg = sh[1:], yh[1:], sg[1:], yg[1:]
+                        k -= 1
+                    else:
+                        row = next(r for r in range(hist) if r not in order)
+                    S[row].copy_(s)
+                    Y[row].copy_(y)
+                    order.append(row)
+                    Gn = np.zeros((2 * k + 2, 2 * k + 2))
+                    old = list(range(k)) + list(range(k + 1, 2 * k + 1))          # positions of the old s / y in the new matrix
+                    if k:
+                        Gn[np.ix_(old, old)] = G
+                    # new s at position k, new y at position 2k+1
+                    Gn[k, old] = Gn[old, k] = np.concatenate([sh[:, 0], yh[:, 0]])
+                    Gn[2 * k + 1, old] = Gn[old, 2 * k + 1] = np.concatenate([sh[:, 1], yh[:, 1]])
+                    Gn[k, k] = self_d[0, 0]
+                    Gn[2 * k + 1, 2 * k + 1] = self_d[1, 1]
+                    Gn[k, 2 * k + 1] = Gn[2 * k + 1, k] = ys
+                    G = Gn
+                    sg = np.append(sg, self_d[0, 2])
+                    yg = np.append(yg, self_d[1, 2])
+                    k += 1
+                    h_diag = ys / self_d[1, 1]
+                # two-loop recursion in coefficient space: direction = sum_i ds[i] s_i + dy[i] y_i + dg g
+                bg = np.concatenate([sg, yg])                  # inner products of the basis with g
+                gg = self_d[2, 2]
+                ds, dy, dg = np.zeros(k), np.zeros(k), -1.0
+                alpha = np.zeros(k)
+
+                def dot_with(col):                              # (current combination) . basis[col]
+                    v = ds @ G[:k, col] + dy @ G[k:, col] if k else 0.0
+                    return v + dg * bg[col]
+                for i in range(k - 1, -1, -1):
+                    alpha[i] = dot_with(i) / G[i, k + i]
+                    dy[i] -= alpha[i]
+                ds *= h_diag; dy *= h_diag; dg *= h_diag
+                for i in range(k):
+                    beta = dot_with(k + i) / G[i, k + i]
+                    ds[i] += alpha[i] - beta
+                d = g * dg
+                if k:
+                    idx = torch.tensor(order, device=g.device)
+                    coef = torch.tensor(np.concatenate([ds, dy]), device=g.device, dtype=g.dtype)
+                    d = d + coef[:k] @ S[idx] + coef[k:] @ Y[idx]
+                gtd = float(ds @ sg + dy @ yg + dg * gg)
+            g_prev = g.clone()
+            loss_prev = loss
+            t = min(1.0, 1.0 / self._abs_sum(g)) * lr if st["n_iter"] == 1 else lr
+            if gtd > -tol_x:
+                break
+            self._add(t, d)
+            new_evals = 0
+            if it != max_iter:
+                loss = float(closure())
+                g = self._flat_grad()
+                new_evals = 1
+            evals += new_evals
+            st["func_evals"] += new_evals
+            if it == max_iter or evals >= max_eval:
+                break
+            norms = self._reduce_vec(torch.stack([g.abs().max(), d.abs().max()]), dist.ReduceOp.MAX)
+            if float(norms[0]) <= tol_g:
+                break
+            if float(norms[1]) * t <= tol_x:
+                break
+            if abs(loss - loss_prev) < tol_x:
+                break
+
+        st.update(d=d, t=t, vf_S=S, vf_Y=Y, vf_order=order, vf_G=G, g_prev=g_prev, h_diag=h_diag, loss_prev=loss_prev)
         return first_loss
