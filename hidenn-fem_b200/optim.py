@@ -199,9 +199,9 @@ class ShardedLBFGS(torch.optim.Optimizer):
         w = self._w
 
         S, Y = st.get("vf_S"), st.get("vf_Y")                  # [hist, n] ring storage, logical order kept in `order`
-        if S is None:
-            S = torch.empty(hist, n, device=g.device, dtype=g.dtype)
-            Y = torch.empty(hist, n, device=g.device, dtype=g.dtype)
+        if S is None:                                          # capacity grows 8 -> 16 -> ... -> hist rows as pairs arrive
+            S = torch.empty(min(hist, 8), n, device=g.device, dtype=g.dtype)
+            Y = torch.empty_like(S)
         order = st.get("vf_order", [])                         # physical rows of the stored pairs, oldest first
         G = st.get("vf_G", np.zeros((0, 0)))                   # Gram of [s_0..s_{k-1}, y_0..y_{k-1}] (logical order)
         d, t = st.get("d"), st.get("t")
@@ -240,7 +240,14 @@ class ShardedLBFGS(torch.optim.Optimizer):
                         sh, yh, sg, yg = sh[1:], yh[1:], sg[1:], yg[1:]
                         k -= 1
                     else:
-                        row = next(r for r in range(hist) if r not in order)
+                        if k == S.shape[0]:                     # all allocated rows in use: double the capacity
+                            cap = min(hist, 2 * S.shape[0])
+                            S2 = torch.empty(cap, n, device=g.device, dtype=g.dtype)
+                            Y2 = torch.empty_like(S2)
+                            S2[:S.shape[0]].copy_(S)
+                            Y2[:Y.shape[0]].copy_(Y)
+                            S, Y = S2, Y2
+                        row = next(r for r in range(S.shape[0]) if r not in order)
                     S[row].copy_(s)
                     Y[row].copy_(y)
                     order.append(row)

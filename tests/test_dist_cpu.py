@@ -229,7 +229,8 @@ def test_sharded_lbfgs_equals_torch_lbfgs_single_process():
         ls = [float(opt.step(closure).detach()) for _ in range(5)]
         return np.array(ls), x.detach().numpy(), y.detach().numpy()
 
-    for kw in (dict(), dict(lr=0.5, max_iter=7, history_size=3), dict(lr=0.3, max_iter=30, history_size=5)):
+    for kw in (dict(), dict(lr=0.5, max_iter=7, history_size=3), dict(lr=0.3, max_iter=30, history_size=5),
+               dict(lr=0.2, max_iter=40, history_size=20)):      # > 8 stored pairs: the history storage grows
         l1, x1, y1 = run(torch.optim.LBFGS, **kw)
         for vf in (False, True):
             l2, x2, y2 = run(ShardedLBFGS, vector_free=vf, **kw)
