@@ -148,7 +148,11 @@ int hidenn_tri_energy_f32(const hidenn_tri_plan* plan,
 
 /* Host-buffer convenience (the end-to-end drop-in for a CPU caller): copies the four parameter
  * arrays host->device, runs the fused step, copies loss and both gradients back and waits.
- * Host buffers should be pinned for full PCIe speed.  `work` is a plan-owned device arena. */
+ * gx_free / gu_free may be NULL (gradients stay on the device, only out[4] comes back).
+ * On large meshes the copies are pipelined with the tile kernels in row blocks over two plan-owned
+ * copy streams (hidenn_tri_plan_pipeline); host buffers must be pinned for the copies to overlap
+ * (pageable buffers work, serialised).  Device buffers live in a plan-owned arena: one call in
+ * flight per plan.  Results are bit-identical to hidenn_tri_energy_* on resident buffers. */
 int hidenn_tri_energy_host_f64(hidenn_tri_plan* plan,
                                const double* x_free_h, const double* x_fixed_h,
                                const double* u_free_h, const double* u_fixed_h,
