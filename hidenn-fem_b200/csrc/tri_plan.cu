@@ -665,6 +665,22 @@ extern "C" int hidenn_tri_plan_tiles(const hidenn_tri_plan* p, int64_t* node_off
     return 0;
 }
 
+extern "C" int hidenn_tri_plan_fold_tables(const hidenn_tri_plan* p, int64_t* elem_off, uint64_t* packs, int64_t* elems, int64_t* owned_off,
+                                           uint32_t* entry_off, int32_t* n_entries) {
+    HIDENN_REQUIRE(p && elem_off && packs && elems && owned_off && entry_off && n_entries, "plan_fold_tables: NULL");
+    const size_t nt = p->tiles.size();
+    for (size_t t = 0; t < nt; ++t) {
+        elem_off[t] = p->tiles[t].elem_off;
+        owned_off[t] = p->tiles[t].off_off;
+        n_entries[t] = p->tiles[t].n_entries;
+    }
+    elem_off[nt] = (int64_t)p->elem_pack.size();
+    owned_off[nt] = (int64_t)p->entry_off.size();
+    for (size_t i = 0; i < p->elem_pack.size(); ++i) { packs[i] = p->elem_pack[i]; elems[i] = p->t_elem[i]; }
+    std::copy(p->entry_off.begin(), p->entry_off.end(), entry_off);
+    return 0;
+}
+
 extern "C" int hidenn_tri_plan_pipeline(const hidenn_tri_plan* p, int32_t* rows2, int32_t* first_need_x, int32_t* last_own_x,
                                         int32_t* first_need_u, int32_t* last_own_u) {
     HIDENN_REQUIRE(p && rows2 && first_need_x && last_own_x && first_need_u && last_own_u, "plan_pipeline: NULL");

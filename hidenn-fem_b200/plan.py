@@ -86,6 +86,20 @@ class TriPlan:
                                                     nodes.ctypes.data_as(C.c_void_p)))
         return off, own, nodes
 
+    def fold_tables(self):
+        """Raw fold tables: dict(elem_off, packs, elems, owned_off, entry_off, n_entries) -- see hidenn_tri_plan_fold_tables."""
+        nt, ev = self.info["n_tiles"], self.info["elem_visits"]
+        _, n_owned, _ = self.tiles()
+        elem_off = np.empty(nt + 1, np.int64)
+        packs = np.empty(ev, np.uint64)
+        elems = np.empty(ev, np.int64)
+        owned_off = np.empty(nt + 1, np.int64)
+        entry_off = np.empty(int(n_owned.sum()), np.uint32)
+        n_entries = np.empty(nt, np.int32)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(_lib.lib().hidenn_tri_plan_fold_tables(self._h, P(elem_off), P(packs), P(elems), P(owned_off), P(entry_off), P(n_entries)))
+        return dict(elem_off=elem_off, packs=packs, elems=elems, owned_off=owned_off, entry_off=entry_off, n_entries=n_entries)
+
     def pipeline(self):
         """Row-block tables of the host-buffer pipeline: dict(rows_x, rows_u, first_need_x, last_own_x, first_need_u, last_own_u)."""
         rows = np.empty(2, np.int32)

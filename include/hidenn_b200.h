@@ -111,6 +111,11 @@ int hidenn_tri_plan_stage_stats(const hidenn_tri_plan* plan, int64_t* out2);
 /* Tile membership (tests): node_off [n_tiles+1] into nodes [info[2] = node_visits] (global node ids, owned nodes of a
  * tile first), n_owned [n_tiles].  Tiles are listed by ascending smallest owned node id. */
 int hidenn_tri_plan_tiles(const hidenn_tri_plan* plan, int64_t* node_off, int32_t* n_owned, int32_t* nodes);
+/* Raw fold tables (tests): per tile t, element visits [elem_off[t], elem_off[t+1]) with their 64-bit packs (3 x 10-bit
+ * local ids, 3 x 11-bit fold-slot positions, bit 63 = owns the element's energy) and global element ids; per owned node
+ * (owned_off[t] + l) the word  slot_start | valence << 16;  n_entries[t] = number of fold slots (= the dump position). */
+int hidenn_tri_plan_fold_tables(const hidenn_tri_plan* plan, int64_t* elem_off, uint64_t* packs, int64_t* elems,
+                                int64_t* owned_off, uint32_t* entry_off, int32_t* n_entries);
 /* Row-block tables of the host-buffer pipeline (hidenn_tri_energy_host_*): the free rows are cut into 64 blocks of
  * rows2[0] (node_coords_free) / rows2[1] (u_free) rows; first_need[b] = first tile reading a row of block b
  * (INT32_MAX: none), last_own[b] = last tile writing one (-1: none).  Each array has 64 entries. */

@@ -216,3 +216,51 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["config"]["workload"] == bench.WORKLOAD and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+@pytest.mark.parametrize("ordering,tile_nodes", [("morton", 0), ("random", 48), ("natural", 200)])
+def test_fold_tables_interpreted_on_the_host(ordering, tile_nodes):
+    """Integer work of the tile kernel replayed with numpy from the plan's raw tables: every owned corner of every
+    element visit lands in a fold slot of its own node (slot = start + k*8, start % 8 == local id % 8), no slot is
+    written twice, halo corners go to the dump position, each element's energy is owned by exactly one visit, and
+    reading a node's slots in order yields its incident elements in ascending element id -- the summation order that
+    makes the gradients independent of the tiling."""
+    from hidenn_fem_b200 import meshgen
+    from hidenn_fem_b200.plan import TriPlan
+    m = meshgen.plate_mesh(81, 41, jitter=0.2, diag="random", seed=3, ordering=ordering)
+    conn = meshgen.invert_some_elements(m.connectivity, 0.3, 1)
+    plan = TriPlan(conn, m.node_coords.shape[0], m.node_coords, m.boundary_mask & ~m.neumann_mask, m.dirichlet_mask,
+                   m.neumann_edges, tile_nodes=tile_nodes, device=-1)
+    node_off, n_owned, nodes = plan.tiles()
+    F = plan.fold_tables()
+    Ne = conn.shape[0]
+    energy_owner = np.zeros(Ne, np.int64)
+    incident = [[] for _ in range(m.node_coords.shape[0])]
+    for e in range(Ne):
+        for c in range(3):
+            incident[conn[e, c]].append(e)
+    for t in range(plan.info["n_tiles"]):
+        loc = nodes[node_off[t]:node_off[t + 1]]
+        no, dump = int(n_owned[t]), int(F["n_entries"][t])
+        off = F["entry_off"][F["owned_off"][t]:F["owned_off"][t + 1]]
+        assert off.shape[0] == no
+        start, cnt = (off & 0xFFFF).astype(np.int64), (off >> 16).astype(np.int64)
+        assert (start % 8 == np.arange(no) % 8).all()
+        slots = np.full(dump + 1, -1, np.int64)
+        for v in range(F["elem_off"][t], F["elem_off"][t + 1]):
+            w, e = int(F["packs"][v]), int(F["elems"][v])
+            energy_owner[e] += (w >> 63) & 1
+            for c in range(3):
+                lid = (w >> (10 * c)) & 1023
+                pos = (w >> (30 + 11 * c)) & 2047
+                assert loc[lid] == conn[e, c]                                   # corner order preserved
+                if lid < no:
+                    k, r = divmod(pos - start[lid], 8)
+                    assert r == 0 and 0 <= k < cnt[lid] and slots[pos] == -1
+                    slots[pos] = e
+                else:
+                    assert pos == dump
+        for l in range(no):
+            got = slots[start[l] + 8 * np.arange(cnt[l])]
+            assert got.tolist() == sorted(incident[loc[l]]), (t, l)
+    assert (energy_owner == 1).all()
