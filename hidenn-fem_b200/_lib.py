@@ -6,6 +6,7 @@ visible when a compute entry point is needed, loading raises.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 import re
 
@@ -91,6 +92,36 @@ def stream_ptr(device=None):
         if idx is None:
             idx = torch.cuda.current_device()
     return c_void_p(torch._C._cuda_getCurrentRawStream(idx))
+
+
+def on_device(f):
+    """Decorator for autograd.Function.forward / backward: run the body with the CUDA current device set to the
+    device of the first CUDA tensor argument, so `stream_ptr()`, allocations and the C-ABI launches all bind to the
+    tensors' device even when the caller's current device is another one (the reference's plain torch ops do)."""
+    @functools.wraps(f)
+    def wrapper(ctx, *args):
+        for t in args:
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                if t.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(t.device):
+                        return f(ctx, *args)
+                break
+        return f(ctx, *args)
+    return wrapper
+
+
+def check_ids(ids, n, what):
+    """Index semantics of torch advanced indexing for user-supplied element / edge ids: negative ids wrap, ids
+    outside [-n, n) raise IndexError (the kernels index raw tables).  Skipped while a CUDA graph is being captured."""
+    if ids.numel() == 0 or torch.cuda.is_current_stream_capturing():
+        return ids
+    lo, hi = torch.aminmax(ids)
+    lo, hi = int(lo), int(hi)
+    if lo < -n or hi >= n:
+        raise IndexError(f"{what}: index {lo if lo < -n else hi} is out of bounds for dimension 0 with size {n}")
+    if lo < 0:
+        ids = torch.where(ids < 0, ids + n, ids)
+    return ids
 
 
 def suffix(dtype):

@@ -26,6 +26,33 @@ void set_error(const std::string& msg);
         }                                                                                      \
     } while (0)
 
+// Binds the calling thread to a plan's device for the duration of a C-ABI call and restores the previous device
+// (a model on cuda:1 must work while the caller's current device is cuda:0, like the reference's torch ops).
+struct DeviceScope {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t enter(int dev) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess || prev == dev) return e;
+        e = cudaSetDevice(dev);
+        switched = (e == cudaSuccess);
+        return e;
+    }
+    ~DeviceScope() { if (switched) cudaSetDevice(prev); }
+};
+constexpr int kMaxDevices = 64;
+// SM count of a device, cached per device id
+inline int sm_count(int dev) {
+    static int cache[kMaxDevices] = {};
+    if (dev < 0 || dev >= kMaxDevices) return 148;
+    if (cache[dev] == 0) {
+        int n = 148;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
 template <typename R> struct Real2;
 template <> struct Real2<double> { using type = double2; };
 template <> struct Real2<float> { using type = float2; };

@@ -597,13 +597,14 @@ static int launch_tile_persistent_mb(const hidenn_tri_plan* p, const R* x_free, 
                                      const R* consts, int flags, R* gx, R* gu, R* scratch, cudaStream_t stream, size_t smem,
                                      int tile_begin, int tile_end) {
     using R2 = typename Real2<R>::type;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[kMaxDevices] = {};        // function attributes are per device
+    size_t& cfg = configured[p->device % kMaxDevices];
+    if (smem > cfg) {
         HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_persistent_kernel<R, BODY, ISO, MINB, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_persistent_kernel<R, BODY, ISO, MINB, BLOCK>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = smem;
+        cfg = smem;
     }
-    static const int n_sm = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+    const int n_sm = sm_count(p->device);
     // a tile range [tile_begin, tile_end) is run by shifting the fixed-stride record pointers: the kernel itself always
     // walks tiles 0 .. n_tiles-1 of the view it is given
     TriPlanDev P = p->dev;
@@ -668,6 +669,8 @@ static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R*
     HIDENN_REQUIRE(!(flags & HIDENN_NEED_GX) || gx, "tri_energy: gx_free NULL");
     HIDENN_REQUIRE(!(flags & HIDENN_NEED_GU) || gu, "tri_energy: gu_free NULL");
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+    DeviceScope scope;
+    HIDENN_CUDA_OK(scope.enter(p->device));
     const bool grad = flags & (HIDENN_NEED_GX | HIDENN_NEED_GU);
     if (tile_end < 0) tile_end = p->dev.n_tiles;
     if (tile_end > tile_begin && !(flags & kFinalizeOnly)) {
@@ -683,8 +686,8 @@ static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R*
             if (rc) return rc;
         } else {
             const size_t smem = (size_t)p->dev.max_local * 4 * sizeof(R) + 64 * 8;
-            static thread_local size_t configured[2] = {0, 0};
-            size_t& cfg = configured[sizeof(R) == 8 ? 0 : 1];
+            static size_t configured[kMaxDevices][2] = {};
+            size_t& cfg = configured[p->device % kMaxDevices][sizeof(R) == 8 ? 0 : 1];
             if (smem > cfg) {
                 HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile_energy_only_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 cfg = smem;
@@ -720,7 +723,8 @@ static int tri_energy_host(hidenn_tri_plan* p, const R* xf, const R* xb, const R
     HIDENN_REQUIRE(p != nullptr && p->device >= 0, "tri_energy_host: needs a device plan");
     HIDENN_REQUIRE(xf && uf && consts_h && out_h, "tri_energy_host: NULL argument");
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
-    HIDENN_CUDA_OK(cudaSetDevice(p->device));
+    DeviceScope scope;
+    HIDENN_CUDA_OK(scope.enter(p->device));
     const size_t nfx = 2 * (size_t)p->n_free_x, nbx = 2 * (size_t)p->n_fixed_x, nfu = 2 * (size_t)p->n_free_u, nbu = 2 * (size_t)p->n_fixed_u;
     const size_t nsc = (size_t)p->dev.n_tiles + 8 + 280;
     const size_t nen = 4 * (size_t)p->dev.n_enodes;

@@ -222,6 +222,8 @@ static int eval_fwd(const hidenn_tri_plan* p, const R* xf, const R* xb, const R*
                     int64_t M, R* u_h, R* detJ, R* grad_u, void* s) {
     using R2 = typename Real2<R>::type;
     HIDENN_REQUIRE(p && p->device >= 0, "tri_eval_fwd: needs a device plan (no CPU fallback)");
+    DeviceScope scope;
+    HIDENN_CUDA_OK(scope.enter(p->device));
     HIDENN_REQUIRE(M == 0 || (x_ref && eid), "tri_eval_fwd: NULL inputs");
     if (plan_ensure_generic(const_cast<hidenn_tri_plan*>(p))) return 1;
     if (M == 0) return 0;
@@ -236,6 +238,8 @@ static int eval_bwd(const hidenn_tri_plan* p, const R* xf, const R* xb, const R*
                     int64_t M, const R* cu, const R* cd, const R* cG, R* row_gx, R* row_gu, void* s) {
     using R2 = typename Real2<R>::type;
     HIDENN_REQUIRE(p && p->device >= 0, "tri_eval_bwd: needs a device plan (no CPU fallback)");
+    DeviceScope scope;
+    HIDENN_CUDA_OK(scope.enter(p->device));
     HIDENN_REQUIRE(M == 0 || (x_ref && eid && row_gx && row_gu), "tri_eval_bwd: NULL inputs");
     if (plan_ensure_generic(const_cast<hidenn_tri_plan*>(p))) return 1;
     if (M == 0) return 0;
@@ -251,6 +255,8 @@ static int fold_rows(const hidenn_tri_plan* p, const R* row_gx, const R* row_gu,
                      R* elem_tmp, R* gx, R* gu, void* s) {
     using R2 = typename Real2<R>::type;
     HIDENN_REQUIRE(p && p->device >= 0, "tri_fold_rows: needs a device plan (no CPU fallback)");
+    DeviceScope scope;
+    HIDENN_CUDA_OK(scope.enter(p->device));
     HIDENN_REQUIRE(order && seg && elem_tmp, "tri_fold_rows: NULL inputs");
     if (plan_ensure_generic(const_cast<hidenn_tri_plan*>(p))) return 1;
     (void)M;
@@ -266,6 +272,8 @@ static int edge_fwd(const hidenn_tri_plan* p, const R* xf, const R* xb, const R*
                     int64_t M, R* u_h, R* ds, void* s) {
     using R2 = typename Real2<R>::type;
     HIDENN_REQUIRE(p && p->device >= 0, "tri_edge_fwd: needs a device plan (no CPU fallback)");
+    DeviceScope scope;
+    HIDENN_CUDA_OK(scope.enter(p->device));
     if (plan_ensure_generic(const_cast<hidenn_tri_plan*>(p))) return 1;
     if (M == 0) return 0;
     HIDENN_REQUIRE(xi && eid && u_h && ds, "tri_edge_fwd: NULL inputs");
@@ -279,6 +287,8 @@ template <typename R>
 static int assemble(const hidenn_tri_plan* p, int which, const R* free_v, const R* fixed_v, R* full, void* s) {
     using R2 = typename Real2<R>::type;
     HIDENN_REQUIRE(p && p->device >= 0, "tri_assemble: needs a device plan (no CPU fallback)");
+    DeviceScope scope;
+    HIDENN_CUDA_OK(scope.enter(p->device));
     HIDENN_REQUIRE(full && (which == 0 || which == 1), "tri_assemble: bad arguments");
     if (plan_ensure_generic(const_cast<hidenn_tri_plan*>(p))) return 1;
     assemble_kernel<R><<<grid_for(p->n_nodes), kBlock, 0, (cudaStream_t)s>>>(which == 0 ? p->dev.xslot : p->dev.uslot, p->n_nodes,

@@ -151,7 +151,8 @@ static void reorder_for_banks(TileBuild& B, int real_bytes) {
 int plan_ensure_generic(hidenn_tri_plan* p) {
     if (p->generic_uploaded) return 0;
     HIDENN_REQUIRE(p->device >= 0, "host-only plan (device=-1) cannot run kernels");
-    HIDENN_CUDA_OK(cudaSetDevice(p->device));
+    DeviceScope scope;
+    HIDENN_CUDA_OK(scope.enter(p->device));
     if (upload(p, p->conn32, &p->dev.conn32)) return 1;
     if (upload(p, p->xslot, &p->dev.xslot)) return 1;
     if (upload(p, p->uslot, &p->dev.uslot)) return 1;
@@ -164,7 +165,8 @@ int plan_ensure_generic(hidenn_tri_plan* p) {
 
 int plan_ensure_arena(hidenn_tri_plan* p, size_t bytes) {
     if (p->arena_bytes >= bytes) return 0;
-    HIDENN_CUDA_OK(cudaSetDevice(p->device));
+    DeviceScope scope;
+    HIDENN_CUDA_OK(scope.enter(p->device));
     if (p->arena) cudaFree(p->arena);
     p->arena = nullptr;
     p->arena_bytes = 0;
@@ -564,7 +566,8 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     int ndev = 0;
     HIDENN_CUDA_OK(cudaGetDeviceCount(&ndev));
     HIDENN_REQUIRE(device >= 0 && device < ndev, "plan_create: no such CUDA device (this library has no CPU fallback)");
-    HIDENN_CUDA_OK(cudaSetDevice(device));
+    DeviceScope scope;
+    HIDENN_CUDA_OK(scope.enter(device));
     TriPlanDev& D = p->dev;
     D.n_tiles = (int32_t)n_tiles;
     D.max_local = max_local; D.max_entries = max_entries; D.max_owned = max_owned; D.max_elem = max_elem;
@@ -593,7 +596,8 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
 
 extern "C" void hidenn_tri_plan_destroy(hidenn_tri_plan* p) {
     if (!p) return;
-    if (p->device >= 0) cudaSetDevice(p->device);
+    DeviceScope scope;
+    if (p->device >= 0) scope.enter(p->device);
     for (void* q : p->dev_allocs) cudaFree(q);
     if (p->arena) cudaFree(p->arena);
     for (void* e : p->pipe_events) cudaEventDestroy((cudaEvent_t)e);

@@ -133,7 +133,10 @@ def partition_elements(mesh: meshgen.PlateMesh, world: int, rank: int) -> meshge
     e_all = np.concatenate([conn[:, [0, 1]], conn[:, [1, 2]], conn[:, [2, 0]]], 0)
     e_all = np.sort(e_all, 1)
     key = e_all[:, 0] * mesh.node_coords.shape[0] + e_all[:, 1]
-    nk = mesh.neumann_edges[:, 0] * mesh.node_coords.shape[0] + mesh.neumann_edges[:, 1]
+    # match on the sorted end nodes, keep the stored orientation (the reference's raw [-1,1] edge rule makes the edge
+    # term orientation-dependent); renumbered / gmsh-style edges need not be stored ascending
+    ns = np.sort(mesh.neumann_edges, axis=1)
+    nk = ns[:, 0] * mesh.node_coords.shape[0] + ns[:, 1]
     mine = np.isin(nk, key)
     ledges = new[mesh.neumann_edges[mine]]
     return meshgen.PlateMesh(mesh.node_coords[used], lconn, mesh.boundary_mask[used], mesh.dirichlet_mask[used],

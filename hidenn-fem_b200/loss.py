@@ -25,10 +25,11 @@ class _TriEnergyFn(torch.autograd.Function):
     launch as the energy and handed to autograd in backward (scaled on device by grad_output)."""
 
     @staticmethod
-    def forward(ctx, x_free, u_free, model, consts, hints, with_edges, t_force, loss_obj):
+    @_lib.on_device
+    def forward(ctx, x_free, u_free, model, consts, hints, with_edges, t_force, loss_obj, need_gx, need_gu):
         plan = model._plan()
         dt, dev = x_free.dtype, x_free.device
-        need_gx, need_gu = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        # need_gx / need_gu come from the caller: ctx.needs_input_grad stays True under torch.no_grad()
         flags = (NEED_GX if need_gx else 0) | (NEED_GU if need_gu else 0) | (WITH_EDGES if with_edges else 0) | hints
         xb, ub = model._fixed_pair()
         out = torch.empty(4, device=dev, dtype=dt)
@@ -61,6 +62,7 @@ class _TriEnergyFn(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_lib.on_device
     def backward(ctx, grad_out):
         if ctx.used:
             raise RuntimeError("EnergyLoss2D: backward called twice on the same loss; the fused path hands its "
@@ -75,7 +77,7 @@ class _TriEnergyFn(torch.autograd.Function):
             _lib.check(_lib.fn("hidenn_scale_inplace2", ref.dtype)(
                 _lib.ptr(gx), C.c_int64(0 if gx is None else gx.numel()), _lib.ptr(gu), C.c_int64(0 if gu is None else gu.numel()),
                 _lib.ptr(go), _lib.stream_ptr()))
-        return gx, gu, None, None, None, None, None, None
+        return gx, gu, None, None, None, None, None, None, None, None
 
 
 class EnergyLoss2D:
@@ -102,8 +104,6 @@ class EnergyLoss2D:
         if self.ng1 > 8:
             raise ValueError("gauss_order_1d > 8 is not supported by the edge kernel")
         self._consts_cache = None
-        self._scratch_cache = {}
-        self._edge_cache = {}
         self.last_parts = None     # device tensor [loss, domain, edge, 0] of the latest fused call
 
     def _post_forward(self, model, out, gx, gu):
@@ -120,7 +120,10 @@ class EnergyLoss2D:
     # -- constants handed to the kernels (include/hidenn_b200.h, HIDENN_TRI_*) --------------------
     def _consts(self, model, b_force):
         dt, dev = model.dtype, model.device
-        key = (self.C._version, self.wg._version, self.xg_1d._version, self.wg_1d._version, self.xg._version, dt, dev)
+        # id + data_ptr + version: an attribute that is reassigned (loss_fn.C = loss_fn.C * 2) is a new tensor whose
+        # version counter restarts at 0; the reference reads self.C / self.wg on every call (loss.py:76,84)
+        key = tuple((id(t), t.data_ptr(), t._version) for t in (self.C, self.wg, self.xg_1d, self.wg_1d, self.xg)) + \
+            (self.ng1, dt, dev)
         if self._consts_cache is None or self._consts_cache[0] != key:
             Cm = self.C.to(device=dev, dtype=dt)
             Cs = 0.5 * (Cm + Cm.T)
@@ -148,17 +151,20 @@ class EnergyLoss2D:
         return c, hint_c
 
     def _scratch(self, plan, dev, dt):
-        key = (id(plan), dev, dt)
-        s = self._scratch_cache.get(key)
-        if s is None or s.numel() < plan.info["scratch"]:
+        cache = plan.__dict__.setdefault("_scratch", {})      # owned by the plan: freed with it, never aliased
+        key = (id(self), dev, dt)
+        s = cache.get(key)
+        if s is None:
             s = torch.zeros(plan.info["scratch"], device=dev, dtype=dt)     # the finalize ticket must start at zero
-            self._scratch_cache[key] = s
+            cache[key] = s
         return s
 
     def _edge_tables(self, model):
         """Per-model static index tables for the user-traction path (small: O(#Neumann edges))."""
-        key = (id(model), model.device)
-        tb = self._edge_cache.get(key)
+        # the tables live on the model (not in a dict keyed by id(model), which CPython reuses after a model is freed)
+        cache = model.__dict__.setdefault("_hidenn_edge_tables", {})
+        key = (model.device, model.neumann_edges.data_ptr(), model.neumann_edges._version)
+        tb = cache.get(key)
         if tb is None:
             dev = model.device
             edges = model.neumann_edges.to(dev)
@@ -177,7 +183,8 @@ class EnergyLoss2D:
             table = torch.full((uniq.numel(), max(maxdeg, 1)), -1, dtype=torch.long, device=dev)
             table[inv[order], pos] = order
             tb = dict(e0=e0, e1=e1, uniq_slot=xs[uniq], table=table)
-            self._edge_cache[key] = tb
+            cache.clear()
+            cache[key] = tb
         return tb
 
     def _edge_points(self, model):
@@ -217,8 +224,10 @@ class EnergyLoss2D:
         if with_edges:
             model.N_edges            # AttributeError if the model has no neumann_edges (reference Q9)
         consts, hints = self._consts(model, b_force)
-        loss = _TriEnergyFn.apply(model.node_coords_free, model.u_free, model, consts, hints, with_edges, t_force, self)
-        return loss
+        grad_on = torch.is_grad_enabled()
+        xf, uf = model.node_coords_free, model.u_free
+        return _TriEnergyFn.apply(xf, uf, model, consts, hints, with_edges, t_force, self,
+                                  grad_on and xf.requires_grad, grad_on and uf.requires_grad)
 
     def domain_energy(self, model, b_force: Optional[Callable[[torch.Tensor], torch.Tensor]] = None) -> torch.Tensor:
         """reference loss.py:55-88 (strain energy minus body work), fused forward+backward."""

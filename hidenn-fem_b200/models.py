@@ -26,6 +26,7 @@ class _AssembleFn(torch.autograd.Function):
     """coords / u_full (reference models.py:292-305): full[n] = free[slot] or fixed[~slot]."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, free_vals, fixed_vals, model, which):
         plan = model._plan()
         full = torch.empty(model.Nnodes, 2, device=free_vals.device, dtype=free_vals.dtype)
@@ -43,12 +44,14 @@ class _TriEvalFn(torch.autograd.Function):
     """forward(x_ref, elem_id) of reference models.py:316-357 with a deterministic VJP."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, x_free, u_free, model, x_ref, elem_id):
         plan = model._plan()
         dt, dev = x_free.dtype, x_free.device
         M = elem_id.shape[0]
         x_ref = x_ref.to(dt).contiguous()
-        elem_id = elem_id.to(torch.int64).contiguous()
+        # x_ref receives no gradient (the reference's forward is differentiable in x_eval; none of its losses use that)
+        elem_id = _lib.check_ids(elem_id.to(torch.int64), model.Nelems, "forward(x_eval, elem_id)").contiguous()
         u_h = torch.empty(M, 2, device=dev, dtype=dt)
         det = torch.empty(M, device=dev, dtype=dt)
         G = torch.empty(M, 2, 2, device=dev, dtype=dt)
@@ -62,6 +65,7 @@ class _TriEvalFn(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_lib.on_device
     def backward(ctx, cu, cd, cG):
         x_free, u_free, x_ref, elem_id = ctx.saved_tensors
         model = ctx.model
@@ -252,13 +256,14 @@ class PiecewiseLinearShapeNN2D(nn.Module):
         dt, dev = self.dtype, self.device
         M = edge_id.shape[0]
         xi = x_eval.reshape(-1).to(dt).contiguous()
-        eid = edge_id.to(torch.int64).contiguous()
+        eid = _lib.check_ids(edge_id.to(torch.int64), self.N_edges, "edge_forward_nograd(x_eval, edge_id)").contiguous()
         u_h = torch.empty(M, 2, device=dev, dtype=dt)
         ds = torch.empty(M, device=dev, dtype=dt)
         xb, ub = self._fixed_pair()
-        _lib.check(_lib.fn("hidenn_tri_edge_fwd", dt)(
-            plan.handle, _lib.ptr(self.node_coords_free.detach()), _lib.ptr(xb), _lib.ptr(self.u_free.detach()), _lib.ptr(ub),
-            _lib.ptr(xi), _lib.ptr(eid), c_i64(M), _lib.ptr(u_h), _lib.ptr(ds), _lib.stream_ptr()))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.fn("hidenn_tri_edge_fwd", dt)(
+                plan.handle, _lib.ptr(self.node_coords_free.detach()), _lib.ptr(xb), _lib.ptr(self.u_free.detach()), _lib.ptr(ub),
+                _lib.ptr(xi), _lib.ptr(eid), c_i64(M), _lib.ptr(u_h), _lib.ptr(ds), _lib.stream_ptr()))
         return u_h, ds
 
 

@@ -46,6 +46,7 @@ def _scratch_1d(n, like):
 # ------------------------------------------------------------------------------------------------
 class _GridFn(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, p, x0, xN):
         _require_cuda(p, "grid")
         p = p.contiguous()
@@ -62,6 +63,7 @@ class _GridFn(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_lib.on_device
     def backward(ctx, dgrid):
         p, cum, x0c, xNc = ctx.saved_tensors
         n = p.shape[0]
@@ -91,6 +93,7 @@ class _Interp1DFn(torch.autograd.Function):
     d u / d x (the element slope) can be differentiated again w.r.t. grid and u (example3.py:56)."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, grid, u_full, x):
         _require_cuda(grid, "forward")
         dt = grid.dtype
@@ -105,6 +108,7 @@ class _Interp1DFn(torch.autograd.Function):
         return u
 
     @staticmethod
+    @_lib.on_device
     def backward(ctx, r):
         grid, u_full, x, elem = ctx.saved_tensors
         dgrid, du, dx = _Interp1DBwdFn.apply(grid, u_full, x, elem, r)
@@ -116,6 +120,7 @@ class _Interp1DBwdFn(torch.autograd.Function):
     cotangent of d x (= r * slope), which is what the double-backward of example3.py needs."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, grid, u_full, x, elem, r):
         dt = grid.dtype
         g, uf, xs, rr = grid.contiguous(), u_full.to(dt).contiguous(), x.to(dt).contiguous(), r.to(dt).contiguous()
@@ -131,6 +136,7 @@ class _Interp1DBwdFn(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_lib.on_device
     def backward(ctx, g_dgrid, g_du, g_dx):
         grid, u_full, x, elem, r = ctx.saved_tensors
         if g_dgrid is not None or g_du is not None:
@@ -220,6 +226,7 @@ class PiecewiseLinearShapeNN(nn.Module):
 # ------------------------------------------------------------------------------------------------
 class _BarEnergyFn(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, grid, u_full, xi, wi, E, b_table, state):
         _require_cuda(grid, "bar_energy")
         dt = grid.dtype
@@ -243,6 +250,7 @@ class _BarEnergyFn(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_lib.on_device
     def backward(ctx, go):
         dg, du = ctx.saved_tensors
         if dg is None:
@@ -379,6 +387,7 @@ class _Q1L2Fn(torch.autograd.Function):
     structured backward on the residual weights."""
 
     @staticmethod
+    @_lib.on_device
     def forward(ctx, gx, gy, u_full, x, target):
         _require_cuda(gx, "l2_projection_loss")
         dt, dev = gx.dtype, gx.device
@@ -402,6 +411,7 @@ class _Q1L2Fn(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_lib.on_device
     def backward(ctx, go):
         if ctx.used:
             raise RuntimeError("l2_projection_loss: backward called twice on the same loss (the residual buffer is scaled in "
@@ -425,6 +435,7 @@ def l2_projection_loss(model, x, u_true):
 
 class _Q1InterpFn(torch.autograd.Function):
     @staticmethod
+    @_lib.on_device
     def forward(ctx, gx, gy, u_full, x):
         _require_cuda(gx, "forward")
         dt = gx.dtype
@@ -442,6 +453,7 @@ class _Q1InterpFn(torch.autograd.Function):
 
     @staticmethod
     @torch.autograd.function.once_differentiable
+    @_lib.on_device
     def backward(ctx, r):
         gx, gy, uf, xs, ix, iy = ctx.saved_tensors
         dt, dev = gx.dtype, gx.device

@@ -235,3 +235,24 @@ def test_sharded_lbfgs_equals_torch_lbfgs_single_process():
         for vf in (False, True):
             l2, x2, y2 = run(ShardedLBFGS, vector_free=vf, **kw)
             assert relmax(l2, l1) < 1e-10 and relmax(x2, x1) < 1e-7 and relmax(y2, y1) < 1e-7, (kw, vf)
+
+
+def test_partition_elements_keeps_unsorted_neumann_edges():
+    """Edges stored with first id > second id (gmsh output, meshes renumbered by reorder_for_locality) must not be
+    dropped by the partitioner; the stored orientation is kept (the reference's edge rule depends on it, Q3)."""
+    from hidenn_fem_b200 import meshgen, dist as hd
+    glob = meshgen.plate_mesh(33, 17, jitter=0.25, diag="random", seed=0, ordering="random")
+    ed = glob.neumann_edges.copy()
+    ed[::2] = ed[::2, ::-1]                               # every other edge descending
+    glob.neumann_edges = ed
+    assert (ed[:, 0] > ed[:, 1]).any() and (ed[:, 0] < ed[:, 1]).any()
+    world, seen = 3, []
+    for rank in range(world):
+        m = hd.partition_elements(glob, world, rank)
+        gid = m.global_node_id[m.neumann_edges]              # back to the generating grid's ids
+        seen.append(gid)
+    got = np.concatenate(seen)
+    want = glob.global_node_id[ed]
+    assert got.shape[0] == ed.shape[0]                       # every edge on exactly one rank
+    key = lambda a: a[:, 0] * (1 << 32) + a[:, 1]            # orientation-sensitive
+    assert np.array_equal(np.sort(key(got)), np.sort(key(want)))

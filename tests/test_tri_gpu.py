@@ -134,6 +134,23 @@ def test_parity_200k_vs_oracle(dtype, ordering):
     assert relmax(model.u_free.grad.cpu().numpy(), gu) < tol
 
 
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_parity_10m_vs_oracle(dtype):
+    """The bench workload itself (BASELINE config C4: 10 M unstructured triangles, locality-ordered): CUDA vs the
+    closed-form oracle on the same inputs at the contract tolerances (reference loss.py:113-116)."""
+    g = _mesh_case(10_000_000, dtype, "morton", u_scale=1e-3)
+    model = build(g)
+    loss_fn = loss_of(g, dtype)
+    loss = loss_fn(model)
+    loss.backward()
+    lo, gx, gu = tri_oracle(dict(g), "default", dtype=np.float64)
+    tol = TOL[dtype]
+    assert g["connectivity"].shape[0] >= 10_000_000
+    assert abs(loss.item() - float(lo)) <= tol * abs(float(lo))
+    assert relmax(model.node_coords_free.grad.cpu().numpy(), gx) < tol
+    assert relmax(model.u_free.grad.cpu().numpy(), gu) < tol
+
+
 def test_determinism_and_plan_invariance():
     g = _mesh_case(100_000, torch.float64, "random", u_scale=1e-3)
     outs = []
@@ -401,3 +418,55 @@ def test_full_size_properties_10m_elements(dtype):
         model.node_coords_fixed.add_(torch.tensor([0.25, -0.5], device="cuda", dtype=dtype))
         pb = loss_fn(model)
     assert abs(pb.item() - pa[0].item()) <= (1e-9 if f64 else 1e-3) * abs(pa[1].item())
+
+
+def test_reassigned_constants_and_index_semantics():
+    """The reference reads loss_fn.C / wg on every call (loss.py:76,84) and indexes with torch semantics
+    (models.py:331: negative ids wrap, out-of-range ids raise)."""
+    g = gold("tri_f64_jitter")
+    model = build(g)
+    loss_fn = loss_of(g, torch.float64)
+    with torch.no_grad():
+        loss_fn(model)
+        d0 = loss_fn.last_parts[1].item()
+        loss_fn.C = loss_fn.C * 2.0            # a NEW tensor whose version counter restarts at 0
+        loss_fn(model)
+        assert loss_fn.last_parts[1].item() == 2.0 * d0
+        loss_fn.wg = loss_fn.wg * 0.5
+        loss_fn(model)
+        assert loss_fn.last_parts[1].item() == d0
+    Ne = model.Nelems
+    x = torch.tensor(g["pt_x"][:4], device="cuda")
+    ids = torch.tensor([0, 1, Ne - 1, 2], device="cuda")
+    u_a, det_a, G_a = model(x, ids)
+    u_b, det_b, G_b = model(x, torch.tensor([-Ne, 1 - Ne, -1, 2 - Ne], device="cuda"))
+    assert torch.equal(u_a, u_b) and torch.equal(det_a, det_b) and torch.equal(G_a, G_b)
+    for bad in (Ne, -Ne - 1):
+        with pytest.raises(IndexError):
+            model(x[:1], torch.tensor([bad], device="cuda"))
+    with pytest.raises(IndexError):
+        model.edge_forward_nograd(torch.zeros(1, 1, device="cuda", dtype=torch.float64), torch.tensor([model.N_edges], device="cuda"))
+
+
+def test_no_grad_skips_gradient_work():
+    """torch.no_grad() evaluations run the energy-only kernel: no gradient buffers are produced or saved."""
+    from hidenn_fem_b200 import loss as hl
+    g = gold("tri_f64_jitter")
+    model = build(g)
+    loss_fn = loss_of(g, torch.float64)
+    seen = {}
+    orig = hl.EnergyLoss2D._post_forward
+
+    def spy(self, model, out, gx, gu):
+        seen["gx"], seen["gu"] = gx, gu
+        return orig(self, model, out, gx, gu)
+    hl.EnergyLoss2D._post_forward = spy
+    try:
+        with torch.no_grad():
+            l0 = loss_fn(model)
+        assert seen["gx"] is None and seen["gu"] is None
+        l1 = loss_fn(model)
+        assert seen["gx"] is not None and seen["gu"] is not None
+    finally:
+        hl.EnergyLoss2D._post_forward = orig
+    assert abs(l0.item() - l1.item()) <= 1e-12 * abs(l1.item())
