@@ -13,8 +13,10 @@
 #include "common.cuh"
 #include "tri_plan.h"
 #include "tri_element.cuh"
+#include "tri_tile8.h"
 
 #include <cstdlib>
+#include <type_traits>
 
 namespace hidenn {
 
@@ -516,6 +518,14 @@ static int launch_tile(const hidenn_tri_plan* p, const R* x_free, const R* x_fix
 #undef HIDENN_LAUNCH_P
 }
 
+// scratch layout: tile energies (one per tile; domain | edge, two per tile, for tile-ordered plans) | 8-byte aligned:
+// double part[2*kEdgeMaxCtas] | unsigned ticket
+static inline size_t scratch_energy_slots(const hidenn_tri_plan* p) { return (size_t)p->dev.n_tiles * (p->tile_order ? 2 : 1); }
+template <typename R> static inline double* scratch_part(const hidenn_tri_plan* p, R* scratch) {
+    const size_t off = ((scratch_energy_slots(p) + 8) * sizeof(R) + 7) / 8 * 8;
+    return reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + off);
+}
+
 // kFinalizeOnly (internal): skip the tile kernels (the host-buffer pipeline has launched them range by range)
 constexpr int kFinalizeOnly = 1 << 30;
 
@@ -536,6 +546,26 @@ static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R*
     HIDENN_CUDA_OK(scope.enter(p->device));
     const bool grad = flags & (HIDENN_NEED_GX | HIDENN_NEED_GU);
     if (tile_end < 0) tile_end = p->dev.n_tiles;
+    if constexpr (std::is_same<R, double>::value) {
+        if (grad && p->tile_order) {
+            // tile-ordered numbering: bulk-copy tile kernel; edges and the final reduction are part of it
+            unsigned* ticket = reinterpret_cast<unsigned*>(scratch_part<R>(p, scratch) + 2 * kEdgeMaxCtas);
+            if (flags & kFinalizeOnly) return tile8_reduce(p, scratch, out, stream);
+            const bool whole = tile_begin == 0 && tile_end == p->dev.n_tiles;
+            HIDENN_REQUIRE(whole || (flags & HIDENN_TILES_ONLY), "tri_energy: a tile range needs HIDENN_TILES_ONLY");
+            // HIDENN_TILE_WS=0: the two-CTA kernel of tri_tile8.cu instead of the warp-specialised one (A/B runs)
+            static const bool ws_off = [] { const char* e = getenv("HIDENN_TILE_WS"); return e && atoi(e) == 0; }();
+            if (tile_end > tile_begin) {
+                const int rc = (!ws_off && tile9_fits(p))
+                                   ? tile9_launch(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket,
+                                                  stream, tile_begin, tile_end)
+                                   : tile8_launch(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket,
+                                                  stream, tile_begin, tile_end);
+                if (rc) return rc;
+            }
+            return 0;
+        }
+    }
     if (tile_end > tile_begin && !(flags & kFinalizeOnly)) {
         if (grad) {
             const bool body = !(flags & HIDENN_HINT_NO_BODY_FORCE), iso = (flags & HIDENN_HINT_C_PLANE_STRESS) != 0;
@@ -562,9 +592,7 @@ static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R*
     }
     if (flags & HIDENN_TILES_ONLY) return 0;
     {
-        // scratch layout: [0,n_tiles) tile energies | 8-byte aligned: double part[2*kEdgeMaxCtas] | unsigned ticket
-        const size_t off = ((size_t)(p->dev.n_tiles + 8) * sizeof(R) + 7) / 8 * 8;
-        double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(scratch) + off);
+        double* part = scratch_part<R>(p, scratch);
         unsigned* ticket = reinterpret_cast<unsigned*>(part + 2 * kEdgeMaxCtas);
         const int work = std::max(std::max(p->dev.n_edges, p->dev.n_enodes), p->dev.n_tiles / 8);
         const int grid = std::max(1, std::min(kEdgeMaxCtas, (work + kEdgeBlock - 1) / kEdgeBlock));
@@ -589,7 +617,7 @@ static int tri_energy_host(hidenn_tri_plan* p, const R* xf, const R* xb, const R
     DeviceScope scope;
     HIDENN_CUDA_OK(scope.enter(p->device));
     const size_t nfx = 2 * (size_t)p->n_free_x, nbx = 2 * (size_t)p->n_fixed_x, nfu = 2 * (size_t)p->n_free_u, nbu = 2 * (size_t)p->n_fixed_u;
-    const size_t nsc = (size_t)p->dev.n_tiles + 8 + 280;
+    const size_t nsc = scratch_energy_slots(p) + 8 + 280;
     const size_t nen = 4 * (size_t)p->dev.n_enodes;
     auto al = [](size_t n) { return (n + 31) / 32 * 32; };
     const size_t total = al(nfx) * 2 + al(nbx) + al(nfu) * 2 + al(nbu) + al(HIDENN_TRI_NCONST) + al(4) + al(nsc) + al(nen);

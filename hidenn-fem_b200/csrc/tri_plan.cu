@@ -61,9 +61,13 @@ struct Rcb {
         const int64_t tl = nt / 2;
         const int64_t nl = (hi - lo) * tl / nt;
         const double* c = xy;
+        // ties are broken by the other coordinate (then by id): the leaves do not depend on the node numbering, so a mesh
+        // renumbered by hidenn_tri_locality_order is cut into the same tiles again by the plan
         auto cmp = [c, ax](int32_t a, int32_t b) {
             const double va = c[2 * (int64_t)a + ax], vb = c[2 * (int64_t)b + ax];
-            return va < vb || (va == vb && a < b);
+            if (va != vb) return va < vb;
+            const double wa = c[2 * (int64_t)a + 1 - ax], wb = c[2 * (int64_t)b + 1 - ax];
+            return wa < wb || (wa == wb && a < b);
         };
         std::nth_element(idx.begin() + lo, idx.begin() + lo + nl, idx.begin() + hi, cmp);
         if (depth < 3 && hi - lo > 200000) {
@@ -86,6 +90,8 @@ struct TileBuild {
     std::vector<uint32_t> off;      // n_owned: fold-slot start | count << 16
     int32_t n_entries = 0;          // padded slot count (= dump slot index)
     int err = 0;
+    std::vector<unsigned long long> epack;   // tile-ordered layout: Neumann edge visits
+    std::vector<int32_t> eid;
 };
 
 // Lane assignment inside a tile.  Which thread handles which element is free (every fold slot is written exactly
@@ -191,6 +197,62 @@ extern "C" int hidenn_device_count(void) {
     return n;
 }
 
+// class of a node in the tile-ordered numbering (tri_plan.h): A 0, B 1, C 2, D 3
+static inline int node_class(uint8_t bmask, uint8_t dmask) { return bmask ? (dmask ? 2 : 1) : (dmask ? 3 : 0); }
+
+extern "C" int hidenn_tri_locality_order(const int64_t* conn, int64_t Ne, int64_t Nn, const double* coords, const uint8_t* bmask,
+                                         const uint8_t* dmask, int tile_nodes, int64_t* new_to_old, int64_t* elem_new_to_old) {
+    HIDENN_REQUIRE(conn && coords && bmask && dmask && new_to_old && elem_new_to_old, "locality_order: NULL argument");
+    HIDENN_REQUIRE(Ne >= 0 && Nn > 0 && Nn < (int64_t)2147483000, "locality_order: sizes out of range");
+    if (tile_nodes <= 0) tile_nodes = 330;
+    HIDENN_REQUIRE(tile_nodes >= 8 && tile_nodes <= 2048, "locality_order: tile_nodes must be in [8,2048]");
+    for (int64_t i = 0; i < 3 * Ne; ++i) HIDENN_REQUIRE(conn[i] >= 0 && conn[i] < Nn, "locality_order: connectivity index out of range");
+    std::vector<int32_t> val(Nn, 0);
+    for (int64_t i = 0; i < 3 * Ne; ++i) val[conn[i]]++;
+    const int64_t n_tiles = (Nn + tile_nodes - 1) / tile_nodes;
+    std::vector<int32_t> order(Nn);
+    std::iota(order.begin(), order.end(), 0);
+    std::vector<int64_t> tile_begin(n_tiles + 1, 0);
+    tile_begin[n_tiles] = Nn;
+    {
+        Rcb r{coords, order, tile_begin};
+        r.run(0, Nn, 0, n_tiles, 0);
+    }
+    // inside a tile: by class, then descending valence (the fold groups of 8 consecutive nodes then have nearly equal
+    // valence), then by old id
+    auto sort_range = [&](int64_t t0, int64_t t1) {
+        for (int64_t t = t0; t < t1; ++t)
+            std::sort(order.begin() + tile_begin[t], order.begin() + tile_begin[t + 1], [&](int32_t a, int32_t b) {
+                const int ca = node_class(bmask[a], dmask[a]), cb = node_class(bmask[b], dmask[b]);
+                if (ca != cb) return ca < cb;
+                if (val[a] != val[b]) return val[a] > val[b];
+                return a < b;
+            });
+    };
+    {
+        unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        if (n_tiles < 64) nthr = 1;
+        std::vector<std::thread> th;
+        const int64_t per = (n_tiles + nthr - 1) / nthr;
+        for (unsigned i = 0; i < nthr; ++i) {
+            const int64_t a = i * per, b = std::min<int64_t>(n_tiles, a + per);
+            if (a < b) th.emplace_back(sort_range, a, b);
+        }
+        for (auto& t : th) t.join();
+    }
+    std::vector<int32_t> old_to_new(Nn);
+    for (int64_t i = 0; i < Nn; ++i) { new_to_old[i] = order[i]; old_to_new[order[i]] = (int32_t)i; }
+    // elements by their smallest new node id (stable): neighbouring elements stay close in memory
+    std::vector<int32_t> key(Ne);
+    for (int64_t e = 0; e < Ne; ++e)
+        key[e] = std::min(old_to_new[conn[3 * e]], std::min(old_to_new[conn[3 * e + 1]], old_to_new[conn[3 * e + 2]]));
+    std::vector<int64_t> eo(Ne);
+    std::iota(eo.begin(), eo.end(), 0);
+    std::stable_sort(eo.begin(), eo.end(), [&](int64_t a, int64_t b) { return key[a] < key[b]; });
+    std::copy(eo.begin(), eo.end(), elem_new_to_old);
+    return 0;
+}
+
 extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t Nn, const double* coords,
                                       const uint8_t* bmask, const uint8_t* dmask, const int64_t* edges, int64_t Ned,
                                       int tile_nodes, int real_bytes, int device, hidenn_tri_plan** out) {
@@ -241,6 +303,20 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     for (int64_t n = 0; n < Nn; ++n)
         HIDENN_REQUIRE(p->n2e_off[n + 1] - p->n2e_off[n] < kMaxValence, "plan_create: node valence >= 255 not supported");
 
+    // Neumann edge ends by node: (node, edge*2+end), sorted -- used by the tile-ordered layout, where the tile that
+    // owns an edge node also folds the edge term into its gradient
+    std::vector<std::pair<int32_t, int32_t>> edge_ends(2 * Ned);
+    for (int64_t i = 0; i < 2 * Ned; ++i) edge_ends[i] = {(int32_t)edges[i], (int32_t)i};
+    std::sort(edge_ends.begin(), edge_ends.end());
+    auto ends_of = [&](int32_t n) {
+        auto lo = std::lower_bound(edge_ends.begin(), edge_ends.end(), std::make_pair(n, (int32_t)INT32_MIN));
+        auto hi = lo;
+        while (hi != edge_ends.end() && hi->first == n) ++hi;
+        return std::make_pair(lo, hi);
+    };
+    const bool no_v8 = getenv("HIDENN_PLAN_NO_V8") != nullptr;      // A/B: treat a tile-ordered mesh like any other
+    bool tile_order = false;
+
     // RCB tiling of the nodes
     int64_t n_tiles = 0;
     std::vector<int32_t> order(Nn);
@@ -254,6 +330,16 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     {
         Rcb r{coords, order, tile_begin};
         r.run(0, Nn, 0, n_tiles, 0);
+    }
+
+    // Tile-ordered numbering?  Every leaf is one contiguous id range and lists its nodes by class (tri_plan.h).
+    tile_order = (real_bytes == 8) && !no_v8;
+    for (int64_t t = 0; t < n_tiles && tile_order; ++t) {
+        int32_t mn = INT32_MAX, mx = INT32_MIN;
+        for (int64_t i = tile_begin[t]; i < tile_begin[t + 1]; ++i) { mn = std::min(mn, order[i]); mx = std::max(mx, order[i]); }
+        if ((int64_t)mx - mn + 1 != tile_begin[t + 1] - tile_begin[t]) { tile_order = false; break; }
+        for (int32_t n = mn; n < mx; ++n)
+            if (node_class(bmask[n], dmask[n]) > node_class(bmask[n + 1], dmask[n + 1])) { tile_order = false; break; }
     }
 
     // per-tile packs, in parallel over tiles
@@ -298,10 +384,26 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
                     int32_t n = c32[3 * (int64_t)e + c];
                     if (owned_id(n) < 0) halo.push_back(n);
                 }
+            if (tile_order && Ned > 0)
+                for (int32_t n : owned_sorted) {
+                    auto r = ends_of(n);
+                    for (auto it = r.first; it != r.second; ++it) {
+                        const int32_t other = (int32_t)edges[it->second ^ 1];
+                        if (owned_id(other) < 0) halo.push_back(other);
+                    }
+                }
             std::sort(halo.begin(), halo.end());
             halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
             const int32_t n_halo = (int32_t)halo.size(), n_local = B.n_owned + n_halo;
             if (n_local > kMaxLocal) { B.err = 1; continue; }
+            if (tile_order) {
+                // tile-ordered layout: local id = memory order (bulk copies land the owned rows at their ids, fold
+                // thread l stores row l of the tile's run); halo nodes follow in ascending id
+                halo_lid.assign(n_halo, 0);
+                B.nodes.assign(n_local, 0);
+                for (int32_t l = 0; l < B.n_owned; ++l) { lid_of[l] = l; B.nodes[l] = owned_sorted[l]; }
+                for (int32_t j = 0; j < n_halo; ++j) { halo_lid[j] = B.n_owned + j; B.nodes[B.n_owned + j] = halo[j]; }
+            } else
             // Local ids within a valence class (and among the halo nodes) are free.  The node records are staged and
             // the gradients flushed in MEMORY order, 8 consecutive records per 128-byte shared-memory pass, each
             // landing at / read from its local id: choose the ids so that the 8 records of a pass have 8 different
@@ -351,11 +453,17 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
             // l % G -- the same as for the gather of that node, so the lane assignment below fixes both at once.
             B.off.resize(B.n_owned);
             int64_t acc = 0;
+            // slots of a node: one per incident element, in the tile-ordered layout followed by one per Neumann edge end
+            auto slots_of = [&](int32_t n) -> int64_t {
+                int64_t c = n2o[n + 1] - n2o[n];
+                if (tile_order && Ned > 0) { auto r = ends_of(n); c += r.second - r.first; }
+                return c;
+            };
             for (int32_t g0 = 0; g0 < B.n_owned; g0 += G) {
                 int64_t mx = 0;
-                for (int32_t l = g0; l < std::min(B.n_owned, g0 + G); ++l) mx = std::max<int64_t>(mx, n2o[B.nodes[l] + 1] - n2o[B.nodes[l]]);
+                for (int32_t l = g0; l < std::min(B.n_owned, g0 + G); ++l) mx = std::max<int64_t>(mx, slots_of(B.nodes[l]));
                 for (int32_t l = g0; l < std::min(B.n_owned, g0 + G); ++l) {
-                    const int64_t cnt = n2o[B.nodes[l] + 1] - n2o[B.nodes[l]];
+                    const int64_t cnt = slots_of(B.nodes[l]);
                     B.off[l] = (uint32_t)(acc + (l - g0)) | ((uint32_t)cnt << 16);
                 }
                 acc += mx * G;
@@ -385,6 +493,39 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
                 B.pack[i] = w;
             }
             reorder_for_banks(B, real_bytes);
+            if (tile_order && Ned > 0) {
+                // Neumann edge visits: every edge with an owned end; the partial of an owned end goes to the slot after
+                // the node's element slots (rank among the node's edge ends), a halo end to the dump slot
+                std::vector<int32_t> ev;
+                for (int32_t n : owned_sorted) {
+                    auto r = ends_of(n);
+                    for (auto it = r.first; it != r.second; ++it) ev.push_back(it->second >> 1);
+                }
+                std::sort(ev.begin(), ev.end());
+                ev.erase(std::unique(ev.begin(), ev.end()), ev.end());
+                for (int32_t e : ev) {
+                    unsigned long long w = 0;
+                    for (int k = 0; k < 2; ++k) {
+                        const int32_t n = (int32_t)edges[2 * (int64_t)e + k];
+                        int32_t lid = owned_id(n);
+                        unsigned long long pos = (unsigned long long)acc;
+                        if (lid >= 0) {
+                            auto r = ends_of(n);
+                            int64_t rank = 0;
+                            for (auto it = r.first; it != r.second; ++it, ++rank)
+                                if (it->second == 2 * e + k) break;
+                            pos = (unsigned long long)((B.off[lid] & 0xFFFFu) + (n2o[n + 1] - n2o[n] + rank) * G);
+                            if (k == 0) w |= 1ull << kOwnerBit;
+                        } else {
+                            lid = halo_lid[std::lower_bound(halo.begin(), halo.end(), n) - halo.begin()];
+                        }
+                        w |= (unsigned long long)lid << (kLidBits * k);
+                        w |= pos << (2 * kLidBits + kPosBits * k);
+                    }
+                    B.epack.push_back(w);
+                    B.eid.push_back(e);
+                }
+            }
         }
     };
     {
@@ -444,6 +585,32 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
         p->t_elem.insert(p->t_elem.end(), B.elems.begin(), B.elems.end());
         p->elem_pack.insert(p->elem_pack.end(), B.pack.begin(), B.pack.end());
         p->entry_off.insert(p->entry_off.end(), B.off.begin(), B.off.end());
+        if (tile_order) {
+            TileDesc8 d8{};
+            d8.n_owned = d.n_owned; d8.n_local = d.n_local; d8.n_elem = d.n_elem; d8.n_entries = d.n_entries;
+            const int32_t first = B.nodes[0];
+            d8.first_node = first;
+            int32_t cnt[4] = {0, 0, 0, 0};
+            for (int32_t l = 0; l < d.n_owned; ++l) cnt[node_class(bmask[first + l], dmask[first + l])]++;
+            d8.nA = cnt[0]; d8.nB = cnt[1]; d8.nC = cnt[2]; d8.nD = cnt[3];
+            // first rows: the class segments are contiguous in each array (free rows ascend with the node id)
+            auto first_row = [&](const std::vector<int32_t>& slot, bool want_free, int32_t l0, int32_t l1) -> int32_t {
+                for (int32_t l = l0; l < l1; ++l) {
+                    const int32_t sl = slot[first + l];
+                    if (want_free == (sl >= 0)) return sl >= 0 ? sl : ~sl;
+                }
+                return 0;
+            };
+            d8.rx_free = first_row(p->xslot, true, 0, d.n_owned);
+            d8.rx_fixed = first_row(p->xslot, false, 0, d.n_owned);
+            d8.ru_free = first_row(p->uslot, true, 0, d.n_owned);
+            d8.ru_fixed = first_row(p->uslot, false, 0, d.n_owned);
+            d8.edge_off = (int32_t)p->edge_pack.size();
+            d8.n_edge = (int32_t)B.epack.size();
+            p->edge_pack.insert(p->edge_pack.end(), B.epack.begin(), B.epack.end());
+            p->edge_id.insert(p->edge_id.end(), B.eid.begin(), B.eid.end());
+            p->tiles8.push_back(d8);
+        }
         max_local = std::max(max_local, d.n_local);
         max_entries = std::max(max_entries, d.n_entries);
         max_owned = std::max(max_owned, d.n_owned);
@@ -454,6 +621,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     }
     p->node_visits = node_visits;
     p->elem_visits = elem_visits;
+    p->tile_order = tile_order;
 
     // device layout: fixed-stride records per tile
     const int32_t SL = (max_local + 1) & ~1, SE = (max_elem + 1) & ~1, SO = (max_owned + 3) & ~3;
@@ -581,6 +749,25 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     rc |= upload(pp, d_pack, &D.elem_pack);
     rc |= upload(pp, d_off, &D.entry_off);
     D.stride_local = SL; D.stride_elem = SE; D.stride_owned = SO;
+    if (tile_order) {
+        int32_t max_halo = 0;
+        for (const TileDesc8& d8 : p->tiles8) max_halo = std::max(max_halo, d8.n_local - d8.n_owned);
+        const int32_t SH = std::max(2, (max_halo + 1) & ~1);
+        std::vector<int2> t_halo((size_t)n_tiles * SH, make_int2(p->n_fixed_x > 0 ? -1 : 0, p->n_fixed_u > 0 ? -1 : 0));
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            const TileDesc& d = p->tiles[t];
+            for (int32_t j = d.n_owned; j < d.n_local; ++j) {
+                const int32_t n = p->t_node[d.node_off + j];
+                t_halo[(size_t)t * SH + (j - d.n_owned)] = make_int2(p->xslot[n], p->uslot[n]);
+            }
+        }
+        TriPlan8Dev& D8 = p->dev8;
+        rc |= upload(pp, p->tiles8, &D8.tiles);
+        rc |= upload(pp, t_halo, &D8.t_halo);
+        rc |= upload(pp, p->edge_pack, &D8.edge_pack);
+        rc |= upload(pp, p->edge_id, &D8.edge_id);
+        D8.stride_halo = SH; D8.max_halo = max_halo; D8.n_edge_visits = (int32_t)p->edge_pack.size();
+    }
     rc |= upload(pp, e_slots, &D.e_slots);
     rc |= upload(pp, en_xslot, &D.en_xslot);
     rc |= upload(pp, en_uslot, &D.en_uslot);
@@ -618,7 +805,7 @@ extern "C" int hidenn_tri_plan_info(const hidenn_tri_plan* p, int64_t* info) {
     info[2] = p->node_visits;
     info[3] = p->dev.max_local;
     info[4] = p->dev.max_entries;
-    info[5] = p->dev.n_tiles + 8 + 280;     // tile energies + finalize partials (64 x 2 doubles) + ticket
+    info[5] = (int64_t)p->dev.n_tiles * (p->tile_order ? 2 : 1) + 8 + 280;     // tile energies + finalize partials (64 x 2 doubles) + ticket
     info[6] = (int64_t)tile_smem_bytes(p, 8);
     info[7] = (int64_t)tile_smem_bytes(p, 4);
     info[8] = p->n_free_x;
@@ -629,6 +816,18 @@ extern "C" int hidenn_tri_plan_info(const hidenn_tri_plan* p, int64_t* info) {
     info[13] = p->dev.max_elem;
     info[14] = p->n_elems;
     info[15] = p->n_nodes;
+    return 0;
+}
+
+extern "C" int hidenn_tri_plan_layout(const hidenn_tri_plan* p, int64_t* out8) {
+    HIDENN_REQUIRE(p && out8, "plan_layout: NULL");
+    int32_t max_halo = 0;
+    for (const TileDesc8& d : p->tiles8) max_halo = std::max(max_halo, d.n_local - d.n_owned);
+    out8[0] = p->tile_order ? 1 : 0;
+    out8[1] = max_halo;
+    out8[2] = (int64_t)p->edge_pack.size();
+    out8[3] = p->tile_order ? (int64_t)((size_t)p->dev.max_local * 64 + (size_t)(p->dev.max_entries + 1) * 32 + 256) : 0;   // smem bytes, FP64 kernel
+    out8[4] = out8[5] = out8[6] = out8[7] = 0;
     return 0;
 }
 

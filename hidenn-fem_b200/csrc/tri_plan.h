@@ -29,6 +29,31 @@ constexpr int kMaxEntries = (1 << kPosBits) - 1;     // fold slots 0..2046 + dum
 constexpr int kMaxValence = 255;
 constexpr int kPipeBlocks = 64;
 
+// ---- "tile-ordered" layout (kernel v8) ----------------------------------------------------------------------------
+// When the node numbering lists every tile's owned nodes as ONE contiguous id range, and inside the range by class
+//   A: coordinate free, displacement free   B: coordinate fixed, displacement free
+//   C: coordinate fixed, displacement fixed  D: coordinate free, displacement fixed
+// (hidenn_tri_locality_order produces such a numbering), the owned rows of a tile are at most two contiguous runs of
+// each Parameter / fixed buffer.  The tile kernel then stages them with bulk copies (cp.async.bulk + mbarrier, one
+// elected thread), uses local id = id - first id (memory order), and the fold threads store the final gradient rows
+// directly (consecutive lanes -> consecutive rows): no per-node slot records, no output staging buffer.
+struct TileDesc8 {           // 64 B
+    int32_t n_owned, n_local, n_elem, n_entries;
+    int32_t nA, nB, nC, nD;                              // owned class sizes, in local-id order
+    int32_t rx_free, rx_fixed, ru_free, ru_fixed;        // first row of the tile's run in each array
+    int32_t edge_off, n_edge;                            // Neumann edge visits (edge_pack / edge_id)
+    int32_t first_node, pad;
+};
+// edge_pack bit layout (uint64): local ids of the two ends 2 x 10 bit, fold-slot positions 2 x 11 bit (dump slot for a
+// halo end), bit 63 = this visit owns the edge's energy (and its d loss / d traction row)
+struct TriPlan8Dev {
+    const TileDesc8* tiles;
+    const int2* t_halo;                    // [n_tiles, stride_halo]: (xslot, uslot) of the halo nodes, ascending node id
+    const unsigned long long* edge_pack;   // [n_edge_visits]
+    const int32_t* edge_id;                // [n_edge_visits]
+    int32_t stride_halo, max_halo, n_edge_visits, pad;
+};
+
 struct TriPlanDev {
     const TileDesc* tiles;
     int32_t n_tiles;
@@ -79,6 +104,11 @@ struct hidenn_tri_plan {
     std::vector<int32_t> n2e_ent;
     std::vector<int32_t> edges32;
     hidenn::TriPlanDev dev{};
+    bool tile_order = false;                // numbering is tile-ordered -> kernel v8 (FP64)
+    hidenn::TriPlan8Dev dev8{};
+    std::vector<hidenn::TileDesc8> tiles8;
+    std::vector<unsigned long long> edge_pack;
+    std::vector<int32_t> edge_id;
     std::vector<void*> dev_allocs;
     size_t dev_bytes = 0;
     bool generic_uploaded = false;

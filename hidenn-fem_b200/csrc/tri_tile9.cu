@@ -1,0 +1,342 @@
+// Tile kernel v9 (FP64, tile-ordered numberings): warp-specialised, one persistent CTA per SM.
+//
+// Same math, fold order and results as tri_tile8.cu (EnergyLoss2D.__call__ + backward of the reference,
+// /root/reference/src/loss.py:55-116 over /root/reference/src/models.py:292-376); what changes is who does what:
+//   * 16 ELEMENT warps (4 warpgroups, raised to 112 registers with setmaxnreg) do nothing but gather -> element closed
+//     form -> partial stores, tile after tile;
+//   * 7 FOLD warps (32 registers) sum the fold slots of the PREVIOUS tile (second partial buffer) and store the final
+//     gradient rows -- the latency-bound slot loops run in the issue slots the FP64 chains leave free instead of
+//     stalling the element warps behind two block barriers per tile;
+//   * 1 LOADER warp keeps a 3-deep ring of tile stages full: lane 0 issues the bulk copies (owned rows, element packs,
+//     fold offsets, descriptor) on the stage's mbarrier, all lanes gather the halo rows with cp.async.
+// Hand-overs are mbarriers (full / empty per stage, full / empty per partial buffer); there is no __syncthreads in the
+// tile loop.  Register budget: 512 x 112 + 256 x 32 = 65536.
+#include "../../include/hidenn_b200.h"
+#include "common.cuh"
+#include "tri_plan.h"
+#include "tri_element.cuh"
+#include "tri_tile8.h"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace hidenn {
+
+constexpr int kEWarps = 16, kFWarps = 7, kThreads9 = (kEWarps + kFWarps + 1) * 32;      // 768
+constexpr int kStages = 3;
+
+namespace {
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
+// arrives on the barrier when all cp.async of this thread issued so far have landed (the barrier's count includes it)
+__device__ __forceinline__ void bar_arrive_cp_async(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src),
+                 "r"(bytes), "r"(s32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(s32(bar)),
+        "r"(parity)
+        : "memory");
+}
+}  // namespace
+
+struct Smem9 {          // offsets (bytes) into the dynamic shared memory
+    int stage_bytes, node_off, pack_off, offs_off, desc_off;      // inside a stage
+    int part_bytes, part0, en0, bar0, total;
+};
+__host__ __device__ inline Smem9 smem9_layout(int max_local, int max_entries, int stride_elem, int stride_owned) {
+    Smem9 L;
+    L.node_off = 0;
+    L.pack_off = max_local * 32;
+    L.offs_off = L.pack_off + stride_elem * 8;
+    L.desc_off = L.offs_off + ((stride_owned * 4 + 15) & ~15);
+    L.stage_bytes = L.desc_off + 64;
+    L.part_bytes = (max_entries + 1) * 32;
+    L.part0 = kStages * L.stage_bytes;
+    L.en0 = L.part0 + 2 * L.part_bytes;
+    L.bar0 = L.en0 + 2 * 32 * 8;
+    L.total = L.bar0 + 16 * 8 + 16;
+    return L;
+}
+
+template <bool BODY, bool ISO>
+__global__ void __launch_bounds__(kThreads9, 1)
+tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __restrict__ x_free, const double2* __restrict__ x_fixed,
+                 const double2* __restrict__ u_free, const double2* __restrict__ u_fixed, const double* __restrict__ consts,
+                 const double* __restrict__ t_table, const int flags, double2* __restrict__ gx_free, double2* __restrict__ gu_free,
+                 double* __restrict__ gt_out, double* __restrict__ e_dom, double* __restrict__ e_edge, const double* e_dom_all,
+                 const double* e_edge_all, const int n_tiles_total, double* __restrict__ out, unsigned* __restrict__ ticket) {
+    using R = double;
+    using R2 = double2;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const Smem9 L = smem9_layout(P.max_local, P.max_entries, P.stride_elem, P.stride_owned);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar0);
+    uint64_t* full_stage = bars;               // [kStages] loader -> element / fold warps
+    uint64_t* empty_stage = bars + kStages;    // [kStages] fold warps -> loader
+    uint64_t* part_full = bars + 2 * kStages;  // [2] element warps -> fold warps
+    uint64_t* part_empty = part_full + 2;      // [2] fold warps -> element warps
+    unsigned* s_flag = reinterpret_cast<unsigned*>(bars + 16);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nct = gridDim.x;
+    const int n_mine = (P.n_tiles - (int)blockIdx.x + nct - 1) / nct;      // tiles blockIdx.x, +nct, ...
+    constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { bar_init(&full_stage[s], 1 + 32); bar_init(&empty_stage[s], kFWarps); }
+        for (int s = 0; s < 2; ++s) { bar_init(&part_full[s], kEWarps); bar_init(&part_empty[s], kFWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (wid < kEWarps) {
+        // ------------------------------------------------------------------ element warps
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const TriConsts<R> K = load_consts<R, BODY>(consts);
+        const bool with_edges = (flags & HIDENN_WITH_EDGES) != 0;
+        const int etid = tid;
+        for (int k = 0; k < n_mine; ++k) {
+            const int tile = blockIdx.x + k * nct;
+            const int st = k % kStages, pb = k & 1;
+            unsigned char* stage = smem + st * L.stage_bytes;
+            const TileDesc8* d = reinterpret_cast<const TileDesc8*>(stage + L.desc_off);
+            const unsigned long long* s_pack = reinterpret_cast<const unsigned long long*>(stage + L.pack_off);
+            const NodeBuf<R> nodes(stage + L.node_off, P.max_local);
+            const PartBuf<R> part(smem + L.part0 + pb * L.part_bytes, P.max_entries + 1);
+            bar_wait(&full_stage[st], (k / kStages) & 1);
+            bar_wait(&part_empty[pb], ((k >> 1) & 1) ^ 1);
+            const int n_elem = d->n_elem, n_edge = d->n_edge;
+            const unsigned dumpv = (unsigned)d->n_entries;
+            R e_acc = R(0), ee_acc = R(0);
+            for (int i = etid; i < n_elem; i += kEWarps * 32) {
+                const unsigned long long w = s_pack[i];
+                const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
+                const unsigned l0 = lo & LM, l1 = (lo >> kLidBits) & LM, l2 = (lo >> (2 * kLidBits)) & LM;
+                const unsigned p0 = (unsigned)(w >> (3 * kLidBits)) & PM, p1 = (hi >> (3 * kLidBits + kPosBits - 32)) & PM,
+                               p2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
+                R e;
+                R2 gu[3], gx[3], v0, v1, v2, U0, U1, U2;
+                nodes.load(l0, v0, U0); nodes.load(l1, v1, U1); nodes.load(l2, v2, U2);
+                tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx);
+                e_acc += (hi >> 31) ? e : R(0);
+                if (p0 != dumpv) part.store(p0, gu[0], gx[0]);
+                if (p1 != dumpv) part.store(p1, gu[1], gx[1]);
+                if (p2 != dumpv) part.store(p2, gu[2], gx[2]);
+            }
+            if (n_edge > 0) {
+                // Neumann edges with an end owned by this tile (a handful of tiles): N = [1-xi, xi] on raw [-1,1] Gauss points
+                const int ng1 = (int)consts[HIDENN_TRI_NG1];
+                const int edge_off = d->edge_off;
+                for (int i = etid; i < n_edge; i += kEWarps * 32) {
+                    const unsigned long long w = __ldg(P8.edge_pack + edge_off + i);
+                    const int e = __ldg(P8.edge_id + edge_off + i);
+                    const unsigned lo = (unsigned)w;
+                    const unsigned l0 = lo & LM, l1 = (lo >> kLidBits) & LM;
+                    const unsigned p0 = (unsigned)(w >> (2 * kLidBits)) & PM, p1 = (unsigned)(w >> (2 * kLidBits + kPosBits)) & PM;
+                    const bool owner = (w >> kOwnerBit) & 1ull;
+                    R2 x0, x1, U0, U1;
+                    nodes.load(l0, x0, U0); nodes.load(l1, x1, U1);
+                    const R dx = x1.x - x0.x, dy = x1.y - x0.y;
+                    const R ds = sqrt(dx * dx + dy * dy);
+                    const R dirx = dx / ds, diry = dy / ds;
+                    R S = R(0), f0x = R(0), f0y = R(0), f1x = R(0), f1y = R(0);
+                    for (int q = 0; q < ng1; ++q) {
+                        const R xi = consts[HIDENN_TRI_XI1 + q], wq = consts[HIDENN_TRI_W1 + q];
+                        const R ux = (R(1) - xi) * U0.x + xi * U1.x, uy = (R(1) - xi) * U0.y + xi * U1.y;
+                        R tx, ty;
+                        if (t_table) { tx = t_table[((size_t)e * ng1 + q) * 2]; ty = t_table[((size_t)e * ng1 + q) * 2 + 1]; }
+                        else { tx = consts[HIDENN_TRI_TX]; ty = consts[HIDENN_TRI_TY]; }
+                        S += wq * (ux * tx + uy * ty);
+                        f0x += wq * (R(1) - xi) * tx; f0y += wq * (R(1) - xi) * ty;
+                        f1x += wq * xi * tx; f1y += wq * xi * ty;
+                        if (owner && gt_out && with_edges) {      // d loss / d t_q = -w_q ds u_q
+                            gt_out[((size_t)e * ng1 + q) * 2] = -wq * ds * ux;
+                            gt_out[((size_t)e * ng1 + q) * 2 + 1] = -wq * ds * uy;
+                        }
+                    }
+                    const R m = with_edges ? R(1) : R(0);      // the slots exist in the fold either way
+                    if (owner) ee_acc += m * S * ds;
+                    if (p0 != dumpv) part.store(p0, mk2<R>(-m * ds * f0x, -m * ds * f0y), mk2<R>(m * S * dirx, m * S * diry));
+                    if (p1 != dumpv) part.store(p1, mk2<R>(-m * ds * f1x, -m * ds * f1y), mk2<R>(-m * S * dirx, -m * S * diry));
+                }
+            }
+            e_acc = warp_sum(e_acc);
+            ee_acc = warp_sum(ee_acc);
+            R* s_en = reinterpret_cast<R*>(smem + L.en0) + pb * 32;
+            if (lane == 0) { s_en[wid] = e_acc; s_en[16 + wid] = ee_acc; }
+            __syncwarp();
+            if (lane == 0) bar_arrive(&part_full[pb]);      // release: this warp's partials and energy are visible
+        }
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (wid == kEWarps + kFWarps) {
+            // -------------------------------------------------------------- loader warp
+            for (int k = 0; k < n_mine; ++k) {
+                const int tile = blockIdx.x + k * nct;
+                const int st = k % kStages;
+                unsigned char* stage = smem + st * L.stage_bytes;
+                bar_wait(&empty_stage[st], ((k / kStages) & 1) ^ 1);
+                const TileDesc8 d = P8.tiles[tile];
+                R2* xy = reinterpret_cast<R2*>(stage + L.node_off);
+                R2* uv = xy + P.max_local;
+                if (lane == 0) {
+                    const int nBC = d.nB + d.nC, nAB = d.nA + d.nB, nCD = d.nC + d.nD;
+                    const unsigned pack_bytes = 8u * (unsigned)((d.n_elem + 1) & ~1), off_bytes = 4u * (unsigned)((d.n_owned + 3) & ~3);
+                    bar_expect_tx(&full_stage[st], 32u * (unsigned)d.n_owned + pack_bytes + off_bytes + 64u);
+                    bulk(stage + L.desc_off, P8.tiles + tile, 64u, &full_stage[st]);
+                    bulk(stage + L.pack_off, P.elem_pack + (size_t)tile * P.stride_elem, pack_bytes, &full_stage[st]);
+                    bulk(stage + L.offs_off, P.entry_off + (size_t)tile * P.stride_owned, off_bytes, &full_stage[st]);
+                    if (d.nA) bulk(xy, x_free + d.rx_free, 16u * d.nA, &full_stage[st]);
+                    if (nBC) bulk(xy + d.nA, x_fixed + d.rx_fixed, 16u * nBC, &full_stage[st]);
+                    if (d.nD) bulk(xy + d.nA + nBC, x_free + d.rx_free + d.nA, 16u * d.nD, &full_stage[st]);
+                    if (nAB) bulk(uv, u_free + d.ru_free, 16u * nAB, &full_stage[st]);
+                    if (nCD) bulk(uv + nAB, u_fixed + d.ru_fixed, 16u * nCD, &full_stage[st]);
+                }
+                const int n_halo = d.n_local - d.n_owned;
+                const int2* __restrict__ hrec = P8.t_halo + (size_t)tile * P8.stride_halo;
+                for (int j = lane; j < n_halo; j += 32) {      // consecutive lanes land at consecutive local ids
+                    const int2 h = __ldg(hrec + j);
+                    cp_async_pair(xy + d.n_owned + j, h.x >= 0 ? (const void*)(x_free + h.x) : (const void*)(x_fixed + (~h.x)), 16);
+                    cp_async_pair(uv + d.n_owned + j, h.y >= 0 ? (const void*)(u_free + h.y) : (const void*)(u_fixed + (~h.y)), 16);
+                }
+                bar_arrive_cp_async(&full_stage[st]);
+            }
+        } else {
+            // -------------------------------------------------------------- fold warps
+            const int ftid = tid - kEWarps * 32;
+            const bool need_gx = flags & HIDENN_NEED_GX, need_gu = flags & HIDENN_NEED_GU;
+            constexpr unsigned G = 8u;
+            for (int k = 0; k < n_mine; ++k) {
+                const int tile = blockIdx.x + k * nct;
+                const int st = k % kStages, pb = k & 1;
+                unsigned char* stage = smem + st * L.stage_bytes;
+                const TileDesc8* d = reinterpret_cast<const TileDesc8*>(stage + L.desc_off);
+                const uint32_t* s_off = reinterpret_cast<const uint32_t*>(stage + L.offs_off);
+                const PartBuf<R> part(smem + L.part0 + pb * L.part_bytes, P.max_entries + 1);
+                bar_wait(&full_stage[st], (k / kStages) & 1);
+                bar_wait(&part_full[pb], (k >> 1) & 1);
+                const int n_owned = d->n_owned, nA = d->nA, nAB = nA + d->nB, nBC = d->nB + d->nC, nABC = nAB + d->nC;
+                const int rx = d->rx_free, ru = d->ru_free;
+                for (int l = ftid; l < n_owned; l += kFWarps * 32) {
+                    const uint32_t oc = s_off[l];
+                    const unsigned fb = oc & 0xFFFFu, fe = fb + (oc >> 16) * G;
+                    R ax = R(0), ay = R(0), bx = R(0), by = R(0);
+                    for (unsigned q = fb; q < fe; q += G) {
+                        R2 u, x;
+                        part.load(q, u, x);
+                        ax += u.x; ay += u.y; bx += x.x; by += x.y;
+                    }
+                    if (need_gu && l < nAB) gu_free[ru + l] = mk2<R>(ax, ay);
+                    if (need_gx && (l < nA || l >= nABC)) gx_free[rx + (l < nA ? l : l - nBC)] = mk2<R>(bx, by);
+                }
+                if (ftid == 0) {        // tile energies, summed in fixed warp order
+                    const R* s_en = reinterpret_cast<const R*>(smem + L.en0) + pb * 32;
+                    R dd = R(0), ee = R(0);
+#pragma unroll
+                    for (int w = 0; w < kEWarps; ++w) { dd += s_en[w]; ee += s_en[16 + w]; }
+                    e_dom[tile] = dd;
+                    e_edge[tile] = ee;
+                }
+                __syncwarp();
+                if (lane == 0) { bar_arrive(&part_empty[pb]); bar_arrive(&empty_stage[st]); }
+            }
+        }
+    }
+
+    if (flags & HIDENN_TILES_ONLY) return;
+    // last CTA to finish adds the per-tile energies in fixed order (the result does not depend on which CTA is last)
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        *s_flag = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (*s_flag && wid >= kEWarps) {        // 8 warps of the small-register groups do the reduction (256 threads)
+        __threadfence();
+        const int t0 = tid - kEWarps * 32;
+        double dsum = 0.0, esum = 0.0;
+        for (int t = t0; t < n_tiles_total; t += 256) { dsum += __ldcg(e_dom_all + t); esum += __ldcg(e_edge_all + t); }
+        dsum = warp_sum(dsum);
+        esum = warp_sum(esum);
+        double* s_red = reinterpret_cast<double*>(smem + L.en0);
+        if (lane == 0) { s_red[wid - kEWarps] = dsum; s_red[8 + wid - kEWarps] = esum; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (t0 == 0) {
+            double dd = 0.0, ee = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { dd += s_red[w]; ee += s_red[8 + w]; }
+            out[0] = dd - ee;
+            out[1] = dd;
+            out[2] = ee;
+            out[3] = 0.0;
+            *ticket = 0u;
+        }
+    }
+}
+
+size_t tile9_smem_bytes(const hidenn_tri_plan* p) {
+    return (size_t)smem9_layout(p->dev.max_local, p->dev.max_entries, p->dev.stride_elem, p->dev.stride_owned).total;
+}
+
+template <bool BODY, bool ISO>
+static int launch9(const hidenn_tri_plan* p, const double* x_free, const double* x_fixed, const double* u_free, const double* u_fixed,
+                   const double* consts, const double* t_table, int flags, double* out, double* gx, double* gu, double* gt,
+                   double* scratch, unsigned* ticket, cudaStream_t stream, int tile_begin, int tile_end) {
+    const size_t smem = tile9_smem_bytes(p);
+    static size_t configured[kMaxDevices] = {};
+    size_t& cfg = configured[p->device % kMaxDevices];
+    if (smem > cfg) {
+        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile9_kernel<BODY, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cfg = smem;
+    }
+    TriPlanDev P = p->dev;
+    TriPlan8Dev P8 = p->dev8;
+    const int n_total = p->dev.n_tiles;
+    P.elem_pack += (size_t)tile_begin * P.stride_elem;
+    P.entry_off += (size_t)tile_begin * P.stride_owned;
+    P.n_tiles = tile_end - tile_begin;
+    P8.tiles += tile_begin;
+    P8.t_halo += (size_t)tile_begin * P8.stride_halo;
+    const int grid = std::min(P.n_tiles, sm_count(p->device));
+    tri_tile9_kernel<BODY, ISO><<<grid, kThreads9, smem, stream>>>(
+        P, P8, (const double2*)x_free, (const double2*)x_fixed, (const double2*)u_free, (const double2*)u_fixed, consts, t_table, flags,
+        (double2*)gx, (double2*)gu, gt, scratch + tile_begin, scratch + n_total + tile_begin, scratch, scratch + n_total, n_total, out, ticket);
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+bool tile9_fits(const hidenn_tri_plan* p) { return tile9_smem_bytes(p) <= (size_t)227 * 1024; }
+
+int tile9_launch(const hidenn_tri_plan* p, const double* x_free, const double* x_fixed, const double* u_free, const double* u_fixed,
+                 const double* consts, const double* t_table, int flags, double* out, double* gx, double* gu, double* gt, double* scratch,
+                 unsigned* ticket, cudaStream_t stream, int tile_begin, int tile_end) {
+    const bool body = !(flags & HIDENN_HINT_NO_BODY_FORCE), iso = (flags & HIDENN_HINT_C_PLANE_STRESS) != 0;
+#define HIDENN_L9(B_, I_) \
+    return launch9<B_, I_>(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket, stream, tile_begin, tile_end)
+    if (body && iso) HIDENN_L9(true, true);
+    if (body) HIDENN_L9(true, false);
+    if (iso) HIDENN_L9(false, true);
+    HIDENN_L9(false, false);
+#undef HIDENN_L9
+}
+
+}  // namespace hidenn

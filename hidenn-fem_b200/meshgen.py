@@ -213,25 +213,56 @@ def invert_some_elements(conn: np.ndarray, fraction: float, seed: int = 0) -> np
 
 
 def reorder_for_locality(node_coords: np.ndarray, connectivity: np.ndarray, boundary_mask: np.ndarray,
-                         dirichlet_mask: np.ndarray, neumann_edges: Optional[np.ndarray] = None, bits: int = 20):
+                         dirichlet_mask: np.ndarray, neumann_edges: Optional[np.ndarray] = None, bits: int = 20,
+                         mode: str = "tiles", tile_nodes: int = 0):
     """Mesh ingestion helper for meshes with arbitrary numbering (gmsh / meshzoo output, the 6-tuple of
-    /root/reference/src/mesh.py:125-153, 252-276): renumber the nodes along a Z (Morton) curve of their coordinates
-    and list the elements by their smallest new node id.  The fused kernels are correct for any numbering but read
-    Parameter rows through 32-byte sectors, so a numbering without locality runs ~3.5x slower (profiles/README.md).
+    /root/reference/src/mesh.py:125-153, 252-276): renumber the nodes for locality and list the elements by their
+    smallest new node id.  The fused kernels are correct for any numbering but read Parameter rows through 32-byte
+    sectors, so a numbering without locality runs ~3.5x slower (profiles/README.md).
+
+    mode="tiles" (default): the native `hidenn_tri_locality_order` -- the plan's own recursive coordinate bisection,
+    nodes numbered tile by tile (inside a tile by free/fixed class, then by valence).  The plan recognises this
+    numbering and stages every tile's rows with bulk copies (the fastest path).  mode="morton": Z curve of the coordinates.
 
     Returns (node_coords, connectivity, boundary_mask, dirichlet_mask, neumann_edges, new_to_old, elem_new_to_old):
     `new_to_old[i]` is the original index of new node i (to map results back: u_old[new_to_old] = u_new); corner
-    order inside every element is kept (the reference's results depend on it)."""
-    xy = np.asarray(node_coords, dtype=np.float64)
-    conn = np.asarray(connectivity, dtype=np.int64)
-    lo, hi = xy.min(0), xy.max(0)
-    span = np.where(hi > lo, hi - lo, 1.0)
-    q = np.minimum(((xy - lo) / span * ((1 << bits) - 1)).astype(np.uint64), np.uint64((1 << bits) - 1))
-    new_to_old = np.argsort(morton2(q[:, 0], q[:, 1]), kind="stable")
-    old_to_new = np.empty_like(new_to_old)
-    old_to_new[new_to_old] = np.arange(new_to_old.size)
-    conn_new = old_to_new[conn]
-    elem_order = np.argsort(conn_new.min(1), kind="stable")
+    order inside every element is kept (the reference's results depend on it), and so is the orientation of every
+    Neumann edge."""
+    xy = np.ascontiguousarray(node_coords, dtype=np.float64)
+    conn = np.ascontiguousarray(connectivity, dtype=np.int64)
+    if mode == "tiles":
+        import ctypes as C
+        from . import _lib
+        bm = np.ascontiguousarray(boundary_mask, dtype=np.uint8)
+        dm = np.ascontiguousarray(dirichlet_mask, dtype=np.uint8)
+        new_to_old = np.empty(xy.shape[0], np.int64)
+        elem_order = np.empty(conn.shape[0], np.int64)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(_lib.lib().hidenn_tri_locality_order(P(conn), C.c_int64(conn.shape[0]), C.c_int64(xy.shape[0]), P(xy), P(bm), P(dm),
+                                                        C.c_int(int(tile_nodes)), P(new_to_old), P(elem_order)),
+                   "hidenn_tri_locality_order")
+        old_to_new = np.empty_like(new_to_old)
+        old_to_new[new_to_old] = np.arange(new_to_old.size)
+        conn_new = old_to_new[conn][elem_order]
+    elif mode == "morton":
+        lo, hi = xy.min(0), xy.max(0)
+        span = np.where(hi > lo, hi - lo, 1.0)
+        q = np.minimum(((xy - lo) / span * ((1 << bits) - 1)).astype(np.uint64), np.uint64((1 << bits) - 1))
+        new_to_old = np.argsort(morton2(q[:, 0], q[:, 1]), kind="stable")
+        old_to_new = np.empty_like(new_to_old)
+        old_to_new[new_to_old] = np.arange(new_to_old.size)
+        conn_new = old_to_new[conn]
+        elem_order = np.argsort(conn_new.min(1), kind="stable")
+        conn_new = conn_new[elem_order]
+    else:
+        raise ValueError(mode)
     edges = None if neumann_edges is None else old_to_new[np.asarray(neumann_edges, dtype=np.int64)]
-    return (np.asarray(node_coords)[new_to_old], conn_new[elem_order], np.asarray(boundary_mask)[new_to_old],
+    return (np.asarray(node_coords)[new_to_old], conn_new, np.asarray(boundary_mask)[new_to_old],
             np.asarray(dirichlet_mask)[new_to_old], edges, new_to_old, elem_order)
+
+
+def reorder_mesh(m: PlateMesh, mode: str = "tiles", tile_nodes: int = 0) -> PlateMesh:
+    """`reorder_for_locality` applied to a PlateMesh (all per-node arrays follow the new numbering)."""
+    xy, conn, bm, dm, ed, n2o, _ = reorder_for_locality(m.node_coords, m.connectivity, m.boundary_mask, m.dirichlet_mask,
+                                                        m.neumann_edges, mode=mode, tile_nodes=tile_nodes)
+    return PlateMesh(xy, conn, bm, dm, m.neumann_mask[n2o], ed, m.global_node_id[n2o], meta=dict(m.meta, ordering=mode))

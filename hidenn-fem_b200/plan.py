@@ -53,6 +53,9 @@ class TriPlan:
         info = (C.c_int64 * 16)()
         _lib.check(L.hidenn_tri_plan_info(self._h, info), "hidenn_tri_plan_info")
         self.info = dict(zip(INFO_KEYS, [int(v) for v in info]))
+        lay = (C.c_int64 * 8)()
+        _lib.check(L.hidenn_tri_plan_layout(self._h, lay), "hidenn_tri_plan_layout")
+        self.info.update(tile_ordered=bool(lay[0]), max_halo=int(lay[1]), edge_visits=int(lay[2]), smem_v8=int(lay[3]))
         self.real_bytes = real_bytes
         self.n_nodes = n_nodes
         self.n_elems = conn.shape[0]

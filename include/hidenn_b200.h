@@ -83,6 +83,22 @@ int hidenn_tri_plan_create(const int64_t* conn, int64_t n_elems, int64_t n_nodes
                            hidenn_tri_plan** out);
 void hidenn_tri_plan_destroy(hidenn_tri_plan* plan);
 
+/* Locality ordering for meshes with arbitrary numbering (the step before the plan; gmsh / meshzoo output,
+ * src/mesh.py:125-153, 252-276): recursive coordinate bisection of the nodes into the same tiles the plan uses,
+ * nodes numbered tile by tile -- inside a tile by class (coordinate free & displacement free, coordinate fixed &
+ * displacement free, both fixed, coordinate free & displacement fixed), then by descending valence -- so that every
+ * tile's rows of node_coords_free / u_free (and of their gradients) are ONE contiguous run per array.
+ * hidenn_tri_plan_create recognises such a numbering ("tile-ordered") and then stages tiles with bulk copies.
+ * new_to_old [Nn]: old index of new node i; elem_new_to_old [Ne]: elements listed by smallest new node id.
+ * Corner order inside every element is the caller's to keep (the reference's results depend on it). */
+int hidenn_tri_locality_order(const int64_t* conn, int64_t n_elems, int64_t n_nodes, const double* coords,
+                              const uint8_t* boundary_mask, const uint8_t* dirichlet_mask, int tile_nodes,
+                              int64_t* new_to_old, int64_t* elem_new_to_old);
+
+/* layout8[0]=1 if the plan found a tile-ordered numbering (FP64 plans; bulk-copy tile kernel in use), [1]=max halo
+ * nodes per tile, [2]=Neumann edge visits, [3]=dynamic smem bytes of that kernel; the rest reserved. */
+int hidenn_tri_plan_layout(const hidenn_tri_plan* plan, int64_t* layout8);
+
 /* info[0]=n_tiles [1]=tile element visits (incl. halo recompute) [2]=tile node visits
  * [3]=max local nodes/tile [4]=max fold entries/tile [5]=scratch elements needed
  * [6]=dynamic smem bytes f64 [7]=same f32 [8]=n_free_x [9]=n_free_u [10]=n_edges [11]=n_edge_nodes

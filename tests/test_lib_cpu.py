@@ -182,16 +182,32 @@ def test_reorder_for_locality_is_a_consistent_renumbering():
     """meshgen.reorder_for_locality: same mesh under a new numbering (coordinates of every element corner, masks and
     Neumann edges follow), and it restores run lengths of a randomly numbered mesh to those of a Morton mesh."""
     from hidenn_fem_b200 import meshgen
+    from hidenn_fem_b200.plan import TriPlan
     m = meshgen.plate_mesh(61, 31, jitter=0.2, diag="random", seed=4, ordering="random")
-    xy, conn, bm, dm, ed, n2o, e2o = meshgen.reorder_for_locality(m.node_coords, m.connectivity, m.boundary_mask,
-                                                                   m.dirichlet_mask, m.neumann_edges)
-    assert sorted(n2o.tolist()) == list(range(m.node_coords.shape[0]))
-    assert np.array_equal(xy[conn], m.node_coords[m.connectivity[e2o]])          # same triangles, same corner order
-    assert np.array_equal(bm, m.boundary_mask[n2o]) and np.array_equal(dm, m.dirichlet_mask[n2o])
-    assert np.array_equal(xy[ed], m.node_coords[m.neumann_edges])
-    # locality: mean |id difference| inside an element drops by an order of magnitude
     spread = lambda c: np.abs(c - c[:, [1, 2, 0]]).mean()
-    assert spread(conn) < 0.1 * spread(m.connectivity)
+    for mode, bound in (("tiles", 0.35), ("morton", 0.1)):
+        xy, conn, bm, dm, ed, n2o, e2o = meshgen.reorder_for_locality(m.node_coords, m.connectivity, m.boundary_mask,
+                                                                       m.dirichlet_mask, m.neumann_edges, mode=mode, tile_nodes=64)
+        assert sorted(n2o.tolist()) == list(range(m.node_coords.shape[0]))
+        assert np.array_equal(xy[conn], m.node_coords[m.connectivity[e2o]])          # same triangles, same corner order
+        assert np.array_equal(bm, m.boundary_mask[n2o]) and np.array_equal(dm, m.dirichlet_mask[n2o])
+        assert np.array_equal(xy[ed], m.node_coords[m.neumann_edges])               # same edges, same orientation
+        # locality: mean |id difference| inside an element drops
+        assert spread(conn) < bound * spread(m.connectivity)
+        # the plan recognises the native tile order (FP64 plans: bulk-copy tile kernel), and only that
+        plan = TriPlan(conn, xy.shape[0], xy, bm, dm, ed, tile_nodes=64, real_bytes=8, device=-1)
+        assert plan.info["tile_ordered"] == (mode == "tiles")
+        if mode == "tiles":
+            # every tile's owned nodes are one contiguous id range, listed by class A,B,C,D (tri_plan.h)
+            off, n_owned, nodes = plan.tiles()
+            cls = np.where(bm, np.where(dm, 2, 1), np.where(dm, 3, 0))
+            for t in range(plan.info["n_tiles"]):
+                own = nodes[off[t]:off[t] + n_owned[t]]
+                assert np.array_equal(own, np.arange(own[0], own[0] + n_owned[t]))
+                assert (np.diff(cls[own]) >= 0).all()
+            assert plan.info["edge_visits"] >= ed.shape[0]
+            assert not TriPlan(conn, xy.shape[0], xy, bm, dm, ed, tile_nodes=64, real_bytes=4, device=-1).info["tile_ordered"]
+            assert not TriPlan(conn, xy.shape[0], xy, bm, dm, ed, tile_nodes=48, real_bytes=8, device=-1).info["tile_ordered"]
 
 
 def test_bench_reference_arm_prints_one_contract_line():

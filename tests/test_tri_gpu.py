@@ -34,6 +34,30 @@ def build(g, device="cuda", dtype=None, tile_nodes=0):
     return model
 
 
+def tile_ordered(g, tile_nodes=0):
+    """The same case renumbered by the ingestion helper (hidenn_tri_locality_order): FP64 plans then run the bulk-copy
+    tile kernel.  Returns the renumbered case and `back(gx_free_new, gu_free_new)` -> gradients in the ORIGINAL
+    parameter layout (so the golden / oracle values apply unchanged)."""
+    from hidenn_fem_b200 import meshgen
+    fm, um = ~g["boundary_mask"], ~g["dirichlet_mask"]
+    n = g["node_coords"].shape[0]
+    xy, conn, bm, dm, ed, n2o, _ = meshgen.reorder_for_locality(g["node_coords"], g["connectivity"], g["boundary_mask"],
+                                                                g["dirichlet_mask"], g["neumann_edges"], tile_nodes=tile_nodes)
+    g2 = dict(g, node_coords=xy, connectivity=conn, boundary_mask=bm, dirichlet_mask=dm, neumann_edges=ed)
+    if "node_coords_free" in g:
+        full_x = cf.assemble_full(g["node_coords_free"], g["node_coords_fixed"], fm)[n2o]
+        full_u = np.zeros((n, 2), g["u_free"].dtype)
+        full_u[um] = g["u_free"]
+        full_u = full_u[n2o]
+        g2.update(node_coords_free=full_x[~bm], node_coords_fixed=full_x[bm], u_free=full_u[~dm])
+
+    def back(gx_new, gu_new):
+        fx = np.zeros((n, 2)); fx[n2o[~bm]] = gx_new
+        fu = np.zeros((n, 2)); fu[n2o[~dm]] = gu_new
+        return fx[fm], fu[um]
+    return g2, back
+
+
 def loss_of(g, dt, **kw):
     from hidenn_fem_b200.loss import EnergyLoss2D
     return EnergyLoss2D(E=10e9, nu=0.3, gauss_order=int(g.get("gauss_order", 4)), gauss_order_1d=int(g.get("gauss_order_1d", 2)),
@@ -43,10 +67,17 @@ def loss_of(g, dt, **kw):
 @pytest.mark.parametrize("case", TRI_CASES)
 @pytest.mark.parametrize("tag", ["default", "forces"])
 @pytest.mark.parametrize("tile_nodes", [0, 16])
-def test_energy_and_grads_vs_reference_golden(case, tag, tile_nodes):
+@pytest.mark.parametrize("numbering", ["as_is", "tile_ordered"])
+def test_energy_and_grads_vs_reference_golden(case, tag, tile_nodes, numbering):
     g = gold(case)
-    model = build(g, tile_nodes=tile_nodes)
+    back = lambda a, b: (a, b)
+    gm = g
+    if numbering == "tile_ordered":
+        gm, back = tile_ordered(g, tile_nodes)
+    model = build(gm, tile_nodes=tile_nodes)
     dt = model.dtype
+    if numbering == "tile_ordered":
+        assert model._plan().info["tile_ordered"] == (dt == torch.float64)
     loss_fn = loss_of(g, dt)
     bf, tf = (forces.b_force_test, forces.t_force_test) if tag == "forces" else (None, None)
     loss = loss_fn(model, bf, tf)
@@ -54,8 +85,9 @@ def test_energy_and_grads_vs_reference_golden(case, tag, tile_nodes):
     tol = TOL[dt]
     ref = float(g[f"loss_{tag}"])
     assert abs(loss.item() - ref) <= tol * abs(ref), (loss.item(), ref)
-    assert relmax(model.node_coords_free.grad.cpu().numpy(), g[f"gx_{tag}"]) < tol
-    assert relmax(model.u_free.grad.cpu().numpy(), g[f"gu_{tag}"]) < tol
+    gx, gu = back(model.node_coords_free.grad.cpu().numpy(), model.u_free.grad.cpu().numpy())
+    assert relmax(gx, g[f"gx_{tag}"]) < tol
+    assert relmax(gu, g[f"gu_{tag}"]) < tol
     parts = loss_fn.last_parts.cpu().numpy()
     assert abs(parts[1] - float(g[f"domain_{tag}"])) <= tol * max(abs(float(g[f"domain_{tag}"])), abs(ref))
     assert abs(parts[2] - float(g[f"edge_{tag}"])) <= tol * max(abs(float(g[f"edge_{tag}"])), abs(ref))
@@ -121,26 +153,30 @@ def test_generic_forward_and_vjp_vs_reference_golden(case):
 def _mesh_case(n_elems, dtype, ordering, jitter=0.25, invert=0.0, seed=0, u_scale=1e-5):
     from hidenn_fem_b200 import meshgen
     nx, ny = meshgen.plate_dims_for_elements(n_elems)
-    m = meshgen.plate_mesh(nx, ny, jitter=jitter, diag="random", seed=seed, ordering=ordering)
+    m = meshgen.plate_mesh(nx, ny, jitter=jitter, diag="random", seed=seed, ordering="random" if ordering == "tiles" else ordering)
     conn = meshgen.invert_some_elements(m.connectivity, invert, seed) if invert else m.connectivity
     bmask = m.boundary_mask & ~m.neumann_mask
+    coords64, dmask, edges = m.node_coords, m.dirichlet_mask, m.neumann_edges
+    if ordering == "tiles":          # a randomly numbered mesh through the ingestion helper -> tile-ordered numbering
+        coords64, conn, bmask, dmask, edges, _, _ = meshgen.reorder_for_locality(coords64, conn, bmask, dmask, edges)
     rng = np.random.default_rng(seed)
     npdt = np.float64 if dtype == torch.float64 else np.float32
-    coords = m.node_coords.astype(npdt)
-    g = dict(node_coords=coords, connectivity=conn, boundary_mask=bmask, dirichlet_mask=m.dirichlet_mask,
-             neumann_edges=m.neumann_edges, u_fixed=np.asarray(0.0), gauss_order=4, gauss_order_1d=2,
+    coords = coords64.astype(npdt)
+    g = dict(node_coords=coords, connectivity=conn, boundary_mask=bmask, dirichlet_mask=dmask,
+             neumann_edges=edges, u_fixed=np.asarray(0.0), gauss_order=4, gauss_order_1d=2,
              node_coords_free=coords[~bmask], node_coords_fixed=coords[bmask],
-             u_free=(u_scale * rng.standard_normal((int((~m.dirichlet_mask).sum()), 2))).astype(npdt))
+             u_free=(u_scale * rng.standard_normal((int((~dmask).sum()), 2))).astype(npdt))
     return g
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-@pytest.mark.parametrize("ordering", ["natural", "random", "morton"])
+@pytest.mark.parametrize("ordering", ["natural", "random", "morton", "tiles"])
 def test_parity_200k_vs_oracle(dtype, ordering):
     """Mid-size unstructured mesh, incl. 20% inverted elements: CUDA vs closed-form oracle (FP64 evaluation of the
     same FP32/FP64 inputs)."""
     g = _mesh_case(200_000, dtype, ordering, invert=0.2, u_scale=1e-3)
     model = build(g)
+    assert model._plan().info["tile_ordered"] == (ordering == "tiles" and dtype == torch.float64)
     loss_fn = loss_of(g, dtype)
     loss = loss_fn(model)
     loss.backward()
@@ -152,12 +188,14 @@ def test_parity_200k_vs_oracle(dtype, ordering):
     assert relmax(model.u_free.grad.cpu().numpy(), gu) < tol
 
 
-@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-def test_parity_10m_vs_oracle(dtype):
+@pytest.mark.parametrize("dtype,ordering", [(torch.float64, "tiles"), (torch.float64, "morton"), (torch.float32, "tiles")])
+def test_parity_10m_vs_oracle(dtype, ordering):
     """The bench workload itself (BASELINE config C4: 10 M unstructured triangles, locality-ordered): CUDA vs the
     closed-form oracle on the same inputs at the contract tolerances (reference loss.py:113-116)."""
-    g = _mesh_case(10_000_000, dtype, "morton", u_scale=1e-3)
+    g = _mesh_case(10_000_000, dtype, ordering, u_scale=1e-3)
     model = build(g)
+    if ordering == "tiles":
+        assert model._plan().info["tile_ordered"] == (dtype == torch.float64)
     loss_fn = loss_of(g, dtype)
     loss = loss_fn(model)
     loss.backward()
@@ -185,6 +223,29 @@ def test_determinism_and_plan_invariance():
     # the energy sum is re-associated across tiles
     assert torch.equal(outs[0][1], outs[2][1]) and torch.equal(outs[0][2], outs[2][2])
     assert abs(outs[0][0] - outs[2][0]) <= 1e-13 * abs(outs[0][0])
+
+
+def test_tile_ordered_kernel_is_deterministic_and_matches_generic_kernel(monkeypatch):
+    """Bulk-copy tile kernel (tile-ordered numbering): bit-identical run to run; against the generic kernel on the same
+    mesh (HIDENN_PLAN_NO_V8=1) element sums are identical, only rows of Neumann edge nodes may differ in the last bits
+    (the edge term is folded after the elements instead of added afterwards)."""
+    g = _mesh_case(100_000, torch.float64, "tiles", u_scale=1e-3)
+    outs = []
+    for k in range(3):
+        if k == 2:
+            monkeypatch.setenv("HIDENN_PLAN_NO_V8", "1")
+        model = build(g)
+        assert model._plan().info["tile_ordered"] == (k < 2)
+        loss_fn = loss_of(g, torch.float64)
+        loss = loss_fn(model)
+        loss.backward()
+        outs.append((loss.item(), model.node_coords_free.grad.clone(), model.u_free.grad.clone(), loss_fn.last_parts.clone()))
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert abs(outs[0][0] - outs[2][0]) <= 1e-13 * abs(outs[0][0])
+    for a, b in ((outs[0][1], outs[2][1]), (outs[0][2], outs[2][2])):
+        diff = (a != b).any(dim=1)
+        assert int(diff.sum()) <= 2 * g["neumann_edges"].shape[0] + 2
+        assert relmax(a.cpu().numpy(), b.cpu().numpy()) < 1e-14
 
 
 def test_no_grad_and_frozen_parameters():
@@ -282,7 +343,7 @@ def test_host_buffer_entry_point():
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
-@pytest.mark.parametrize("ordering", ["morton", "natural", "random"])
+@pytest.mark.parametrize("ordering", ["morton", "natural", "random", "tiles"])
 def test_host_buffer_pipeline_matches_resident(dtype, ordering, monkeypatch):
     """The chunked three-stream host entry (rows in / tiles / gradient rows out, overlapped) returns the same bits as
     the resident entry point, for numberings where the row windows are narrow (morton, natural) and where they
