@@ -53,6 +53,11 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the CUDA-graph replay of the step")
     ap.add_argument("--watchdog-s", type=int, default=1500, help="dump all thread stacks and exit if the run takes longer")
     ap.add_argument("--extra", action="store_true", help="also time the random-ordering and FP32 variants (N=1)")
+    ap.add_argument("--no-grid", action="store_true", help="skip the C2 / C3 lines (other_configs) of the default run")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 1 s back-to-back leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --elems per GPU (driver default); strong: --elems-total over all GPUs (C5 as north_star words it)")
+    ap.add_argument("--elems-total", type=int, default=80_000_000, help="total elements of the strong-scaling run")
     return ap.parse_args()
 
 
@@ -172,21 +177,23 @@ def make_workload(args, rank, world, device, dtype, ordering, n_elems_per_gpu, t
     return m, model, loss_fn, (nx, ny)
 
 
-def time_steps(model, loss_fn, steps, warmup, world, graph=True):
-    import torch.distributed as dist
-
+def make_step(model, loss_fn, graph=True):
     if graph:
         # public API: hidenn_fem_b200.graph.GraphedEnergyStep == zero_grad + loss_fn(model) + backward, replayed
         from hidenn_fem_b200.graph import GraphedEnergyStep
-        step = GraphedEnergyStep(model, loss_fn)
-    else:
-        def step():
-            model.zero_grad(set_to_none=True)
-            loss = loss_fn(model)
-            loss.backward()
-            return loss
-    for _ in range(warmup):
-        step()
+        return GraphedEnergyStep(model, loss_fn)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        loss = loss_fn(model)
+        loss.backward()
+        return loss
+    return step
+
+
+def timed_loop(step, steps, world):
+    """`steps` calls bracketed by barrier + synchronize, CUDA events on the launch stream, max over ranks -> (ms total, last loss)."""
+    import torch.distributed as dist
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -203,7 +210,49 @@ def time_steps(model, loss_fn, steps, warmup, world, graph=True):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.barrier()
         ms = float(t.item())
+    return ms, loss
+
+
+def time_steps(step, steps, warmup, world):
+    for _ in range(warmup):
+        step()
+    ms, loss = timed_loop(step, steps, world)
     return ms / steps, float(loss.item())
+
+
+def time_e2e_dist(model, step, steps, warmup, world):
+    """End to end at N > 1 through the Python API: every step copies the rank's Parameter rows from pinned host memory,
+    runs the (graphed) step incl. the halo exchange, and reads the loss and both gradients back into pinned host memory.
+    Wall clock between barriers, max over ranks."""
+    import torch.distributed as dist
+    xf_h = model.node_coords_free.detach().cpu().pin_memory()
+    uf_h = model.u_free.detach().cpu().pin_memory()
+    gx_h, gu_h = torch.empty_like(xf_h).pin_memory(), torch.empty_like(uf_h).pin_memory()
+    loss_h = torch.empty(1, dtype=xf_h.dtype).pin_memory()
+
+    def call():
+        with torch.no_grad():
+            model.node_coords_free.copy_(xf_h, non_blocking=True)
+            model.u_free.copy_(uf_h, non_blocking=True)
+        loss = step()
+        gx_h.copy_(model.node_coords_free.grad, non_blocking=True)
+        gu_h.copy_(model.u_free.grad, non_blocking=True)
+        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+    for _ in range(max(1, min(warmup, 3))):
+        call()
+    n = max(3, min(steps, 10))
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(n):
+        call()
+    t = torch.tensor([(time.perf_counter() - t0) / n], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    h2d = (xf_h.numel() + uf_h.numel()) * xf_h.element_size()
+    d2h = (gx_h.numel() + gu_h.numel() + 1) * xf_h.element_size()
+    b = torch.tensor([h2d, d2h], device="cuda", dtype=torch.float64)
+    dist.all_reduce(b)
+    return float(t.item()) * 1e3, int(b[0].item()), int(b[1].item()), float(loss_h[0])
 
 
 def time_kernel(model, loss_fn, steps, warmup):
@@ -373,6 +422,31 @@ def bench_grid_paths(device, steps, warmup, peak, full_c3=False):
     return out
 
 
+def kernel_source_hash():
+    """sha256 (first 16 hex digits) over the triangle kernel / plan sources: stamps profiles/traffic.json."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "hidenn-fem_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.startswith("tri_") or f == "common.cuh":
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def fp64_peak(device):
+    """DFMA instructions / s of this GPU measured by the library's microbenchmark (None if the symbol is missing)."""
+    import ctypes as C
+    from hidenn_fem_b200 import _lib
+    L = _lib.lib()
+    if not hasattr(L, "hidenn_fp64_peak"):
+        return None
+    out = C.c_double(0.0)
+    L.hidenn_fp64_peak.restype = C.c_int
+    with torch.cuda.device(device):
+        rc = L.hidenn_fp64_peak(C.byref(out), _lib.stream_ptr())
+    return float(out.value) if rc == 0 else None
+
+
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_step_factory(n_elems, dtype):
     """The reference's CPU torch path restated in oracle/torch_port.py, same generator, bounded size."""
@@ -407,9 +481,11 @@ def run_reference(args):
         return
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
     step, ne = cpu_reference_step_factory(args.cpu_sample_elems, dtype)
-    for _ in range(max(1, min(args.warmup, 2))):
+    # --steps / --warmup are honoured as given: one step of the 1 M-element sample is ~1 s of CPU work on 16 cores,
+    # so the driver's 20 + 5 fit in half a minute
+    k, w = max(1, args.steps), max(0, args.warmup)
+    for _ in range(w):
         step()
-    k = max(1, min(args.steps, 5))
     t0 = time.perf_counter()
     for _ in range(k):
         step()
@@ -419,7 +495,7 @@ def run_reference(args):
     sample = f"{ne} triangles of the same plate generator (C4 scaled down), 1 step = loss+backward, mean of {k}"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": k,
-        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": w, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": WORKLOAD, "elements_total": args.elems, "sample_elements": ne, "gauss_points": NG,
                    "note": "CPU arm: every step is a bounded sample of the workload (same generator, scaled down)"},
@@ -456,16 +532,26 @@ def main():
     sz = 8 if dtype == torch.float64 else 4
 
     t0 = time.time()
-    m, model, loss_fn, dims = make_workload(args, rank, world, device, dtype, args.ordering, args.elems, args.tile_nodes)
+    elems_per_gpu = args.elems if args.scaling == "weak" else max(1, args.elems_total // world)
+    m, model, loss_fn, dims = make_workload(args, rank, world, device, dtype, args.ordering, elems_per_gpu, args.tile_nodes)
     plan = model._plan()
     setup_s = time.time() - t0
     ne_local = m.connectivity.shape[0]
     nn_local = m.node_coords.shape[0]
 
+    step = make_step(model, loss_fn, graph=not args.no_graph)
     sampler = ClockSampler(physical_index(local))
     sampler.start()
-    ms_step, loss_val = time_steps(model, loss_fn, args.steps, args.warmup, world, graph=not args.no_graph)
+    ms_step, loss_val = time_steps(step, args.steps, args.warmup, world)
     clocks = sampler.stop()
+    # sustained leg: >= 1 s of back-to-back steps with its own clock record (the K-step figure above is a burst of a few ms)
+    sustained = None
+    if not args.no_sustained:
+        n_sus = int(min(20000, max(args.steps, np.ceil(1100.0 / max(ms_step, 1e-3)))))
+        s2 = ClockSampler(physical_index(local))
+        s2.start()
+        ms_sus, _ = timed_loop(step, n_sus, world)
+        sustained = {"steps": n_sus, "seconds": ms_sus * 1e-3, "ms_per_step": ms_sus / n_sus, "clocks": s2.stop()}
     ms_kernel = time_kernel(model, loss_fn, args.steps, args.warmup)
 
     ne_tot = torch.tensor([ne_local, nn_local], device=device, dtype=torch.float64)
@@ -473,6 +559,8 @@ def main():
         dist.all_reduce(ne_tot)
     ne_total, nn_total = int(ne_tot[0].item()), int(ne_tot[1].item())
     value = ne_total * NG / (ms_step * 1e-3)
+    if sustained is not None:
+        sustained["value"] = ne_total * NG / (sustained["ms_per_step"] * 1e-3)
 
     peaks = {}
     try:
@@ -490,12 +578,29 @@ def main():
                                             else "tri_tile_persistent_kernel<%s>" % ("double" if sz == 8 else "float")),
                 "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_element": alg_bytes / ne_local, "peak_source": peak_src}
+    # DRAM bytes of one launch from the committed ncu capture -- only if that capture was made from the kernel sources
+    # that are running now (profiles/traffic.json carries their hash), else null
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    src_hash = kernel_source_hash()
+    roofline["kernel_source_sha256_16"] = src_hash
     if os.path.exists(tpath):
         try:
-            roofline["traffic"] = json.load(open(tpath)).get(args.dtype)
+            tj = json.load(open(tpath))
+            ent = tj.get(args.dtype + ("_tiles" if plan.info.get("tile_ordered") else ""))
+            if isinstance(ent, dict) and ent.get("source_sha256_16") == src_hash:
+                roofline["traffic"] = ent.get("dram_bytes_per_launch")
+                roofline["traffic_source"] = ent.get("from")
         except Exception:
             pass
+    fp = fp64_peak(device)
+    if fp is not None and sz == 8:
+        # FP64 instructions one launch issues (thread level): 68 per element visit (closed form, SASS count) + 4 per fold slot
+        # + 8 per merged pair partial; against the DFMA issue rate measured by hidenn_fp64_peak on this GPU
+        n_slots = plan.info.get("fold_slots", 0) or 3 * plan.info["elem_visits"]
+        fp64_instr = 68.0 * plan.info["elem_visits"] + 4.0 * n_slots
+        roofline["fp64_pipe"] = {"measured_peak_dfma_per_s": fp, "measured_peak_tflops": 2.0 * fp / 1e12,
+                                 "kernel_fp64_instr_per_launch": fp64_instr,
+                                 "frac": fp64_instr / (ms_kernel * 1e-3) / fp}
 
     e2e = None
     if not args.no_e2e and world == 1:
@@ -504,9 +609,12 @@ def main():
                "ms_per_step": ms_e2e, "ms_per_step_unpipelined": ms_serial, "ms_per_step_loss_only_readback": ms_lossonly,
                "api": "hidenn_tri_energy_host_%s (pinned host buffers; rows in / tiles / gradient rows out overlapped on 3 streams)" % args.dtype,
                "loss_matches_resident": bool(abs(l_e2e - loss_val) <= 1e-9 * abs(loss_val))}
-    elif world > 1:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "host-buffer entry point measured at N=1 only"}
+    elif not args.no_e2e and world > 1:
+        ms_e2e, h2d, d2h, l_e2e = time_e2e_dist(model, step, args.steps, args.warmup, world)
+        e2e = {"value": ne_total * NG / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+               "api": "pinned host Parameter rows -> device, GraphedEnergyStep incl. halo exchange, loss + both gradients -> pinned host "
+                      "(all ranks, bytes summed over ranks)",
+               "loss_matches_resident": bool(abs(l_e2e - loss_val) <= 1e-9 * abs(loss_val))}
 
     extra = {}
     if args.extra and world == 1:
@@ -517,7 +625,7 @@ def main():
             del model, loss_fn
             torch.cuda.empty_cache()
             m2, model, loss_fn, _ = make_workload(args, 0, 1, device, dt2, ordr, args.elems, args.tile_nodes)
-            ms2, _ = time_steps(model, loss_fn, args.steps, args.warmup, 1, graph=not args.no_graph)
+            ms2, _ = time_steps(make_step(model, loss_fn, graph=not args.no_graph), args.steps, args.warmup, 1)
             k2 = time_kernel(model, loss_fn, args.steps, args.warmup)
             s2 = 8 if dt2 == torch.float64 else 4
             p2 = model._plan()
@@ -525,13 +633,14 @@ def main():
             extra[tag] = {"ms_per_step": ms2, "kernel_ms": k2, "evals_per_s": m2.connectivity.shape[0] * NG / (ms2 * 1e-3),
                           "roofline_frac": ab / (k2 * 1e-3) / 1e9 / peak}
 
-    if args.extra and world == 1:
+    other = None
+    if not args.no_grid and world == 1:
         try:
-            del model, loss_fn
+            del model, loss_fn, step
             torch.cuda.empty_cache()
-            extra.update(bench_grid_paths(device, args.steps, args.warmup, peak, full_c3=True))
-        except Exception as e:      # the headline must survive a failure of the informational lines
-            extra["grid_paths_error"] = repr(e)
+            other = bench_grid_paths(device, args.steps, args.warmup, peak, full_c3=True)
+        except Exception as e:      # the headline must survive a failure of these lines
+            other = {"error": repr(e)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -549,7 +658,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "elements_total": ne_total, "nodes_total": nn_total, "elements_per_gpu": ne_local,
@@ -559,6 +668,7 @@ def main():
                        "tile_nodes": plan.info["max_local"], "n_tiles": plan.info["n_tiles"],
                        "halo_recompute": plan.info["elem_visits"] / max(1, ne_local), "setup_s": setup_s},
             "loss": loss_val,
+            "sustained": sustained,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": args.steps * ((2 if plan.info.get("tile_ordered") else 3) + (2 if world > 1 else 0)),
             "gpu_launches_note": ("per step: tri_tile8_kernel (edges + final reduction inside) + scale_inplace2_kernel"
@@ -566,6 +676,8 @@ def main():
                                   "per step: tri_tile_persistent_kernel + tri_edge_finalize_kernel + scale_inplace2_kernel")
                                  + (" + halo pack_all + unpack_all (plus one copy and the NCCL all-reduce)" if world > 1 else ""),
         }
+        if other is not None:
+            line["other_configs"] = other      # BASELINE configs C2 (1D bar, 1 M elements) and C3 (structured L2, 4097^2 nodes)
         if extra:
             line["extra"] = extra
         sys.stdout.flush()

@@ -729,7 +729,9 @@ static int tri_energy_host(hidenn_tri_plan* p, const R* xf, const R* xb, const R
     if (tri_energy_launch<R>(p, d_xf, d_xb, d_uf, d_ub, d_c, nullptr, flags | kFinalizeOnly, d_out, d_gx, d_gu, nullptr, d_sc, stream_v, 0, -1,
                              d_en))
         return 1;
-    const bool edges = (flags & HIDENN_WITH_EDGES) && p->dev.n_edges > 0 && (want_gx || want_gu);
+    // rows the separate edge kernel updates after the tiles are patched in from a compact buffer; tile-ordered plans fold
+    // the edge term inside the tiles, so their rows are already final
+    const bool edges = !p->tile_order && (flags & HIDENN_WITH_EDGES) && p->dev.n_edges > 0 && (want_gx || want_gu);
     std::vector<R> en_h(edges ? nen : 0);
     HIDENN_CUDA_OK(cudaMemcpyAsync(out_h, d_out, 4 * sizeof(R), cudaMemcpyDeviceToHost, stream));
     if (edges) HIDENN_CUDA_OK(cudaMemcpyAsync(en_h.data(), d_en, nen * sizeof(R), cudaMemcpyDeviceToHost, stream));
@@ -779,6 +781,23 @@ extern "C" int hidenn_tri_energy_f32(const hidenn_tri_plan* plan, const float* x
                                      void* stream) {
     return tri_energy_launch<float>(plan, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx_free, gu_free,
                                     gt_out, scratch, stream);
+}
+extern "C" int hidenn_tri_energy_range_f64(const hidenn_tri_plan* plan, const double* x_free, const double* x_fixed, const double* u_free,
+                                           const double* u_fixed, const double* consts, const double* t_table, int flags,
+                                           double* gx_free, double* gu_free, double* gt_out, double* scratch, int tile_begin,
+                                           int tile_end, void* stream) {
+    HIDENN_REQUIRE(plan && plan->tile_order, "tri_energy_range: needs a tile-ordered FP64 plan");
+    HIDENN_REQUIRE(flags & (HIDENN_NEED_GX | HIDENN_NEED_GU), "tri_energy_range: at least one gradient must be requested");
+    HIDENN_REQUIRE(0 <= tile_begin && tile_begin <= tile_end && tile_end <= plan->dev.n_tiles, "tri_energy_range: bad tile range");
+    double dummy_out[1];
+    return tri_energy_launch<double>(plan, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags | HIDENN_TILES_ONLY, dummy_out, gx_free,
+                                     gu_free, gt_out, scratch, stream, tile_begin, tile_end);
+}
+extern "C" int hidenn_tri_energy_finish_f64(const hidenn_tri_plan* plan, double* scratch, double* out, void* stream) {
+    HIDENN_REQUIRE(plan && plan->tile_order && scratch && out, "tri_energy_finish: needs a tile-ordered FP64 plan, scratch and out");
+    DeviceScope scope;
+    HIDENN_CUDA_OK(scope.enter(plan->device));
+    return tile8_reduce(plan, scratch, out, reinterpret_cast<cudaStream_t>(stream));
 }
 extern "C" int hidenn_tri_energy_host_f64(hidenn_tri_plan* plan, const double* a, const double* b, const double* c,
                                           const double* d, const double* k, int flags, double* out, double* gx, double* gu,

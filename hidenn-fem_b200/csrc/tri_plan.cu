@@ -20,12 +20,16 @@
 #include <atomic>
 #include <cstring>
 #include <cstdlib>
+#include <functional>
 #include <future>
 #include <memory>
 #include <numeric>
 #include <thread>
 
 namespace hidenn {
+
+// default owned nodes per tile: close to the largest tile whose fold slots fit the 11-bit position fields at valence ~6
+constexpr int kDefaultTileNodes = 320;
 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
@@ -92,6 +96,9 @@ struct TileBuild {
     int err = 0;
     std::vector<unsigned long long> epack;   // tile-ordered layout: Neumann edge visits
     std::vector<int32_t> eid;
+    std::vector<unsigned long long> pack9, epack9;   // paired layout (2 words per entry)
+    std::vector<uint32_t> off9;
+    int32_t n_entries9 = 0;
 };
 
 // Lane assignment inside a tile.  Which thread handles which element is free (every fold slot is written exactly
@@ -154,6 +161,63 @@ static void reorder_for_banks(TileBuild& B, int real_bytes) {
     B.elems.swap(ne);
 }
 
+// Same greedy lane assignment for the pair entries of the paired layout (2 words per entry): six gather columns (corners
+// of the first and second element) and six store columns; a null second word contributes nothing.
+static void reorder_pairs_for_banks(std::vector<unsigned long long>& pack9, unsigned dump) {
+    const int E = (int)(pack9.size() / 2);
+    const int G = 8;
+    if (E <= G) return;
+    static const int W = [] { const char* e = getenv("HIDENN_PLAN_WINDOW"); return e ? atoi(e) : 512; }();
+    if (W <= 0) return;
+    constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
+    struct Item { uint16_t lid[6], pos[6]; int nc; };
+    std::vector<Item> it(E);
+    for (int i = 0; i < E; ++i) {
+        it[i].nc = ((unsigned)pack9[2 * i + 1] & 0x3FFFFFFFu) == 0x3FFFFFFFu ? 3 : 6;
+        for (int h = 0; h < 2; ++h) {
+            const unsigned long long w = pack9[2 * i + h];
+            for (int c = 0; c < 3; ++c) {
+                it[i].lid[3 * h + c] = (uint16_t)((w >> (kLidBits * c)) & LM);
+                it[i].pos[3 * h + c] = (uint16_t)((w >> (3 * kLidBits + kPosBits * c)) & PM);
+            }
+        }
+    }
+    std::vector<char> used(E, 0);
+    std::vector<int> ord;
+    ord.reserve(E);
+    int head = 0;
+    while ((int)ord.size() < E) {
+        int cg[6][8] = {}, cp[6][8] = {};
+        int lidat[6][8];
+        for (int c = 0; c < 6; ++c) for (int b = 0; b < 8; ++b) lidat[c][b] = -1;
+        for (int slot = 0; slot < G && (int)ord.size() < E; ++slot) {
+            int best = -1, best_cost = 1 << 30, seen = 0;
+            for (int j = head; j < E && seen < W; ++j) {
+                if (used[j]) continue;
+                ++seen;
+                int cost = 0;
+                for (int c = 0; c < it[j].nc; ++c) {
+                    const int b = it[j].lid[c] % G;
+                    if (cg[c][b] > 0 && lidat[c][b] != (int)it[j].lid[c]) cost += cg[c][b];     // same address = broadcast
+                    if (it[j].pos[c] != dump) cost += cp[c][it[j].pos[c] % G];
+                }
+                if (cost < best_cost) { best_cost = cost; best = j; if (cost == 0) break; }
+            }
+            used[best] = 1;
+            ord.push_back(best);
+            for (int c = 0; c < it[best].nc; ++c) {
+                const int b = it[best].lid[c] % G;
+                if (lidat[c][b] != (int)it[best].lid[c]) { cg[c][b]++; lidat[c][b] = it[best].lid[c]; }
+                if (it[best].pos[c] != dump) cp[c][it[best].pos[c] % G]++;
+            }
+            while (head < E && used[head]) ++head;
+        }
+    }
+    std::vector<unsigned long long> np(pack9.size());
+    for (int i = 0; i < E; ++i) { np[2 * i] = pack9[2 * ord[i]]; np[2 * i + 1] = pack9[2 * ord[i] + 1]; }
+    pack9.swap(np);
+}
+
 int plan_ensure_generic(hidenn_tri_plan* p) {
     if (p->generic_uploaded) return 0;
     HIDENN_REQUIRE(p->device >= 0, "host-only plan (device=-1) cannot run kernels");
@@ -200,46 +264,137 @@ extern "C" int hidenn_device_count(void) {
 // class of a node in the tile-ordered numbering (tri_plan.h): A 0, B 1, C 2, D 3
 static inline int node_class(uint8_t bmask, uint8_t dmask) { return bmask ? (dmask ? 2 : 1) : (dmask ? 3 : 0); }
 
+// Fold slots a tile needs when its owned nodes are listed by (class, descending slot count) and padded in groups of 8:
+// the numbering-independent bound both the locality ordering and the plan test against the pack limit, so that they
+// settle on the same tile size.  cs = (class, slots) per owned node; sorted in place.
+static int64_t canon_padded_entries(std::vector<std::pair<int32_t, int32_t>>& cs) {
+    std::sort(cs.begin(), cs.end(), [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) {
+        return a.first != b.first ? a.first < b.first : a.second > b.second;
+    });
+    int64_t acc = 0;
+    for (size_t g0 = 0; g0 < cs.size(); g0 += 8) {
+        int32_t mx = 0;
+        for (size_t g = g0; g < std::min(cs.size(), g0 + 8); ++g) mx = std::max(mx, cs[g].second);
+        acc += (int64_t)mx * 8;
+    }
+    return acc;
+}
+
+struct EdgeEnds {       // Neumann edge ends by node: (node, edge*2+end), sorted
+    std::vector<std::pair<int32_t, int32_t>> v;
+    void build(const int64_t* edges, int64_t Ned) {
+        v.resize(2 * Ned);
+        for (int64_t i = 0; i < 2 * Ned; ++i) v[i] = {(int32_t)edges[i], (int32_t)i};
+        std::sort(v.begin(), v.end());
+    }
+    std::pair<const std::pair<int32_t, int32_t>*, const std::pair<int32_t, int32_t>*> of(int32_t n) const {
+        auto lo = std::lower_bound(v.begin(), v.end(), std::make_pair(n, (int32_t)INT32_MIN));
+        auto hi = lo;
+        while (hi != v.end() && hi->first == n) ++hi;
+        return {v.data() + (lo - v.begin()), v.data() + (hi - v.begin())};
+    }
+};
+
+// Does a leaf of the bisection fit the pack limits (local ids <= 1022, fold slots <= 2047)?  Depends only on the set of
+// owned nodes, not on the numbering: local nodes = owned + nodes of incident elements + other ends of incident Neumann
+// edges; slots by canon_padded_entries.
+static bool leaf_feasible(const int32_t* ids, int64_t n, const int32_t* c32, const int64_t* n2o, const int32_t* n2e, const uint8_t* bmask,
+                          const uint8_t* dmask, const EdgeEnds& ee, const int64_t* edges, std::vector<int32_t>& owned,
+                          std::vector<int32_t>& loc, std::vector<std::pair<int32_t, int32_t>>& cs) {
+    owned.assign(ids, ids + n);
+    std::sort(owned.begin(), owned.end());
+    loc.clear();
+    cs.clear();
+    for (int32_t nd : owned) {
+        for (int64_t k = n2o[nd]; k < n2o[nd + 1]; ++k) {
+            const int64_t e = n2e[k] >> 2;
+            for (int c = 0; c < 3; ++c) loc.push_back(c32[3 * e + c]);
+        }
+        auto r = ee.of(nd);
+        for (auto it = r.first; it != r.second; ++it) loc.push_back((int32_t)edges[it->second ^ 1]);
+        cs.push_back({node_class(bmask[nd], dmask[nd]), (int32_t)(n2o[nd + 1] - n2o[nd] + (r.second - r.first))});
+        loc.push_back(nd);
+    }
+    std::sort(loc.begin(), loc.end());
+    loc.erase(std::unique(loc.begin(), loc.end()), loc.end());
+    if ((int64_t)loc.size() > kMaxLocal) return false;
+    return canon_padded_entries(cs) <= kMaxEntries;
+}
+
 extern "C" int hidenn_tri_locality_order(const int64_t* conn, int64_t Ne, int64_t Nn, const double* coords, const uint8_t* bmask,
-                                         const uint8_t* dmask, int tile_nodes, int64_t* new_to_old, int64_t* elem_new_to_old) {
+                                         const uint8_t* dmask, const int64_t* edges, int64_t Ned, int tile_nodes, int64_t* new_to_old,
+                                         int64_t* elem_new_to_old) {
     HIDENN_REQUIRE(conn && coords && bmask && dmask && new_to_old && elem_new_to_old, "locality_order: NULL argument");
     HIDENN_REQUIRE(Ne >= 0 && Nn > 0 && Nn < (int64_t)2147483000, "locality_order: sizes out of range");
-    if (tile_nodes <= 0) tile_nodes = 330;
+    HIDENN_REQUIRE(Ned == 0 || edges != nullptr, "locality_order: edges NULL");
+    if (tile_nodes <= 0) tile_nodes = kDefaultTileNodes;
     HIDENN_REQUIRE(tile_nodes >= 8 && tile_nodes <= 2048, "locality_order: tile_nodes must be in [8,2048]");
     for (int64_t i = 0; i < 3 * Ne; ++i) HIDENN_REQUIRE(conn[i] >= 0 && conn[i] < Nn, "locality_order: connectivity index out of range");
-    std::vector<int32_t> val(Nn, 0);
-    for (int64_t i = 0; i < 3 * Ne; ++i) val[conn[i]]++;
-    const int64_t n_tiles = (Nn + tile_nodes - 1) / tile_nodes;
-    std::vector<int32_t> order(Nn);
-    std::iota(order.begin(), order.end(), 0);
-    std::vector<int64_t> tile_begin(n_tiles + 1, 0);
-    tile_begin[n_tiles] = Nn;
+    for (int64_t i = 0; i < 2 * Ned; ++i) HIDENN_REQUIRE(edges[i] >= 0 && edges[i] < Nn, "locality_order: edge node index out of range");
+    // node -> element lists (same as the plan's)
+    std::vector<int32_t> c32(3 * Ne);
+    for (int64_t i = 0; i < 3 * Ne; ++i) c32[i] = (int32_t)conn[i];
+    std::vector<int64_t> n2o(Nn + 1, 0);
+    for (int64_t i = 0; i < 3 * Ne; ++i) n2o[c32[i] + 1]++;
+    for (int64_t n = 0; n < Nn; ++n) n2o[n + 1] += n2o[n];
+    std::vector<int32_t> n2e(3 * Ne);
     {
-        Rcb r{coords, order, tile_begin};
-        r.run(0, Nn, 0, n_tiles, 0);
+        std::vector<int64_t> cur(n2o.begin(), n2o.end() - 1);
+        for (int64_t e = 0; e < Ne; ++e)
+            for (int c = 0; c < 3; ++c) n2e[cur[c32[3 * e + c]]++] = (int32_t)(e * 4 + c);
     }
-    // inside a tile: by class, then descending valence (the fold groups of 8 consecutive nodes then have nearly equal
-    // valence), then by old id
-    auto sort_range = [&](int64_t t0, int64_t t1) {
-        for (int64_t t = t0; t < t1; ++t)
-            std::sort(order.begin() + tile_begin[t], order.begin() + tile_begin[t + 1], [&](int32_t a, int32_t b) {
-                const int ca = node_class(bmask[a], dmask[a]), cb = node_class(bmask[b], dmask[b]);
-                if (ca != cb) return ca < cb;
-                if (val[a] != val[b]) return val[a] > val[b];
-                return a < b;
-            });
-    };
-    {
+    EdgeEnds ee;
+    ee.build(edges, Ned);
+    std::vector<int32_t> slots(Nn);
+    for (int64_t n = 0; n < Nn; ++n) { auto r = ee.of((int32_t)n); slots[n] = (int32_t)(n2o[n + 1] - n2o[n] + (r.second - r.first)); }
+    int64_t n_tiles = 0;
+    std::vector<int32_t> order(Nn);
+    std::vector<int64_t> tile_begin;
+    auto run_parallel = [&](const std::function<void(int64_t, int64_t)>& f) {
         unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
         if (n_tiles < 64) nthr = 1;
         std::vector<std::thread> th;
         const int64_t per = (n_tiles + nthr - 1) / nthr;
         for (unsigned i = 0; i < nthr; ++i) {
             const int64_t a = i * per, b = std::min<int64_t>(n_tiles, a + per);
-            if (a < b) th.emplace_back(sort_range, a, b);
+            if (a < b) th.emplace_back(f, a, b);
         }
         for (auto& t : th) t.join();
+    };
+    // the plan's own search: bisect, test every leaf against the pack limits, shrink the tiles by 3/4 until all fit
+    for (int attempt = 0;; ++attempt) {
+        n_tiles = (Nn + tile_nodes - 1) / tile_nodes;
+        std::iota(order.begin(), order.end(), 0);
+        tile_begin.assign(n_tiles + 1, 0);
+        tile_begin[n_tiles] = Nn;
+        {
+            Rcb r{coords, order, tile_begin};
+            r.run(0, Nn, 0, n_tiles, 0);
+        }
+        std::atomic<int> bad{0};
+        run_parallel([&](int64_t t0, int64_t t1) {
+            std::vector<int32_t> owned, loc;
+            std::vector<std::pair<int32_t, int32_t>> cs;
+            for (int64_t t = t0; t < t1 && !bad.load(std::memory_order_relaxed); ++t)
+                if (!leaf_feasible(order.data() + tile_begin[t], tile_begin[t + 1] - tile_begin[t], c32.data(), n2o.data(), n2e.data(), bmask,
+                                   dmask, ee, edges, owned, loc, cs))
+                    bad.store(1);
+        });
+        if (!bad.load()) break;
+        HIDENN_REQUIRE(attempt < 12 && tile_nodes > 8, "locality_order: cannot tile this mesh within the pack limits");
+        tile_nodes = std::max(8, tile_nodes * 3 / 4);
     }
+    // inside a tile: by class, then descending slot count (the fold groups of 8 consecutive nodes then have nearly equal
+    // slot counts), then by old id
+    run_parallel([&](int64_t t0, int64_t t1) {
+        for (int64_t t = t0; t < t1; ++t)
+            std::sort(order.begin() + tile_begin[t], order.begin() + tile_begin[t + 1], [&](int32_t a, int32_t b) {
+                const int ca = node_class(bmask[a], dmask[a]), cb = node_class(bmask[b], dmask[b]);
+                if (ca != cb) return ca < cb;
+                if (slots[a] != slots[b]) return slots[a] > slots[b];
+                return a < b;
+            });
+    });
     std::vector<int32_t> old_to_new(Nn);
     for (int64_t i = 0; i < Nn; ++i) { new_to_old[i] = order[i]; old_to_new[order[i]] = (int32_t)i; }
     // elements by their smallest new node id (stable): neighbouring elements stay close in memory
@@ -256,13 +411,22 @@ extern "C" int hidenn_tri_locality_order(const int64_t* conn, int64_t Ne, int64_
 extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t Nn, const double* coords,
                                       const uint8_t* bmask, const uint8_t* dmask, const int64_t* edges, int64_t Ned,
                                       int tile_nodes, int real_bytes, int device, hidenn_tri_plan** out) {
+    return hidenn_tri_plan_create_ex(conn, Ne, Nn, coords, bmask, dmask, edges, Ned, nullptr, 0, tile_nodes, real_bytes, device, out);
+}
+
+extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_t Nn, const double* coords,
+                                         const uint8_t* bmask, const uint8_t* dmask, const int64_t* edges, int64_t Ned,
+                                         const int64_t* first_nodes, int64_t n_first, int tile_nodes, int real_bytes, int device,
+                                         hidenn_tri_plan** out) {
     HIDENN_REQUIRE(out != nullptr, "plan_create: out is NULL");
     *out = nullptr;
     HIDENN_REQUIRE(conn && coords && bmask && dmask, "plan_create: NULL input");
     HIDENN_REQUIRE(Ne >= 0 && Nn > 0 && Nn < (int64_t)2147483000 && Ne < (int64_t)500000000, "plan_create: sizes out of range");
     HIDENN_REQUIRE(real_bytes == 8 || real_bytes == 4, "plan_create: real_bytes must be 8 or 4");
     HIDENN_REQUIRE(Ned == 0 || edges != nullptr, "plan_create: edges NULL");
-    if (tile_nodes <= 0) tile_nodes = 330;      // largest tile whose fold slots fit the 11-bit position fields at valence ~6
+    HIDENN_REQUIRE(n_first == 0 || first_nodes != nullptr, "plan_create: first_nodes NULL");
+    for (int64_t i = 0; i < n_first; ++i) HIDENN_REQUIRE(first_nodes[i] >= 0 && first_nodes[i] < Nn, "plan_create: first_nodes index out of range");
+    if (tile_nodes <= 0) tile_nodes = kDefaultTileNodes;
     HIDENN_REQUIRE(tile_nodes >= 8 && tile_nodes <= 2048, "plan_create: tile_nodes must be in [8,2048]");
 
     for (int64_t i = 0; i < 3 * Ne; ++i)
@@ -303,19 +467,63 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     for (int64_t n = 0; n < Nn; ++n)
         HIDENN_REQUIRE(p->n2e_off[n + 1] - p->n2e_off[n] < kMaxValence, "plan_create: node valence >= 255 not supported");
 
-    // Neumann edge ends by node: (node, edge*2+end), sorted -- used by the tile-ordered layout, where the tile that
-    // owns an edge node also folds the edge term into its gradient
-    std::vector<std::pair<int32_t, int32_t>> edge_ends(2 * Ned);
-    for (int64_t i = 0; i < 2 * Ned; ++i) edge_ends[i] = {(int32_t)edges[i], (int32_t)i};
-    std::sort(edge_ends.begin(), edge_ends.end());
-    auto ends_of = [&](int32_t n) {
-        auto lo = std::lower_bound(edge_ends.begin(), edge_ends.end(), std::make_pair(n, (int32_t)INT32_MIN));
-        auto hi = lo;
-        while (hi != edge_ends.end() && hi->first == n) ++hi;
-        return std::make_pair(lo, hi);
-    };
+    // Neumann edge ends by node: in the tile-ordered layout the tile that owns an edge node also folds the edge term into
+    // its gradient; the other end of such an edge is a local node of the tile in every layout
+    EdgeEnds edge_ends;
+    edge_ends.build(edges, Ned);
+    auto ends_of = [&](int32_t n) { return edge_ends.of(n); };
     const bool no_v8 = getenv("HIDENN_PLAN_NO_V8") != nullptr;      // A/B: treat a tile-ordered mesh like any other
-    bool tile_order = false;
+    bool tile_order = false, force_generic = false;
+    // Global matching of the elements into edge-sharing pairs (paired layout of kernel v9; tri_plan.h).  It depends only
+    // on the mesh, not on the tiling: the neighbour across each edge is looked up through the node->element lists, then a
+    // greedy pass in element order matches every free element with its free neighbour that has the fewest free
+    // neighbours left (ties: smallest id).
+    const int32_t* c32g = p->conn32.data();
+    auto elem_has = [c32g](int32_t f, int32_t n) { return c32g[3 * (int64_t)f] == n || c32g[3 * (int64_t)f + 1] == n || c32g[3 * (int64_t)f + 2] == n; };
+    // opt-in: measured slower than one element per thread on B200 (profiles/README.md: the twelve accesses of a pair cannot
+    // be kept bank-conflict free, and the merge costs issue slots); kept for the record and for meshes where it may pay
+    const bool want_pairs = getenv("HIDENN_PLAN_PAIRS") != nullptr && atoi(getenv("HIDENN_PLAN_PAIRS")) != 0;
+    if (want_pairs && real_bytes == 8 && !no_v8 && Ne > 0) {
+        std::vector<int32_t> nb(3 * Ne, -1);
+        auto nb_range = [&](int64_t e0, int64_t e1) {
+            for (int64_t e = e0; e < e1; ++e)
+                for (int c = 0; c < 3; ++c) {
+                    const int32_t a = c32g[3 * e + c], b = c32g[3 * e + (c + 1) % 3];
+                    for (int64_t k = p->n2e_off[a]; k < p->n2e_off[a + 1]; ++k) {
+                        const int32_t f = p->n2e_ent[k] >> 2;
+                        if (f != e && elem_has(f, b)) { nb[3 * e + c] = f; break; }
+                    }
+                }
+        };
+        {
+            unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            if (Ne < 100000) nthr = 1;
+            std::vector<std::thread> th;
+            const int64_t per = (Ne + nthr - 1) / nthr;
+            for (unsigned i = 0; i < nthr; ++i) {
+                const int64_t a = i * per, b = std::min<int64_t>(Ne, a + per);
+                if (a < b) th.emplace_back(nb_range, a, b);
+            }
+            for (auto& t : th) t.join();
+        }
+        p->mate.assign(Ne, -1);
+        std::vector<int32_t>& mate = p->mate;
+        for (int64_t e = 0; e < Ne; ++e) {
+            if (mate[e] >= 0) continue;
+            int32_t best = -1, best_deg = 99;
+            for (int c = 0; c < 3; ++c) {
+                const int32_t f = nb[3 * e + c];
+                if (f < 0 || mate[f] >= 0 || f == best) continue;
+                int deg = 0;
+                for (int c2 = 0; c2 < 3; ++c2) {
+                    const int32_t g = nb[3 * (int64_t)f + c2];
+                    if (g >= 0 && g != e && mate[g] < 0) ++deg;
+                }
+                if (deg < best_deg || (deg == best_deg && f < best)) { best = f; best_deg = deg; }
+            }
+            if (best >= 0) { mate[e] = best; mate[best] = (int32_t)e; p->n_pairs++; }
+        }
+    }
 
     // RCB tiling of the nodes
     int64_t n_tiles = 0;
@@ -333,7 +541,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     }
 
     // Tile-ordered numbering?  Every leaf is one contiguous id range and lists its nodes by class (tri_plan.h).
-    tile_order = (real_bytes == 8) && !no_v8;
+    tile_order = (real_bytes == 8) && !no_v8 && !force_generic;
     for (int64_t t = 0; t < n_tiles && tile_order; ++t) {
         int32_t mn = INT32_MAX, mx = INT32_MIN;
         for (int64_t i = tile_begin[t]; i < tile_begin[t + 1]; ++i) { mn = std::min(mn, order[i]); mx = std::max(mx, order[i]); }
@@ -349,7 +557,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
     const int32_t* n2e = p->n2e_ent.data();
     auto build_range = [&](int64_t t0, int64_t t1) {
         std::vector<int32_t> cand, halo, owned_sorted, perm, lid_of, halo_lid, pool_of;
-        std::vector<std::pair<int32_t, int32_t>> pools;
+        std::vector<std::pair<int32_t, int32_t>> pools, cs;
         std::vector<std::vector<int32_t>> free_res;
         const int G = 8;
         for (int64_t t = t0; t < t1; ++t) {
@@ -384,7 +592,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
                     int32_t n = c32[3 * (int64_t)e + c];
                     if (owned_id(n) < 0) halo.push_back(n);
                 }
-            if (tile_order && Ned > 0)
+            if (Ned > 0)
                 for (int32_t n : owned_sorted) {
                     auto r = ends_of(n);
                     for (auto it = r.first; it != r.second; ++it) {
@@ -396,6 +604,14 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
             halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
             const int32_t n_halo = (int32_t)halo.size(), n_local = B.n_owned + n_halo;
             if (n_local > kMaxLocal) { B.err = 1; continue; }
+            {       // numbering-independent slot bound (same test as hidenn_tri_locality_order)
+                cs.clear();
+                for (int32_t n : owned_sorted) {
+                    auto r = ends_of(n);
+                    cs.push_back({node_class(bmask[n], dmask[n]), (int32_t)(n2o[n + 1] - n2o[n] + (r.second - r.first))});
+                }
+                if (canon_padded_entries(cs) > kMaxEntries) { B.err = 2; continue; }
+            }
             if (tile_order) {
                 // tile-ordered layout: local id = memory order (bulk copies land the owned rows at their ids, fold
                 // thread l stores row l of the tile's run); halo nodes follow in ascending id
@@ -467,7 +683,7 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
                     B.off[l] = (uint32_t)(acc + (l - g0)) | ((uint32_t)cnt << 16);
                 }
                 acc += mx * G;
-                if (acc > kMaxEntries) { B.err = 2; break; }
+                if (acc > kMaxEntries) { B.err = 3; break; }      // only a tile-ordered numbering that is not slot-sorted can get here
             }
             if (B.err) continue;
             B.n_entries = (int32_t)acc;
@@ -526,6 +742,101 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
                     B.eid.push_back(e);
                 }
             }
+            if (tile_order && !p->mate.empty()) {
+                // ---- paired layout (kernel v9, opt-in) ----
+                const std::vector<int32_t>& mate = p->mate;
+                // the partial of element e at node n is merged away when e's partner is the smaller id and holds n too
+                auto merged_away = [&](int32_t e, int32_t n) { const int32_t f = mate[e]; return f >= 0 && f < e && elem_has(f, n); };
+                auto elem_slots9 = [&](int32_t n) -> int64_t {
+                    int64_t c = 0;
+                    for (int64_t k = n2o[n]; k < n2o[n + 1]; ++k) c += merged_away(n2e[k] >> 2, n) ? 0 : 1;
+                    return c;
+                };
+                auto slots9 = [&](int32_t n) -> int64_t {
+                    int64_t c = elem_slots9(n);
+                    if (Ned > 0) { auto r = ends_of(n); c += r.second - r.first; }
+                    return c;
+                };
+                B.off9.resize(B.n_owned);
+                int64_t acc9 = 0;
+                for (int32_t g0 = 0; g0 < B.n_owned; g0 += G) {
+                    int64_t mx = 0;
+                    for (int32_t l = g0; l < std::min(B.n_owned, g0 + G); ++l) mx = std::max<int64_t>(mx, slots9(B.nodes[l]));
+                    for (int32_t l = g0; l < std::min(B.n_owned, g0 + G); ++l)
+                        B.off9[l] = (uint32_t)(acc9 + (l - g0)) | ((uint32_t)slots9(B.nodes[l]) << 16);
+                    acc9 += mx * G;
+                }
+                B.n_entries9 = (int32_t)acc9;
+                auto word9 = [&](int32_t e) {
+                    unsigned long long w = 0;
+                    for (int c = 0; c < 3; ++c) {
+                        const int32_t n = c32[3 * (int64_t)e + c];
+                        int32_t lid = owned_id(n);
+                        unsigned long long pos = (unsigned long long)acc9;
+                        if (lid >= 0) {
+                            if (!merged_away(e, n)) {
+                                int64_t rank = 0;
+                                for (int64_t k = n2o[n]; k < n2o[n + 1]; ++k) {
+                                    if (n2e[k] == e * 4 + c) break;
+                                    rank += merged_away(n2e[k] >> 2, n) ? 0 : 1;
+                                }
+                                pos = (unsigned long long)((B.off9[lid] & 0xFFFFu) + rank * G);
+                            }
+                        } else {
+                            lid = halo_lid[std::lower_bound(halo.begin(), halo.end(), n) - halo.begin()];
+                        }
+                        w |= (unsigned long long)lid << (kLidBits * c);
+                        w |= pos << (3 * kLidBits + kPosBits * c);
+                    }
+                    if (owned_id(c32[3 * (int64_t)e]) >= 0) w |= 1ull << kOwnerBit;
+                    return w;
+                };
+                // B.elems is in lane order after reorder_for_banks: membership through a sorted copy
+                std::vector<int32_t> visited(B.elems);
+                std::sort(visited.begin(), visited.end());
+                auto is_visited = [&](int32_t f) { return f >= 0 && std::binary_search(visited.begin(), visited.end(), f); };
+                const unsigned long long null_word = kNullPack | ((unsigned long long)acc9 << (3 * kLidBits)) |
+                                                     ((unsigned long long)acc9 << (3 * kLidBits + kPosBits)) |
+                                                     ((unsigned long long)acc9 << (3 * kLidBits + 2 * kPosBits));
+                std::vector<unsigned long long> singles;
+                for (int32_t e : visited) {
+                    const int32_t f = mate[e];
+                    if (is_visited(f)) {
+                        if (f < e) continue;                       // listed with its partner
+                        B.pack9.push_back(word9(e));
+                        B.pack9.push_back(word9(f));
+                    } else {
+                        singles.push_back(word9(e));
+                    }
+                }
+                // pairs and singles are ordered separately (singles stay at the end: whole warps skip the second element)
+                reorder_pairs_for_banks(B.pack9, (unsigned)acc9);
+                {
+                    std::vector<unsigned long long> sp;
+                    for (unsigned long long w : singles) { sp.push_back(w); sp.push_back(null_word); }
+                    reorder_pairs_for_banks(sp, (unsigned)acc9);
+                    B.pack9.insert(B.pack9.end(), sp.begin(), sp.end());
+                }
+                for (size_t i = 0; i < B.epack.size(); ++i) {      // edge visits: same ends, positions of the paired layout
+                    const int32_t e = B.eid[i];
+                    unsigned long long w = B.epack[i] & ((1ull << (2 * kLidBits)) - 1ull);
+                    w |= B.epack[i] & (1ull << kOwnerBit);
+                    for (int k = 0; k < 2; ++k) {
+                        const int32_t n = (int32_t)edges[2 * (int64_t)e + k];
+                        const int32_t lid = owned_id(n);
+                        unsigned long long pos = (unsigned long long)acc9;
+                        if (lid >= 0) {
+                            auto r = ends_of(n);
+                            int64_t rank = 0;
+                            for (auto it = r.first; it != r.second; ++it, ++rank)
+                                if (it->second == 2 * e + k) break;
+                            pos = (unsigned long long)((B.off9[lid] & 0xFFFFu) + (elem_slots9(n) + rank) * G);
+                        }
+                        w |= pos << (2 * kLidBits + kPosBits * k);
+                    }
+                    B.epack9.push_back(w);
+                }
+            }
         }
     };
     {
@@ -539,8 +850,13 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
         }
         for (auto& t : th) t.join();
     }
-    bool bad = false;
-    for (auto& B : tb) bad |= (B.err != 0);
+    bool bad = false, bad_layout = false;
+    for (auto& B : tb) { bad |= (B.err == 1 || B.err == 2); bad_layout |= (B.err == 3); }
+    if (!bad && bad_layout) {       // keep the tiling, fall back to the generic layout (its slot count is below the bound)
+        HIDENN_REQUIRE(!force_generic, "plan_create: internal error (generic layout exceeds the slot bound)");
+        force_generic = true;
+        continue;
+    }
     if (!bad) break;
     // a tile exceeded the pack limits (1023 local nodes / 2047 fold slots): shrink the tiles and retry
     HIDENN_REQUIRE(attempt < 12 && tile_nodes > 8, "plan_create: cannot tile this mesh within the pack limits");
@@ -567,8 +883,20 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
         std::vector<int32_t> key(n_tiles, INT32_MAX);
         for (int64_t t = 0; t < n_tiles; ++t)
             for (int32_t l = 0; l < tb[t].n_owned; ++l) key[t] = std::min(key[t], tb[t].nodes[l]);
+        // tiles that own one of the caller's `first_nodes` (multi-GPU: nodes shared with another rank) are listed first,
+        // so that the launch can be split into [0, n_first_tiles) and the rest and the halo exchange overlaps the second part
+        std::vector<char> prio(n_tiles, 0);
+        if (n_first > 0) {
+            std::vector<char> mark(Nn, 0);
+            for (int64_t i = 0; i < n_first; ++i) mark[first_nodes[i]] = 1;
+            for (int64_t t = 0; t < n_tiles; ++t)
+                for (int32_t l = 0; l < tb[t].n_owned && !prio[t]; ++l) prio[t] = mark[tb[t].nodes[l]];
+            for (int64_t t = 0; t < n_tiles; ++t) p->n_first_tiles += prio[t];
+        }
         if (!getenv("HIDENN_PLAN_RCB_ORDER"))      // debug: keep the recursive-bisection order
-            std::stable_sort(tord.begin(), tord.end(), [&](int64_t a, int64_t b) { return key[a] < key[b]; });
+            std::stable_sort(tord.begin(), tord.end(), [&](int64_t a, int64_t b) {
+                return prio[a] != prio[b] ? prio[a] > prio[b] : key[a] < key[b];
+            });
     }
     for (int64_t t = 0; t < n_tiles; ++t) {
         TileBuild& B = tb[tord[t]];
@@ -589,7 +917,6 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
             TileDesc8 d8{};
             d8.n_owned = d.n_owned; d8.n_local = d.n_local; d8.n_elem = d.n_elem; d8.n_entries = d.n_entries;
             const int32_t first = B.nodes[0];
-            d8.first_node = first;
             int32_t cnt[4] = {0, 0, 0, 0};
             for (int32_t l = 0; l < d.n_owned; ++l) cnt[node_class(bmask[first + l], dmask[first + l])]++;
             d8.nA = cnt[0]; d8.nB = cnt[1]; d8.nC = cnt[2]; d8.nD = cnt[3];
@@ -607,6 +934,12 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
             d8.ru_fixed = first_row(p->uslot, false, 0, d.n_owned);
             d8.edge_off = (int32_t)p->edge_pack.size();
             d8.n_edge = (int32_t)B.epack.size();
+            d8.n_pent = (int32_t)(B.pack9.size() / 2);
+            d8.n_entries9 = B.n_entries9;
+            p->pair_pack.insert(p->pair_pack.end(), B.pack9.begin(), B.pack9.end());
+            p->entry_off9.insert(p->entry_off9.end(), B.off9.begin(), B.off9.end());
+            p->edge_pack9.insert(p->edge_pack9.end(), B.epack9.begin(), B.epack9.end());
+            p->pair_entries += d8.n_pent;
             p->edge_pack.insert(p->edge_pack.end(), B.epack.begin(), B.epack.end());
             p->edge_id.insert(p->edge_id.end(), B.eid.begin(), B.eid.end());
             p->tiles8.push_back(d8);
@@ -767,6 +1100,26 @@ extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t N
         rc |= upload(pp, p->edge_pack, &D8.edge_pack);
         rc |= upload(pp, p->edge_id, &D8.edge_id);
         D8.stride_halo = SH; D8.max_halo = max_halo; D8.n_edge_visits = (int32_t)p->edge_pack.size();
+        // paired layout (opt-in): fixed-stride records like elem_pack / entry_off
+        if (!p->mate.empty()) {
+        int32_t max_pent = 0, max_entries9 = 0;
+        for (const TileDesc8& d8 : p->tiles8) { max_pent = std::max(max_pent, d8.n_pent); max_entries9 = std::max(max_entries9, d8.n_entries9); }
+        const int32_t SP = std::max(1, max_pent);
+        std::vector<unsigned long long> d_pair((size_t)n_tiles * SP * 2, 0ull);
+        std::vector<uint32_t> d_off9((size_t)n_tiles * SO, 0u);
+        size_t pp_off = 0, po_off = 0;
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            const TileDesc8& d8 = p->tiles8[t];
+            std::copy(p->pair_pack.begin() + pp_off, p->pair_pack.begin() + pp_off + 2 * (size_t)d8.n_pent, d_pair.begin() + (size_t)t * SP * 2);
+            std::copy(p->entry_off9.begin() + po_off, p->entry_off9.begin() + po_off + d8.n_owned, d_off9.begin() + (size_t)t * SO);
+            pp_off += 2 * (size_t)d8.n_pent;
+            po_off += d8.n_owned;
+        }
+        rc |= upload(pp, d_pair, &D8.pair_pack);
+        rc |= upload(pp, d_off9, &D8.entry_off9);
+        rc |= upload(pp, p->edge_pack9, &D8.edge_pack9);
+        D8.stride_pent = SP; D8.max_entries9 = max_entries9;
+        }
     }
     rc |= upload(pp, e_slots, &D.e_slots);
     rc |= upload(pp, en_xslot, &D.en_xslot);
@@ -827,7 +1180,12 @@ extern "C" int hidenn_tri_plan_layout(const hidenn_tri_plan* p, int64_t* out8) {
     out8[1] = max_halo;
     out8[2] = (int64_t)p->edge_pack.size();
     out8[3] = p->tile_order ? (int64_t)((size_t)p->dev.max_local * 64 + (size_t)(p->dev.max_entries + 1) * 32 + 256) : 0;   // smem bytes, FP64 kernel
-    out8[4] = out8[5] = out8[6] = out8[7] = 0;
+    int32_t max_entries9 = 0;
+    for (const TileDesc8& d : p->tiles8) max_entries9 = std::max(max_entries9, d.n_entries9);
+    out8[4] = p->n_pairs;            // matched element pairs of the mesh
+    out8[5] = p->pair_entries;       // pair-or-single entries over all tiles
+    out8[6] = max_entries9;          // max fold slots per tile in the paired layout
+    out8[7] = p->n_first_tiles;      // tiles owning the caller's first_nodes: they are tiles [0, n_first_tiles)
     return 0;
 }
 
@@ -881,6 +1239,24 @@ extern "C" int hidenn_tri_plan_fold_tables(const hidenn_tri_plan* p, int64_t* el
     owned_off[nt] = (int64_t)p->entry_off.size();
     for (size_t i = 0; i < p->elem_pack.size(); ++i) { packs[i] = p->elem_pack[i]; elems[i] = p->t_elem[i]; }
     std::copy(p->entry_off.begin(), p->entry_off.end(), entry_off);
+    return 0;
+}
+
+extern "C" int hidenn_tri_plan_pair_tables(const hidenn_tri_plan* p, int64_t* pent_off, uint64_t* packs, int64_t* owned_off,
+                                           uint32_t* entry_off9, int32_t* n_entries9, int32_t* mate) {
+    HIDENN_REQUIRE(p && pent_off && packs && owned_off && entry_off9 && n_entries9 && mate, "plan_pair_tables: NULL");
+    HIDENN_REQUIRE(p->tile_order && !p->mate.empty(),
+                   "plan_pair_tables: the plan has no paired layout (needs HIDENN_PLAN_PAIRS=1, a tile-ordered numbering and FP64)");
+    const size_t nt = p->tiles8.size();
+    int64_t a = 0, b = 0;
+    for (size_t t = 0; t < nt; ++t) {
+        pent_off[t] = a; owned_off[t] = b; n_entries9[t] = p->tiles8[t].n_entries9;
+        a += p->tiles8[t].n_pent; b += p->tiles8[t].n_owned;
+    }
+    pent_off[nt] = a; owned_off[nt] = b;
+    for (size_t i = 0; i < p->pair_pack.size(); ++i) packs[i] = p->pair_pack[i];
+    std::copy(p->entry_off9.begin(), p->entry_off9.end(), entry_off9);
+    std::copy(p->mate.begin(), p->mate.end(), mate);
     return 0;
 }
 

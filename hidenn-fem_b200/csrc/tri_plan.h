@@ -42,17 +42,27 @@ struct TileDesc8 {           // 64 B
     int32_t nA, nB, nC, nD;                              // owned class sizes, in local-id order
     int32_t rx_free, rx_fixed, ru_free, ru_fixed;        // first row of the tile's run in each array
     int32_t edge_off, n_edge;                            // Neumann edge visits (edge_pack / edge_id)
-    int32_t first_node, pad;
+    int32_t n_pent, n_entries9;                          // pair entries / fold slots of the paired layout (kernel v9)
 };
 // edge_pack bit layout (uint64): local ids of the two ends 2 x 10 bit, fold-slot positions 2 x 11 bit (dump slot for a
 // halo end), bit 63 = this visit owns the edge's energy (and its d loss / d traction row)
+// Paired layout (kernel v9): the elements of the mesh are matched once, globally, into edge-sharing pairs (greedy
+// matching of the dual graph); a thread evaluates both elements of a pair and adds the two partials of each shared node
+// in registers, so that node receives ONE partial for the pair: 4 instead of 6 partial stores and fold reads per pair.
+// pair_pack holds two 64-bit words of the elem_pack format per entry (first element = smaller element id; corners of
+// the second element that are merged carry the dump position; a single element has the null word kNullPack second).
 struct TriPlan8Dev {
     const TileDesc8* tiles;
     const int2* t_halo;                    // [n_tiles, stride_halo]: (xslot, uslot) of the halo nodes, ascending node id
     const unsigned long long* edge_pack;   // [n_edge_visits]
     const int32_t* edge_id;                // [n_edge_visits]
     int32_t stride_halo, max_halo, n_edge_visits, pad;
+    const unsigned long long* pair_pack;   // [n_tiles, stride_pent, 2]
+    const uint32_t* entry_off9;            // [n_tiles, stride_owned]: fold-slot start | count << 16 (paired layout)
+    const unsigned long long* edge_pack9;  // [n_edge_visits]: edge_pack with the slot positions of the paired layout
+    int32_t stride_pent, max_entries9, pad2, pad3;
 };
+constexpr unsigned long long kNullPack = 0x3FFFFFFFull;      // local ids 1023,1023,1023: no element
 
 struct TriPlanDev {
     const TileDesc* tiles;
@@ -107,8 +117,13 @@ struct hidenn_tri_plan {
     bool tile_order = false;                // numbering is tile-ordered -> kernel v8 (FP64)
     hidenn::TriPlan8Dev dev8{};
     std::vector<hidenn::TileDesc8> tiles8;
-    std::vector<unsigned long long> edge_pack;
+    std::vector<unsigned long long> edge_pack, edge_pack9;
     std::vector<int32_t> edge_id;
+    std::vector<unsigned long long> pair_pack;      // compact: 2 words per entry, tiles back to back
+    std::vector<uint32_t> entry_off9;               // compact, like entry_off
+    std::vector<int32_t> mate;                      // global matching: partner element or -1
+    int64_t n_pairs = 0, pair_entries = 0;
+    int32_t n_first_tiles = 0;                      // tiles owning the caller's first_nodes, listed first
     std::vector<void*> dev_allocs;
     size_t dev_bytes = 0;
     bool generic_uploaded = false;

@@ -2,15 +2,16 @@
 //
 // Same math, fold order and results as tri_tile8.cu (EnergyLoss2D.__call__ + backward of the reference,
 // /root/reference/src/loss.py:55-116 over /root/reference/src/models.py:292-376); what changes is who does what:
-//   * 16 ELEMENT warps (4 warpgroups, raised to 112 registers with setmaxnreg) do nothing but gather -> element closed
+//   * 12 ELEMENT warps (3 warpgroups, raised to 120 registers with setmaxnreg) do nothing but gather -> element closed
 //     form -> partial stores, tile after tile;
-//   * 7 FOLD warps (32 registers) sum the fold slots of the PREVIOUS tile (second partial buffer) and store the final
+//   * 11 FOLD warps (40 registers; one thread per owned node of a 330-node tile) sum the fold slots of the PREVIOUS tile (second partial buffer) and store the final
 //     gradient rows -- the latency-bound slot loops run in the issue slots the FP64 chains leave free instead of
 //     stalling the element warps behind two block barriers per tile;
 //   * 1 LOADER warp keeps a 3-deep ring of tile stages full: lane 0 issues the bulk copies (owned rows, element packs,
 //     fold offsets, descriptor) on the stage's mbarrier, all lanes gather the halo rows with cp.async.
 // Hand-overs are mbarriers (full / empty per stage, full / empty per partial buffer); there is no __syncthreads in the
-// tile loop.  Register budget: 512 x 112 + 256 x 32 = 65536.
+// tile loop.  Register budget: the CTA is launched with 768 x 80 registers (its pool); setmaxnreg moves them to
+// 384 x 120 + 384 x 40 = 61440 (HIDENN_WS_EWARPS=16: 512 x 104 + 256 x 32).
 #include "../../include/hidenn_b200.h"
 #include "common.cuh"
 #include "tri_plan.h"
@@ -22,8 +23,13 @@
 
 namespace hidenn {
 
-constexpr int kEWarps = 16, kFWarps = 7, kThreads9 = (kEWarps + kFWarps + 1) * 32;      // 768
-constexpr int kStages = 3;
+#ifndef HIDENN_WS_EWARPS
+#define HIDENN_WS_EWARPS 12
+#endif
+constexpr int kEWarps = HIDENN_WS_EWARPS, kFWarps = 23 - kEWarps, kThreads9 = 24 * 32;      // 768 threads = 6 warpgroups
+constexpr int kRedWarp0 = 16;      // the last 8 warps (small-register groups in every configuration) do the final reduction
+static_assert(kEWarps % 4 == 0 && kEWarps <= 16, "element warps come in warpgroups; 512 x 104 + 256 x 32 or 384 x 128 + 384 x 32 registers");
+constexpr int kMaxStages = 4;
 
 namespace {
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -45,6 +51,13 @@ __device__ __forceinline__ void bulk(void* dst, const void* src, unsigned bytes,
                  "r"(bytes), "r"(s32(bar))
                  : "memory");
 }
+// shared-memory load the compiler may not sink below later volatile loads: the fold issues the loads of two slots
+// back to back, then adds in slot order
+__device__ __forceinline__ double2 lds_pair(const double2* p) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(s32(p)));
+    return v;
+}
 __device__ __forceinline__ void bar_wait(uint64_t* bar, unsigned parity) {
     asm volatile(
         "{\n"
@@ -64,36 +77,39 @@ struct Smem9 {          // offsets (bytes) into the dynamic shared memory
     int stage_bytes, node_off, pack_off, offs_off, desc_off;      // inside a stage
     int part_bytes, part0, en0, bar0, total;
 };
-__host__ __device__ inline Smem9 smem9_layout(int max_local, int max_entries, int stride_elem, int stride_owned) {
+__host__ __device__ inline Smem9 smem9_layout(int max_local, int max_entries9, int pack_bytes, int stride_owned, int n_stages) {
     Smem9 L;
     L.node_off = 0;
     L.pack_off = max_local * 32;
-    L.offs_off = L.pack_off + stride_elem * 8;
+    L.offs_off = L.pack_off + pack_bytes;
     L.desc_off = L.offs_off + ((stride_owned * 4 + 15) & ~15);
     L.stage_bytes = L.desc_off + 64;
-    L.part_bytes = (max_entries + 1) * 32;
-    L.part0 = kStages * L.stage_bytes;
+    L.part_bytes = (max_entries9 + 1) * 32;
+    L.part0 = n_stages * L.stage_bytes;
     L.en0 = L.part0 + 2 * L.part_bytes;
     L.bar0 = L.en0 + 2 * 32 * 8;
     L.total = L.bar0 + 16 * 8 + 16;
     return L;
 }
 
-template <bool BODY, bool ISO>
+// PAIRS: paired layout (tri_plan.h; opt-in, HIDENN_PLAN_PAIRS=1) instead of one element per entry
+template <bool BODY, bool ISO, bool PAIRS>
 __global__ void __launch_bounds__(kThreads9, 1)
 tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __restrict__ x_free, const double2* __restrict__ x_fixed,
                  const double2* __restrict__ u_free, const double2* __restrict__ u_fixed, const double* __restrict__ consts,
                  const double* __restrict__ t_table, const int flags, double2* __restrict__ gx_free, double2* __restrict__ gu_free,
                  double* __restrict__ gt_out, double* __restrict__ e_dom, double* __restrict__ e_edge, const double* e_dom_all,
-                 const double* e_edge_all, const int n_tiles_total, double* __restrict__ out, unsigned* __restrict__ ticket) {
+                 const double* e_edge_all, const int n_tiles_total, double* __restrict__ out, unsigned* __restrict__ ticket,
+                 const int kStages) {
     using R = double;
     using R2 = double2;
     extern __shared__ __align__(128) unsigned char smem[];
-    const Smem9 L = smem9_layout(P.max_local, P.max_entries, P.stride_elem, P.stride_owned);
+    const int max_entries = PAIRS ? P8.max_entries9 : P.max_entries;
+    const Smem9 L = smem9_layout(P.max_local, max_entries, PAIRS ? P8.stride_pent * 16 : P.stride_elem * 8, P.stride_owned, kStages);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar0);
-    uint64_t* full_stage = bars;               // [kStages] loader -> element / fold warps
-    uint64_t* empty_stage = bars + kStages;    // [kStages] fold warps -> loader
-    uint64_t* part_full = bars + 2 * kStages;  // [2] element warps -> fold warps
+    uint64_t* full_stage = bars;                  // [kStages] loader -> element / fold warps
+    uint64_t* empty_stage = bars + kMaxStages;    // [kStages] fold warps -> loader
+    uint64_t* part_full = bars + 2 * kMaxStages;  // [2] element warps -> fold warps
     uint64_t* part_empty = part_full + 2;      // [2] fold warps -> element warps
     unsigned* s_flag = reinterpret_cast<unsigned*>(bars + 16);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -110,7 +126,8 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
 
     if (wid < kEWarps) {
         // ------------------------------------------------------------------ element warps
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        if (kEWarps == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
         const TriConsts<R> K = load_consts<R, BODY>(consts);
         const bool with_edges = (flags & HIDENN_WITH_EDGES) != 0;
         const int etid = tid;
@@ -119,25 +136,57 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
             const int st = k % kStages, pb = k & 1;
             unsigned char* stage = smem + st * L.stage_bytes;
             const TileDesc8* d = reinterpret_cast<const TileDesc8*>(stage + L.desc_off);
-            const unsigned long long* s_pack = reinterpret_cast<const unsigned long long*>(stage + L.pack_off);
+            const ulonglong2* s_pack = reinterpret_cast<const ulonglong2*>(stage + L.pack_off);
+            const unsigned long long* s_pack1 = reinterpret_cast<const unsigned long long*>(stage + L.pack_off);
             const NodeBuf<R> nodes(stage + L.node_off, P.max_local);
-            const PartBuf<R> part(smem + L.part0 + pb * L.part_bytes, P.max_entries + 1);
+            const PartBuf<R> part(smem + L.part0 + pb * L.part_bytes, max_entries + 1);
             bar_wait(&full_stage[st], (k / kStages) & 1);
             bar_wait(&part_empty[pb], ((k >> 1) & 1) ^ 1);
-            const int n_elem = d->n_elem, n_edge = d->n_edge;
-            const unsigned dumpv = (unsigned)d->n_entries;
+            const int n_pent = PAIRS ? d->n_pent : d->n_elem, n_edge = d->n_edge;
+            const unsigned dumpv = (unsigned)(PAIRS ? d->n_entries9 : d->n_entries);
             R e_acc = R(0), ee_acc = R(0);
-            for (int i = etid; i < n_elem; i += kEWarps * 32) {
-                const unsigned long long w = s_pack[i];
-                const unsigned lo = (unsigned)w, hi = (unsigned)(w >> 32);
-                const unsigned l0 = lo & LM, l1 = (lo >> kLidBits) & LM, l2 = (lo >> (2 * kLidBits)) & LM;
-                const unsigned p0 = (unsigned)(w >> (3 * kLidBits)) & PM, p1 = (hi >> (3 * kLidBits + kPosBits - 32)) & PM,
-                               p2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
-                R e;
-                R2 gu[3], gx[3], v0, v1, v2, U0, U1, U2;
-                nodes.load(l0, v0, U0); nodes.load(l1, v1, U1); nodes.load(l2, v2, U2);
-                tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx);
-                e_acc += (hi >> 31) ? e : R(0);
+            // one entry = an edge-sharing element pair (or a single element): both elements are evaluated by this thread,
+            // the partials of the two shared nodes are added in registers (first element + second), so each shared node
+            // gets one partial store / one fold read for the pair
+            for (int i = etid; i < n_pent; i += kEWarps * 32) {
+                ulonglong2 pw;
+                if (PAIRS) pw = s_pack[i];
+                else { pw.x = s_pack1[i]; pw.y = kNullPack; }
+                R2 gu[3], gx[3];
+                unsigned l0, l1, l2, p0, p1, p2;
+                {
+                    const unsigned lo = (unsigned)pw.x, hi = (unsigned)(pw.x >> 32);
+                    l0 = lo & LM; l1 = (lo >> kLidBits) & LM; l2 = (lo >> (2 * kLidBits)) & LM;
+                    p0 = (unsigned)(pw.x >> (3 * kLidBits)) & PM; p1 = (hi >> (3 * kLidBits + kPosBits - 32)) & PM;
+                    p2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
+                    R e;
+                    R2 v0, v1, v2, U0, U1, U2;
+                    nodes.load(l0, v0, U0); nodes.load(l1, v1, U1); nodes.load(l2, v2, U2);
+                    tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx);
+                    e_acc += (hi >> 31) ? e : R(0);
+                }
+                if (PAIRS && ((unsigned)pw.y & 0x3FFFFFFFu) != 0x3FFFFFFFu) {
+                    const unsigned lo = (unsigned)pw.y, hi = (unsigned)(pw.y >> 32);
+                    const unsigned m0 = lo & LM, m1 = (lo >> kLidBits) & LM, m2 = (lo >> (2 * kLidBits)) & LM;
+                    const unsigned q0 = (unsigned)(pw.y >> (3 * kLidBits)) & PM, q1 = (hi >> (3 * kLidBits + kPosBits - 32)) & PM,
+                                   q2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
+                    R e;
+                    R2 hu[3], hx[3], v0, v1, v2, U0, U1, U2;
+                    nodes.load(m0, v0, U0); nodes.load(m1, v1, U1); nodes.load(m2, v2, U2);
+                    tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, hu, hx);
+                    e_acc += (hi >> 31) ? e : R(0);
+                    const unsigned ll[3] = {l0, l1, l2}, mm[3] = {m0, m1, m2};
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            if (ll[a] == mm[c]) {      // same node: one partial for the pair
+                                gu[a].x += hu[c].x; gu[a].y += hu[c].y; gx[a].x += hx[c].x; gx[a].y += hx[c].y;
+                            }
+                    if (q0 != dumpv) part.store(q0, hu[0], hx[0]);
+                    if (q1 != dumpv) part.store(q1, hu[1], hx[1]);
+                    if (q2 != dumpv) part.store(q2, hu[2], hx[2]);
+                }
                 if (p0 != dumpv) part.store(p0, gu[0], gx[0]);
                 if (p1 != dumpv) part.store(p1, gu[1], gx[1]);
                 if (p2 != dumpv) part.store(p2, gu[2], gx[2]);
@@ -147,7 +196,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                 const int ng1 = (int)consts[HIDENN_TRI_NG1];
                 const int edge_off = d->edge_off;
                 for (int i = etid; i < n_edge; i += kEWarps * 32) {
-                    const unsigned long long w = __ldg(P8.edge_pack + edge_off + i);
+                    const unsigned long long w = __ldg((PAIRS ? P8.edge_pack9 : P8.edge_pack) + edge_off + i);
                     const int e = __ldg(P8.edge_id + edge_off + i);
                     const unsigned lo = (unsigned)w;
                     const unsigned l0 = lo & LM, l1 = (lo >> kLidBits) & LM;
@@ -187,37 +236,58 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
             if (lane == 0) bar_arrive(&part_full[pb]);      // release: this warp's partials and energy are visible
         }
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (kEWarps == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (wid == kEWarps + kFWarps) {
             // -------------------------------------------------------------- loader warp
+            // The per-tile chain  descriptor -> bulk copies, halo records -> gathers  is two dependent global loads; the
+            // records of the tile kAhead iterations later are pulled into L2 now, so the chain costs L2 hits, not DRAM misses.
+            constexpr int kAhead = 4;
+            auto prefetch_tile = [&](const int t) {
+                const char* rec = reinterpret_cast<const char*>(P8.t_halo + (size_t)t * P8.stride_halo);
+                if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(P8.tiles + t));
+                else if (lane * 128 < P8.stride_halo * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + lane * 128));
+            };
+            for (int k = 0; k < kAhead && k < n_mine; ++k) prefetch_tile(blockIdx.x + k * nct);
             for (int k = 0; k < n_mine; ++k) {
                 const int tile = blockIdx.x + k * nct;
                 const int st = k % kStages;
                 unsigned char* stage = smem + st * L.stage_bytes;
-                bar_wait(&empty_stage[st], ((k / kStages) & 1) ^ 1);
+                if (k + kAhead < n_mine) prefetch_tile(tile + kAhead * nct);
                 const TileDesc8 d = P8.tiles[tile];
+                const int n_halo = d.n_local - d.n_owned;
+                const int2* __restrict__ hrec = P8.t_halo + (size_t)tile * P8.stride_halo;
+                int2 h0 = make_int2(0, 0), h1 = h0, h2 = h0;              // the first 96 halo records, in flight during the wait
+                if (lane < n_halo) h0 = __ldg(hrec + lane);
+                if (lane + 32 < n_halo) h1 = __ldg(hrec + lane + 32);
+                if (lane + 64 < n_halo) h2 = __ldg(hrec + lane + 64);
+                bar_wait(&empty_stage[st], ((k / kStages) & 1) ^ 1);
                 R2* xy = reinterpret_cast<R2*>(stage + L.node_off);
                 R2* uv = xy + P.max_local;
                 if (lane == 0) {
                     const int nBC = d.nB + d.nC, nAB = d.nA + d.nB, nCD = d.nC + d.nD;
-                    const unsigned pack_bytes = 8u * (unsigned)((d.n_elem + 1) & ~1), off_bytes = 4u * (unsigned)((d.n_owned + 3) & ~3);
+                    const unsigned pack_bytes = PAIRS ? 16u * (unsigned)d.n_pent : 8u * (unsigned)((d.n_elem + 1) & ~1);
+                    const unsigned off_bytes = 4u * (unsigned)((d.n_owned + 3) & ~3);
                     bar_expect_tx(&full_stage[st], 32u * (unsigned)d.n_owned + pack_bytes + off_bytes + 64u);
                     bulk(stage + L.desc_off, P8.tiles + tile, 64u, &full_stage[st]);
-                    bulk(stage + L.pack_off, P.elem_pack + (size_t)tile * P.stride_elem, pack_bytes, &full_stage[st]);
-                    bulk(stage + L.offs_off, P.entry_off + (size_t)tile * P.stride_owned, off_bytes, &full_stage[st]);
+                    const void* pack_src = PAIRS ? (const void*)(P8.pair_pack + (size_t)tile * P8.stride_pent * 2)
+                                                 : (const void*)(P.elem_pack + (size_t)tile * P.stride_elem);
+                    if (pack_bytes) bulk(stage + L.pack_off, pack_src, pack_bytes, &full_stage[st]);
+                    bulk(stage + L.offs_off, (PAIRS ? P8.entry_off9 : P.entry_off) + (size_t)tile * P.stride_owned, off_bytes, &full_stage[st]);
                     if (d.nA) bulk(xy, x_free + d.rx_free, 16u * d.nA, &full_stage[st]);
                     if (nBC) bulk(xy + d.nA, x_fixed + d.rx_fixed, 16u * nBC, &full_stage[st]);
                     if (d.nD) bulk(xy + d.nA + nBC, x_free + d.rx_free + d.nA, 16u * d.nD, &full_stage[st]);
                     if (nAB) bulk(uv, u_free + d.ru_free, 16u * nAB, &full_stage[st]);
                     if (nCD) bulk(uv + nAB, u_fixed + d.ru_fixed, 16u * nCD, &full_stage[st]);
                 }
-                const int n_halo = d.n_local - d.n_owned;
-                const int2* __restrict__ hrec = P8.t_halo + (size_t)tile * P8.stride_halo;
-                for (int j = lane; j < n_halo; j += 32) {      // consecutive lanes land at consecutive local ids
-                    const int2 h = __ldg(hrec + j);
+                auto gather = [&](const int j, const int2 h) {      // consecutive lanes land at consecutive local ids
                     cp_async_pair(xy + d.n_owned + j, h.x >= 0 ? (const void*)(x_free + h.x) : (const void*)(x_fixed + (~h.x)), 16);
                     cp_async_pair(uv + d.n_owned + j, h.y >= 0 ? (const void*)(u_free + h.y) : (const void*)(u_fixed + (~h.y)), 16);
-                }
+                };
+                if (lane < n_halo) gather(lane, h0);
+                if (lane + 32 < n_halo) gather(lane + 32, h1);
+                if (lane + 64 < n_halo) gather(lane + 64, h2);
+                for (int j = lane + 96; j < n_halo; j += 32) gather(j, __ldg(hrec + j));
                 bar_arrive_cp_async(&full_stage[st]);
             }
         } else {
@@ -231,7 +301,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                 unsigned char* stage = smem + st * L.stage_bytes;
                 const TileDesc8* d = reinterpret_cast<const TileDesc8*>(stage + L.desc_off);
                 const uint32_t* s_off = reinterpret_cast<const uint32_t*>(stage + L.offs_off);
-                const PartBuf<R> part(smem + L.part0 + pb * L.part_bytes, P.max_entries + 1);
+                const PartBuf<R> part(smem + L.part0 + pb * L.part_bytes, max_entries + 1);
                 bar_wait(&full_stage[st], (k / kStages) & 1);
                 bar_wait(&part_full[pb], (k >> 1) & 1);
                 const int n_owned = d->n_owned, nA = d->nA, nAB = nA + d->nB, nBC = d->nB + d->nC, nABC = nAB + d->nC;
@@ -240,7 +310,14 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     const uint32_t oc = s_off[l];
                     const unsigned fb = oc & 0xFFFFu, fe = fb + (oc >> 16) * G;
                     R ax = R(0), ay = R(0), bx = R(0), by = R(0);
-                    for (unsigned q = fb; q < fe; q += G) {
+                    unsigned q = fb;
+#pragma unroll 1
+                    for (; q + G < fe; q += 2 * G) {      // two slots in flight per step, summed pairwise: acc += (s_q + s_q+1)
+                        const R2 u0 = lds_pair(part.pu + q), u1 = lds_pair(part.pu + q + G);
+                        const R2 x0 = lds_pair(part.px + q), x1 = lds_pair(part.px + q + G);
+                        ax += u0.x + u1.x; ay += u0.y + u1.y; bx += x0.x + x1.x; by += x0.y + x1.y;
+                    }
+                    if (q < fe) {
                         R2 u, x;
                         part.load(q, u, x);
                         ax += u.x; ay += u.y; bx += x.x; by += x.y;
@@ -270,15 +347,15 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
         *s_flag = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (*s_flag && wid >= kEWarps) {        // 8 warps of the small-register groups do the reduction (256 threads)
+    if (*s_flag && wid >= kRedWarp0) {        // 8 warps of the small-register groups do the reduction (256 threads)
         __threadfence();
-        const int t0 = tid - kEWarps * 32;
+        const int t0 = tid - kRedWarp0 * 32;
         double dsum = 0.0, esum = 0.0;
         for (int t = t0; t < n_tiles_total; t += 256) { dsum += __ldcg(e_dom_all + t); esum += __ldcg(e_edge_all + t); }
         dsum = warp_sum(dsum);
         esum = warp_sum(esum);
         double* s_red = reinterpret_cast<double*>(smem + L.en0);
-        if (lane == 0) { s_red[wid - kEWarps] = dsum; s_red[8 + wid - kEWarps] = esum; }
+        if (lane == 0) { s_red[wid - kRedWarp0] = dsum; s_red[8 + wid - kRedWarp0] = esum; }
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (t0 == 0) {
             double dd = 0.0, ee = 0.0;
@@ -293,11 +370,20 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
     }
 }
 
-size_t tile9_smem_bytes(const hidenn_tri_plan* p) {
-    return (size_t)smem9_layout(p->dev.max_local, p->dev.max_entries, p->dev.stride_elem, p->dev.stride_owned).total;
+static bool pairs9(const hidenn_tri_plan* p) { return p->dev8.pair_pack != nullptr; }
+static size_t smem9_for(const hidenn_tri_plan* p, int n_stages) {
+    return pairs9(p) ? (size_t)smem9_layout(p->dev.max_local, p->dev8.max_entries9, p->dev8.stride_pent * 16, p->dev.stride_owned, n_stages).total
+                     : (size_t)smem9_layout(p->dev.max_local, p->dev.max_entries, p->dev.stride_elem * 8, p->dev.stride_owned, n_stages).total;
 }
+// as many tile stages as fit (4 if possible: one more tile of slack between the bulk copies and the element warps)
+static int stages9_for(const hidenn_tri_plan* p) {
+    static const int env = [] { const char* e = getenv("HIDENN_WS_STAGES"); return e ? atoi(e) : 0; }();
+    if (env >= 2 && env <= kMaxStages) return env;
+    return smem9_for(p, kMaxStages) <= (size_t)227 * 1024 ? kMaxStages : 3;
+}
+size_t tile9_smem_bytes(const hidenn_tri_plan* p) { return smem9_for(p, stages9_for(p)); }
 
-template <bool BODY, bool ISO>
+template <bool BODY, bool ISO, bool PAIRS>
 static int launch9(const hidenn_tri_plan* p, const double* x_free, const double* x_fixed, const double* u_free, const double* u_fixed,
                    const double* consts, const double* t_table, int flags, double* out, double* gx, double* gu, double* gt,
                    double* scratch, unsigned* ticket, cudaStream_t stream, int tile_begin, int tile_end) {
@@ -305,21 +391,27 @@ static int launch9(const hidenn_tri_plan* p, const double* x_free, const double*
     static size_t configured[kMaxDevices] = {};
     size_t& cfg = configured[p->device % kMaxDevices];
     if (smem > cfg) {
-        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile9_kernel<BODY, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile9_kernel<BODY, ISO, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cfg = smem;
     }
     TriPlanDev P = p->dev;
     TriPlan8Dev P8 = p->dev8;
     const int n_total = p->dev.n_tiles;
-    P.elem_pack += (size_t)tile_begin * P.stride_elem;
-    P.entry_off += (size_t)tile_begin * P.stride_owned;
     P.n_tiles = tile_end - tile_begin;
     P8.tiles += tile_begin;
     P8.t_halo += (size_t)tile_begin * P8.stride_halo;
+    if (PAIRS) {
+        P8.pair_pack += (size_t)tile_begin * P8.stride_pent * 2;
+        P8.entry_off9 += (size_t)tile_begin * P.stride_owned;
+    } else {
+        P.elem_pack += (size_t)tile_begin * P.stride_elem;
+        P.entry_off += (size_t)tile_begin * P.stride_owned;
+    }
     const int grid = std::min(P.n_tiles, sm_count(p->device));
-    tri_tile9_kernel<BODY, ISO><<<grid, kThreads9, smem, stream>>>(
+    tri_tile9_kernel<BODY, ISO, PAIRS><<<grid, kThreads9, smem, stream>>>(
         P, P8, (const double2*)x_free, (const double2*)x_fixed, (const double2*)u_free, (const double2*)u_fixed, consts, t_table, flags,
-        (double2*)gx, (double2*)gu, gt, scratch + tile_begin, scratch + n_total + tile_begin, scratch, scratch + n_total, n_total, out, ticket);
+        (double2*)gx, (double2*)gu, gt, scratch + tile_begin, scratch + n_total + tile_begin, scratch, scratch + n_total, n_total, out, ticket,
+        stages9_for(p));
     HIDENN_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -330,12 +422,18 @@ int tile9_launch(const hidenn_tri_plan* p, const double* x_free, const double* x
                  const double* consts, const double* t_table, int flags, double* out, double* gx, double* gu, double* gt, double* scratch,
                  unsigned* ticket, cudaStream_t stream, int tile_begin, int tile_end) {
     const bool body = !(flags & HIDENN_HINT_NO_BODY_FORCE), iso = (flags & HIDENN_HINT_C_PLANE_STRESS) != 0;
-#define HIDENN_L9(B_, I_) \
-    return launch9<B_, I_>(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket, stream, tile_begin, tile_end)
-    if (body && iso) HIDENN_L9(true, true);
-    if (body) HIDENN_L9(true, false);
-    if (iso) HIDENN_L9(false, true);
-    HIDENN_L9(false, false);
+#define HIDENN_L9(B_, I_, P_) \
+    return launch9<B_, I_, P_>(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket, stream, tile_begin, tile_end)
+    if (pairs9(p)) {
+        if (body && iso) HIDENN_L9(true, true, true);
+        if (body) HIDENN_L9(true, false, true);
+        if (iso) HIDENN_L9(false, true, true);
+        HIDENN_L9(false, false, true);
+    }
+    if (body && iso) HIDENN_L9(true, true, false);
+    if (body) HIDENN_L9(true, false, false);
+    if (iso) HIDENN_L9(false, true, false);
+    HIDENN_L9(false, false, false);
 #undef HIDENN_L9
 }
 

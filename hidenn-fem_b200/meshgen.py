@@ -238,8 +238,10 @@ def reorder_for_locality(node_coords: np.ndarray, connectivity: np.ndarray, boun
         new_to_old = np.empty(xy.shape[0], np.int64)
         elem_order = np.empty(conn.shape[0], np.int64)
         P = lambda a: a.ctypes.data_as(C.c_void_p)
+        ed = np.zeros((0, 2), np.int64) if neumann_edges is None else np.ascontiguousarray(neumann_edges, dtype=np.int64).reshape(-1, 2)
         _lib.check(_lib.lib().hidenn_tri_locality_order(P(conn), C.c_int64(conn.shape[0]), C.c_int64(xy.shape[0]), P(xy), P(bm), P(dm),
-                                                        C.c_int(int(tile_nodes)), P(new_to_old), P(elem_order)),
+                                                        P(ed), C.c_int64(ed.shape[0]), C.c_int(int(tile_nodes)), P(new_to_old),
+                                                        P(elem_order)),
                    "hidenn_tri_locality_order")
         old_to_new = np.empty_like(new_to_old)
         old_to_new[new_to_old] = np.arange(new_to_old.size)

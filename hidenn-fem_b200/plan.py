@@ -55,7 +55,8 @@ class TriPlan:
         self.info = dict(zip(INFO_KEYS, [int(v) for v in info]))
         lay = (C.c_int64 * 8)()
         _lib.check(L.hidenn_tri_plan_layout(self._h, lay), "hidenn_tri_plan_layout")
-        self.info.update(tile_ordered=bool(lay[0]), max_halo=int(lay[1]), edge_visits=int(lay[2]), smem_v8=int(lay[3]))
+        self.info.update(tile_ordered=bool(lay[0]), max_halo=int(lay[1]), edge_visits=int(lay[2]), smem_v8=int(lay[3]),
+                         n_pairs=int(lay[4]), pair_entries=int(lay[5]), max_entries9=int(lay[6]))
         self.real_bytes = real_bytes
         self.n_nodes = n_nodes
         self.n_elems = conn.shape[0]
@@ -102,6 +103,20 @@ class TriPlan:
         P = lambda a: a.ctypes.data_as(C.c_void_p)
         _lib.check(_lib.lib().hidenn_tri_plan_fold_tables(self._h, P(elem_off), P(packs), P(elems), P(owned_off), P(entry_off), P(n_entries)))
         return dict(elem_off=elem_off, packs=packs, elems=elems, owned_off=owned_off, entry_off=entry_off, n_entries=n_entries)
+
+    def pair_tables(self):
+        """Paired layout (tile-ordered FP64 plans): dict(pent_off, packs [entries,2], owned_off, entry_off9, n_entries9, mate)."""
+        nt = self.info["n_tiles"]
+        _, n_owned, _ = self.tiles()
+        pent_off = np.empty(nt + 1, np.int64)
+        packs = np.empty((self.info["pair_entries"], 2), np.uint64)
+        owned_off = np.empty(nt + 1, np.int64)
+        entry_off9 = np.empty(int(n_owned.sum()), np.uint32)
+        n_entries9 = np.empty(nt, np.int32)
+        mate = np.empty(self.n_elems, np.int32)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(_lib.lib().hidenn_tri_plan_pair_tables(self._h, P(pent_off), P(packs), P(owned_off), P(entry_off9), P(n_entries9), P(mate)))
+        return dict(pent_off=pent_off, packs=packs, owned_off=owned_off, entry_off9=entry_off9, n_entries9=n_entries9, mate=mate)
 
     def pipeline(self):
         """Row-block tables of the host-buffer pipeline: dict(rows_x, rows_u, first_need_x, last_own_x, first_need_u, last_own_u)."""

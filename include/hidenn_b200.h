@@ -59,6 +59,10 @@ int hidenn_version(void);
 /* number of CUDA devices visible; <0 on error (used by the loader to fail loudly) */
 int hidenn_device_count(void);
 
+/* Measurement aid: DFMA instructions per second (thread level) this GPU sustains on independent chains -- the measured
+ * FP64-pipe peak bench.py prints the kernels' FP64 utilisation against.  Synchronises `stream`. */
+int hidenn_fp64_peak(double* dfma_per_s, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Triangle plan: static topology preprocessing, once per mesh (connectivity never changes
  * during r-adaptation; src/models.py:252 keeps it as a buffer).  Replaces, for the hot path,
@@ -81,6 +85,16 @@ int hidenn_tri_plan_create(const int64_t* conn, int64_t n_elems, int64_t n_nodes
                            const int64_t* edges, int64_t n_edges,
                            int tile_nodes, int real_bytes, int device,
                            hidenn_tri_plan** out);
+/* Same, with `first_nodes` [n_first] (may be NULL/0): tiles owning one of these nodes are listed first
+ * (tiles [0, layout8[7])).  Multi-GPU callers pass the nodes shared with other ranks, run the tiles in two ranges
+ * (hidenn_tri_energy_range_*) and exchange the finished shared rows while the second range computes. */
+int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t n_elems, int64_t n_nodes,
+                              const double* coords_init,
+                              const uint8_t* boundary_mask, const uint8_t* dirichlet_mask,
+                              const int64_t* edges, int64_t n_edges,
+                              const int64_t* first_nodes, int64_t n_first,
+                              int tile_nodes, int real_bytes, int device,
+                              hidenn_tri_plan** out);
 void hidenn_tri_plan_destroy(hidenn_tri_plan* plan);
 
 /* Locality ordering for meshes with arbitrary numbering (the step before the plan; gmsh / meshzoo output,
@@ -92,11 +106,14 @@ void hidenn_tri_plan_destroy(hidenn_tri_plan* plan);
  * new_to_old [Nn]: old index of new node i; elem_new_to_old [Ne]: elements listed by smallest new node id.
  * Corner order inside every element is the caller's to keep (the reference's results depend on it). */
 int hidenn_tri_locality_order(const int64_t* conn, int64_t n_elems, int64_t n_nodes, const double* coords,
-                              const uint8_t* boundary_mask, const uint8_t* dirichlet_mask, int tile_nodes,
+                              const uint8_t* boundary_mask, const uint8_t* dirichlet_mask,
+                              const int64_t* edges, int64_t n_edges, int tile_nodes,
                               int64_t* new_to_old, int64_t* elem_new_to_old);
 
-/* layout8[0]=1 if the plan found a tile-ordered numbering (FP64 plans; bulk-copy tile kernel in use), [1]=max halo
- * nodes per tile, [2]=Neumann edge visits, [3]=dynamic smem bytes of that kernel; the rest reserved. */
+/* layout8[0]=1 if the plan found a tile-ordered numbering (FP64 plans; bulk-copy tile kernels in use), [1]=max halo
+ * nodes per tile, [2]=Neumann edge visits, [3]=dynamic smem bytes of the two-CTA kernel, [4]=element pairs of the global
+ * matching, [5]=pair-or-single entries over all tiles, [6]=max fold slots per tile in the paired layout,
+ * [7]=number of leading tiles that own the caller's first_nodes (hidenn_tri_plan_create_ex). */
 int hidenn_tri_plan_layout(const hidenn_tri_plan* plan, int64_t* layout8);
 
 /* info[0]=n_tiles [1]=tile element visits (incl. halo recompute) [2]=tile node visits
@@ -132,6 +149,14 @@ int hidenn_tri_plan_tiles(const hidenn_tri_plan* plan, int64_t* node_off, int32_
  * (owned_off[t] + l) the word  slot_start | valence << 16;  n_entries[t] = number of fold slots (= the dump position). */
 int hidenn_tri_plan_fold_tables(const hidenn_tri_plan* plan, int64_t* elem_off, uint64_t* packs, int64_t* elems,
                                 int64_t* owned_off, uint32_t* entry_off, int32_t* n_entries);
+/* Paired layout of a tile-ordered plan (tests): per tile t, entries [pent_off[t], pent_off[t+1]) of two 64-bit words each
+ * (elem_pack format; first word = element with the smaller id, second word = its partner of the global matching or the
+ * null word with local ids 1023; corners of the second element whose partial is merged into the first carry the dump
+ * position n_entries9[t]); entry_off9 per owned node (owned_off[t] + l) = slot_start | slots << 16;  mate [Ne] = partner
+ * element of the global matching or -1. */
+int hidenn_tri_plan_pair_tables(const hidenn_tri_plan* plan, int64_t* pent_off, uint64_t* packs, int64_t* owned_off,
+                                uint32_t* entry_off9, int32_t* n_entries9, int32_t* mate);
+
 /* Row-block tables of the host-buffer pipeline (hidenn_tri_energy_host_*): the free rows are cut into 64 blocks of
  * rows2[0] (node_coords_free) / rows2[1] (u_free) rows; first_need[b] = first tile reading a row of block b
  * (INT32_MAX: none), last_own[b] = last tile writing one (-1: none).  Each array has 64 entries. */
@@ -166,6 +191,18 @@ int hidenn_tri_energy_f32(const hidenn_tri_plan* plan,
                           const float* consts, const float* t_table, int flags,
                           float* out, float* gx_free, float* gu_free, float* gt_out,
                           float* scratch, void* stream);
+
+/* The same evaluation in pieces, for callers that overlap something with it (multi-GPU halo exchange): tiles
+ * [tile_begin, tile_end) only -- their energies go to scratch, their owned gradient rows are final when the launch ends
+ * -- and, after all ranges, hidenn_tri_energy_finish_* reduces the tile energies into out[0..3].  Tile-ordered FP64
+ * plans only (the Neumann edge term is part of the tiles there); others return an error. */
+int hidenn_tri_energy_range_f64(const hidenn_tri_plan* plan,
+                                const double* x_free, const double* x_fixed,
+                                const double* u_free, const double* u_fixed,
+                                const double* consts, const double* t_table, int flags,
+                                double* gx_free, double* gu_free, double* gt_out,
+                                double* scratch, int tile_begin, int tile_end, void* stream);
+int hidenn_tri_energy_finish_f64(const hidenn_tri_plan* plan, double* scratch, double* out, void* stream);
 
 /* Host-buffer convenience (the end-to-end drop-in for a CPU caller): copies the four parameter
  * arrays host->device, runs the fused step, copies loss and both gradients back and waits.

@@ -280,3 +280,80 @@ def test_fold_tables_interpreted_on_the_host(ordering, tile_nodes):
             got = slots[start[l] + 8 * np.arange(cnt[l])]
             assert got.tolist() == sorted(incident[loc[l]]), (t, l)
     assert (energy_owner == 1).all()
+
+
+@pytest.mark.parametrize("tile_nodes,invert", [(0, 0.0), (40, 0.3)])
+def test_paired_layout_interpreted_on_the_host(tile_nodes, invert, monkeypatch):
+    """(opt-in layout, HIDENN_PLAN_PAIRS=1)  The warp-specialised tile kernel's integer work replayed with numpy from the paired tables of a tile-ordered plan:
+    the matching is a matching (mate[mate[e]] == e, partners share an edge), every visited element appears in exactly one
+    entry per tile that visits it, the first word of a pair is the smaller element id, merging by equal local ids and
+    storing at the non-dump positions gives every owned node exactly the partials of its incident elements (each element
+    once), no slot is written twice, and the slot order (first element id of each partial, ascending) does not depend on
+    the tile size."""
+    from hidenn_fem_b200 import meshgen
+    from hidenn_fem_b200.plan import TriPlan
+    monkeypatch.setenv("HIDENN_PLAN_PAIRS", "1")
+    m0 = meshgen.plate_mesh(61, 41, jitter=0.2, diag="random", seed=5, ordering="random")
+    m0.connectivity = meshgen.invert_some_elements(m0.connectivity, invert, 1) if invert else m0.connectivity
+    xy, conn, bm, dm, ed, n2o, _ = meshgen.reorder_for_locality(m0.node_coords, m0.connectivity, m0.boundary_mask & ~m0.neumann_mask,
+                                                                m0.dirichlet_mask, m0.neumann_edges, tile_nodes=tile_nodes)
+    plan = TriPlan(conn, xy.shape[0], xy, bm, dm, ed, tile_nodes=tile_nodes, real_bytes=8, device=-1)
+    assert plan.info["tile_ordered"]
+    node_off, n_owned, nodes = plan.tiles()
+    T = plan.pair_tables()
+    mate = T["mate"]
+    Ne = conn.shape[0]
+    paired = np.nonzero(mate >= 0)[0]
+    assert (mate[mate[paired]] == paired).all()
+    assert all(len(set(conn[e]) & set(conn[mate[e]])) == 2 for e in paired[:500])
+    assert plan.info["n_pairs"] == paired.size // 2 and paired.size > 0.8 * Ne          # a good matching of the dual graph
+    elem_of = {tuple(conn[e]): e for e in range(Ne)}
+    incident = [[] for _ in range(xy.shape[0])]
+    for e in range(Ne):
+        for c in range(3):
+            incident[conn[e, c]].append(e)
+    energy_owner = np.zeros(Ne, np.int64)
+    for t in range(plan.info["n_tiles"]):
+        loc = nodes[node_off[t]:node_off[t + 1]]
+        no, dump = int(n_owned[t]), int(T["n_entries9"][t])
+        off = T["entry_off9"][T["owned_off"][t]:T["owned_off"][t + 1]]
+        start, cnt = (off & 0xFFFF).astype(np.int64), (off >> 16).astype(np.int64)
+        assert (start % 8 == np.arange(no) % 8).all()
+        slots = {}
+        seen = set()
+        for v in range(T["pent_off"][t], T["pent_off"][t + 1]):
+            words = [int(T["packs"][v, 0]), int(T["packs"][v, 1])]
+            parts = []                                             # per word: [(lid, pos, {elements})]
+            for w in words:
+                if (w & 0x3FFFFFFF) == 0x3FFFFFFF:
+                    continue
+                lids = [(w >> (10 * c)) & 1023 for c in range(3)]
+                e = elem_of[tuple(int(loc[l]) for l in lids)]       # corner order preserved
+                assert e not in seen
+                seen.add(e)
+                energy_owner[e] += (w >> 63) & 1
+                parts.append([[lids[c], (w >> (30 + 11 * c)) & 2047, {e}] for c in range(3)])
+            if len(parts) == 2:
+                e1, e2 = min(parts[0][0][2]), min(parts[1][0][2])
+                assert mate[e1] == e2 and e1 < e2
+                for a in parts[0]:
+                    for c in parts[1]:
+                        if a[0] == c[0]:
+                            a[2] |= c[2]                            # merged in registers
+                            assert c[1] == dump or c[0] >= no
+            for word in parts:
+                for lid, pos, es in word:
+                    if pos != dump:
+                        assert lid < no and pos not in slots
+                        k, r = divmod(pos - start[lid], 8)
+                        assert r == 0 and 0 <= k < cnt[lid]
+                        slots[pos] = es
+                    else:
+                        assert lid >= no or any(lid == a[0] and a[1] != dump for a in parts[0])
+        for l in range(no):
+            n_edge_slots = int((ed == loc[l]).sum())
+            got = [slots[start[l] + 8 * k] for k in range(cnt[l] - n_edge_slots)]
+            flat = sorted(e for s in got for e in s)
+            assert flat == sorted(incident[loc[l]]), (t, l)
+            assert [min(s) for s in got] == sorted(min(s) for s in got)          # ascending first element id
+    assert (energy_owner == 1).all()

@@ -227,8 +227,8 @@ def test_determinism_and_plan_invariance():
 
 def test_tile_ordered_kernel_is_deterministic_and_matches_generic_kernel(monkeypatch):
     """Bulk-copy tile kernel (tile-ordered numbering): bit-identical run to run; against the generic kernel on the same
-    mesh (HIDENN_PLAN_NO_V8=1) element sums are identical, only rows of Neumann edge nodes may differ in the last bits
-    (the edge term is folded after the elements instead of added afterwards)."""
+    mesh (HIDENN_PLAN_NO_V8=1) the gradients agree to rounding (the fold adds the slots of a node pairwise, and the edge
+    term is folded with the elements instead of added afterwards)."""
     g = _mesh_case(100_000, torch.float64, "tiles", u_scale=1e-3)
     outs = []
     for k in range(3):
@@ -243,8 +243,6 @@ def test_tile_ordered_kernel_is_deterministic_and_matches_generic_kernel(monkeyp
     assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
     assert abs(outs[0][0] - outs[2][0]) <= 1e-13 * abs(outs[0][0])
     for a, b in ((outs[0][1], outs[2][1]), (outs[0][2], outs[2][2])):
-        diff = (a != b).any(dim=1)
-        assert int(diff.sum()) <= 2 * g["neumann_edges"].shape[0] + 2
         assert relmax(a.cpu().numpy(), b.cpu().numpy()) < 1e-14
 
 
@@ -549,3 +547,27 @@ def test_no_grad_skips_gradient_work():
     finally:
         hl.EnergyLoss2D._post_forward = orig
     assert abs(l0.item() - l1.item()) <= 1e-12 * abs(l1.item())
+
+
+def test_paired_layout_opt_in(monkeypatch):
+    """HIDENN_PLAN_PAIRS=1: edge-sharing element pairs per thread with the shared-node partials merged in registers
+    (tri_plan.h).  Same contract tolerance; kept opt-in because it measured slower (profiles/README.md)."""
+    monkeypatch.setenv("HIDENN_PLAN_PAIRS", "1")
+    g = _mesh_case(120_000, torch.float64, "tiles", invert=0.2, u_scale=1e-3)
+    model = build(g)
+    info = model._plan().info
+    assert info["tile_ordered"] and info["n_pairs"] > 0.4 * g["connectivity"].shape[0]
+    loss_fn = loss_of(g, torch.float64)
+    loss = loss_fn(model, forces.b_force_test, None)
+    loss.backward()
+    xg, wg = cf.triangle_gauss_points(4, np.float64)
+    g2 = dict(g)
+    fm, um = ~g["boundary_mask"], ~g["dirichlet_mask"]
+    coords = cf.assemble_full(g["node_coords_free"], g["node_coords_fixed"], fm)
+    U = cf.assemble_full(g["u_free"], np.zeros((int((~um).sum()), 2)), um)
+    xi1, w1 = cf.interval_gauss_points(2, np.float64)
+    lo, dX, dU = cf.tri_energy_full(coords, U, g["connectivity"], cf.plane_stress_C(10e9, 0.3, np.float64), xg, wg,
+                                    forces.b_force_np(xg), g["neumann_edges"], xi1, w1)
+    assert abs(loss.item() - float(lo)) <= 1e-10 * abs(float(lo))
+    assert relmax(model.node_coords_free.grad.cpu().numpy(), dX[fm]) < 1e-10
+    assert relmax(model.u_free.grad.cpu().numpy(), dU[um]) < 1e-10
