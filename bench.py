@@ -171,6 +171,7 @@ def make_workload(args, rank, world, device, dtype, ordering, n_elems_per_gpu, t
     model = model.to(device)
     if world > 1:
         halo = hd.setup_strip_halo(m, m.boundary_mask, m.dirichlet_mask, device, dtype)
+        model.priority_nodes = halo.priority_nodes      # tiles owning shared nodes run first: the exchange overlaps the rest
         loss_fn = hd.DistributedEnergyLoss2D(E=10e9, nu=0.3, length=2.0, height=1.0, device=device, dtype=dtype, halo=halo)
     else:
         loss_fn = EnergyLoss2D(E=10e9, nu=0.3, length=2.0, height=1.0, device=device, dtype=dtype)
@@ -663,6 +664,8 @@ def main():
             "config": {"workload": WORKLOAD,
                        "elements_total": ne_total, "nodes_total": nn_total, "elements_per_gpu": ne_local,
                        "grid_nodes": list(dims), "ordering": args.ordering, "partition": "column strips + halo nodes" if world > 1 else "none",
+                       "halo_exchange": (getattr(getattr(loss_fn, "halo", None), "backend", None) if world > 1 else None),
+                       "first_tiles": plan.info.get("n_first_tiles", 0),
                        "launch": "eager" if args.no_graph else "CUDA-graph replay of zero_grad+loss+backward (hidenn_fem_b200.graph.GraphedEnergyStep)",
                        "l2_policy": "inputs+outputs+plan per launch (> 400 MB) exceed the 126 MB L2; no flush needed",
                        "tile_nodes": plan.info["max_local"], "n_tiles": plan.info["n_tiles"],
@@ -670,11 +673,12 @@ def main():
             "loss": loss_val,
             "sustained": sustained,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": args.steps * ((2 if plan.info.get("tile_ordered") else 3) + (2 if world > 1 else 0)),
+            "gpu_launches": args.steps * ((2 if plan.info.get("tile_ordered") else 3) + (5 if world > 1 else 0)),
             "gpu_launches_note": ("per step: tri_tile8_kernel (edges + final reduction inside) + scale_inplace2_kernel"
                                   if plan.info.get("tile_ordered") else
                                   "per step: tri_tile_persistent_kernel + tri_edge_finalize_kernel + scale_inplace2_kernel")
-                                 + (" + halo pack_all + unpack_all (plus one copy and the NCCL all-reduce)" if world > 1 else ""),
+                                 + (" + second tile range + finish + halo_p2p push / pull / loss (peer-memory exchange; "
+                                    "pack_all + NCCL all-reduce + unpack_all with HIDENN_HALO=nccl)" if world > 1 else ""),
         }
         if other is not None:
             line["other_configs"] = other      # BASELINE configs C2 (1D bar, 1 M elements) and C3 (structured L2, 4097^2 nodes)

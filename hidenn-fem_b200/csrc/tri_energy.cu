@@ -14,6 +14,7 @@
 #include "tri_plan.h"
 #include "tri_element.cuh"
 #include "tri_tile8.h"
+#include "halo_p2p.cuh"
 
 #include <cstdlib>
 #include <type_traits>
@@ -532,7 +533,8 @@ constexpr int kFinalizeOnly = 1 << 30;
 template <typename R>
 static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R* x_fixed, const R* u_free, const R* u_fixed,
                              const R* consts, const R* t_table, int flags, R* out, R* gx, R* gu, R* gt, R* scratch,
-                             void* stream_v, int tile_begin = 0, int tile_end = -1, R* en_final = nullptr) {
+                             void* stream_v, int tile_begin = 0, int tile_end = -1, R* en_final = nullptr, unsigned* first_done = nullptr,
+                             int reserve_sms = 0, const P2PLossArgs* loss_args = nullptr) {
     using R2 = typename Real2<R>::type;
     HIDENN_REQUIRE(p != nullptr, "tri_energy: plan is NULL");
     HIDENN_REQUIRE(p->device >= 0, "tri_energy: host-only plan (device=-1) cannot run kernels; there is no CPU fallback");
@@ -556,9 +558,11 @@ static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R*
             // HIDENN_TILE_WS=0: the two-CTA kernel of tri_tile8.cu instead of the warp-specialised one (A/B runs)
             static const bool ws_off = [] { const char* e = getenv("HIDENN_TILE_WS"); return e && atoi(e) == 0; }();
             if (tile_end > tile_begin) {
+                HIDENN_REQUIRE(first_done == nullptr || (!ws_off && tile9_fits(p)),
+                               "tri_energy_overlap: needs the warp-specialised tile kernel (hidenn_tri_plan_overlap_target > 0)");
                 const int rc = (!ws_off && tile9_fits(p))
                                    ? tile9_launch(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket,
-                                                  stream, tile_begin, tile_end)
+                                                  stream, tile_begin, tile_end, first_done, reserve_sms, loss_args)
                                    : tile8_launch(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket,
                                                   stream, tile_begin, tile_end);
                 if (rc) return rc;
@@ -792,6 +796,24 @@ extern "C" int hidenn_tri_energy_range_f64(const hidenn_tri_plan* plan, const do
     double dummy_out[1];
     return tri_energy_launch<double>(plan, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags | HIDENN_TILES_ONLY, dummy_out, gx_free,
                                      gu_free, gt_out, scratch, stream, tile_begin, tile_end);
+}
+extern "C" int hidenn_tri_energy_overlap_f64(const hidenn_tri_plan* plan, const double* x_free, const double* x_fixed, const double* u_free,
+                                             const double* u_fixed, const double* consts, const double* t_table, int flags, double* out,
+                                             double* gx_free, double* gu_free, double* gt_out, double* scratch, uint32_t* first_done,
+                                             int reserve_sms, void* const* peer_bufs, void* my_buf, int me, int world, int64_t smax,
+                                             uint64_t* loss_step, void* stream) {
+    HIDENN_REQUIRE(plan && plan->tile_order && first_done, "tri_energy_overlap: needs a tile-ordered FP64 plan and a counter");
+    HIDENN_REQUIRE(flags & (HIDENN_NEED_GX | HIDENN_NEED_GU), "tri_energy_overlap: at least one gradient must be requested");
+    HIDENN_REQUIRE(!(flags & HIDENN_TILES_ONLY), "tri_energy_overlap: HIDENN_TILES_ONLY makes no sense here");
+    HIDENN_REQUIRE(peer_bufs == nullptr || (my_buf && loss_step && world >= 1 && world <= 64), "tri_energy_overlap: bad peer-memory arguments");
+    const P2PLossArgs A{(unsigned char* const*)peer_bufs, (unsigned char*)my_buf, (unsigned long long*)loss_step, (long long)smax, me, world};
+    return tri_energy_launch<double>(plan, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx_free, gu_free, gt_out, scratch,
+                                     stream, 0, -1, nullptr, first_done, reserve_sms, peer_bufs ? &A : nullptr);
+}
+extern "C" int hidenn_tri_plan_overlap_target(const hidenn_tri_plan* plan) {
+    static const bool ws_off = [] { const char* e = getenv("HIDENN_TILE_WS"); return e && atoi(e) == 0; }();
+    if (!plan || !plan->tile_order || plan->n_first_tiles <= 0 || ws_off || !tile9_fits(plan)) return 0;
+    return plan->n_first_tiles * tile9_fold_warps();
 }
 extern "C" int hidenn_tri_energy_finish_f64(const hidenn_tri_plan* plan, double* scratch, double* out, void* stream) {
     HIDENN_REQUIRE(plan && plan->tile_order && scratch && out, "tri_energy_finish: needs a tile-ordered FP64 plan, scratch and out");

@@ -17,6 +17,7 @@
 #include "tri_plan.h"
 #include "tri_element.cuh"
 #include "tri_tile8.h"
+#include "halo_p2p.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -100,7 +101,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                  const double* __restrict__ t_table, const int flags, double2* __restrict__ gx_free, double2* __restrict__ gu_free,
                  double* __restrict__ gt_out, double* __restrict__ e_dom, double* __restrict__ e_edge, const double* e_dom_all,
                  const double* e_edge_all, const int n_tiles_total, double* __restrict__ out, unsigned* __restrict__ ticket,
-                 const int kStages) {
+                 const int kStages, unsigned* __restrict__ first_done, const int n_first, const P2PLossArgs loss_args) {
     using R = double;
     using R2 = double2;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -334,7 +335,16 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     e_edge[tile] = ee;
                 }
                 __syncwarp();
-                if (lane == 0) { bar_arrive(&part_empty[pb]); bar_arrive(&empty_stage[st]); }
+                if (lane == 0) {
+                    bar_arrive(&part_empty[pb]);
+                    bar_arrive(&empty_stage[st]);
+                    // multi-GPU overlap: the first n_first tiles own the nodes shared with other ranks; a kernel on another
+                    // stream waits until first_done == n_first * kFWarps and then puts their rows into the peers' memory
+                    if (first_done != nullptr && tile < n_first) {
+                        __threadfence();
+                        atomicAdd(first_done, 1u);
+                    }
+                }
             }
         }
     }
@@ -367,6 +377,10 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
             out[3] = 0.0;
             *ticket = 0u;
         }
+        if (loss_args.peer_bufs != nullptr) {      // multi-GPU: exchange the rank partials over peer memory right here
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            p2p_loss_exchange<double>(out, loss_args, t0, [] { asm volatile("bar.sync 1, 256;" ::: "memory"); });
+        }
     }
 }
 
@@ -386,7 +400,8 @@ size_t tile9_smem_bytes(const hidenn_tri_plan* p) { return smem9_for(p, stages9_
 template <bool BODY, bool ISO, bool PAIRS>
 static int launch9(const hidenn_tri_plan* p, const double* x_free, const double* x_fixed, const double* u_free, const double* u_fixed,
                    const double* consts, const double* t_table, int flags, double* out, double* gx, double* gu, double* gt,
-                   double* scratch, unsigned* ticket, cudaStream_t stream, int tile_begin, int tile_end) {
+                   double* scratch, unsigned* ticket, cudaStream_t stream, int tile_begin, int tile_end, unsigned* first_done,
+                   int reserve_sms, const P2PLossArgs* loss_args) {
     const size_t smem = tile9_smem_bytes(p);
     static size_t configured[kMaxDevices] = {};
     size_t& cfg = configured[p->device % kMaxDevices];
@@ -407,23 +422,26 @@ static int launch9(const hidenn_tri_plan* p, const double* x_free, const double*
         P.elem_pack += (size_t)tile_begin * P.stride_elem;
         P.entry_off += (size_t)tile_begin * P.stride_owned;
     }
-    const int grid = std::min(P.n_tiles, sm_count(p->device));
+    const int grid = std::min(P.n_tiles, std::max(1, sm_count(p->device) - reserve_sms));
     tri_tile9_kernel<BODY, ISO, PAIRS><<<grid, kThreads9, smem, stream>>>(
         P, P8, (const double2*)x_free, (const double2*)x_fixed, (const double2*)u_free, (const double2*)u_fixed, consts, t_table, flags,
         (double2*)gx, (double2*)gu, gt, scratch + tile_begin, scratch + n_total + tile_begin, scratch, scratch + n_total, n_total, out, ticket,
-        stages9_for(p));
+        stages9_for(p), first_done, tile_begin == 0 ? p->n_first_tiles : 0, loss_args ? *loss_args : P2PLossArgs{nullptr, nullptr, nullptr, 0, 0, 0});
     HIDENN_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
+int tile9_fold_warps() { return kFWarps; }
 bool tile9_fits(const hidenn_tri_plan* p) { return tile9_smem_bytes(p) <= (size_t)227 * 1024; }
 
 int tile9_launch(const hidenn_tri_plan* p, const double* x_free, const double* x_fixed, const double* u_free, const double* u_fixed,
                  const double* consts, const double* t_table, int flags, double* out, double* gx, double* gu, double* gt, double* scratch,
-                 unsigned* ticket, cudaStream_t stream, int tile_begin, int tile_end) {
+                 unsigned* ticket, cudaStream_t stream, int tile_begin, int tile_end, unsigned* first_done, int reserve_sms,
+                 const P2PLossArgs* loss_args) {
     const bool body = !(flags & HIDENN_HINT_NO_BODY_FORCE), iso = (flags & HIDENN_HINT_C_PLANE_STRESS) != 0;
 #define HIDENN_L9(B_, I_, P_) \
-    return launch9<B_, I_, P_>(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket, stream, tile_begin, tile_end)
+    return launch9<B_, I_, P_>(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket, stream, tile_begin, \
+                               tile_end, first_done, reserve_sms, loss_args)
     if (pairs9(p)) {
         if (body && iso) HIDENN_L9(true, true, true);
         if (body) HIDENN_L9(true, false, true);

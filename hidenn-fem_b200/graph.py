@@ -68,8 +68,10 @@ class GraphedEnergyStep(GraphedStep):
     def __init__(self, model, loss_fn, *loss_fn_args, warmup: int = 3, **loss_fn_kw):
         self.loss_fn = loss_fn
         self._halo = getattr(loss_fn, "halo", None)
+        if self._halo is not None and getattr(self._halo, "capturable", False):
+            self._halo = None             # peer-memory exchange (dist.HaloP2P): its kernels are part of the captured step
         if self._halo is not None:
-            loss_fn.halo = None           # the graph holds the rank-local part; the exchange follows each replay
+            loss_fn.halo = None           # NCCL exchange: the graph holds the rank-local part, the exchange follows each replay
         try:
             super().__init__(model, lambda: loss_fn(model, *loss_fn_args, **loss_fn_kw), warmup=warmup)
             self._parts = loss_fn.last_parts          # [loss, domain, edge, 0] written by the finalize kernel;

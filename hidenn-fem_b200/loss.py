@@ -45,20 +45,18 @@ class _TriEnergyFn(torch.autograd.Function):
             t_table = t_live.detach().to(dt).contiguous()
             if t_live.requires_grad and need_gx:
                 gt = torch.empty_like(t_table)
-        with _lib.nvtx("hidenn.tri_energy"):
-            _lib.check(_lib.fn("hidenn_tri_energy", dt)(
-                plan.handle, _lib.ptr(x_free), _lib.ptr(xb), _lib.ptr(u_free), _lib.ptr(ub), _lib.ptr(consts), _lib.ptr(t_table),
-                C.c_int(flags), _lib.ptr(out), _lib.ptr(gx), _lib.ptr(gu), _lib.ptr(gt), _lib.ptr(scratch), _lib.stream_ptr()))
-        if gt is not None:
-            # chain d loss/d t_q through the user's traction to the edge end points (last line)
-            (gxq,) = torch.autograd.grad(t_live, xq, gt.reshape(t_live.shape))
-            loss_obj._scatter_edge_point_grads(model, gxq, gx)
-        with _lib.nvtx("hidenn.halo_exchange"):
-            loss_obj._post_forward(model, out, gx, gu)  # multi-GPU halo all-reduce hook (dist.py); no-op on one GPU
+        loss_obj._launch(model, plan, (x_free, xb, u_free, ub, consts, t_table), flags, out, gx, gu, gt, scratch,
+                         post=(lambda: _TriEnergyFn._chain_traction(loss_obj, model, t_live, xq, gt, gx)) if gt is not None else None)
         ctx.save_for_backward(gx if need_gx else None, gu if need_gu else None)
         ctx.used = False
         loss_obj.last_parts = out
         return out[0]
+
+    @staticmethod
+    def _chain_traction(loss_obj, model, t_live, xq, gt, gx):
+        # chain d loss/d t_q through the user's traction to the edge end points (last line)
+        (gxq,) = torch.autograd.grad(t_live, xq, gt.reshape(t_live.shape))
+        loss_obj._scatter_edge_point_grads(model, gxq, gx)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -108,6 +106,21 @@ class EnergyLoss2D:
 
     def _post_forward(self, model, out, gx, gu):
         """Hook after the fused launch (overridden by dist.DistributedEnergyLoss2D)."""
+
+    def _launch(self, model, plan, inputs, flags, out, gx, gu, gt, scratch, post=None):
+        """The fused evaluation: one C-ABI call (tile kernel [+ edge / finalize kernel for generic numberings]), the
+        x-dependent traction chain if any, then the `_post_forward` hook.  dist.DistributedEnergyLoss2D overrides this to
+        run the tiles in two ranges and exchange the halo while the second one computes."""
+        x_free, xb, u_free, ub, consts, t_table = inputs
+        dt = x_free.dtype
+        with _lib.nvtx("hidenn.tri_energy"):
+            _lib.check(_lib.fn("hidenn_tri_energy", dt)(
+                plan.handle, _lib.ptr(x_free), _lib.ptr(xb), _lib.ptr(u_free), _lib.ptr(ub), _lib.ptr(consts), _lib.ptr(t_table),
+                C.c_int(flags), _lib.ptr(out), _lib.ptr(gx), _lib.ptr(gu), _lib.ptr(gt), _lib.ptr(scratch), _lib.stream_ptr()))
+        if post is not None:
+            post()
+        with _lib.nvtx("hidenn.halo_exchange"):
+            self._post_forward(model, out, gx, gu)  # multi-GPU halo exchange hook (dist.py); no-op on one GPU
 
     # -- default forces (reference loss.py:43-51) ----------------------------------------------
     def uniform_body_force(self, x: torch.Tensor) -> torch.Tensor:

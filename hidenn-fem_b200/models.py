@@ -166,6 +166,7 @@ class PiecewiseLinearShapeNN2D(nn.Module):
         self._plans = {}
         self._ufix_cache = None
         self.tile_nodes = 0          # 0 = library default for the dtype
+        self.priority_nodes = None   # multi-GPU: local ids of the nodes shared with other ranks (their tiles run first)
 
     # -- reference properties ---------------------------------------------------------------
     @property
@@ -217,7 +218,8 @@ class PiecewiseLinearShapeNN2D(nn.Module):
             edges = self.neumann_edges if hasattr(self, "neumann_edges") else None
             plan = TriPlan(self.connectivity, self.Nnodes, self.initial_node_coords.double(), self.boundary_mask,
                            self.dirichlet_mask, edges, tile_nodes=self.tile_nodes,
-                           real_bytes=8 if p.dtype == torch.float64 else 4, device=torch.device("cuda", key[0]))
+                           real_bytes=8 if p.dtype == torch.float64 else 4, device=torch.device("cuda", key[0]),
+                           first_nodes=self.priority_nodes)
             self._plans[key] = plan
         return plan
 

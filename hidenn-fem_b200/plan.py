@@ -23,7 +23,7 @@ class TriPlan:
     /root/reference/src/models.py:248-282 keeps them as buffers)."""
 
     def __init__(self, connectivity, n_nodes, coords_init, boundary_mask, dirichlet_mask, neumann_edges=None,
-                 tile_nodes=0, real_bytes=8, device=None):
+                 tile_nodes=0, real_bytes=8, device=None, first_nodes=None):
         L = _lib.lib()
         conn = _np(connectivity, np.int64).reshape(-1, 3)
         xy = _np(coords_init, np.float64).reshape(-1, 2)
@@ -44,19 +44,22 @@ class TriPlan:
             dev_index = device.index if device.index is not None else torch.cuda.current_device()
         self.device_index = dev_index
         self._h = C.c_void_p(0)
-        rc = L.hidenn_tri_plan_create(conn.ctypes.data_as(C.c_void_p), C.c_int64(conn.shape[0]), C.c_int64(n_nodes),
-                                      xy.ctypes.data_as(C.c_void_p), bm.ctypes.data_as(C.c_void_p),
-                                      dm.ctypes.data_as(C.c_void_p), ed.ctypes.data_as(C.c_void_p),
-                                      C.c_int64(ed.shape[0]), C.c_int(int(tile_nodes)), C.c_int(int(real_bytes)),
-                                      C.c_int(dev_index), C.byref(self._h))
-        _lib.check(rc, "hidenn_tri_plan_create")
+        # first_nodes: nodes whose owner tiles are listed first (multi-GPU: the nodes shared with other ranks)
+        fn = np.zeros(0, np.int64) if first_nodes is None else _np(first_nodes, np.int64).reshape(-1)
+        rc = L.hidenn_tri_plan_create_ex(conn.ctypes.data_as(C.c_void_p), C.c_int64(conn.shape[0]), C.c_int64(n_nodes),
+                                         xy.ctypes.data_as(C.c_void_p), bm.ctypes.data_as(C.c_void_p),
+                                         dm.ctypes.data_as(C.c_void_p), ed.ctypes.data_as(C.c_void_p),
+                                         C.c_int64(ed.shape[0]), fn.ctypes.data_as(C.c_void_p), C.c_int64(fn.shape[0]),
+                                         C.c_int(int(tile_nodes)), C.c_int(int(real_bytes)),
+                                         C.c_int(dev_index), C.byref(self._h))
+        _lib.check(rc, "hidenn_tri_plan_create_ex")
         info = (C.c_int64 * 16)()
         _lib.check(L.hidenn_tri_plan_info(self._h, info), "hidenn_tri_plan_info")
         self.info = dict(zip(INFO_KEYS, [int(v) for v in info]))
         lay = (C.c_int64 * 8)()
         _lib.check(L.hidenn_tri_plan_layout(self._h, lay), "hidenn_tri_plan_layout")
         self.info.update(tile_ordered=bool(lay[0]), max_halo=int(lay[1]), edge_visits=int(lay[2]), smem_v8=int(lay[3]),
-                         n_pairs=int(lay[4]), pair_entries=int(lay[5]), max_entries9=int(lay[6]))
+                         n_pairs=int(lay[4]), pair_entries=int(lay[5]), max_entries9=int(lay[6]), n_first_tiles=int(lay[7]))
         self.real_bytes = real_bytes
         self.n_nodes = n_nodes
         self.n_elems = conn.shape[0]

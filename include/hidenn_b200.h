@@ -203,6 +203,23 @@ int hidenn_tri_energy_range_f64(const hidenn_tri_plan* plan,
                                 double* gx_free, double* gu_free, double* gt_out,
                                 double* scratch, int tile_begin, int tile_end, void* stream);
 int hidenn_tri_energy_finish_f64(const hidenn_tri_plan* plan, double* scratch, double* out, void* stream);
+/* One launch with a progress signal: like hidenn_tri_energy_f64, and the kernel adds to the device counter *first_done
+ * (zero before the launch) as the plan's leading tiles (hidenn_tri_plan_create_ex first_nodes) finish; when it reaches
+ * hidenn_tri_plan_overlap_target(plan) the gradient rows of those nodes are final and a kernel on ANOTHER stream
+ * (hidenn_halo_p2p_push_* with wait_counter) may read them while the remaining tiles still compute.  reserve_sms SMs are
+ * left free for that kernel.  With peer_bufs != NULL (arguments of hidenn_halo_p2p_loss_*) the last CTA also exchanges
+ * the rank's out[0..2] with the other ranks over peer memory, so out holds the GLOBAL sums when the launch ends.
+ * hidenn_tri_plan_overlap_target returns 0 when the plan cannot signal (not tile-ordered, no first nodes, tiles too
+ * large for the warp-specialised kernel): use the ranged calls above instead. */
+int hidenn_tri_energy_overlap_f64(const hidenn_tri_plan* plan,
+                                  const double* x_free, const double* x_fixed,
+                                  const double* u_free, const double* u_fixed,
+                                  const double* consts, const double* t_table, int flags,
+                                  double* out, double* gx_free, double* gu_free, double* gt_out,
+                                  double* scratch, uint32_t* first_done, int reserve_sms,
+                                  void* const* peer_bufs, void* my_buf, int me, int world, int64_t smax, uint64_t* loss_step,
+                                  void* stream);
+int hidenn_tri_plan_overlap_target(const hidenn_tri_plan* plan);
 
 /* Host-buffer convenience (the end-to-end drop-in for a CPU caller): copies the four parameter
  * arrays host->device, runs the fused step, copies loss and both gradients back and waits.
@@ -309,6 +326,43 @@ int hidenn_halo_pack_all_f32(const float* gx, const int32_t* xrows, const int32_
 int hidenn_halo_unpack_all_f32(float* gx, const int32_t* xrows, const int32_t* xpos, int64_t nx,
                                float* gu, const int32_t* urows, const int32_t* upos, int64_t nu,
                                float* loss, int64_t S, const float* buf, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Halo exchange over NVLink peer memory (one box).  Every rank allocates one buffer of
+ * hidenn_halo_p2p_bytes(world, smax, real_bytes) bytes in memory all ranks map (torch symmetric memory / CUDA IPC),
+ * zero-initialised; peer_bufs [world] (device array) holds every rank's buffer address as mapped in THIS process.
+ * smax = largest number of nodes any two ranks share; the k-th node (ascending global id) two ranks share uses slot k
+ * in both directions.  Two device counters starting at 1 number the steps (graph-capturable): `grad_step` for the
+ * gradient channel (read by push, advanced by pull) and `step` of the loss call for the loss channel (advanced by it).
+ *   push:  (first spin until *wait_counter >= wait_target and reset it to 0, when wait_counter != NULL;) for i < n_send:
+ *          put (gx[s_xrow[i]], gu[s_urow[i]]) (rows < 0: zeros) into rank s_peer[i]'s buffer, slot s_k[i] of sender
+ *          `me`; then raise my flag on every peer.
+ *   pull:  wait for the flags of wait_ranks [n_wait]; for shared node j < n_nodes with sources [n_off[j], n_off[j+1])
+ *          (src_rank ascending, including `me` itself; src_k = slot in the pair's list): gradient rows n_xrow[j] /
+ *          n_urow[j] (< 0: none) <- sum over the sources in that order.  Every holder computes the same bits.
+ *   loss:  out[0..2] <- sum over ranks (ascending) of every rank's out[0..2]; advances *step.
+ * One push -> pull pair and one loss call per step; the loss call is independent of the pair (it may also run in the
+ * tail of the tile kernel: hidenn_tri_energy_overlap_*).
+ * ------------------------------------------------------------------------------------------ */
+int64_t hidenn_halo_p2p_bytes(int world, int64_t smax, int real_bytes);
+int hidenn_halo_p2p_push_f64(const double* gx, const double* gu, const int32_t* s_xrow, const int32_t* s_urow,
+                             const int32_t* s_peer, const int32_t* s_k, int64_t n_send, void* const* peer_bufs,
+                             int me, int world, int64_t smax, const uint64_t* grad_step,
+                             uint32_t* wait_counter, uint32_t wait_target, void* stream);
+int hidenn_halo_p2p_pull_f64(double* gx, double* gu, const int32_t* n_xrow, const int32_t* n_urow, const int32_t* n_off,
+                             const int32_t* src_rank, const int32_t* src_k, int64_t n_nodes, const int32_t* wait_ranks,
+                             int n_wait, void* my_buf, int me, int world, int64_t smax, uint64_t* grad_step, void* stream);
+int hidenn_halo_p2p_loss_f64(double* out, void* const* peer_bufs, void* my_buf, int me, int world, int64_t smax,
+                             uint64_t* step, void* stream);
+int hidenn_halo_p2p_push_f32(const float* gx, const float* gu, const int32_t* s_xrow, const int32_t* s_urow,
+                             const int32_t* s_peer, const int32_t* s_k, int64_t n_send, void* const* peer_bufs,
+                             int me, int world, int64_t smax, const uint64_t* grad_step,
+                             uint32_t* wait_counter, uint32_t wait_target, void* stream);
+int hidenn_halo_p2p_pull_f32(float* gx, float* gu, const int32_t* n_xrow, const int32_t* n_urow, const int32_t* n_off,
+                             const int32_t* src_rank, const int32_t* src_k, int64_t n_nodes, const int32_t* wait_ranks,
+                             int n_wait, void* my_buf, int me, int world, int64_t smax, uint64_t* grad_step, void* stream);
+int hidenn_halo_p2p_loss_f32(float* out, void* const* peer_bufs, void* my_buf, int me, int world, int64_t smax,
+                             uint64_t* step, void* stream);
 
 #ifdef __cplusplus
 }
