@@ -450,16 +450,37 @@ def fp64_peak(device):
 
 # ------------------------------------------------------------------------------------------------
 def cpu_reference_step_factory(n_elems, dtype):
-    """The reference's CPU torch path restated in oracle/torch_port.py, same generator, bounded size."""
+    """The reference's CPU torch path on the same generator at a bounded size: the UNMODIFIED reference classes when their
+    snapshot exists (oracle/_ref, made by oracle/make_ref.py at build time; kind "reference"), else the op-for-op
+    restatement oracle/torch_port.py (kind "port").  Returns (step, elements, kind)."""
     from hidenn_fem_b200 import meshgen
     from oracle import torch_port as tp
     from oracle import closed_form as cf
+    from oracle import make_ref
     torch.set_num_threads(os.cpu_count() or 1)
     nx, ny = meshgen.plate_dims_for_elements(n_elems)
     m = meshgen.plate_mesh(nx, ny, jitter=0.25, diag="random", seed=0, ordering="morton")
     T = torch.tensor
     npdt = np.float64 if dtype == torch.float64 else np.float32
     u0 = 1e-5 * (2.0 * meshgen._hash_u01(np.stack([m.global_node_id * 2, m.global_node_id * 2 + 1], 1) + (1 << 50), 7) - 1.0)
+    ref = make_ref.load()
+    if ref is not None:
+        ref_models, ref_loss = ref
+        torch.manual_seed(0)
+        model = ref_models.PiecewiseLinearShapeNN2D(T(m.node_coords.astype(npdt)), T(m.connectivity), T(m.boundary_mask),
+                                                    T(m.dirichlet_mask), 0.0, T(m.neumann_edges))
+        with torch.no_grad():
+            model.u_free.copy_(T(u0[~m.dirichlet_mask].astype(np.float32)))
+        if dtype == torch.float64:
+            model = model.double()
+        loss_fn = ref_loss.EnergyLoss2D(E=10e9, nu=0.3, length=2.0, height=1.0, device=torch.device("cpu"), dtype=dtype)
+
+        def step():
+            model.zero_grad()
+            loss = loss_fn(model)
+            loss.backward()
+            return float(loss.detach())
+        return step, m.connectivity.shape[0], "reference"
     port = tp.TriPort(T(m.node_coords.astype(npdt)), T(m.connectivity), T(m.boundary_mask), T(m.dirichlet_mask), 0.0,
                       T(m.neumann_edges), u_free=T(u0[~m.dirichlet_mask].astype(npdt)))
     xg, wg = cf.triangle_gauss_points(4, npdt)
@@ -473,7 +494,7 @@ def cpu_reference_step_factory(n_elems, dtype):
         loss = tp.tri_energy(port, Cm, xg, wg, xi1, w1)
         loss.backward()
         return float(loss.detach())
-    return step, m.connectivity.shape[0]
+    return step, m.connectivity.shape[0], "port"
 
 
 def run_reference(args):
@@ -481,7 +502,7 @@ def run_reference(args):
     if rank != 0:
         return
     dtype = torch.float64 if args.dtype == "f64" else torch.float32
-    step, ne = cpu_reference_step_factory(args.cpu_sample_elems, dtype)
+    step, ne, kind = cpu_reference_step_factory(args.cpu_sample_elems, dtype)
     # --steps / --warmup are honoured as given: one step of the 1 M-element sample is ~1 s of CPU work on 16 cores,
     # so the driver's 20 + 5 fit in half a minute
     k, w = max(1, args.steps), max(0, args.warmup)
@@ -500,7 +521,7 @@ def run_reference(args):
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": WORKLOAD, "elements_total": args.elems, "sample_elements": ne, "gauss_points": NG,
                    "note": "CPU arm: every step is a bounded sample of the workload (same generator, scaled down)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -645,16 +666,18 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        step, ne_s = cpu_reference_step_factory(args.cpu_sample_elems, dtype)
+        step, ne_s, cpu_kind = cpu_reference_step_factory(args.cpu_sample_elems, dtype)
         step()
         best = 1e30
         for _ in range(3):
             t1 = time.perf_counter()
             step()
             best = min(best, time.perf_counter() - t1)
-        cpu_baseline = {"value": ne_s * NG / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"{ne_s} triangles, same generator, torch-autograd port of the reference path "
-                                  f"(oracle/torch_port.py), 1 warm-up + best of 3, {best * 1e3:.0f} ms/step"}
+        cpu_baseline = {"value": ne_s * NG / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": cpu_kind,
+                        "sample": f"{ne_s} triangles, same generator, "
+                                  + ("the unmodified reference classes (oracle/_ref snapshot)" if cpu_kind == "reference"
+                                     else "torch-autograd port of the reference path (oracle/torch_port.py)")
+                                  + f", 1 warm-up + best of 3, {best * 1e3:.0f} ms/step"}
 
     if rank == 0:
         line = {

@@ -37,8 +37,12 @@ __device__ __forceinline__ void tri_element(const typename Real2<R>::type v0, co
                                             const typename Real2<R>::type v2, const typename Real2<R>::type U0,
                                             const typename Real2<R>::type U1, const typename Real2<R>::type U2,
                                             const TriConsts<R>& K, R& energy, typename Real2<R>::type gu[3],
-                                            typename Real2<R>::type gx[3]) {
-    const R a = v0.x - v2.x, b = v1.x - v2.x, c = v0.y - v2.y, d = v1.y - v2.y;
+                                            typename Real2<R>::type gx[3], const bool jt = false) {
+    // jt (correct-math switch, default off): the energy with J^-T is the reference's J^-1 expression evaluated on the
+    // transposed Jacobian (b and c exchanged; det is the same), so its derivatives w.r.t. b and c come out exchanged
+    const R a = v0.x - v2.x, d = v1.y - v2.y;
+    const R b_in = v1.x - v2.x, c_in = v0.y - v2.y;
+    const R b = jt ? c_in : b_in, c = jt ? b_in : c_in;
     const R det = a * d - b * c;
     const R inv = fast_rcp(det);
     const R p0 = U0.x - U2.x, p1 = U1.x - U2.x, q0 = U0.y - U2.y, q1 = U1.y - U2.y;
@@ -81,6 +85,10 @@ __device__ __forceinline__ void tri_element(const typename Real2<R>::type v0, co
         gu[0] = mk2<R>(g00, g10);
         gu[1] = mk2<R>(g01, g11);
         gu[2] = mk2<R>(-(g00 + g01), -(g10 + g11));
+    }
+    {       // D01 = d/db, D10 = d/dc of the expression above: with jt they are d/dc and d/db of the true Jacobian entries
+        const R t01 = jt ? D10 : D01, t10 = jt ? D01 : D10;
+        D01 = t01; D10 = t10;
     }
     gx[0] = mk2<R>(D00, D10);
     gx[1] = mk2<R>(D01, D11);

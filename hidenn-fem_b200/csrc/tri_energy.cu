@@ -171,7 +171,7 @@ tri_tile_persistent_kernel(const TriPlanDev P, const typename Real2<R>::type* __
             R e;
             R2 gu[3], gx[3], v0, v1, v2, U0, U1, U2;
             nodes.load(l0, v0, U0); nodes.load(l1, v1, U1); nodes.load(l2, v2, U2);
-            tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx);
+            tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx, P.jinv_t != 0);
             e_acc += (hi >> 31) ? e : R(0);
             // halo corners carry the tile's dump position: skip their stores (predicated, no branch)
             if (p0 != dumpv) part.store(p0, gu[0], gx[0]);
@@ -295,7 +295,7 @@ tri_tile_energy_only_kernel(const TriPlanDev P, const typename Real2<R>::type* _
         const unsigned l0 = (unsigned)(w) & LM, l1 = (unsigned)(w >> kLidBits) & LM, l2 = (unsigned)(w >> (2 * kLidBits)) & LM;
         R e;
         R2 gu[3], gx[3];
-        tri_element<R, true, false>(s_xy[l0], s_xy[l1], s_xy[l2], s_uv[l0], s_uv[l1], s_uv[l2], K, e, gu, gx);
+        tri_element<R, true, false>(s_xy[l0], s_xy[l1], s_xy[l2], s_uv[l0], s_uv[l1], s_uv[l2], K, e, gu, gx, P.jinv_t != 0);
         e_acc += e;
     }
     const R tot = block_sum<R, kTileBlock>(e_acc, s_red);

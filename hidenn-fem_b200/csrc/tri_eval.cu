@@ -44,7 +44,9 @@ tri_eval_fwd_kernel(const TriPlanDev P, const typename Real2<R>::type* __restric
         const R2 xr = x_ref[m];
         const R z = R(1) - xr.x - xr.y;
         if (u_h) u_h[m] = mk2<R>(xr.x * N.U0.x + xr.y * N.U1.x + z * N.U2.x, xr.x * N.U0.y + xr.y * N.U1.y + z * N.U2.y);
-        const R a = N.v0.x - N.v2.x, b = N.v1.x - N.v2.x, c = N.v0.y - N.v2.y, d = N.v1.y - N.v2.y;
+        // P.jinv_t (correct-math switch): J^-T instead of the reference's J^-1 = the same expressions on the transposed Jacobian
+        const R a = N.v0.x - N.v2.x, d = N.v1.y - N.v2.y;
+        const R b = P.jinv_t ? N.v0.y - N.v2.y : N.v1.x - N.v2.x, c = P.jinv_t ? N.v1.x - N.v2.x : N.v0.y - N.v2.y;
         const R det = a * d - b * c;
         if (detJ) detJ[m] = det;
         if (grad_u) {
@@ -71,7 +73,8 @@ tri_eval_bwd_kernel(const TriPlanDev P, const typename Real2<R>::type* __restric
         const ElemNodes<R> N = gather_elem<R>(P, e, x_free, x_fixed, u_free, u_fixed);
         const R2 xr = x_ref[m];
         const R z = R(1) - xr.x - xr.y;
-        const R a = N.v0.x - N.v2.x, b = N.v1.x - N.v2.x, c = N.v0.y - N.v2.y, d = N.v1.y - N.v2.y;
+        const R a = N.v0.x - N.v2.x, d = N.v1.y - N.v2.y;
+        const R b = P.jinv_t ? N.v0.y - N.v2.y : N.v1.x - N.v2.x, c = P.jinv_t ? N.v1.x - N.v2.x : N.v0.y - N.v2.y;
         const R det = a * d - b * c;
         const R inv = rcp(det);
         const R j00 = d * inv, j01 = -b * inv, j10 = -c * inv, j11 = a * inv;
@@ -84,8 +87,9 @@ tri_eval_bwd_kernel(const TriPlanDev P, const typename Real2<R>::type* __restric
         // M = cG . Jinv  (cotangent of dU);  dJ = kd * adj - M^T G
         const R M00 = c00 * j00 + c01 * j10, M01 = c00 * j01 + c01 * j11;
         const R M10 = c10 * j00 + c11 * j10, M11 = c10 * j01 + c11 * j11;
-        const R D00 = kd * d - (M00 * G00 + M10 * G10), D01 = -kd * c - (M00 * G01 + M10 * G11);
-        const R D10 = -kd * b - (M01 * G00 + M11 * G10), D11 = kd * a - (M01 * G01 + M11 * G11);
+        const R D00 = kd * d - (M00 * G00 + M10 * G10), D11 = kd * a - (M01 * G01 + M11 * G11);
+        const R Db = -kd * c - (M00 * G01 + M10 * G11), Dc = -kd * b - (M01 * G00 + M11 * G10);      // d/db, d/dc of the expression
+        const R D01 = P.jinv_t ? Dc : Db, D10 = P.jinv_t ? Db : Dc;                                    // ... of the true Jacobian entries
         R* gx = row_gx + 6 * m;
         R* gu = row_gu + 6 * m;
         gx[0] = D00; gx[1] = D10; gx[2] = D01; gx[3] = D11; gx[4] = -(D00 + D01); gx[5] = -(D10 + D11);

@@ -408,16 +408,58 @@ extern "C" int hidenn_tri_locality_order(const int64_t* conn, int64_t Ne, int64_
     return 0;
 }
 
+// Mesh ingestion (the step before the plan; /root/reference/src/mesh.py:70-88, 202-215 get the geometric boundary from
+// gmsh entities / hole rims): topological boundary of a triangle mesh = nodes of the edges that belong to exactly one
+// element.  The neighbour across an edge is looked up through the node -> element lists; host threads, no sort.
+extern "C" int hidenn_mesh_boundary_nodes(const int64_t* conn, int64_t Ne, int64_t Nn, uint8_t* mask) {
+    HIDENN_REQUIRE(conn && mask && Ne >= 0 && Nn > 0 && Nn < (int64_t)2147483000, "mesh_boundary_nodes: bad arguments");
+    for (int64_t i = 0; i < 3 * Ne; ++i) HIDENN_REQUIRE(conn[i] >= 0 && conn[i] < Nn, "mesh_boundary_nodes: connectivity index out of range");
+    std::vector<int64_t> off(Nn + 1, 0);
+    for (int64_t i = 0; i < 3 * Ne; ++i) off[conn[i] + 1]++;
+    for (int64_t n = 0; n < Nn; ++n) off[n + 1] += off[n];
+    std::vector<int32_t> ent(3 * Ne);
+    {
+        std::vector<int64_t> cur(off.begin(), off.end() - 1);
+        for (int64_t e = 0; e < Ne; ++e)
+            for (int c = 0; c < 3; ++c) ent[cur[conn[3 * e + c]]++] = (int32_t)e;
+    }
+    std::vector<std::atomic<uint8_t>> m(Nn);
+    for (auto& v : m) v.store(0, std::memory_order_relaxed);
+    auto range = [&](int64_t e0, int64_t e1) {
+        for (int64_t e = e0; e < e1; ++e)
+            for (int c = 0; c < 3; ++c) {
+                const int64_t a = conn[3 * e + c], b = conn[3 * e + (c + 1) % 3];
+                bool shared = false;
+                for (int64_t k = off[a]; k < off[a + 1] && !shared; ++k) {
+                    const int64_t f = ent[k];
+                    if (f != e && (conn[3 * f] == b || conn[3 * f + 1] == b || conn[3 * f + 2] == b)) shared = true;
+                }
+                if (!shared) { m[a].store(1, std::memory_order_relaxed); m[b].store(1, std::memory_order_relaxed); }
+            }
+    };
+    unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (Ne < 100000) nthr = 1;
+    std::vector<std::thread> th;
+    const int64_t per = (Ne + nthr - 1) / nthr;
+    for (unsigned i = 0; i < nthr; ++i) {
+        const int64_t a = i * per, b = std::min<int64_t>(Ne, a + per);
+        if (a < b) th.emplace_back(range, a, b);
+    }
+    for (auto& t : th) t.join();
+    for (int64_t n = 0; n < Nn; ++n) mask[n] = m[n].load(std::memory_order_relaxed);
+    return 0;
+}
+
 extern "C" int hidenn_tri_plan_create(const int64_t* conn, int64_t Ne, int64_t Nn, const double* coords,
                                       const uint8_t* bmask, const uint8_t* dmask, const int64_t* edges, int64_t Ned,
                                       int tile_nodes, int real_bytes, int device, hidenn_tri_plan** out) {
-    return hidenn_tri_plan_create_ex(conn, Ne, Nn, coords, bmask, dmask, edges, Ned, nullptr, 0, tile_nodes, real_bytes, device, out);
+    return hidenn_tri_plan_create_ex(conn, Ne, Nn, coords, bmask, dmask, edges, Ned, nullptr, 0, 0, tile_nodes, real_bytes, device, out);
 }
 
 extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_t Nn, const double* coords,
                                          const uint8_t* bmask, const uint8_t* dmask, const int64_t* edges, int64_t Ned,
-                                         const int64_t* first_nodes, int64_t n_first, int tile_nodes, int real_bytes, int device,
-                                         hidenn_tri_plan** out) {
+                                         const int64_t* first_nodes, int64_t n_first, int options, int tile_nodes, int real_bytes,
+                                         int device, hidenn_tri_plan** out) {
     HIDENN_REQUIRE(out != nullptr, "plan_create: out is NULL");
     *out = nullptr;
     HIDENN_REQUIRE(conn && coords && bmask && dmask, "plan_create: NULL input");
@@ -976,6 +1018,22 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
                 t_lid[(size_t)t * SL + j] = (uint16_t)byid[j].second;
             }
         }
+        {       // locality of the numbering: contiguous Parameter-row runs per tile (1-2 for a tile-ordered numbering,
+                // ~n_local for a random one); hidenn_tri_plan_locality, the Python plan warns when it is poor
+            int64_t runs = 0, nl = 0;
+            for (int64_t t = 0; t < n_tiles; ++t) {
+                const TileDesc& d = p->tiles[t];
+                int prev = INT32_MIN;
+                for (int32_t j = 0; j < d.n_local; ++j) {
+                    const int c = t_slots[(size_t)t * SL + j].x;
+                    if (!(c == prev + 1 && c > 0) && !(c < 0 && c == prev - 1)) ++runs;
+                    prev = c;
+                }
+                nl += d.n_local;
+            }
+            p->runs_per_tile = n_tiles ? (double)runs / n_tiles : 0.0;
+            p->local_per_tile = n_tiles ? (double)nl / n_tiles : 0.0;
+        }
         if (getenv("HIDENN_PLAN_RUNSTATS")) {       // debug: contiguous-row runs per tile (bulk-copy feasibility)
             int64_t rx = 0, ru = 0, ro = 0, nl = 0, no = 0;
             for (int64_t t = 0; t < n_tiles; ++t) {
@@ -1074,6 +1132,7 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
     D.max_local = max_local; D.max_entries = max_entries; D.max_owned = max_owned; D.max_elem = max_elem;
     D.n_edges = (int32_t)Ned; D.n_enodes = n_en;
     D.n_elems = Ne; D.n_nodes = Nn; D.n_free_x = p->n_free_x; D.n_free_u = p->n_free_u;
+    D.jinv_t = (options & HIDENN_PLAN_JINV_TRANSPOSE) ? 1 : 0;
     hidenn_tri_plan* pp = p.get();
     int rc = 0;
     rc |= upload(pp, p->tiles, &D.tiles);
@@ -1186,6 +1245,13 @@ extern "C" int hidenn_tri_plan_layout(const hidenn_tri_plan* p, int64_t* out8) {
     out8[5] = p->pair_entries;       // pair-or-single entries over all tiles
     out8[6] = max_entries9;          // max fold slots per tile in the paired layout
     out8[7] = p->n_first_tiles;      // tiles owning the caller's first_nodes: they are tiles [0, n_first_tiles)
+    return 0;
+}
+
+extern "C" int hidenn_tri_plan_locality(const hidenn_tri_plan* p, double* out2) {
+    HIDENN_REQUIRE(p && out2, "plan_locality: NULL");
+    out2[0] = p->runs_per_tile;
+    out2[1] = p->local_per_tile;
     return 0;
 }
 

@@ -93,6 +93,8 @@ struct TriPlanDev {
     const int32_t* n2e_ent;      // element*4 + corner, ascending element id per node
     const int32_t* edges32;      // [Ned,2]
     int64_t n_elems, n_nodes, n_free_x, n_free_u;
+    // correct-math switch (default 0 = the reference's J^-1 quirk): 1 = physical gradients use J^-T
+    int32_t jinv_t, pad_opt;
 };
 
 }  // namespace hidenn
@@ -123,6 +125,7 @@ struct hidenn_tri_plan {
     std::vector<uint32_t> entry_off9;               // compact, like entry_off
     std::vector<int32_t> mate;                      // global matching: partner element or -1
     int64_t n_pairs = 0, pair_entries = 0;
+    double runs_per_tile = 0.0, local_per_tile = 0.0;      // numbering locality (hidenn_tri_plan_locality)
     int32_t n_first_tiles = 0;                      // tiles owning the caller's first_nodes, listed first
     std::vector<void*> dev_allocs;
     size_t dev_bytes = 0;

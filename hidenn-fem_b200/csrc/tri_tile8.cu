@@ -186,7 +186,7 @@ tri_tile8_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
             R e;
             R2 gu[3], gx[3], v0, v1, v2, U0, U1, U2;
             nodes.load(l0, v0, U0); nodes.load(l1, v1, U1); nodes.load(l2, v2, U2);
-            tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx);
+            tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx, P.jinv_t != 0);
             e_acc += (hi >> 31) ? e : R(0);
             if (p0 != dumpv) part.store(p0, gu[0], gx[0]);
             if (p1 != dumpv) part.store(p1, gu[1], gx[1]);

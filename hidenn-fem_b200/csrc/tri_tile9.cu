@@ -163,7 +163,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     R e;
                     R2 v0, v1, v2, U0, U1, U2;
                     nodes.load(l0, v0, U0); nodes.load(l1, v1, U1); nodes.load(l2, v2, U2);
-                    tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx);
+                    tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx, P.jinv_t != 0);
                     e_acc += (hi >> 31) ? e : R(0);
                 }
                 if (PAIRS && ((unsigned)pw.y & 0x3FFFFFFFu) != 0x3FFFFFFFu) {
@@ -174,7 +174,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     R e;
                     R2 hu[3], hx[3], v0, v1, v2, U0, U1, U2;
                     nodes.load(m0, v0, U0); nodes.load(m1, v1, U1); nodes.load(m2, v2, U2);
-                    tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, hu, hx);
+                    tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, hu, hx, P.jinv_t != 0);
                     e_acc += (hi >> 31) ? e : R(0);
                     const unsigned ll[3] = {l0, l1, l2}, mm[3] = {m0, m1, m2};
 #pragma unroll

@@ -83,7 +83,9 @@ class EnergyLoss2D:
 
     def __init__(self, E: float = 10e9, nu: float = 0.3, length: float = 1.0, height: float = 1.0,
                  gauss_order: int = 4, gauss_order_1d: int = 2, device: Optional[torch.device] = None,
-                 dtype: torch.dtype = torch.float32):
+                 dtype: torch.dtype = torch.float32, fix_weights: bool = False, edge_rule_unit: bool = False):
+        # fix_weights / edge_rule_unit: correct-math switches, default off = the reference's tables.
+        # The third switch, jinv_transpose, belongs to the model (PiecewiseLinearShapeNN2D(..., jinv_transpose=True)).
         self.E = E
         self.nu = nu
         self.length = length
@@ -95,9 +97,11 @@ class EnergyLoss2D:
         factor = E / (1 - nu ** 2)
         self.C = torch.tensor([[1.0, nu, 0.0], [nu, 1.0, 0.0], [0.0, 0.0, (1.0 - nu) / 2.0]],
                               dtype=dtype, device=self.device) * factor
-        self.xg, self.wg = triangle_gauss_points(order=self.gauss_order, device=self.device, dtype=self.dtype)
+        self.fix_weights, self.edge_rule_unit = fix_weights, edge_rule_unit
+        self.xg, self.wg = triangle_gauss_points(order=self.gauss_order, device=self.device, dtype=self.dtype, fix_weights=fix_weights)
         self.ng = self.xg.shape[0]
-        self.xg_1d, self.wg_1d = interval_gauss_points(order=self.gauss_order_1d, device=self.device, dtype=self.dtype)
+        self.xg_1d, self.wg_1d = interval_gauss_points(order=self.gauss_order_1d, device=self.device, dtype=self.dtype,
+                                                       unit_interval=edge_rule_unit)
         self.ng1 = self.xg_1d.shape[0]
         if self.ng1 > 8:
             raise ValueError("gauss_order_1d > 8 is not supported by the edge kernel")

@@ -268,3 +268,53 @@ def reorder_mesh(m: PlateMesh, mode: str = "tiles", tile_nodes: int = 0) -> Plat
     xy, conn, bm, dm, ed, n2o, _ = reorder_for_locality(m.node_coords, m.connectivity, m.boundary_mask, m.dirichlet_mask,
                                                         m.neumann_edges, mode=mode, tile_nodes=tile_nodes)
     return PlateMesh(xy, conn, bm, dm, m.neumann_mask[n2o], ed, m.global_node_id[n2o], meta=dict(m.meta, ordering=mode))
+
+
+def ingest_mesh(node_coords, connectivity, length: float = 2.0, height: float = 1.0, boundaries: Optional[dict] = None,
+                tol: float = 1e-6, reorder: Optional[str] = "tiles", tile_nodes: int = 0, dtype=None):
+    """From a raw triangulation (any generator: gmsh, meshzoo, Delaunay; any numbering) to the reference's 6-tuple
+    `(node_coords, connectivity, geom_boundary_mask, bc_mask, mn_mask, neumann_edges)` -- the part of
+    /root/reference/src/mesh.py:70-153 and :202-276 that follows the mesher:
+
+      geom_boundary_mask  nodes on the boundary of the domain incl. hole rims (topological: edges of exactly one
+                          element, native `hidenn_mesh_boundary_nodes`; the reference asks gmsh / tests the hole radius)
+      bc_mask / mn_mask   faces "up" / "down" / "left" / "right" with condition 1 (Dirichlet) / 2 (Neumann), |coordinate
+                          - face| < tol as in mesh.py:108-124
+      neumann_edges       the sorted-unique element edges whose two nodes are both in mn_mask (mesh.py:125-134)
+
+    then (reorder="tiles" | "morton" | None) renumbered for locality with `reorder_for_locality`.  Returns torch tensors
+    like the reference (`dtype` of the coordinates: float32 there; default keeps the input's), plus `new_to_old`
+    (identity when reorder is None)."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    xy = np.ascontiguousarray(np.asarray(node_coords), dtype=np.float64)
+    conn = np.ascontiguousarray(np.asarray(connectivity), dtype=np.int64).reshape(-1, 3)
+    boundaries = boundaries or {"left": 1, "right": 2}
+    geom = np.zeros(xy.shape[0], np.uint8)
+    _lib.check(_lib.lib().hidenn_mesh_boundary_nodes(conn.ctypes.data_as(C.c_void_p), C.c_int64(conn.shape[0]), C.c_int64(xy.shape[0]),
+                                                     geom.ctypes.data_as(C.c_void_p)), "hidenn_mesh_boundary_nodes")
+    geom = geom.astype(bool)
+    bc = np.zeros(xy.shape[0], bool)
+    mn = np.zeros(xy.shape[0], bool)
+    face_of = {"up": (1, height), "down": (1, 0.0), "left": (0, 0.0), "right": (0, length)}
+    for face, cond in boundaries.items():
+        if cond == 0 or face not in face_of:
+            continue
+        ax, val = face_of[face]
+        on = np.abs(xy[:, ax] - val) < tol
+        if cond == 1:
+            bc |= on
+        elif cond == 2:
+            mn |= on
+    e_all = np.concatenate([conn[:, [0, 1]], conn[:, [1, 2]], conn[:, [2, 0]]], axis=0)
+    cand = mn[e_all[:, 0]] & mn[e_all[:, 1]]                     # restrict first: the unique over all edges is the slow part
+    e_c = np.sort(e_all[cand], axis=1)
+    edges = np.unique(e_c, axis=0) if e_c.size else np.zeros((0, 2), np.int64)
+    n2o = np.arange(xy.shape[0])
+    if reorder:
+        xy, conn, geom, bc, edges, n2o, _ = reorder_for_locality(xy, conn, geom, bc, edges, mode=reorder, tile_nodes=tile_nodes)
+        mn = mn[n2o]
+    out_dt = dtype or (torch.float32 if np.asarray(node_coords).dtype == np.float32 else torch.float64)
+    T = torch.tensor
+    return (T(xy, dtype=out_dt), T(conn), T(geom), T(bc), T(mn), T(np.ascontiguousarray(edges), dtype=torch.long), n2o)

@@ -136,8 +136,11 @@ class PiecewiseLinearShapeNN2D(nn.Module):
         return super().__new__(cls)
 
     def __init__(self, node_coords, connectivity, boundary_mask=None, dirichlet_mask=None, u_fixed=None,
-                 neumann_edges=None):
+                 neumann_edges=None, jinv_transpose=False):
         super().__init__()
+        # correct-math switch (keyword only in spirit; default off = the reference's J^-1 in dN/dx): with True
+        # every kernel of this model (forward, fused energy, gradients) uses dN/dx = J^-T dN/dxi
+        self.jinv_transpose = bool(jinv_transpose)
         self.scale = 1e-5
         self.dim_u = 2
         self.register_buffer("initial_node_coords", node_coords.clone())
@@ -219,7 +222,7 @@ class PiecewiseLinearShapeNN2D(nn.Module):
             plan = TriPlan(self.connectivity, self.Nnodes, self.initial_node_coords.double(), self.boundary_mask,
                            self.dirichlet_mask, edges, tile_nodes=self.tile_nodes,
                            real_bytes=8 if p.dtype == torch.float64 else 4, device=torch.device("cuda", key[0]),
-                           first_nodes=self.priority_nodes)
+                           first_nodes=self.priority_nodes, options=1 if self.jinv_transpose else 0)
             self._plans[key] = plan
         return plan
 

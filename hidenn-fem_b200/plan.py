@@ -23,7 +23,7 @@ class TriPlan:
     /root/reference/src/models.py:248-282 keeps them as buffers)."""
 
     def __init__(self, connectivity, n_nodes, coords_init, boundary_mask, dirichlet_mask, neumann_edges=None,
-                 tile_nodes=0, real_bytes=8, device=None, first_nodes=None):
+                 tile_nodes=0, real_bytes=8, device=None, first_nodes=None, options=0):
         L = _lib.lib()
         conn = _np(connectivity, np.int64).reshape(-1, 3)
         xy = _np(coords_init, np.float64).reshape(-1, 2)
@@ -50,7 +50,7 @@ class TriPlan:
                                          xy.ctypes.data_as(C.c_void_p), bm.ctypes.data_as(C.c_void_p),
                                          dm.ctypes.data_as(C.c_void_p), ed.ctypes.data_as(C.c_void_p),
                                          C.c_int64(ed.shape[0]), fn.ctypes.data_as(C.c_void_p), C.c_int64(fn.shape[0]),
-                                         C.c_int(int(tile_nodes)), C.c_int(int(real_bytes)),
+                                         C.c_int(int(options)), C.c_int(int(tile_nodes)), C.c_int(int(real_bytes)),
                                          C.c_int(dev_index), C.byref(self._h))
         _lib.check(rc, "hidenn_tri_plan_create_ex")
         info = (C.c_int64 * 16)()
@@ -60,6 +60,15 @@ class TriPlan:
         _lib.check(L.hidenn_tri_plan_layout(self._h, lay), "hidenn_tri_plan_layout")
         self.info.update(tile_ordered=bool(lay[0]), max_halo=int(lay[1]), edge_visits=int(lay[2]), smem_v8=int(lay[3]),
                          n_pairs=int(lay[4]), pair_entries=int(lay[5]), max_entries9=int(lay[6]), n_first_tiles=int(lay[7]))
+        loc = (C.c_double * 2)()
+        _lib.check(L.hidenn_tri_plan_locality(self._h, loc), "hidenn_tri_plan_locality")
+        self.info.update(runs_per_tile=float(loc[0]), local_per_tile=float(loc[1]))
+        if self.info["n_tiles"] >= 64 and loc[0] > 0.5 * loc[1]:
+            import warnings
+            warnings.warn("HiDeNN B200: the node numbering of this mesh has no locality (%.0f contiguous row runs per tile of %.0f "
+                          "nodes): the fused kernels run ~3x slower on it.  Pass the mesh through "
+                          "hidenn_fem_b200.meshgen.ingest_mesh / reorder_for_locality (keeps elements, corner order and results)."
+                          % (loc[0], loc[1]), RuntimeWarning, stacklevel=3)
         self.real_bytes = real_bytes
         self.n_nodes = n_nodes
         self.n_elems = conn.shape[0]

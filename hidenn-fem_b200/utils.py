@@ -9,9 +9,12 @@ import numpy as np
 import torch
 
 
-def interval_gauss_points(order=1, device=None, dtype=torch.float32):
-    """Gauss-Legendre points/weights exactly as reference utils.py:4-11 (raw leggauss, [-1,1])."""
+def interval_gauss_points(order=1, device=None, dtype=torch.float32, unit_interval=False):
+    """Gauss-Legendre points/weights exactly as reference utils.py:4-11 (raw leggauss, [-1,1]).
+    unit_interval=True (correct-math switch, default off): the rule its docstring promises, mapped to [0,1]."""
     xi, wi = np.polynomial.legendre.leggauss(order)
+    if unit_interval:
+        xi, wi = 0.5 * (xi + 1.0), 0.5 * wi
     return torch.tensor(xi, dtype=dtype, device=device), torch.tensor(wi, dtype=dtype, device=device)
 
 
@@ -29,8 +32,9 @@ _TRI_RULES = {
 }
 
 
-def triangle_gauss_points(order=1, device=None, dtype=torch.float32):
-    """Points (r,s) and weights on the reference triangle, values of reference utils.py:13-81."""
+def triangle_gauss_points(order=1, device=None, dtype=torch.float32, fix_weights=False):
+    """Points (r,s) and weights on the reference triangle, values of reference utils.py:13-81.
+    fix_weights=True (correct-math switch, default off): orders 4 and 6 sum to the triangle area 0.5 instead of 0.25."""
     if device is None:
         device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
     if order not in _TRI_RULES:
@@ -38,7 +42,7 @@ def triangle_gauss_points(order=1, device=None, dtype=torch.float32):
     pts, wts, scale = _TRI_RULES[order]
     rs = torch.tensor(pts, dtype=dtype, device=device)
     w = torch.tensor(wts, dtype=dtype, device=device)
-    if scale != 1.0:
+    if scale != 1.0 and not (fix_weights and order in (4, 6)):
         w = scale * w
     return rs, w
 

@@ -88,11 +88,15 @@ int hidenn_tri_plan_create(const int64_t* conn, int64_t n_elems, int64_t n_nodes
 /* Same, with `first_nodes` [n_first] (may be NULL/0): tiles owning one of these nodes are listed first
  * (tiles [0, layout8[7])).  Multi-GPU callers pass the nodes shared with other ranks, run the tiles in two ranges
  * (hidenn_tri_energy_range_*) and exchange the finished shared rows while the second range computes. */
+/* options: HIDENN_PLAN_JINV_TRANSPOSE = correct-math switch (default off): every kernel of this plan forms the physical
+ * shape-function gradients with J^-T (dN/dx = J^-T dN/dxi) instead of the reference's J^-1 (src/models.py:339-351,
+ * SURVEY Q1); gradients follow consistently. */
+#define HIDENN_PLAN_JINV_TRANSPOSE 1
 int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t n_elems, int64_t n_nodes,
                               const double* coords_init,
                               const uint8_t* boundary_mask, const uint8_t* dirichlet_mask,
                               const int64_t* edges, int64_t n_edges,
-                              const int64_t* first_nodes, int64_t n_first,
+                              const int64_t* first_nodes, int64_t n_first, int options,
                               int tile_nodes, int real_bytes, int device,
                               hidenn_tri_plan** out);
 void hidenn_tri_plan_destroy(hidenn_tri_plan* plan);
@@ -116,11 +120,21 @@ int hidenn_tri_locality_order(const int64_t* conn, int64_t n_elems, int64_t n_no
  * [7]=number of leading tiles that own the caller's first_nodes (hidenn_tri_plan_create_ex). */
 int hidenn_tri_plan_layout(const hidenn_tri_plan* plan, int64_t* layout8);
 
+/* Mesh ingestion: mask [Nn] <- 1 for the nodes on the topological boundary of the triangle mesh (edges that belong to
+ * exactly one element: outer boundary and hole rims; what src/mesh.py:70-88, 202-215 take from gmsh / the hole test). */
+int hidenn_mesh_boundary_nodes(const int64_t* conn, int64_t n_elems, int64_t n_nodes, uint8_t* mask);
+
 /* info[0]=n_tiles [1]=tile element visits (incl. halo recompute) [2]=tile node visits
  * [3]=max local nodes/tile [4]=max fold entries/tile [5]=scratch elements needed
  * [6]=dynamic smem bytes f64 [7]=same f32 [8]=n_free_x [9]=n_free_u [10]=n_edges [11]=n_edge_nodes
  * [12]=plan bytes on device [13]=max elements/tile [14]=n_elems [15]=n_nodes */
 int hidenn_tri_plan_info(const hidenn_tri_plan* plan, int64_t* info16);
+
+/* Locality of the node numbering as the tile kernels see it: out2[0] = mean number of contiguous node_coords_free /
+ * node_coords_fixed row runs per tile, out2[1] = mean local nodes per tile.  ~1-10 runs: tile-ordered; tens: a Z-curve
+ * or natural numbering (fine); close to out2[1]: no locality (the kernels then run ~3x slower -- renumber the mesh with
+ * hidenn_tri_locality_order first). */
+int hidenn_tri_plan_locality(const hidenn_tri_plan* plan, double* out2);
 
 /* Bit-exact integer views for tests (host copies): slot maps of src/models.py:292-305.
  * xslot[n] >= 0: row of node n in node_coords_free; < 0: ~row in node_coords_fixed. Same for uslot. */

@@ -20,14 +20,18 @@ import numpy as np
 # quadrature tables  (/root/reference/src/utils.py:4-81)
 # --------------------------------------------------------------------------------------
 
-def interval_gauss_points(order=1, dtype=np.float64):
-    """utils.py:4-11 -- raw Gauss-Legendre on [-1,1] (Q3: *not* mapped to [0,1])."""
+def interval_gauss_points(order=1, dtype=np.float64, unit_interval=False):
+    """utils.py:4-11 -- raw Gauss-Legendre on [-1,1] (Q3: *not* mapped to [0,1]).
+    unit_interval=True: the correct-math variant (points and weights mapped to [0,1]), not the reference's."""
     xi, wi = np.polynomial.legendre.leggauss(order)
+    if unit_interval:
+        xi, wi = 0.5 * (xi + 1.0), 0.5 * wi
     return xi.astype(dtype), wi.astype(dtype)
 
 
-def triangle_gauss_points(order=1, dtype=np.float64):
-    """utils.py:13-81 -- orders 1,3,4,6,7; orders 4 and 6 carry the extra 0.5 (Q2)."""
+def triangle_gauss_points(order=1, dtype=np.float64, fix_weights=False):
+    """utils.py:13-81 -- orders 1,3,4,6,7; orders 4 and 6 carry the extra 0.5 (Q2).
+    fix_weights=True: the correct-math variant (orders 4 and 6 sum to the triangle area 0.5), not the reference's."""
     if order == 1:
         rs = [[1 / 3, 1 / 3]]
         w = [0.5]
@@ -53,7 +57,7 @@ def triangle_gauss_points(order=1, dtype=np.float64):
     # the reference builds the table in `dtype` and multiplies by python 0.5 in that dtype
     rs = np.asarray(rs, dtype=dtype)
     w = np.asarray(w, dtype=dtype)
-    if order in (4, 6, 7):
+    if order in (4, 6, 7) and not (fix_weights and order in (4, 6)):
         w = (np.asarray(0.5, dtype=dtype) * w).astype(dtype)
     return rs, w
 
@@ -80,8 +84,9 @@ def assemble_full(free_vals, fixed_vals, free_mask):
     return out
 
 
-def tri_forward_points(coords, U, conn, x_ref, elem_id):
-    """models.py:316-357 -- (u_h, detJ signed, grad_u) at reference points of given elements."""
+def tri_forward_points(coords, U, conn, x_ref, elem_id, jinv_transpose=False):
+    """models.py:316-357 -- (u_h, detJ signed, grad_u) at reference points of given elements.
+    jinv_transpose=True: correct-math variant grad_u = dU . J^-1 (i.e. dN/dx = J^-T dN/dxi), not the reference's."""
     n = conn[elem_id]
     v = coords[n]                       # [M,3,2]
     u = U[n]
@@ -98,8 +103,12 @@ def tri_forward_points(coords, U, conn, x_ref, elem_id):
     du0 = u[:, 0] - u[:, 2]
     du1 = u[:, 1] - u[:, 2]
     G = np.empty((n.shape[0], 2, 2), dtype=coords.dtype)
-    G[:, :, 0] = du0 * J00[:, None] + du1 * J01[:, None]
-    G[:, :, 1] = du0 * J10[:, None] + du1 * J11[:, None]
+    if jinv_transpose:
+        G[:, :, 0] = du0 * J00[:, None] + du1 * J10[:, None]
+        G[:, :, 1] = du0 * J01[:, None] + du1 * J11[:, None]
+    else:
+        G[:, :, 0] = du0 * J00[:, None] + du1 * J01[:, None]
+        G[:, :, 1] = du0 * J10[:, None] + du1 * J11[:, None]
     return u_h, det, G
 
 
@@ -121,7 +130,7 @@ def _fold(idx, vals, n):
 
 
 def tri_energy_full(coords, U, conn, C, xg, wg, bg=None, edges=None, xi1=None, w1=None,
-                    t_q=None, dt_dx=None, want_grad=True):
+                    t_q=None, dt_dx=None, want_grad=True, jinv_transpose=False):
     """Total potential  E_dom - E_edge  and its gradient w.r.t. the FULL coords / U arrays.
 
     Restates loss.py:55-116 over models.py:316-376 with SURVEY Appendix A.1.
@@ -145,11 +154,18 @@ def tri_energy_full(coords, U, conn, C, xg, wg, bg=None, edges=None, xi1=None, w
     inv = 1.0 / det
     J00, J01, J10, J11 = d * inv, -b * inv, -c * inv, a * inv       # Jinv
     du0, du1 = U0 - U2, U1 - U2                                       # [Ne,2] (component i)
-    # G[i][j] = sum_m dU[i][m] Jinv[j][m]
-    G00 = du0[:, 0] * J00 + du1[:, 0] * J01
-    G01 = du0[:, 0] * J10 + du1[:, 0] * J11
-    G10 = du0[:, 1] * J00 + du1[:, 1] * J01
-    G11 = du0[:, 1] * J10 + du1[:, 1] * J11
+    if jinv_transpose:
+        # correct-math variant (not the reference's): G = dU . Jinv, i.e. G[i][j] = sum_m dU[i][m] Jinv[m][j]
+        G00 = du0[:, 0] * J00 + du1[:, 0] * J10
+        G01 = du0[:, 0] * J01 + du1[:, 0] * J11
+        G10 = du0[:, 1] * J00 + du1[:, 1] * J10
+        G11 = du0[:, 1] * J01 + du1[:, 1] * J11
+    else:
+        # G[i][j] = sum_m dU[i][m] Jinv[j][m]
+        G00 = du0[:, 0] * J00 + du1[:, 0] * J01
+        G01 = du0[:, 0] * J10 + du1[:, 0] * J11
+        G10 = du0[:, 1] * J00 + du1[:, 1] * J01
+        G11 = du0[:, 1] * J10 + du1[:, 1] * J11
     e0, e1, e2 = G00, G11, G01 + G10
     s0 = C[0, 0] * e0 + C[0, 1] * e1 + C[0, 2] * e2
     s1 = C[1, 0] * e0 + C[1, 1] * e1 + C[1, 2] * e2
@@ -173,20 +189,33 @@ def tri_energy_full(coords, U, conn, C, xg, wg, bg=None, edges=None, xi1=None, w
         q0 = Cs[0, 0] * e0 + Cs[0, 1] * e1 + Cs[0, 2] * e2
         q1 = Cs[1, 0] * e0 + Cs[1, 1] * e1 + Cs[1, 2] * e2
         q2 = Cs[2, 0] * e0 + Cs[2, 1] * e1 + Cs[2, 2] * e2
-        # P = d psi / d G = [[q0,q2],[q2,q1]] ;  M = P . Jinv  (d psi / d dU)
-        M00 = q0 * J00 + q2 * J10
-        M01 = q0 * J01 + q2 * J11
-        M10 = q2 * J00 + q1 * J10
-        M11 = q2 * J01 + q1 * J11
+        # P = d psi / d G = [[q0,q2],[q2,q1]] ;  M = d psi / d dU = P . Jinv  (P . Jinv^T in the correct-math variant)
+        if jinv_transpose:
+            M00 = q0 * J00 + q2 * J01
+            M01 = q0 * J10 + q2 * J11
+            M10 = q2 * J00 + q1 * J01
+            M11 = q2 * J10 + q1 * J11
+        else:
+            M00 = q0 * J00 + q2 * J10
+            M01 = q0 * J01 + q2 * J11
+            M10 = q2 * J00 + q1 * J10
+            M11 = q2 * J01 + q1 * J11
         AW = A * W
         gU0 = np.stack([AW * M00, AW * M10], 1) - A[:, None] * Fb[0]
         gU1 = np.stack([AW * M01, AW * M11], 1) - A[:, None] * Fb[1]
         gU2 = -np.stack([AW * (M00 + M01), AW * (M10 + M11)], 1) - A[:, None] * Fb[2]
-        # d psi / d J = -M^T G
-        K00 = -(M00 * G00 + M10 * G10)
-        K01 = -(M00 * G01 + M10 * G11)
-        K10 = -(M01 * G00 + M11 * G10)
-        K11 = -(M01 * G01 + M11 * G11)
+        if jinv_transpose:
+            # d psi / d J = -G^T M   (from dG = -G dJ Jinv)
+            K00 = -(G00 * M00 + G10 * M10)
+            K01 = -(G00 * M01 + G10 * M11)
+            K10 = -(G01 * M00 + G11 * M10)
+            K11 = -(G01 * M01 + G11 * M11)
+        else:
+            # d psi / d J = -M^T G
+            K00 = -(M00 * G00 + M10 * G10)
+            K01 = -(M00 * G01 + M10 * G11)
+            K10 = -(M01 * G00 + M11 * G10)
+            K11 = -(M01 * G01 + M11 * G11)
         sd = s * dens
         # d|det|/dJ = s * [[d,-c],[-b,a]]
         D00 = sd * d + AW * K00

@@ -54,8 +54,9 @@ class TriPort:
         return _assemble(self.u_free, self.u_fixed, self.umask, self.dmask, self.Nn)
 
 
-def tri_points(m: TriPort, x_ref, elem_id):
-    """models.py:316-357."""
+def tri_points(m: TriPort, x_ref, elem_id, jinv_transpose=False):
+    """models.py:316-357.  jinv_transpose=True: the correct-math variant dN/dx = J^-T dN/dxi (the package's default-off
+    switch), NOT what the reference computes."""
     nodes = m.conn[elem_id]
     v = m.coords()[nodes]
     xi, eta = x_ref[:, 0:1], x_ref[:, 1:2]
@@ -66,7 +67,7 @@ def tri_points(m: TriPort, x_ref, elem_id):
     det = torch.linalg.det(Jm)
     Jinv = torch.linalg.inv(Jm)
     R = torch.tensor([[1., 0., -1.], [0., 1., -1.]], dtype=v.dtype)
-    dN = torch.einsum("mij,jk->mik", Jinv, R)
+    dN = torch.einsum("mji,jk->mik", Jinv, R) if jinv_transpose else torch.einsum("mij,jk->mik", Jinv, R)
     G = torch.einsum("mai,mja->mij", un, dN)
     return u_h, det, G
 
@@ -81,13 +82,13 @@ def tri_edge_points(m: TriPort, xi, edge_id):
     return torch.sum(N.unsqueeze(2) * un, dim=1), torch.norm(x1 - x0, dim=1)
 
 
-def tri_energy(m: TriPort, C, xg, wg, xi1, w1, b_force=None, t_force=None):
+def tri_energy(m: TriPort, C, xg, wg, xi1, w1, b_force=None, t_force=None, jinv_transpose=False):
     """loss.py:55-116."""
     Ne, ng = m.conn.shape[0], xg.shape[0]
     x_eval = xg.unsqueeze(0).expand(Ne, ng, 2).reshape(-1, 2)
     elem_id = torch.arange(Ne).unsqueeze(1).repeat(1, ng).reshape(-1)
     wflat = wg.unsqueeze(0).repeat(Ne, 1).reshape(-1)
-    u_h, det, G = tri_points(m, x_eval, elem_id)
+    u_h, det, G = tri_points(m, x_eval, elem_id, jinv_transpose)
     eps = torch.stack([G[:, 0, 0], G[:, 1, 1], 2 * (0.5 * (G[:, 0, 1] + G[:, 1, 0]))], dim=1)
     sig = eps @ C.T
     psi = 0.5 * torch.sum(eps * sig, dim=1)

@@ -324,3 +324,36 @@ def test_peer_tables_emulated_exchange(world, mode):
         assert relmax(loc[r][1], full_gx[idx][loc[r][3]]) < 1e-12
         assert relmax(loc[r][2], full_gu[idx][loc[r][4]]) < 1e-12
     assert abs(sum(l[0] for l in loc) - gl) <= 1e-12 * abs(gl)
+
+
+def test_sharded_lbfgs_strong_wolfe_follows_the_stock_optimiser():
+    """ShardedLBFGS(line_search_fn="strong_wolfe") on one process: same trajectory as torch.optim.LBFGS with its
+    strong-Wolfe line search (both the two-loop and the vector-free form); FP32 history stays within single precision."""
+    from hidenn_fem_b200.optim import ShardedLBFGS
+    torch.manual_seed(0)
+    A = torch.randn(40, 40, dtype=torch.float64)
+    A = A @ A.T + torch.eye(40, dtype=torch.float64)
+    b = torch.randn(40, dtype=torch.float64)
+    f = lambda x: 0.5 * x @ A @ x - b @ x + 0.1 * (x ** 4).sum()
+
+    def run(make):
+        x = torch.nn.Parameter(torch.zeros(40, dtype=torch.float64))
+        o = make([x])
+        tr = []
+        for _ in range(4):
+            def c():
+                o.zero_grad()
+                l = f(x)
+                l.backward()
+                return l
+            tr.append(float(o.step(c).detach()))
+        return tr, x.detach().clone()
+    kw = dict(max_iter=8, history_size=10, line_search_fn="strong_wolfe")
+    ref_tr, ref_x = run(lambda p: torch.optim.LBFGS(p, **kw))
+    assert ref_tr[-1] < ref_tr[1] < ref_tr[0] + 1e-12
+    for extra, tol in ((dict(), 1e-12), (dict(vector_free=True), 1e-12), (dict(history_dtype=torch.float32), 1e-6)):
+        tr, x = run(lambda p: ShardedLBFGS(p, **kw, **extra))
+        assert np.allclose(tr[1:], ref_tr[1:], rtol=tol, atol=0), (extra, tr, ref_tr)
+        assert float((x - ref_x).abs().max()) < 1e3 * tol
+    with pytest.raises(RuntimeError):
+        ShardedLBFGS([torch.nn.Parameter(torch.zeros(2))], line_search_fn="armijo")

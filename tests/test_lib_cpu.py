@@ -230,7 +230,7 @@ def test_bench_reference_arm_prints_one_contract_line():
     import bench
     assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT
     assert d["config"]["workload"] == bench.WORKLOAD and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["value"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
@@ -357,3 +357,51 @@ def test_paired_layout_interpreted_on_the_host(tile_nodes, invert, monkeypatch):
             assert flat == sorted(incident[loc[l]]), (t, l)
             assert [min(s) for s in got] == sorted(min(s) for s in got)          # ascending first element id
     assert (energy_owner == 1).all()
+
+
+def test_ingest_mesh_matches_the_reference_rules():
+    """meshgen.ingest_mesh (raw triangulation -> the reference's 6-tuple): the Neumann edges equal the reference's rule
+    restated directly (/root/reference/src/mesh.py:125-134: unique sorted element edges with both nodes in mn_mask), the
+    face masks follow mesh.py:108-124, the geometric boundary mask (topological here) marks the outer rectangle and the
+    hole rims, and the renumbered output is the same mesh (tile-ordered for the plan)."""
+    from hidenn_fem_b200 import meshgen
+    from hidenn_fem_b200.plan import TriPlan
+    m = meshgen.plate_mesh(81, 41, jitter=0.25, diag="random", seed=2, ordering="random")
+    xy, conn = m.node_coords, m.connectivity
+    bnd = {"left": 1, "right": 2, "up": 0}
+    c0, k0, g0, b0, n0, e0, _ = meshgen.ingest_mesh(xy, conn, 2.0, 1.0, bnd, reorder=None)
+    all_edges = np.sort(np.vstack([conn[:, [0, 1]], conn[:, [1, 2]], conn[:, [2, 0]]]), axis=1)
+    uniq = np.unique(all_edges, axis=0)
+    mn = np.abs(xy[:, 0] - 2.0) < 1e-6
+    assert np.array_equal(n0.numpy(), mn) and np.array_equal(b0.numpy(), np.abs(xy[:, 0]) < 1e-6)
+    assert np.array_equal(e0.numpy(), uniq[np.all(mn[uniq], axis=1)])
+    cnt = {}
+    for a, b in all_edges:
+        cnt[(a, b)] = cnt.get((a, b), 0) + 1
+    on_boundary = np.zeros(xy.shape[0], bool)
+    for (a, b), c in cnt.items():
+        if c == 1:
+            on_boundary[a] = on_boundary[b] = True
+    assert np.array_equal(g0.numpy(), on_boundary) and np.array_equal(on_boundary, m.boundary_mask)
+    # with the default renumbering: same mesh, tile-ordered
+    c1, k1, g1, b1, n1, e1, n2o = meshgen.ingest_mesh(xy, conn, 2.0, 1.0, bnd, tile_nodes=64)
+    assert np.array_equal(c1.numpy(), xy[n2o]) and np.array_equal(g1.numpy(), on_boundary[n2o]) and np.array_equal(n1.numpy(), mn[n2o])
+    assert sorted(map(tuple, np.sort(n2o[e1.numpy()], axis=1).tolist())) == sorted(map(tuple, e0.numpy().tolist()))
+    key = lambda X, K: sorted(map(tuple, np.round(X[K].reshape(K.shape[0], 6), 12).tolist()))
+    assert key(c1.numpy(), k1.numpy()) == key(xy, conn)                       # same triangles, same corner order
+    plan = TriPlan(k1, c1.shape[0], c1.numpy(), g1, b1, e1, tile_nodes=64, real_bytes=8, device=-1)
+    assert plan.info["tile_ordered"]
+
+
+def test_plan_warns_on_a_numbering_without_locality():
+    import warnings
+    from hidenn_fem_b200 import meshgen
+    from hidenn_fem_b200.plan import TriPlan
+    for ordering, expect in (("random", True), ("morton", False), ("natural", False)):
+        m = meshgen.plate_mesh(241, 121, jitter=0.25, diag="random", seed=0, ordering=ordering)
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            plan = TriPlan(m.connectivity, m.node_coords.shape[0], m.node_coords, m.boundary_mask, m.dirichlet_mask, m.neumann_edges,
+                           real_bytes=8, device=-1)
+        hit = [x for x in w if "no locality" in str(x.message)]
+        assert bool(hit) == expect, (ordering, plan.info["runs_per_tile"], plan.info["local_per_tile"])

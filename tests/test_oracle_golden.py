@@ -162,3 +162,37 @@ def test_structured_closed_form(tag, ftag):
     dpy = cf.grid_1d_backward(dgy, g[k + "_py"], ay)
     gtol = 1e-10 if dt == np.float64 else 2e-3
     assert relmax(dpx, g[k + "_gpx"]) < gtol and relmax(dpy, g[k + "_gpy"]) < gtol
+
+
+def test_correct_math_variants_of_the_oracle():
+    """The default-off correct-math switches (J^-T, proper order-4/6 weights, [0,1] edge rule) have their own oracle
+    variants: the closed form agrees with torch autograd over the same op sequence, a linear field on skew triangles
+    returns its exact gradient (SURVEY Q1's counter-example is fixed), and the quadrature tables integrate 1 exactly."""
+    import torch
+    from oracle import torch_port as tp
+    from hidenn_fem_b200 import meshgen
+    m = meshgen.plate_mesh(13, 9, jitter=0.3, diag="random", seed=1, ordering="random")
+    rng = np.random.default_rng(0)
+    U = rng.standard_normal(m.node_coords.shape) * 1e-3
+    C = cf.plane_stress_C()
+    for order in (4, 6):
+        assert abs(cf.triangle_gauss_points(order, fix_weights=True)[1].sum() - 0.5) < 1e-12
+        assert abs(cf.triangle_gauss_points(order)[1].sum() - 0.25) < 1e-12                 # the reference's tables are untouched
+    xg, wg = cf.triangle_gauss_points(4, fix_weights=True)
+    xi1, w1 = cf.interval_gauss_points(2, unit_interval=True)
+    assert abs(w1.sum() - 1.0) < 1e-15 and (xi1 > 0).all() and (xi1 < 1).all()
+    lo, dX, dU = cf.tri_energy_full(m.node_coords, U, m.connectivity, C, xg, wg, None, m.neumann_edges, xi1, w1, jinv_transpose=True)
+    T = torch.tensor
+    none = np.zeros(m.node_coords.shape[0], bool)
+    port = tp.TriPort(T(m.node_coords), T(m.connectivity), T(none), T(none), 0.0, T(m.neumann_edges), u_free=T(U))
+    l = tp.tri_energy(port, T(C), T(xg), T(wg), T(xi1), T(w1), jinv_transpose=True)
+    l.backward()
+    assert abs(float(l.detach()) - lo) <= 1e-13 * abs(lo)
+    assert relmax(dX, port.x_free.grad.numpy()) < 1e-13 and relmax(dU, port.u_free.grad.numpy()) < 1e-13
+    A = np.array([[3.0, 5.0], [7.0, 11.0]])
+    Ne = m.connectivity.shape[0]
+    xr = np.full((Ne, 2), 1.0 / 3.0)
+    _, _, G = cf.tri_forward_points(m.node_coords, m.node_coords @ A.T, m.connectivity, xr, np.arange(Ne), jinv_transpose=True)
+    assert np.abs(G - A).max() < 1e-11
+    _, _, Gq = cf.tri_forward_points(m.node_coords, m.node_coords @ A.T, m.connectivity, xr, np.arange(Ne))
+    assert np.abs(Gq - A).max() > 0.1                                                      # the reference's J^-1 does not

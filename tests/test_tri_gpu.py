@@ -571,3 +571,94 @@ def test_paired_layout_opt_in(monkeypatch):
     assert abs(loss.item() - float(lo)) <= 1e-10 * abs(float(lo))
     assert relmax(model.node_coords_free.grad.cpu().numpy(), dX[fm]) < 1e-10
     assert relmax(model.u_free.grad.cpu().numpy(), dU[um]) < 1e-10
+
+
+@pytest.mark.parametrize("numbering", ["as_is", "tiles"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_correct_math_switches(numbering, dtype):
+    """Default-off switches (reference models.py:351, utils.py:31-55, loss.py:96-103 fixed): jinv_transpose on the model,
+    fix_weights / edge_rule_unit on the loss.  CUDA vs the oracle's correct-math variant; a linear displacement field
+    returns its exact gradient from forward(); a patch test gives strain energy = area x psi exactly."""
+    from hidenn_fem_b200.models import PiecewiseLinearShapeNN2D
+    from hidenn_fem_b200.loss import EnergyLoss2D
+    g = _mesh_case(40_000, dtype, "tiles" if numbering == "tiles" else "random", u_scale=1e-3, invert=0.1)
+    T = torch.tensor
+    model = PiecewiseLinearShapeNN2D(T(g["node_coords"]), T(g["connectivity"]), T(g["boundary_mask"]), T(g["dirichlet_mask"]), 0.0,
+                                     T(g["neumann_edges"]), jinv_transpose=True)
+    model = (model.double() if dtype == torch.float64 else model).cuda()
+    with torch.no_grad():
+        model.u_free.copy_(T(g["u_free"]))
+    loss_fn = EnergyLoss2D(E=10e9, nu=0.3, device=torch.device("cuda"), dtype=dtype, fix_weights=True, edge_rule_unit=True)
+    assert abs(loss_fn.wg.sum().item() - 0.5) < 1e-6 and abs(loss_fn.wg_1d.sum().item() - 1.0) < 1e-6
+    loss = loss_fn(model, forces.b_force_test, None)
+    loss.backward()
+    fm, um = ~g["boundary_mask"], ~g["dirichlet_mask"]
+    coords = cf.assemble_full(g["node_coords_free"], g["node_coords_fixed"], fm).astype(np.float64)
+    U = cf.assemble_full(g["u_free"], np.zeros((int((~um).sum()), 2), g["u_free"].dtype), um).astype(np.float64)
+    xg, wg = cf.triangle_gauss_points(4, np.float64, fix_weights=True)
+    xi1, w1 = cf.interval_gauss_points(2, np.float64, unit_interval=True)
+    C = cf.plane_stress_C(10e9, 0.3, np.float64)
+    lo, dX, dU = cf.tri_energy_full(coords, U, g["connectivity"], C, xg, wg, forces.b_force_np(xg), g["neumann_edges"], xi1, w1,
+                                    jinv_transpose=True)
+    tol = TOL[dtype]
+    assert abs(loss.item() - float(lo)) <= tol * abs(float(lo))
+    assert relmax(model.node_coords_free.grad.cpu().numpy(), dX[fm]) < tol
+    assert relmax(model.u_free.grad.cpu().numpy(), dU[um]) < tol
+    # the reference's own (default) math gives a different answer on the same inputs
+    lq, _, _ = cf.tri_energy_full(coords, U, g["connectivity"], C, *cf.triangle_gauss_points(4, np.float64), forces.b_force_np(xg),
+                                  g["neumann_edges"], *cf.interval_gauss_points(2, np.float64))
+    assert abs(float(lq) - float(lo)) > 1e-3 * abs(float(lo))
+    # linear field u = A x on every node (incl. the Dirichlet ones through u_fixed is not possible: use a free-only model)
+    A = np.array([[3.0, 5.0], [7.0, 11.0]])
+    none = np.zeros(coords.shape[0], bool)
+    m2 = PiecewiseLinearShapeNN2D(T(coords.astype(g["node_coords"].dtype)), T(g["connectivity"]), T(none), T(none), 0.0, None,
+                                  jinv_transpose=True)
+    m2 = (m2.double() if dtype == torch.float64 else m2).cuda()
+    with torch.no_grad():
+        m2.u_free.copy_(T((coords.astype(g["node_coords"].dtype).astype(np.float64) @ A.T)))
+    Ne = g["connectivity"].shape[0]
+    xr = torch.full((Ne, 2), 1.0 / 3.0, device="cuda", dtype=dtype)
+    _, det, G = m2(xr, torch.arange(Ne, device="cuda"))
+    assert (G.detach().cpu().numpy() - A).__abs__().max() < (1e-8 if dtype == torch.float64 else 2e-2)
+    # patch test: constant strain -> E_dom = sum_e |A_e| psi(A) with the fixed weights
+    eps = np.array([A[0, 0], A[1, 1], A[0, 1] + A[1, 0]])
+    psi = 0.5 * eps @ C @ eps
+    area = 0.5 * np.abs(det.detach().double().cpu().numpy()).sum()
+    with torch.no_grad():
+        dom = loss_fn.domain_energy(m2)
+    assert abs(dom.item() - psi * area) <= (1e-9 if dtype == torch.float64 else 1e-4) * psi * area
+
+
+@pytest.mark.parametrize("tag,dtype", [("tri_traj_f64", torch.float64)])
+def test_sharded_lbfgs_with_line_search_on_the_plate(tag, dtype):
+    """examples/example4.py:68-80 with a line search: ShardedLBFGS(line_search_fn="strong_wolfe") on one GPU follows
+    torch.optim.LBFGS(line_search_fn="strong_wolfe") on the C4 trajectory mesh of the golden fixtures, decreases the
+    energy monotonically over the outer steps (the reference's fixed step lr = 1 does not), and the FP32-history and
+    vector-free forms stay on the same trajectory."""
+    from hidenn_fem_b200.optim import ShardedLBFGS
+    g = dict(gold(tag), u_fixed=np.asarray(0.0))
+    loss_fn = loss_of(g, dtype)
+
+    def run(make, steps=4):
+        m = build(g, dtype=dtype)
+        with torch.no_grad():
+            m.u_free.copy_(torch.tensor(g["u_free0"]))
+        o = make(m.parameters())
+        tr = []
+        for _ in range(steps):
+            def closure():
+                o.zero_grad()
+                l = loss_fn(m)
+                l.backward()
+                return l
+            tr.append(o.step(closure).item())
+        with torch.no_grad():
+            tr.append(loss_fn(m).item())
+        return np.asarray(tr), m.u_free.detach().clone()
+    kw = dict(max_iter=6, history_size=8, line_search_fn="strong_wolfe")
+    ref, u_ref = run(lambda p: torch.optim.LBFGS(p, **kw))
+    assert (np.diff(ref) <= 1e-9 * np.abs(ref[:-1])).all()                       # a descent method
+    for extra, tol in ((dict(), 1e-9), (dict(vector_free=True), 1e-9), (dict(history_dtype=torch.float32), 1e-4)):
+        tr, u = run(lambda p: ShardedLBFGS(p, **kw, **extra))
+        assert np.allclose(tr, ref, rtol=tol), (extra, tr, ref)
+        assert relmax(u.cpu().numpy(), u_ref.cpu().numpy()) < 1e3 * tol
