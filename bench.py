@@ -375,14 +375,16 @@ def bench_grid_paths(device, steps, warmup, peak, full_c3=False):
     mg._bar_state.check(block=True)
     out["C2_bar_1M_f64_fused"] = {"ms_per_step": ms, "evals_per_s": (N - 1) * 2 / (ms * 1e-3),
                                   "hbm_frac_informational": 4 * 8 * (N - 1) / (ms * 1e-3) / 1e9 / peak,
-                                  "note": "32 MB working set is L2-resident: launch/latency-bound (8 small kernels)"}
+                                  "note": "eager: fused bar step = 3 launches (+ ones_like fill and grad_output scale of autograd)"}
 
     from hidenn_fem_b200.graph import GraphedStep
     g2 = GraphedStep(m1, lambda: mg.bar_energy_loss(m1, xi, wi, None, 175.0, b_builtin=True))
     ms = time_loop(lambda: g2(), steps, warmup)
     mg._bar_state.check(block=True)
     out["C2_bar_1M_f64_fused_graph_replay"] = {"ms_per_step": ms, "evals_per_s": (N - 1) * 2 / (ms * 1e-3),
-                                               "hbm_frac_informational": 4 * 8 * (N - 1) / (ms * 1e-3) / 1e9 / peak}
+                                               "hbm_frac_informational": 4 * 8 * (N - 1) / (ms * 1e-3) / 1e9 / peak,
+                                               "note": "32 MB working set is L2-resident; the step is bound by the FP64 exponentials of "
+                                                       "the example's body force (4 per element) and the softplus / sigmoid of the grid"}
     del g2
 
     def step_c2g():
@@ -596,8 +598,10 @@ def main():
     alg_bytes = 12 * ne_local + 2 * sz * (2 * nn_local) + 2 * sz * (nfree_x + nfree_u)
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": ("tri_tile8_kernel (bulk-copy staging, tile-ordered numbering)" if plan.info.get("tile_ordered")
-                                            else "tri_tile_persistent_kernel<%s>" % ("double" if sz == 8 else "float")),
+                "traffic": None, "kernel": {9: "tri_tile9_kernel<double> (warp-specialised: 12 element warps, 11 fold warps, 1 loader warp; "
+                                               "bulk-copy stage ring; tile-ordered numbering)",
+                                            8: "tri_tile8_kernel<double> (two CTAs per SM, bulk-copy staging; tile-ordered numbering)"}.get(
+                                                plan.info.get("kernel"), "tri_tile_persistent_kernel<%s>" % ("double" if sz == 8 else "float")),
                 "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
                 "bytes_per_element": alg_bytes / ne_local, "peak_source": peak_src}
     # DRAM bytes of one launch from the committed ncu capture -- only if that capture was made from the kernel sources
@@ -696,12 +700,12 @@ def main():
             "loss": loss_val,
             "sustained": sustained,
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": args.steps * ((2 if plan.info.get("tile_ordered") else 3) + (5 if world > 1 else 0)),
-            "gpu_launches_note": ("per step: tri_tile8_kernel (edges + final reduction inside) + scale_inplace2_kernel"
+            "gpu_launches": args.steps * ((1 if plan.info.get("tile_ordered") else 2) + (2 if world > 1 else 0)),
+            "gpu_launches_note": ("per replayed step: the tile kernel (Neumann edges, final reduction and the loss exchange inside)"
                                   if plan.info.get("tile_ordered") else
-                                  "per step: tri_tile_persistent_kernel + tri_edge_finalize_kernel + scale_inplace2_kernel")
-                                 + (" + second tile range + finish + halo_p2p push / pull / loss (peer-memory exchange; "
-                                    "pack_all + NCCL all-reduce + unpack_all with HIDENN_HALO=nccl)" if world > 1 else ""),
+                                  "per replayed step: tri_tile_persistent_kernel + tri_edge_finalize_kernel")
+                                 + (" + halo_p2p push + pull on a side stream (peer-memory exchange; pack_all + NCCL all-reduce + "
+                                    "unpack_all after the replay with HIDENN_HALO=nccl)" if world > 1 else ""),
         }
         if other is not None:
             line["other_configs"] = other      # BASELINE configs C2 (1D bar, 1 M elements) and C3 (structured L2, 4097^2 nodes)

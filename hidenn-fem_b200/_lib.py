@@ -54,7 +54,7 @@ def lib():
         if name in ("hidenn_last_error", "hidenn_tri_plan_destroy"):
             continue
         getattr(L, name).restype = c_int
-    for name in ("hidenn_1d_scratch_size", "hidenn_q1_l2_partials", "hidenn_halo_p2p_bytes"):
+    for name in ("hidenn_1d_scratch_size", "hidenn_q1_l2_partials", "hidenn_halo_p2p_bytes", "hidenn_1d_bar_step_scratch"):
         getattr(L, name).restype = C.c_int64
     L.hidenn_tri_plan_destroy.restype = None
     L.hidenn_tri_plan_destroy.argtypes = [c_void_p]

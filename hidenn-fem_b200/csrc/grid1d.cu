@@ -8,7 +8,7 @@ namespace hidenn {
 
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
-constexpr int kScanChunk = kScanThreads * kScanItems;   // 2048 items per block
+constexpr int kScanChunk = kScanThreads * kScanItems;   // items per block
 
 template <typename R> __device__ __forceinline__ R softplus_inc(R p) {
     // torch.clamp(F.softplus(p), min=1e-6): softplus with beta=1, threshold=20
@@ -45,6 +45,13 @@ template <typename R> __device__ __forceinline__ R block_excl_scan(R v, R* s_war
     const R r = s_warp[w] + inc - v;
     __syncthreads();
     return r;
+}
+
+// inclusive prefix of item i as every kernel defines it: the running sum inside a block, the scanned offset of the next
+// block at a block's last item (partial[nb] = S at the last item of the array)
+template <typename R>
+__device__ __forceinline__ R canonical_cum(R run, int64_t i, int64_t n, const R* __restrict__ partial, int64_t b) {
+    return (i == n - 1 || ((i + 1) % kScanChunk) == 0) ? partial[b + 1] : run;
 }
 
 // ---- phase a: per-block sums of up to two channels -----------------------------------------------------
@@ -117,8 +124,11 @@ grid_fwd_final_kernel(const R* __restrict__ p, int64_t n, const R* __restrict__ 
         const int64_t i = base + k;
         run += v[k];
         if (i < n) {
-            cum[i] = run;
-            grid[i + 1] = x0 + L * run / S;
+            // canonical value at the end of a block (and of the array): the scanned offset of the next block, so that
+            // every kernel that recomputes the prefix (bar_step_energy_kernel) sees the same bits, and cum[n-1] == S
+            const R c = canonical_cum<R>(run, i, n, partial, blockIdx.x);
+            cum[i] = c;
+            grid[i + 1] = x0 + L * c / S;
         }
     }
 }
@@ -247,12 +257,13 @@ fold1d_nodes_kernel(const R* __restrict__ elem_tmp, int64_t N, R* __restrict__ d
 
 // ---- fused bar energy ------------------------------------------------------------------------------------
 template <typename R> __device__ __forceinline__ R example3_b(R x) {
-    // examples/example3.py:16-24 (IEEE semantics: exp overflow -> inf -> N/D = 0)
+    // examples/example3.py:16-24: -N1/D1 - N2/D2 with D = exp(pi a^2), evaluated as N * exp(-pi a^2): one exponential and no
+    // division per term (the step is bound by these FP64 exponentials); underflow -> 0 where the reference's D overflows -> N/inf = 0
     const R pi = R(3.14159265358979323846);
     const R a = x - R(2.5), b = x - R(7.5);
-    const R N1 = R(4) * pi * pi * a * a - R(2) * pi, D1 = exp(pi * a * a);
-    const R N2 = R(8) * pi * pi * b * b - R(4) * pi, D2 = exp(pi * b * b);
-    return -N1 / D1 - N2 / D2;
+    const R N1 = R(4) * pi * pi * a * a - R(2) * pi, E1 = exp(-pi * a * a);
+    const R N2 = R(8) * pi * pi * b * b - R(4) * pi, E2 = exp(-pi * b * b);
+    return -N1 * E1 - N2 * E2;
 }
 
 constexpr int kBarBlock = 256;
@@ -317,6 +328,251 @@ __global__ void __launch_bounds__(1024) sum_partials_kernel(const R* __restrict_
     for (int64_t i = threadIdx.x; i < nb; i += 1024) a += (double)partial[i];
     const double tot = block_sum<double, 1024>(a, s_red);
     if (threadIdx.x == 0) out[0] = (R)tot;
+}
+
+// =========================================================================================================
+// Fused bar step (examples/example3.py:27-70 over models.py:45-90 for an r-adaptive model): grid, energy, d loss/d u and
+// d loss/d increments in THREE launches --
+//   1  block sums of the increments; the last block to finish (integer ticket) scans them          (bar_step_sums)
+//   2  per element: prefix -> both grid values -> quadrature -> energy and the four nodal pieces; nodes finalised in
+//      registers / shared memory / one recomputed overlap element per block; block sums of gamma = d loss/d grid[1:]
+//      and gamma*cum; the last block scans them and adds the energy partials in fixed order          (bar_step_energy)
+//   3  the softplus / cumsum / normalise chain: d loss/d increments                                  (grid_bwd_final)
+// Scratch (reals): part0 [nb+1] | part1 [nb+1] | part2 [nb+1] | partE [nb] | 2 tickets (as reals' storage).
+// u_free holds the trainable values; node k reads u_free[k - has_u0] (u0 / uN: fixed end values or NULL).
+// =========================================================================================================
+template <typename R> __device__ __forceinline__ void scan_partials_block(R* __restrict__ p, int64_t nb, R* s_warp) {
+    R carry = R(0);
+    for (int64_t base = 0; base < nb; base += kScanThreads) {
+        const int64_t i = base + threadIdx.x;
+        const R v = i < nb ? p[i] : R(0);
+        R tot;
+        const R ex = block_excl_scan<R>(v, s_warp, &tot);
+        if (i < nb) p[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) p[nb] = carry;
+    __syncthreads();
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kScanThreads)
+bar_step_sums_kernel(const R* __restrict__ p, int64_t n, R* __restrict__ part0, int64_t nb, unsigned* __restrict__ ticket,
+                     int32_t* __restrict__ flag) {
+    __shared__ R s_warp[kScanThreads / 32 + 1];
+    __shared__ unsigned s_last;
+    const int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
+    R s0 = R(0);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = base + k;
+        if (i < n) s0 += softplus_inc<R>(p[i]);
+    }
+    R tot;
+    block_excl_scan<R>(s0, s_warp, &tot);
+    if (threadIdx.x == 0) {
+        part0[blockIdx.x] = tot;
+        if (blockIdx.x == 0) *flag = 0;
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        scan_partials_block<R>(part0, nb, s_warp);
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
+template <typename R>
+__device__ __forceinline__ void bar_element(const R ge, const R gp, const R ue, const R up, const int64_t e, const int64_t N,
+                                            const R* __restrict__ xi, const R* __restrict__ wi, const int ng, const R E,
+                                            const R* __restrict__ b_table, int32_t* __restrict__ flag, R& en, R& lu, R& lg, R& ru, R& rg) {
+    const R hd = gp - ge;                           // detached spacing used for xq, wq (example3.py:41-52)
+    const bool act = hd >= R(1e-10);
+    const R h = act ? hd : R(1e-10);
+    const R ih = R(1) / h;
+    const R dudx = (up - ue) * ih;
+    en = lu = lg = ru = rg = R(0);
+    for (int q = 0; q < ng; ++q) {
+        const R xq = R(0.5) * hd * xi[q] + R(0.5) * (gp + ge);
+        const R wq = R(0.5) * hd * wi[q];
+        const bool ok = (ge < xq || e == 0) && (xq <= gp || e == N - 2);
+        if (!ok) *flag = 1;
+        const R b = b_table ? b_table[e * ng + q] : example3_b<R>(xq);
+        const R N1 = (gp - xq) * ih, N2 = (xq - ge) * ih;
+        const R u = ue * N1 + up * N2;
+        en += wq * (R(0.5) * E * dudx * dudx - b * u);
+        const R r_u = -wq * b, r_s = wq * E * dudx;
+        const R num = ue * (gp - xq) + up * (xq - ge);
+        const R qq = act ? num * ih * ih : R(0);
+        const R sl = act ? (up - ue) * ih * ih : R(0);
+        lu += r_u * N1 - r_s * ih;
+        ru += r_u * N2 + r_s * ih;
+        lg += r_u * (-up * ih + qq) + r_s * sl;
+        rg += r_u * (ue * ih - qq) - r_s * sl;
+    }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kScanThreads)
+bar_step_energy_kernel(const R* __restrict__ p, int64_t n, const R* __restrict__ x0p, const R* __restrict__ xNp,
+                       const R* __restrict__ u_free, const R* __restrict__ u0p, const R* __restrict__ uNp, const R* __restrict__ xi,
+                       const R* __restrict__ wi, int ng, R E, const R* __restrict__ b_table, R* __restrict__ part0, int64_t nb,
+                       R* __restrict__ gam, R* __restrict__ du_free, R* __restrict__ loss, unsigned* __restrict__ ticket,
+                       int32_t* __restrict__ flag) {
+    __shared__ R s_warp[kScanThreads / 32 + 1];
+    __shared__ R s_c[kScanThreads], s_lu[kScanThreads], s_lg[kScanThreads];
+    __shared__ double s_red[kScanThreads / 32];
+    __shared__ unsigned s_last;
+    R* part1 = part0 + (nb + 1);
+    R* part2 = part1 + (nb + 1);
+    R* partE = part2 + (nb + 1);
+    const int64_t N = n + 1;                      // nodes
+    const int t = threadIdx.x;
+    const int64_t b = blockIdx.x;
+    const int64_t base = b * kScanChunk + (int64_t)t * kScanItems;
+    const int has_u0 = u0p != nullptr;
+    auto u_at = [&](int64_t k) -> R {
+        if (k == 0 && u0p) return *u0p;
+        if (k == N - 1 && uNp) return *uNp;
+        return u_free[k - has_u0];
+    };
+    R v[kScanItems], c[kScanItems];
+    R s = R(0);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = base + k;
+        v[k] = i < n ? softplus_inc<R>(p[i]) : R(0);
+        s += v[k];
+    }
+    R tot;
+    R run = block_excl_scan<R>(s, s_warp, &tot) + part0[b];
+    const R S = part0[nb], x0 = *x0p, L = *xNp - *x0p;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = base + k;
+        run += v[k];
+        c[k] = i < n ? canonical_cum<R>(run, i, n, part0, b) : R(0);
+    }
+    s_c[t] = c[kScanItems - 1];
+    __syncthreads();
+    // left grid value of the thread's first element: canonical prefix of the item before it
+    const R c_left = base == 0 ? R(0) : (t == 0 ? part0[b] : s_c[t - 1]);
+    R gl = base == 0 ? x0 : x0 + L * c_left / S;
+    R ul = base < n ? u_at(base) : R(0);
+    R en_acc = R(0), g1 = R(0), g2 = R(0);
+    R gamma[kScanItems];
+    R first_lu = R(0), first_lg = R(0);
+    R prev_ru = R(0), prev_rg = R(0);             // right pieces of the previous element, waiting for the next one's left pieces
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = base + k;
+        gamma[k] = R(0);
+        if (i < n) {
+            const R gr = x0 + L * c[k] / S;
+            const R ur = u_at(i + 1);
+            R en, lu, lg, ru, rg;
+            bar_element<R>(gl, gr, ul, ur, i, N, xi, wi, ng, E, b_table, flag, en, lu, lg, ru, rg);
+            en_acc += en;
+            if (k == 0) { first_lu = lu; first_lg = lg; }
+            else {      // node i (between elements i-1 and i) is complete
+                gamma[k - 1] = lg + prev_rg;
+                const R dun = lu + prev_ru;
+                if (!(i == N - 1 && uNp)) du_free[i - has_u0] = dun;
+            }
+            prev_ru = ru; prev_rg = rg;
+            gl = gr; ul = ur;
+        }
+    }
+    s_lu[t] = first_lu; s_lg[t] = first_lg;
+    __syncthreads();
+    {
+        // node after the thread's last element: left pieces from the next thread, from the recomputed first element of the
+        // next block (last thread), or nothing (last element of the bar)
+        const int64_t ilast = min(base + kScanItems, n) - 1;        // last element of this thread
+        if (base < n) {
+            R nlu = R(0), nlg = R(0);
+            const int64_t inext = ilast + 1;
+            if (inext < n) {
+                if (t + 1 < kScanThreads && base + kScanItems < (b + 1) * (int64_t)kScanChunk && inext == base + kScanItems) {
+                    nlu = s_lu[t + 1]; nlg = s_lg[t + 1];
+                } else {
+                    // first element of the next block: same canonical prefix as that block computes
+                    const R cn = canonical_cum<R>(part0[b + 1] + softplus_inc<R>(p[inext]), inext, n, part0, b + 1);
+                    R en, ru, rg;
+                    bar_element<R>(gl, x0 + L * cn / S, ul, u_at(inext + 1), inext, N, xi, wi, ng, E, b_table, flag, en, nlu, nlg, ru, rg);
+                }
+            }
+            const int kl = (int)(ilast - base);
+            const R gnode = nlg + prev_rg, dun = nlu + prev_ru;
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k)
+                if (k == kl) gamma[k] = gnode;
+            const int64_t node = ilast + 1;
+            if (!(node == N - 1 && uNp)) du_free[node - has_u0] = dun;
+            if (base == 0 && !u0p) du_free[0] = first_lu;          // node 0 has one element
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = base + k;
+        if (i < n) { gam[i] = gamma[k]; g1 += gamma[k]; g2 += gamma[k] * c[k]; }
+    }
+    R t1, t2;
+    block_excl_scan<R>(g1, s_warp, &t1);
+    block_excl_scan<R>(g2, s_warp, &t2);
+    const double eb = block_sum<double, kScanThreads>((double)en_acc, s_red);
+    if (t == 0) {
+        part1[b] = t1; part2[b] = t2; partE[b] = (R)eb;
+        __threadfence();
+        s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        scan_partials_block<R>(part1, nb, s_warp);            // exclusive prefix of gamma per block, total at [nb]
+        scan_partials_block<R>(part2, nb, s_warp);            // only the total T = sum gamma*cum at [nb] is used
+        double a = 0.0;
+        for (int64_t i = t; i < nb; i += kScanThreads) a += (double)partE[i];
+        const double e_tot = block_sum<double, kScanThreads>(a, s_red);
+        if (t == 0) { loss[0] = (R)e_tot; *ticket = 0u; }
+    }
+}
+
+// phase 3: d loss / d increments from gamma, the prefix offsets of gamma (part1), T (part2[nb]) and S (part0[nb])
+template <typename R>
+__global__ void __launch_bounds__(kScanThreads)
+bar_step_chain_kernel(const R* __restrict__ gam, const R* __restrict__ p, int64_t n, const R* __restrict__ x0p, const R* __restrict__ xNp,
+                      const R* __restrict__ part0, int64_t nb, R* __restrict__ dp) {
+    __shared__ R s_warp[kScanThreads / 32 + 1];
+    const R* part1 = part0 + (nb + 1);
+    const R* part2 = part1 + (nb + 1);
+    const int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
+    R g[kScanItems];
+    R s = R(0);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = base + k;
+        g[k] = i < n ? gam[i] : R(0);
+        s += g[k];
+    }
+    R tot;
+    R run = block_excl_scan<R>(s, s_warp, &tot) + part1[blockIdx.x];
+    const R G = part1[nb], T = part2[nb], S = part0[nb], L = *xNp - *x0p;
+    const R c = L / S, corr = L * T / (S * S);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = base + k;
+        if (i < n) {
+            const R dinc = c * (G - run) - corr;
+            const R pi = p[i];
+            const R sp = softplus_raw<R>(pi);
+            const R dsp = pi > R(20) ? R(1) : R(1) / (R(1) + exp(-pi));
+            dp[i] = sp >= R(1e-6) ? dinc * dsp : R(0);
+        }
+        run += g[k];
+    }
 }
 
 static inline int grid_for(int64_t n, int block = 256) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + block - 1) / block, 148 * 32)); }
@@ -400,9 +656,27 @@ static int bar_energy(const R* grid, int64_t N, const R* uf, const R* xi, const 
     return 0;
 }
 
+template <typename R>
+static int bar_step(const R* p, int64_t n, const R* x0, const R* xN, const R* u_free, const R* u0, const R* uN, const R* xi, const R* wi,
+                    int ng, R E, const R* b_table, R* loss, R* dp, R* du_free, R* gam, int32_t* flag, R* scratch, void* s) {
+    HIDENN_REQUIRE(n >= 1 && p && x0 && xN && u_free && xi && wi && loss && dp && du_free && gam && flag && scratch, "1d_bar_step: bad arguments");
+    HIDENN_REQUIRE(ng >= 1 && ng <= 8, "1d_bar_step: ng must be in [1,8]");
+    cudaStream_t st = (cudaStream_t)s;
+    const int64_t nb = nblocks_scan(n);
+    unsigned* ticket = reinterpret_cast<unsigned*>(scratch + 3 * (nb + 1) + nb + 2);      // zero before the first call; kernels reset it
+    bar_step_sums_kernel<R><<<(int)nb, kScanThreads, 0, st>>>(p, n, scratch, nb, ticket, flag);
+    bar_step_energy_kernel<R><<<(int)nb, kScanThreads, 0, st>>>(p, n, x0, xN, u_free, u0, uN, xi, wi, ng, E, b_table, scratch, nb, gam, du_free,
+                                                                loss, ticket + 1, flag);
+    bar_step_chain_kernel<R><<<(int)nb, kScanThreads, 0, st>>>(gam, p, n, x0, xN, scratch, nb, dp);
+    HIDENN_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace hidenn
 
 using namespace hidenn;
+
+extern "C" int64_t hidenn_1d_bar_step_scratch(int64_t n) { return 4 * (nblocks_scan(n) + 1) + 16; }
 
 extern "C" int64_t hidenn_1d_scratch_size(int64_t n) {
     const int64_t a = 2 * (nblocks_scan(n) + 1) + 8;
@@ -440,3 +714,14 @@ extern "C" int64_t hidenn_1d_scratch_size(int64_t n) {
 
 HIDENN_GRID1D_API(f64, double)
 HIDENN_GRID1D_API(f32, float)
+
+extern "C" int hidenn_1d_bar_step_f64(const double* p, int64_t n, const double* x0, const double* xN, const double* u_free, const double* u0,
+                                      const double* uN, const double* xi, const double* wi, int ng, double E, const double* b_table,
+                                      double* loss, double* dp, double* du_free, double* gam, int32_t* flag, double* scratch, void* s) {
+    return bar_step<double>(p, n, x0, xN, u_free, u0, uN, xi, wi, ng, E, b_table, loss, dp, du_free, gam, flag, scratch, s);
+}
+extern "C" int hidenn_1d_bar_step_f32(const float* p, int64_t n, const float* x0, const float* xN, const float* u_free, const float* u0,
+                                      const float* uN, const float* xi, const float* wi, int ng, float E, const float* b_table, float* loss,
+                                      float* dp, float* du_free, float* gam, int32_t* flag, float* scratch, void* s) {
+    return bar_step<float>(p, n, x0, xN, u_free, u0, uN, xi, wi, ng, E, b_table, loss, dp, du_free, gam, flag, scratch, s);
+}

@@ -810,6 +810,14 @@ extern "C" int hidenn_tri_energy_overlap_f64(const hidenn_tri_plan* plan, const 
     return tri_energy_launch<double>(plan, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx_free, gu_free, gt_out, scratch,
                                      stream, 0, -1, nullptr, first_done, reserve_sms, peer_bufs ? &A : nullptr);
 }
+// which gradient tile kernel hidenn_tri_energy_* launches for this plan: 7 = tri_tile_persistent_kernel (any numbering,
+// FP64 / FP32), 8 = tri_tile8_kernel, 9 = tri_tile9_kernel (tile-ordered FP64 plans)
+extern "C" int hidenn_tri_plan_kernel(const hidenn_tri_plan* plan) {
+    static const bool ws_off = [] { const char* e = getenv("HIDENN_TILE_WS"); return e && atoi(e) == 0; }();
+    if (!plan) return 0;
+    if (!plan->tile_order) return 7;
+    return (!ws_off && tile9_fits(plan)) ? 9 : 8;
+}
 extern "C" int hidenn_tri_plan_overlap_target(const hidenn_tri_plan* plan) {
     static const bool ws_off = [] { const char* e = getenv("HIDENN_TILE_WS"); return e && atoi(e) == 0; }();
     if (!plan || !plan->tile_order || plan->n_first_tiles <= 0 || ws_off || !tile9_fits(plan)) return 0;

@@ -1,10 +1,11 @@
 """CUDA-graph replay of one energy step (loss forward + backward).
 
-A step of the fused path is 3 launches on one GPU and 6 with the halo exchange (tile kernel, edge/finalize,
-grad_output scale, pack, NCCL all-reduce, unpack); at ~0.25 ms of GPU time per 10 M elements the Python / autograd
-enqueue cost (~0.2 ms) is of the same size and decides multi-GPU scaling.  Capturing the local part of the step once
-and replaying it removes most of that cost.  The halo exchange (when the loss has one) stays outside the graph: one
-pack launch, one eager NCCL all-reduce, one unpack launch after every replay -- no collective is captured.
+A step of the fused path is one launch on one GPU for tile-ordered FP64 plans (tile kernel with the Neumann edges, the
+final reduction and, with several GPUs, the loss exchange in its tail) plus the put / complete kernels of the peer-memory
+halo exchange on a side stream; at ~0.2 ms of GPU time per 10 M elements the Python / autograd enqueue cost (~0.2 ms) is
+of the same size.  Capturing the step once and replaying it removes that cost.  The peer-memory halo exchange
+(dist.HaloP2P) is captured with the step; the NCCL variant stays outside the graph (pack launch, eager all-reduce, unpack
+launch after every replay).
 The parameters keep their storage (optimisers update them in place), the gradients live in buffers owned by the
 graph and are overwritten by every replay -- the usual whole-step capture contract of torch.cuda.graphs.
 """
@@ -22,16 +23,17 @@ class GraphedStep:
     every trainable parameter holds the fresh gradient (same tensors every time) and the returned 0-dim tensor the
     loss.  Gradient accumulation across calls is not available in this mode."""
 
-    def __init__(self, model, fn, warmup: int = 3):
+    def __init__(self, model, fn, warmup: int = 3, one=None):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedStep needs CUDA parameters (no CPU fallback)")
         self.model = model
 
-        def one():
-            loss = fn()
-            loss.backward()
-            return loss
+        if one is None:
+            def one():
+                loss = fn()
+                loss.backward()
+                return loss
 
         # warm-up on a side stream (constant tables, scratch, plan upload), as capture requires
         side = torch.cuda.Stream(device=dev)
@@ -72,8 +74,19 @@ class GraphedEnergyStep(GraphedStep):
             self._halo = None             # peer-memory exchange (dist.HaloP2P): its kernels are part of the captured step
         if self._halo is not None:
             loss_fn.halo = None           # NCCL exchange: the graph holds the rank-local part, the exchange follows each replay
+        def one():
+            # zero_grad(); loss = loss_fn(model); loss.backward() with the implicit grad_output = 1: the fused launch has
+            # already produced d loss / d parameters, so they are attached directly -- no autograd pass, no ones_like fill, no
+            # scale kernel in the replayed step (a frozen Parameter gets no gradient, as in the eager path)
+            loss = loss_fn(model, *loss_fn_args, **loss_fn_kw)
+            gx, gu = loss_fn.last_grads
+            if model.node_coords_free.requires_grad:
+                model.node_coords_free.grad = gx
+            if model.u_free.requires_grad:
+                model.u_free.grad = gu
+            return loss
         try:
-            super().__init__(model, lambda: loss_fn(model, *loss_fn_args, **loss_fn_kw), warmup=warmup)
+            super().__init__(model, None, warmup=warmup, one=one)
             self._parts = loss_fn.last_parts          # [loss, domain, edge, 0] written by the finalize kernel;
         finally:                                      # self.loss is a view of _parts[0]: the exchange completes it in place
             if self._halo is not None:

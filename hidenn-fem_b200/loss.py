@@ -50,6 +50,7 @@ class _TriEnergyFn(torch.autograd.Function):
         ctx.save_for_backward(gx if need_gx else None, gu if need_gu else None)
         ctx.used = False
         loss_obj.last_parts = out
+        loss_obj.last_grads = (gx, gu)       # d loss / d (node_coords_free, u_free) of this evaluation, unscaled (graph.GraphedEnergyStep)
         return out[0]
 
     @staticmethod
@@ -107,6 +108,7 @@ class EnergyLoss2D:
             raise ValueError("gauss_order_1d > 8 is not supported by the edge kernel")
         self._consts_cache = None
         self.last_parts = None     # device tensor [loss, domain, edge, 0] of the latest fused call
+        self.last_grads = (None, None)
 
     def _post_forward(self, model, out, gx, gu):
         """Hook after the fused launch (overridden by dist.DistributedEnergyLoss2D)."""

@@ -261,6 +261,54 @@ class _BarEnergyFn(torch.autograd.Function):
         return dg, du.to(ctx.udtype), None, None, None, None, None
 
 
+class _BarStepFn(torch.autograd.Function):
+    """Fused r-adaptive bar step (hidenn_1d_bar_step_*): grid, energy and both gradients in three launches; backward only
+    applies grad_output (device side, exits at once when it is 1)."""
+
+    @staticmethod
+    @_lib.on_device
+    def forward(ctx, p, u, x0, xN, u0, uN, xi, wi, E, b_table, state):
+        _require_cuda(p, "bar_energy")
+        dt, dev = p.dtype, p.device
+        pc, uc = p.contiguous(), u.to(dt).contiguous().reshape(-1)
+        n = pc.shape[0]
+        x0c, xNc = x0.to(dt).contiguous(), xN.to(dt).contiguous()
+        u0c = None if u0 is None else u0.to(device=dev, dtype=dt).contiguous()
+        uNc = None if uN is None else uN.to(device=dev, dtype=dt).contiguous()
+        loss = torch.empty(1, device=dev, dtype=dt)
+        dp, du, gam = torch.empty_like(pc), torch.empty_like(uc), torch.empty_like(pc)
+        flag = torch.empty(1, device=dev, dtype=torch.int32)
+        key = ("bar_step", n, dev, dt, torch.cuda.current_stream(dev).cuda_stream)
+        sc = _scratch_cache.get(key)
+        if sc is None:
+            sc = torch.zeros(int(_lib.lib().hidenn_1d_bar_step_scratch(c_i64(n))), device=dev, dtype=dt)     # tickets start at zero
+            _scratch_cache[key] = sc
+        Ec = C.c_double(float(E)) if dt == torch.float64 else C.c_float(float(E))
+        _lib.check(_lib.fn("hidenn_1d_bar_step", dt)(
+            _lib.ptr(pc), c_i64(n), _lib.ptr(x0c), _lib.ptr(xNc), _lib.ptr(uc), _lib.ptr(u0c), _lib.ptr(uNc), _lib.ptr(xi), _lib.ptr(wi),
+            C.c_int(int(xi.numel())), Ec, _lib.ptr(b_table), _lib.ptr(loss), _lib.ptr(dp), _lib.ptr(du), _lib.ptr(gam), _lib.ptr(flag),
+            _lib.ptr(sc), _lib.stream_ptr()))
+        state.note_flag(flag)
+        ctx.save_for_backward(dp, du)
+        ctx.ushape, ctx.udtype = u.shape, u.dtype
+        ctx.used = False
+        return loss[0]
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    @_lib.on_device
+    def backward(ctx, go):
+        if ctx.used:
+            raise RuntimeError("bar_energy_loss: backward called twice on the same loss (the gradient buffers are scaled in place); "
+                               "evaluate the loss again instead")
+        ctx.used = True
+        dp, du = ctx.saved_tensors
+        g1 = go.reshape(1).to(dp.dtype).contiguous()
+        _lib.check(_lib.fn("hidenn_scale_inplace2", dp.dtype)(_lib.ptr(dp), c_i64(dp.numel()), _lib.ptr(du), c_i64(du.numel()),
+                                                              _lib.ptr(g1), _lib.stream_ptr()))
+        return dp, du.reshape(ctx.ushape).to(ctx.udtype), None, None, None, None, None, None, None, None, None
+
+
 class _FlagState:
     """Deferred check of the kernel's degenerate-lookup flag (no host sync on the hot path)."""
 
@@ -317,6 +365,14 @@ def bar_energy_loss(model, xi, wi, b_force, E, L=10.0, b_builtin=False):
     """Fused drop-in for `energy_loss(model, xi, wi, b_force, E, L)` of examples/example3.py:27-70.
     `b_builtin=True` evaluates that example's own b_force (example3.py:16-24) inside the kernel instead of
     calling the Python callable on the [Ne, ng] quadrature points."""
+    fused_step = b_builtin and getattr(model, "r_adapt", False) and model.N > 2 and torch.is_grad_enabled() \
+        and model.x_increments.requires_grad and model.u.requires_grad
+    if fused_step:
+        # the whole step in three launches (no grid / u_full tensors are materialised)
+        p = model.x_increments
+        dt = p.dtype
+        xi_c, wi_c = xi.to(device=p.device, dtype=dt).contiguous(), wi.to(device=p.device, dtype=dt).contiguous()
+        return _BarStepFn.apply(p, model.u, model.x0, model.xN, model.u0_fixed, model.uN_fixed, xi_c, wi_c, E, None, _bar_state)
     grid = model.grid
     dt = grid.dtype
     xi_c, wi_c = xi.to(device=grid.device, dtype=dt).contiguous(), wi.to(device=grid.device, dtype=dt).contiguous()

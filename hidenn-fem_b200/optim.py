@@ -186,7 +186,7 @@ class ShardedLBFGS(torch.optim.Optimizer):
             self._add(tt - cur[0], d)
             cur[0] = tt
             with torch.enable_grad():
-                l = float(closure())
+                l = float(closure().detach())
             return l, self._flat_grad()
         loss, g, t, n = self._strong_wolfe(evaluate, t, d, loss, g, gtd, tol_x=tol_x)
         self._add(t - cur[0], d)                              # the accepted point is in general not the last one evaluated

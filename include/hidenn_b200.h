@@ -234,6 +234,10 @@ int hidenn_tri_energy_overlap_f64(const hidenn_tri_plan* plan,
                                   void* const* peer_bufs, void* my_buf, int me, int world, int64_t smax, uint64_t* loss_step,
                                   void* stream);
 int hidenn_tri_plan_overlap_target(const hidenn_tri_plan* plan);
+/* Which gradient tile kernel hidenn_tri_energy_* launches for this plan: 7 = tri_tile_persistent_kernel (any numbering;
+ * FP32), 8 = tri_tile8_kernel, 9 = tri_tile9_kernel (tile-ordered FP64 plans; 8 when the tiles do not fit the
+ * warp-specialised kernel's shared memory or HIDENN_TILE_WS=0). */
+int hidenn_tri_plan_kernel(const hidenn_tri_plan* plan);
 
 /* Host-buffer convenience (the end-to-end drop-in for a CPU caller): copies the four parameter
  * arrays host->device, runs the fused step, copies loss and both gradients back and waits.

@@ -67,6 +67,20 @@ int hidenn_1d_bar_energy_f32(const float* grid, int64_t N, const float* u_full, 
                              int ng, float E, const float* b_table, int need_grad, float* loss, float* du_full,
                              float* dgrid, int32_t* flag, float* scratch, void* stream);
 
+/* Fused r-adaptive bar step (examples/example3.py:27-70 over src/models.py:45-90): from the increments p [n = N-1] and the
+ * trainable values u_free (node k reads u_free[k - (u0 != NULL)]; u0 / uN = fixed end values on the device, or NULL) to
+ * loss [1], d loss / d p [n] and d loss / d u_free in THREE launches (block sums + scan by the last block; elements, node
+ * folds, gamma sums, energy by the last block; softplus / cumsum / normalise chain).  gam [n] receives d loss / d grid[1:].
+ * scratch: hidenn_1d_bar_step_scratch(n) reals, ZERO before the first call (the kernels leave it reusable).
+ * *flag != 0 afterwards: a Gauss point fell outside its own element (degenerate grid) -- the result is then invalid. */
+int64_t hidenn_1d_bar_step_scratch(int64_t n);
+int hidenn_1d_bar_step_f64(const double* p, int64_t n, const double* x0, const double* xN, const double* u_free, const double* u0,
+                           const double* uN, const double* xi, const double* wi, int ng, double E, const double* b_table,
+                           double* loss, double* dp, double* du_free, double* gam, int32_t* flag, double* scratch, void* stream);
+int hidenn_1d_bar_step_f32(const float* p, int64_t n, const float* x0, const float* xN, const float* u_free, const float* u0,
+                           const float* uN, const float* xi, const float* wi, int ng, float E, const float* b_table,
+                           float* loss, float* dp, float* du_free, float* gam, int32_t* flag, float* scratch, void* stream);
+
 /* structured Q1 forward (src/models.py:180-212): x dev [M,2] -> u dev [M], ix/iy dev [M] */
 int hidenn_q1_interp_fwd_f64(const double* gx, int64_t Nx, const double* gy, int64_t Ny, const double* u_full,
                              const double* x, int64_t M, double* u, int32_t* ix, int32_t* iy, void* stream);
