@@ -384,6 +384,49 @@ extern "C" int hidenn_tri_locality_order(const int64_t* conn, int64_t Ne, int64_
         HIDENN_REQUIRE(attempt < 12 && tile_nodes > 8, "locality_order: cannot tile this mesh within the pack limits");
         tile_nodes = std::max(8, tile_nodes * 3 / 4);
     }
+    // Order of the tiles: a boustrophedon sweep along the long axis of the mesh (strips about one tile wide across the
+    // short axis) instead of the bisection order.  A tile's neighbours are then at most one strip away in the numbering:
+    // the row window a range of tiles reads is barely wider than the rows it owns, which is what lets the host-buffer
+    // entry point stream rows in and gradient rows out at the same time (tri_plan.h), and neighbouring CTAs still share
+    // their halo rows through L2.
+    {
+        std::vector<double> cx(n_tiles), cy(n_tiles);
+        double mn[2] = {1e300, 1e300}, mx[2] = {-1e300, -1e300};
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            double sx = 0.0, sy = 0.0;
+            for (int64_t i = tile_begin[t]; i < tile_begin[t + 1]; ++i) { sx += coords[2 * (int64_t)order[i]]; sy += coords[2 * (int64_t)order[i] + 1]; }
+            const double cnt = (double)std::max<int64_t>(1, tile_begin[t + 1] - tile_begin[t]);
+            cx[t] = sx / cnt; cy[t] = sy / cnt;
+            mn[0] = std::min(mn[0], cx[t]); mx[0] = std::max(mx[0], cx[t]);
+            mn[1] = std::min(mn[1], cy[t]); mx[1] = std::max(mx[1], cy[t]);
+        }
+        const int lg = (mx[1] - mn[1] > mx[0] - mn[0]) ? 1 : 0;                 // long axis
+        const double ext_l = std::max(1e-300, mx[lg] - mn[lg]), ext_s = std::max(1e-300, mx[1 - lg] - mn[1 - lg]);
+        const double per_strip = std::max(1.0, std::sqrt((double)n_tiles * ext_s / ext_l));
+        const int64_t n_strips = std::max<int64_t>(1, (int64_t)std::llround((double)n_tiles / per_strip));
+        std::vector<int64_t> tord(n_tiles), strip(n_tiles);
+        std::iota(tord.begin(), tord.end(), 0);
+        const std::vector<double>& cl = lg ? cy : cx;
+        const std::vector<double>& cs = lg ? cx : cy;
+        for (int64_t t = 0; t < n_tiles; ++t)
+            strip[t] = std::min<int64_t>(n_strips - 1, (int64_t)((cl[t] - mn[lg]) / ext_l * (double)n_strips));
+        std::stable_sort(tord.begin(), tord.end(), [&](int64_t a, int64_t b) {
+            if (strip[a] != strip[b]) return strip[a] < strip[b];
+            const double ka = (strip[a] & 1) ? -cs[a] : cs[a], kb = (strip[b] & 1) ? -cs[b] : cs[b];
+            return ka < kb;
+        });
+        std::vector<int32_t> order2(Nn);
+        std::vector<int64_t> begin2(n_tiles + 1, 0);
+        int64_t pos = 0;
+        for (int64_t k = 0; k < n_tiles; ++k) {
+            const int64_t t = tord[k];
+            begin2[k] = pos;
+            for (int64_t i = tile_begin[t]; i < tile_begin[t + 1]; ++i) order2[pos++] = order[i];
+        }
+        begin2[n_tiles] = pos;
+        order.swap(order2);
+        tile_begin.swap(begin2);
+    }
     // inside a tile: by class, then descending slot count (the fold groups of 8 consecutive nodes then have nearly equal
     // slot counts), then by old id
     run_parallel([&](int64_t t0, int64_t t1) {

@@ -11,7 +11,7 @@
 //     fold offsets, descriptor) on the stage's mbarrier, all lanes gather the halo rows with cp.async.
 // Hand-overs are mbarriers (full / empty per stage, full / empty per partial buffer); there is no __syncthreads in the
 // tile loop.  Register budget: the CTA is launched with 768 x 80 registers (its pool); setmaxnreg moves them to
-// 384 x 120 + 384 x 40 = 61440 (HIDENN_WS_EWARPS=16: 512 x 104 + 256 x 32).
+// 384 x 120 + 384 x 40 = 61440 (HIDENN_WS_EWARPS=16: 512 x 96 + 256 x 48).
 #include "../../include/hidenn_b200.h"
 #include "common.cuh"
 #include "tri_plan.h"
@@ -24,6 +24,9 @@
 
 namespace hidenn {
 
+#ifndef HIDENN_WS_FOLD
+#define HIDENN_WS_FOLD 2      // slots in flight per fold step (1: one at a time)
+#endif
 #ifndef HIDENN_WS_EWARPS
 #define HIDENN_WS_EWARPS 12
 #endif
@@ -127,7 +130,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
 
     if (wid < kEWarps) {
         // ------------------------------------------------------------------ element warps
-        if (kEWarps == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        if (kEWarps == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
         const TriConsts<R> K = load_consts<R, BODY>(consts);
         const bool with_edges = (flags & HIDENN_WITH_EDGES) != 0;
@@ -237,7 +240,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
             if (lane == 0) bar_arrive(&part_full[pb]);      // release: this warp's partials and energy are visible
         }
     } else {
-        if (kEWarps == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        if (kEWarps == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (wid == kEWarps + kFWarps) {
             // -------------------------------------------------------------- loader warp
@@ -307,18 +310,24 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                 bar_wait(&part_full[pb], (k >> 1) & 1);
                 const int n_owned = d->n_owned, nA = d->nA, nAB = nA + d->nB, nBC = d->nB + d->nC, nABC = nAB + d->nC;
                 const int rx = d->rx_free, ru = d->ru_free;
+                // one node per thread and pass, two slots in flight per step (summed pairwise: acc += (s_q + s_q+1)).  More
+                // loads in flight (two nodes per thread, four slots) make the WHOLE kernel slower: the fold warps have slack,
+                // the element warps do not, and both share the SM's load/store pipe (profiles/README.md)
                 for (int l = ftid; l < n_owned; l += kFWarps * 32) {
                     const uint32_t oc = s_off[l];
                     const unsigned fb = oc & 0xFFFFu, fe = fb + (oc >> 16) * G;
                     R ax = R(0), ay = R(0), bx = R(0), by = R(0);
                     unsigned q = fb;
+#if HIDENN_WS_FOLD == 2
 #pragma unroll 1
-                    for (; q + G < fe; q += 2 * G) {      // two slots in flight per step, summed pairwise: acc += (s_q + s_q+1)
+                    for (; q + G < fe; q += 2 * G) {
                         const R2 u0 = lds_pair(part.pu + q), u1 = lds_pair(part.pu + q + G);
                         const R2 x0 = lds_pair(part.px + q), x1 = lds_pair(part.px + q + G);
                         ax += u0.x + u1.x; ay += u0.y + u1.y; bx += x0.x + x1.x; by += x0.y + x1.y;
                     }
-                    if (q < fe) {
+#endif
+#pragma unroll 1
+                    for (; q < fe; q += G) {
                         R2 u, x;
                         part.load(q, u, x);
                         ax += u.x; ay += u.y; bx += x.x; by += x.y;

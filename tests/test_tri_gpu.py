@@ -662,3 +662,82 @@ def test_sharded_lbfgs_with_line_search_on_the_plate(tag, dtype):
         tr, u = run(lambda p: ShardedLBFGS(p, **kw, **extra))
         assert np.allclose(tr, ref, rtol=tol), (extra, tr, ref)
         assert relmax(u.cpu().numpy(), u_ref.cpu().numpy()) < 1e3 * tol
+
+
+def test_peer_memory_halo_kernels_two_ranks_in_one_process():
+    """csrc/halo_p2p.cu (put / complete / loss exchange over peer memory) with both ranks of a 2-rank strip partition
+    played by ONE process on one GPU: each rank has its own receive buffer, gradient arrays, step counters and stream, the
+    `peer_bufs` tables point at each other's buffers.  Two steps in a row (both parities of the receive buffers).  Expected
+    values: the same sums in ascending rank order done with numpy -- bit for bit, and identical on both holders."""
+    import ctypes as C
+    from hidenn_fem_b200 import _lib, meshgen, dist as hd
+    L = _lib.lib()
+    nx, ny, world = 161, 81, 2
+    parts, cands = [], []
+    for rank in range(world):
+        m = hd.strip_mesh(nx, ny, rank, world, jitter=0.25, diag="random", seed=0, ordering="morton")
+        parts.append(m)
+        cands.append(hd.strip_candidates(m))
+    shared = hd.shared_ids_from_candidates(cands)
+    tabs = [hd.build_peer_tables(cands, shared, r, parts[r].global_node_id, ~parts[r].boundary_mask, ~parts[r].dirichlet_mask)
+            for r in range(world)]
+    smax = tabs[0].smax
+    dev = torch.device("cuda")
+    nbytes = int(L.hidenn_halo_p2p_bytes(C.c_int(world), C.c_int64(smax), C.c_int(8)))
+    bufs = [torch.zeros((nbytes + 7) // 8, dtype=torch.int64, device=dev) for _ in range(world)]
+    peer = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=dev)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+    T = [dict(sx=d(t.send_xrow), su=d(t.send_urow), sp=d(t.send_peer), sk=d(t.send_k), nx=d(t.node_xrow), nu=d(t.node_urow),
+              off=d(t.node_off), sr=d(t.src_rank), skk=d(t.src_k), wait=d(t.wait_ranks)) for t in tabs]
+    gstep = [torch.ones(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    lstep = [torch.ones(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    rng = np.random.default_rng(0)
+    for it in range(2):
+        gx = [rng.standard_normal((int((~p.boundary_mask).sum()), 2)) for p in parts]
+        gu = [rng.standard_normal((int((~p.dirichlet_mask).sum()), 2)) for p in parts]
+        outs = [rng.standard_normal(4) for _ in parts]
+        dgx, dgu = [torch.tensor(a, device=dev) for a in gx], [torch.tensor(a, device=dev) for a in gu]
+        dout = [torch.tensor(a, device=dev) for a in outs]
+        torch.cuda.synchronize()
+        for phase in ("push", "pull", "loss"):
+            for r in range(world):
+                t, k = tabs[r], T[r]
+                with torch.cuda.stream(streams[r]):
+                    s = _lib.stream_ptr()
+                    if phase == "push":
+                        _lib.check(L.hidenn_halo_p2p_push_f64(_lib.ptr(dgx[r]), _lib.ptr(dgu[r]), _lib.ptr(k["sx"]), _lib.ptr(k["su"]), _lib.ptr(k["sp"]),
+                                                              _lib.ptr(k["sk"]), C.c_int64(t.send_xrow.size), _lib.ptr(peer), C.c_int(r), C.c_int(world),
+                                                              C.c_int64(smax), _lib.ptr(gstep[r]), _lib.ptr(None), C.c_uint32(0), s))
+                    elif phase == "pull":
+                        _lib.check(L.hidenn_halo_p2p_pull_f64(_lib.ptr(dgx[r]), _lib.ptr(dgu[r]), _lib.ptr(k["nx"]), _lib.ptr(k["nu"]), _lib.ptr(k["off"]),
+                                                              _lib.ptr(k["sr"]), _lib.ptr(k["skk"]), C.c_int64(t.node_xrow.size), _lib.ptr(k["wait"]),
+                                                              C.c_int(t.wait_ranks.size), _lib.ptr(bufs[r]), C.c_int(r), C.c_int(world), C.c_int64(smax),
+                                                              _lib.ptr(gstep[r]), s))
+                    else:       # the two loss kernels wait for each other: they run concurrently on their streams
+                        _lib.check(L.hidenn_halo_p2p_loss_f64(_lib.ptr(dout[r]), _lib.ptr(peer), _lib.ptr(bufs[r]), C.c_int(r), C.c_int(world),
+                                                              C.c_int64(smax), _lib.ptr(lstep[r]), s))
+        torch.cuda.synchronize()
+        # numpy: the same exchange
+        recv = np.zeros((world, world, smax, 4))
+        for r, t in enumerate(tabs):
+            for xr, ur, q, k in zip(t.send_xrow, t.send_urow, t.send_peer, t.send_k):
+                recv[q, r, k, :2] = gx[r][xr] if xr >= 0 else 0.0
+                recv[q, r, k, 2:] = gu[r][ur] if ur >= 0 else 0.0
+        for r, t in enumerate(tabs):
+            ex, eu = gx[r].copy(), gu[r].copy()
+            for j in range(t.node_xrow.size):
+                acc = np.zeros(4)
+                for s_ in range(t.node_off[j], t.node_off[j + 1]):
+                    q = t.src_rank[s_]
+                    own = np.concatenate([gx[r][t.node_xrow[j]] if t.node_xrow[j] >= 0 else np.zeros(2),
+                                          gu[r][t.node_urow[j]] if t.node_urow[j] >= 0 else np.zeros(2)])
+                    acc = acc + (own if q == r else recv[r, q, t.src_k[s_]])
+                if t.node_xrow[j] >= 0:
+                    ex[t.node_xrow[j]] = acc[:2]
+                if t.node_urow[j] >= 0:
+                    eu[t.node_urow[j]] = acc[2:]
+            assert np.array_equal(dgx[r].cpu().numpy(), ex) and np.array_equal(dgu[r].cpu().numpy(), eu), (it, r)
+            want = outs[0][:3] + outs[1][:3]
+            assert np.array_equal(dout[r].cpu().numpy()[:3], want), (it, r)
+        assert int(gstep[0].item()) == it + 2 and int(lstep[1].item()) == it + 2
