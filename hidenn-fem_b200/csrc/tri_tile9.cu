@@ -30,10 +30,39 @@ namespace hidenn {
 #ifndef HIDENN_WS_EWARPS
 #define HIDENN_WS_EWARPS 12
 #endif
-constexpr int kEWarps = HIDENN_WS_EWARPS, kFWarps = 23 - kEWarps, kThreads9 = 24 * 32;      // 768 threads = 6 warpgroups
+// Measurement-only ablations (profiles/v9_ablate.py; results are WRONG on purpose, never shipped): fraction of the
+// shared-memory exchange kept per element -- 1: two of three corners (what edge-sharing pairs would move), 2: one of
+// three (triangle strips), 3: none (FP64 + issue + global traffic floor).  The FP64 work is unchanged.
+#ifndef HIDENN_ABL
+#define HIDENN_ABL 0
+#endif
+// HIDENN_PROF9 (measurement-only): per-warp clock64 totals of the mbarrier waits, written over the tile-energy scratch
+// as doubles [cta][warp][4] = total, wait A, wait B, tiles (A/B: element = stage full / partial buffer free, fold = stage
+// full / partials full, loader = stage empty / -)
+#ifndef HIDENN_PROF9
+#define HIDENN_PROF9 0
+#endif
+#if HIDENN_PROF9
+#define PROF_DECL long long pf_t0 = clock64(), pf_a = 0, pf_b = 0
+#define PROF_WAIT(acc, stmt) { const long long pf_s = clock64(); stmt; acc += clock64() - pf_s; }
+#define PROF_END(ntiles) if (lane == 0) { double* o = e_dom + ((size_t)blockIdx.x * 24 + wid) * 4; o[0] = (double)(clock64() - pf_t0); o[1] = (double)pf_a; o[2] = (double)pf_b; o[3] = (double)(ntiles); }
+#else
+#define PROF_DECL
+#define PROF_WAIT(acc, stmt) stmt;
+#define PROF_END(ntiles)
+#endif
+// Loader warps: the per-tile chain  descriptor -> halo records -> gathers  is 2-3 dependent global loads (~3000 cycles);
+// with ONE loader warp that chain is the critical path of the whole CTA (HIDENN_PROF9: the loader never waits, the
+// element warps wait 19 % of the time for a full stage), so the tiles are dealt round-robin to kLWarps loader warps.
+#ifndef HIDENN_WS_LWARPS
+#define HIDENN_WS_LWARPS 2
+#endif
+constexpr int kLWarps = HIDENN_WS_LWARPS;
+constexpr int kEWarps = HIDENN_WS_EWARPS, kFWarps = 24 - kLWarps - kEWarps, kThreads9 = 24 * 32;      // 768 threads = 6 warpgroups
 constexpr int kRedWarp0 = 16;      // the last 8 warps (small-register groups in every configuration) do the final reduction
 static_assert(kEWarps % 4 == 0 && kEWarps <= 16, "element warps come in warpgroups; 512 x 104 + 256 x 32 or 384 x 128 + 384 x 32 registers");
 constexpr int kMaxStages = 4;
+constexpr int kEnSlots = kEWarps * 32 + 16;
 
 namespace {
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,13 +120,14 @@ __host__ __device__ inline Smem9 smem9_layout(int max_local, int max_entries9, i
     L.part_bytes = (max_entries9 + 1) * 32;
     L.part0 = n_stages * L.stage_bytes;
     L.en0 = L.part0 + 2 * L.part_bytes;
-    L.bar0 = L.en0 + 2 * 32 * 8;
+    L.bar0 = L.en0 + 2 * kEnSlots * 8;      // per partial buffer: one energy slot per element lane + 16 edge-energy warp sums
     L.total = L.bar0 + 16 * 8 + 16;
     return L;
 }
 
 // PAIRS: paired layout (tri_plan.h; opt-in, HIDENN_PLAN_PAIRS=1) instead of one element per entry
-template <bool BODY, bool ISO, bool PAIRS>
+// JT: correct-math switch jinv_transpose (compile-time here: the selects would sit at both ends of the FP64 chain)
+template <bool BODY, bool ISO, bool PAIRS, bool JT>
 __global__ void __launch_bounds__(kThreads9, 1)
 tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __restrict__ x_free, const double2* __restrict__ x_fixed,
                  const double2* __restrict__ u_free, const double2* __restrict__ u_fixed, const double* __restrict__ consts,
@@ -135,18 +165,22 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
         const TriConsts<R> K = load_consts<R, BODY>(consts);
         const bool with_edges = (flags & HIDENN_WITH_EDGES) != 0;
         const int etid = tid;
+        PROF_DECL;
+        int st = 0;
+        unsigned st_ph = 0;      // stage index / phase parity of tile k (k % kStages, (k / kStages) & 1 without the divisions)
         for (int k = 0; k < n_mine; ++k) {
-            const int tile = blockIdx.x + k * nct;
-            const int st = k % kStages, pb = k & 1;
+            const int pb = k & 1;
             unsigned char* stage = smem + st * L.stage_bytes;
             const TileDesc8* d = reinterpret_cast<const TileDesc8*>(stage + L.desc_off);
             const ulonglong2* s_pack = reinterpret_cast<const ulonglong2*>(stage + L.pack_off);
             const unsigned long long* s_pack1 = reinterpret_cast<const unsigned long long*>(stage + L.pack_off);
             const NodeBuf<R> nodes(stage + L.node_off, P.max_local);
             const PartBuf<R> part(smem + L.part0 + pb * L.part_bytes, max_entries + 1);
-            bar_wait(&full_stage[st], (k / kStages) & 1);
-            bar_wait(&part_empty[pb], ((k >> 1) & 1) ^ 1);
+            PROF_WAIT(pf_a, bar_wait(&full_stage[st], st_ph))
             const int n_pent = PAIRS ? d->n_pent : d->n_elem, n_edge = d->n_edge;
+            // the pack of the next pass is loaded one pass ahead (the first one before the wait for the partial buffer)
+            unsigned long long pw_next = (!PAIRS && etid < n_pent) ? s_pack1[etid] : 0ull;
+            PROF_WAIT(pf_b, bar_wait(&part_empty[pb], ((k >> 1) & 1) ^ 1))
             const unsigned dumpv = (unsigned)(PAIRS ? d->n_entries9 : d->n_entries);
             R e_acc = R(0), ee_acc = R(0);
             // one entry = an edge-sharing element pair (or a single element): both elements are evaluated by this thread,
@@ -155,7 +189,10 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
             for (int i = etid; i < n_pent; i += kEWarps * 32) {
                 ulonglong2 pw;
                 if (PAIRS) pw = s_pack[i];
-                else { pw.x = s_pack1[i]; pw.y = kNullPack; }
+                else {
+                    pw.x = pw_next; pw.y = kNullPack;
+                    pw_next = (i + kEWarps * 32 < n_pent) ? s_pack1[i + kEWarps * 32] : 0ull;
+                }
                 R2 gu[3], gx[3];
                 unsigned l0, l1, l2, p0, p1, p2;
                 {
@@ -165,9 +202,31 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     p2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
                     R e;
                     R2 v0, v1, v2, U0, U1, U2;
+#if HIDENN_ABL == 0
                     nodes.load(l0, v0, U0); nodes.load(l1, v1, U1); nodes.load(l2, v2, U2);
-                    tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx, P.jinv_t != 0);
+#elif HIDENN_ABL == 1
+                    nodes.load(l0, v0, U0); nodes.load(l1, v1, U1);
+                    v2 = mk2<R>(v0.x + 3e-4, v1.y - 1e-4); U2 = mk2<R>(U0.x * 0.5, U1.y * 1.5);
+#elif HIDENN_ABL == 2
+                    nodes.load(l0, v0, U0);
+                    v1 = mk2<R>(v0.x + 1e-4 * (R)(l1 & 3u), v0.y + 3e-4); U1 = mk2<R>(U0.y, U0.x * 2.0);
+                    v2 = mk2<R>(v0.x + 3e-4, v0.y - 1e-4 * (R)(l2 & 3u)); U2 = mk2<R>(U0.x * 0.5, U0.y * 1.5);
+#else
+                    v0 = mk2<R>(1e-3 * (R)l0, 2e-3 * (R)l1); U0 = mk2<R>(1e-5 * (R)l2, 2e-5 * (R)l0);
+                    v1 = mk2<R>(v0.x + 1e-4 * (R)(l1 & 3u), v0.y + 3e-4); U1 = mk2<R>(U0.y, U0.x * 2.0);
+                    v2 = mk2<R>(v0.x + 3e-4, v0.y - 1e-4 * (R)(l2 & 3u)); U2 = mk2<R>(U0.x * 0.5, U0.y * 1.5);
+#endif
+                    tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, gu, gx, JT);
                     e_acc += (hi >> 31) ? e : R(0);
+#if HIDENN_ABL >= 1      // keep every result live
+                    gu[0].x += gu[2].x * 0.5; gu[0].y += gu[2].y * 0.5; gx[0].x += gx[2].x * 0.5; gx[0].y += gx[2].y * 0.5;
+#endif
+#if HIDENN_ABL >= 2
+                    gu[0].x += gu[1].x * 0.25; gu[0].y += gu[1].y * 0.25; gx[0].x += gx[1].x * 0.25; gx[0].y += gx[1].y * 0.25;
+#endif
+#if HIDENN_ABL >= 3
+                    e_acc += gu[0].x + gu[0].y + gx[0].x + gx[0].y;
+#endif
                 }
                 if (PAIRS && ((unsigned)pw.y & 0x3FFFFFFFu) != 0x3FFFFFFFu) {
                     const unsigned lo = (unsigned)pw.y, hi = (unsigned)(pw.y >> 32);
@@ -177,7 +236,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     R e;
                     R2 hu[3], hx[3], v0, v1, v2, U0, U1, U2;
                     nodes.load(m0, v0, U0); nodes.load(m1, v1, U1); nodes.load(m2, v2, U2);
-                    tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, hu, hx, P.jinv_t != 0);
+                    tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, hu, hx, JT);
                     e_acc += (hi >> 31) ? e : R(0);
                     const unsigned ll[3] = {l0, l1, l2}, mm[3] = {m0, m1, m2};
 #pragma unroll
@@ -191,9 +250,15 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     if (q1 != dumpv) part.store(q1, hu[1], hx[1]);
                     if (q2 != dumpv) part.store(q2, hu[2], hx[2]);
                 }
+#if HIDENN_ABL <= 2
                 if (p0 != dumpv) part.store(p0, gu[0], gx[0]);
+#endif
+#if HIDENN_ABL <= 1
                 if (p1 != dumpv) part.store(p1, gu[1], gx[1]);
+#endif
+#if HIDENN_ABL == 0
                 if (p2 != dumpv) part.store(p2, gu[2], gx[2]);
+#endif
             }
             if (n_edge > 0) {
                 // Neumann edges with an end owned by this tile (a handful of tiles): N = [1-xi, xi] on raw [-1,1] Gauss points
@@ -232,17 +297,23 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     if (p1 != dumpv) part.store(p1, mk2<R>(-m * ds * f1x, -m * ds * f1y), mk2<R>(-m * S * dirx, -m * S * diry));
                 }
             }
-            e_acc = warp_sum(e_acc);
-            ee_acc = warp_sum(ee_acc);
-            R* s_en = reinterpret_cast<R*>(smem + L.en0) + pb * 32;
-            if (lane == 0) { s_en[wid] = e_acc; s_en[16 + wid] = ee_acc; }
+            // tile energy: every lane leaves its sum in its own slot, the last fold warp adds the slots in fixed order (a
+            // shuffle tree here cost each element warp ~400 cycles per tile); edge energies only where the tile has edges
+            R* s_en = reinterpret_cast<R*>(smem + L.en0) + pb * kEnSlots;
+            s_en[etid] = e_acc;
+            if (n_edge > 0) {
+                ee_acc = warp_sum(ee_acc);
+                if (lane == 0) s_en[kEWarps * 32 + wid] = ee_acc;
+            }
             __syncwarp();
             if (lane == 0) bar_arrive(&part_full[pb]);      // release: this warp's partials and energy are visible
+            if (++st == kStages) { st = 0; st_ph ^= 1u; }
         }
+        PROF_END(n_mine)
     } else {
         if (kEWarps == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (wid == kEWarps + kFWarps) {
+        if (wid >= kEWarps + kFWarps) {
             // -------------------------------------------------------------- loader warp
             // The per-tile chain  descriptor -> bulk copies, halo records -> gathers  is two dependent global loads; the
             // records of the tile kAhead iterations later are pulled into L2 now, so the chain costs L2 hits, not DRAM misses.
@@ -252,12 +323,15 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                 if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(P8.tiles + t));
                 else if (lane * 128 < P8.stride_halo * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + lane * 128));
             };
-            for (int k = 0; k < kAhead && k < n_mine; ++k) prefetch_tile(blockIdx.x + k * nct);
-            for (int k = 0; k < n_mine; ++k) {
+            const int lw = wid - (kEWarps + kFWarps);
+            for (int k = lw; k < kAhead * kLWarps && k < n_mine; k += kLWarps) prefetch_tile(blockIdx.x + k * nct);
+            PROF_DECL;
+            int st = lw % kStages;
+            unsigned st_ph = (lw / kStages) & 1;
+            for (int k = lw; k < n_mine; k += kLWarps) {
                 const int tile = blockIdx.x + k * nct;
-                const int st = k % kStages;
                 unsigned char* stage = smem + st * L.stage_bytes;
-                if (k + kAhead < n_mine) prefetch_tile(tile + kAhead * nct);
+                if (k + kAhead * kLWarps < n_mine) prefetch_tile(tile + kAhead * kLWarps * nct);
                 const TileDesc8 d = P8.tiles[tile];
                 const int n_halo = d.n_local - d.n_owned;
                 const int2* __restrict__ hrec = P8.t_halo + (size_t)tile * P8.stride_halo;
@@ -265,7 +339,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                 if (lane < n_halo) h0 = __ldg(hrec + lane);
                 if (lane + 32 < n_halo) h1 = __ldg(hrec + lane + 32);
                 if (lane + 64 < n_halo) h2 = __ldg(hrec + lane + 64);
-                bar_wait(&empty_stage[st], ((k / kStages) & 1) ^ 1);
+                PROF_WAIT(pf_a, bar_wait(&empty_stage[st], st_ph ^ 1u))
                 R2* xy = reinterpret_cast<R2*>(stage + L.node_off);
                 R2* uv = xy + P.max_local;
                 if (lane == 0) {
@@ -293,21 +367,27 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                 if (lane + 64 < n_halo) gather(lane + 64, h2);
                 for (int j = lane + 96; j < n_halo; j += 32) gather(j, __ldg(hrec + j));
                 bar_arrive_cp_async(&full_stage[st]);
+                st += kLWarps;
+                while (st >= kStages) { st -= kStages; st_ph ^= 1u; }
             }
+            PROF_END(n_mine)
         } else {
             // -------------------------------------------------------------- fold warps
             const int ftid = tid - kEWarps * 32;
             const bool need_gx = flags & HIDENN_NEED_GX, need_gu = flags & HIDENN_NEED_GU;
             constexpr unsigned G = 8u;
+            PROF_DECL;
+            int st = 0;
+            unsigned st_ph = 0;
             for (int k = 0; k < n_mine; ++k) {
                 const int tile = blockIdx.x + k * nct;
-                const int st = k % kStages, pb = k & 1;
+                const int pb = k & 1;
                 unsigned char* stage = smem + st * L.stage_bytes;
                 const TileDesc8* d = reinterpret_cast<const TileDesc8*>(stage + L.desc_off);
                 const uint32_t* s_off = reinterpret_cast<const uint32_t*>(stage + L.offs_off);
                 const PartBuf<R> part(smem + L.part0 + pb * L.part_bytes, max_entries + 1);
-                bar_wait(&full_stage[st], (k / kStages) & 1);
-                bar_wait(&part_full[pb], (k >> 1) & 1);
+                PROF_WAIT(pf_a, bar_wait(&full_stage[st], st_ph))
+                PROF_WAIT(pf_b, bar_wait(&part_full[pb], (k >> 1) & 1))
                 const int n_owned = d->n_owned, nA = d->nA, nAB = nA + d->nB, nBC = d->nB + d->nC, nABC = nAB + d->nC;
                 const int rx = d->rx_free, ru = d->ru_free;
                 // one node per thread and pass, two slots in flight per step (summed pairwise: acc += (s_q + s_q+1)).  More
@@ -315,7 +395,11 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                 // the element warps do not, and both share the SM's load/store pipe (profiles/README.md)
                 for (int l = ftid; l < n_owned; l += kFWarps * 32) {
                     const uint32_t oc = s_off[l];
+#if HIDENN_ABL == 0
                     const unsigned fb = oc & 0xFFFFu, fe = fb + (oc >> 16) * G;
+#else
+                    const unsigned fb = oc & 0xFFFFu, fe = fb + (((oc >> 16) * (3u - HIDENN_ABL) + 1u) / 3u) * G;
+#endif
                     R ax = R(0), ay = R(0), bx = R(0), by = R(0);
                     unsigned q = fb;
 #if HIDENN_WS_FOLD == 2
@@ -335,13 +419,21 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     if (need_gu && l < nAB) gu_free[ru + l] = mk2<R>(ax, ay);
                     if (need_gx && (l < nA || l >= nABC)) gx_free[rx + (l < nA ? l : l - nBC)] = mk2<R>(bx, by);
                 }
-                if (ftid == 0) {        // tile energies, summed in fixed warp order
-                    const R* s_en = reinterpret_cast<const R*>(smem + L.en0) + pb * 32;
-                    R dd = R(0), ee = R(0);
+                if (wid == kEWarps + kFWarps - 1 && !HIDENN_PROF9) {
+                    // tile energies in fixed order: lane j adds the slots of lane j of the element warps 0, 1, ..., then a
+                    // shuffle tree (this fold warp has the fewest second-pass nodes)
+                    const R* s_en = reinterpret_cast<const R*>(smem + L.en0) + pb * kEnSlots;
+                    R dd = R(0);
 #pragma unroll
-                    for (int w = 0; w < kEWarps; ++w) { dd += s_en[w]; ee += s_en[16 + w]; }
-                    e_dom[tile] = dd;
-                    e_edge[tile] = ee;
+                    for (int w = 0; w < kEWarps; ++w) dd += s_en[w * 32 + lane];
+                    dd = warp_sum(dd);
+                    if (lane == 0) {
+                        R ee = R(0);
+                        if (d->n_edge > 0)
+                            for (int w = 0; w < kEWarps; ++w) ee += s_en[kEWarps * 32 + w];
+                        e_dom[tile] = dd;
+                        e_edge[tile] = ee;
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -354,7 +446,9 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                         atomicAdd(first_done, 1u);
                     }
                 }
+                if (++st == kStages) { st = 0; st_ph ^= 1u; }
             }
+            PROF_END(n_mine)
         }
     }
 
@@ -406,16 +500,16 @@ static int stages9_for(const hidenn_tri_plan* p) {
 }
 size_t tile9_smem_bytes(const hidenn_tri_plan* p) { return smem9_for(p, stages9_for(p)); }
 
-template <bool BODY, bool ISO, bool PAIRS>
+template <bool BODY, bool ISO, bool PAIRS, bool JT>
 static int launch9(const hidenn_tri_plan* p, const double* x_free, const double* x_fixed, const double* u_free, const double* u_fixed,
                    const double* consts, const double* t_table, int flags, double* out, double* gx, double* gu, double* gt,
                    double* scratch, unsigned* ticket, cudaStream_t stream, int tile_begin, int tile_end, unsigned* first_done,
                    int reserve_sms, const P2PLossArgs* loss_args) {
     const size_t smem = tile9_smem_bytes(p);
-    static size_t configured[kMaxDevices] = {};
+    static size_t configured[kMaxDevices] = {};      // per instantiation (static local of a function template)
     size_t& cfg = configured[p->device % kMaxDevices];
     if (smem > cfg) {
-        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile9_kernel<BODY, ISO, PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HIDENN_CUDA_OK(cudaFuncSetAttribute(tri_tile9_kernel<BODY, ISO, PAIRS, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cfg = smem;
     }
     TriPlanDev P = p->dev;
@@ -432,7 +526,7 @@ static int launch9(const hidenn_tri_plan* p, const double* x_free, const double*
         P.entry_off += (size_t)tile_begin * P.stride_owned;
     }
     const int grid = std::min(P.n_tiles, std::max(1, sm_count(p->device) - reserve_sms));
-    tri_tile9_kernel<BODY, ISO, PAIRS><<<grid, kThreads9, smem, stream>>>(
+    tri_tile9_kernel<BODY, ISO, PAIRS, JT><<<grid, kThreads9, smem, stream>>>(
         P, P8, (const double2*)x_free, (const double2*)x_fixed, (const double2*)u_free, (const double2*)u_fixed, consts, t_table, flags,
         (double2*)gx, (double2*)gu, gt, scratch + tile_begin, scratch + n_total + tile_begin, scratch, scratch + n_total, n_total, out, ticket,
         stages9_for(p), first_done, tile_begin == 0 ? p->n_first_tiles : 0, loss_args ? *loss_args : P2PLossArgs{nullptr, nullptr, nullptr, 0, 0, 0});
@@ -449,8 +543,13 @@ int tile9_launch(const hidenn_tri_plan* p, const double* x_free, const double* x
                  const P2PLossArgs* loss_args) {
     const bool body = !(flags & HIDENN_HINT_NO_BODY_FORCE), iso = (flags & HIDENN_HINT_C_PLANE_STRESS) != 0;
 #define HIDENN_L9(B_, I_, P_) \
-    return launch9<B_, I_, P_>(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket, stream, tile_begin, \
-                               tile_end, first_done, reserve_sms, loss_args)
+    do { \
+        if (p->dev.jinv_t) \
+            return launch9<B_, I_, P_, true>(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket, stream, \
+                                             tile_begin, tile_end, first_done, reserve_sms, loss_args); \
+        return launch9<B_, I_, P_, false>(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket, stream, \
+                                          tile_begin, tile_end, first_done, reserve_sms, loss_args); \
+    } while (0)
     if (pairs9(p)) {
         if (body && iso) HIDENN_L9(true, true, true);
         if (body) HIDENN_L9(true, false, true);

@@ -1,0 +1,72 @@
+"""Upper bounds for the tile kernel (C4, FP64, tile-ordered): build tri_tile9.cu with -DHIDENN_ABL=k (k = 1, 2, 3: two
+thirds / one third / none of the per-element shared-memory exchange; results wrong on purpose) into gpurun_alt/ and time
+the kernel alone.  `--build` here (no GPU), `--run` on the GPU box.  Extra -D flags: --defs "-DX=1 -DY=2" --tag name."""
+import argparse, os, subprocess, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+ALT = os.path.join(ROOT, "gpurun_alt")
+
+
+def build(tag, defs, srcs=("tri_tile9.cu",)):
+    from hidenn_fem_b200 import build as b
+    b.build()
+    os.makedirs(ALT, exist_ok=True)
+    objs = []
+    for src in b.sources():
+        base = os.path.basename(src)
+        obj = os.path.join(os.path.dirname(b.LIB), "build", base[:-3] + ".o")
+        if base in srcs:
+            obj = os.path.join(ALT, f"{tag}_{base[:-3]}.o")
+            subprocess.check_call([b._nvcc(), *b.NVCC_FLAGS, *defs, "-c", src, "-o", obj])
+        objs.append(obj)
+    out = os.path.join(ALT, f"lib_{tag}.so")
+    subprocess.check_call([b._nvcc(), "-shared", *b.NVCC_FLAGS, "-o", out, *objs])
+    return out
+
+
+def run_one():
+    import torch, bench
+    args = bench.parse()
+    dev = torch.device("cuda:0")
+    m, model, loss_fn, _ = bench.make_workload(args, 0, 1, dev, torch.float64, "tiles", args.elems)
+    ms = min(bench.time_kernel(model, loss_fn, 20, 5) for _ in range(3))
+    rec = {"lib": os.path.basename(os.environ.get("HIDENN_LIB", "default")), "kernel_us": round(ms * 1e3, 1)}
+    if "prof" in rec["lib"]:      # HIDENN_PROF9 build: per-warp wait cycles sit in the tile-energy scratch
+        torch.cuda.synchronize()
+        plan = model._plan()
+        sc = loss_fn._scratch(plan, dev, torch.float64)[:148 * 24 * 4].reshape(148, 24, 4).cpu().numpy()
+        import re
+        ew = int((re.search(r"_e(\d+)", rec["lib"]) or [0, "12"])[1])      # tags: prof_e12_l2 ...
+        lw = int((re.search(r"_l(\d+)", rec["lib"]) or [0, "2"])[1])
+        for name, sl in (("element", slice(0, ew)), ("fold", slice(ew, 24 - lw)), ("loader", slice(24 - lw, 24))):
+            w = sc[:, sl]
+            tot = w[..., 0].mean()
+            rec[name] = {"total_cyc": round(float(tot)), "waitA_frac": round(float((w[..., 1] / w[..., 0]).mean()), 3),
+                         "waitB_frac": round(float((w[..., 2] / w[..., 0]).mean()), 3), "tiles": float(w[..., 3].mean())}
+    print(json.dumps(rec), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--build", action="store_true")
+    ap.add_argument("--run", action="store_true")
+    ap.add_argument("--one", action="store_true")
+    ap.add_argument("--defs", default="")
+    ap.add_argument("--tag", default="")
+    a, rest = ap.parse_known_args()
+    if a.one:
+        sys.argv = [sys.argv[0]] + rest
+        run_one()
+    elif a.build:
+        if a.tag:
+            print(build(a.tag, a.defs.split()))
+        else:
+            for k in (1, 2, 3):
+                print(build(f"abl{k}", [f"-DHIDENN_ABL={k}"]))
+    elif a.run:
+        libs = [None] + sorted(os.path.join(ALT, f) for f in os.listdir(ALT) if f.startswith("lib_") and f.endswith(".so"))
+        for lib in libs:
+            env = dict(os.environ)
+            if lib:
+                env["HIDENN_LIB"] = lib
+            subprocess.call([sys.executable, os.path.abspath(__file__), "--one"], env=env, cwd=ROOT)
