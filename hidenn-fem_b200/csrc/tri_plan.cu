@@ -163,6 +163,25 @@ static void reorder_for_banks(TileBuild& B, int real_bytes) {
 
 // Same greedy lane assignment for the pair entries of the paired layout (2 words per entry): six gather columns (corners
 // of the first and second element) and six store columns; a null second word contributes nothing.
+// Class of a pair entry (tri_plan.h): 3 * i + r for a pair whose second element has its new corner at position r and
+// shares the edge (corner i -> corner i+1) of the first element, run through in the opposite direction; kPairSingle for
+// a single element; -1 if the two words are not such a pair.
+int pair_class(unsigned long long w1, unsigned long long w2) {
+    constexpr unsigned LM = (1u << kLidBits) - 1u;
+    if (((unsigned)w2 & 0x3FFFFFFFu) == 0x3FFFFFFFu) return kPairSingle;
+    unsigned l[3], m[3];
+    for (int c = 0; c < 3; ++c) { l[c] = (unsigned)(w1 >> (kLidBits * c)) & LM; m[c] = (unsigned)(w2 >> (kLidBits * c)) & LM; }
+    for (int r = 0; r < 3; ++r) {
+        if (m[r] == l[0] || m[r] == l[1] || m[r] == l[2]) continue;
+        for (int i = 0; i < 3; ++i)
+            if (m[(r + 1) % 3] == l[(i + 1) % 3] && m[(r + 2) % 3] == l[i]) return 3 * i + r;
+        return -1;
+    }
+    return -1;
+}
+
+// (pairs of one class: the kernel gathers the three corners of the first element and the new corner of the second,
+// four columns; singles: three)
 static void reorder_pairs_for_banks(std::vector<unsigned long long>& pack9, unsigned dump) {
     const int E = (int)(pack9.size() / 2);
     const int G = 8;
@@ -173,13 +192,17 @@ static void reorder_pairs_for_banks(std::vector<unsigned long long>& pack9, unsi
     struct Item { uint16_t lid[6], pos[6]; int nc; };
     std::vector<Item> it(E);
     for (int i = 0; i < E; ++i) {
-        it[i].nc = ((unsigned)pack9[2 * i + 1] & 0x3FFFFFFFu) == 0x3FFFFFFFu ? 3 : 6;
-        for (int h = 0; h < 2; ++h) {
-            const unsigned long long w = pack9[2 * i + h];
-            for (int c = 0; c < 3; ++c) {
-                it[i].lid[3 * h + c] = (uint16_t)((w >> (kLidBits * c)) & LM);
-                it[i].pos[3 * h + c] = (uint16_t)((w >> (3 * kLidBits + kPosBits * c)) & PM);
-            }
+        const int cls = pair_class(pack9[2 * i], pack9[2 * i + 1]);
+        it[i].nc = cls == kPairSingle ? 3 : 4;
+        const unsigned long long w = pack9[2 * i], w2 = pack9[2 * i + 1];
+        for (int c = 0; c < 3; ++c) {
+            it[i].lid[c] = (uint16_t)((w >> (kLidBits * c)) & LM);
+            it[i].pos[c] = (uint16_t)((w >> (3 * kLidBits + kPosBits * c)) & PM);
+        }
+        if (cls != kPairSingle) {
+            const int r = cls < 0 ? 0 : cls % 3;
+            it[i].lid[3] = (uint16_t)((w2 >> (kLidBits * r)) & LM);
+            it[i].pos[3] = (uint16_t)((w2 >> (3 * kLidBits + kPosBits * r)) & PM);
         }
     }
     std::vector<char> used(E, 0);
@@ -573,10 +596,14 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
         auto nb_range = [&](int64_t e0, int64_t e1) {
             for (int64_t e = e0; e < e1; ++e)
                 for (int c = 0; c < 3; ++c) {
+                    // only a neighbour that runs through the shared edge in the opposite direction (b -> a; both elements
+                    // counter-clockwise or both clockwise) can be this element's partner: the kernel has one register wiring
+                    // per (edge of the first element, position of the new corner in the second) = 9 classes
                     const int32_t a = c32g[3 * e + c], b = c32g[3 * e + (c + 1) % 3];
                     for (int64_t k = p->n2e_off[a]; k < p->n2e_off[a + 1]; ++k) {
                         const int32_t f = p->n2e_ent[k] >> 2;
-                        if (f != e && elem_has(f, b)) { nb[3 * e + c] = f; break; }
+                        const int cf = p->n2e_ent[k] & 3;      // corner of f that is a
+                        if (f != e && c32g[3 * (int64_t)f + (cf + 2) % 3] == b) { nb[3 * e + c] = f; break; }
                     }
                 }
         };
@@ -894,8 +921,22 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
                         singles.push_back(word9(e));
                     }
                 }
-                // pairs and singles are ordered separately (singles stay at the end: whole warps skip the second element)
-                reorder_pairs_for_banks(B.pack9, (unsigned)acc9);
+                // entries are listed class by class (a warp whose lanes are all of one class runs one wiring of the second
+                // element; a warp across a class boundary just runs both), bank-aware inside each class; singles at the end
+                {
+                    std::vector<unsigned long long> by_cls[9];
+                    for (size_t i = 0; i + 1 < B.pack9.size(); i += 2) {
+                        const int cls = pair_class(B.pack9[i], B.pack9[i + 1]);
+                        if (cls < 0 || cls >= 9) { B.err = 3; break; }
+                        by_cls[cls].push_back(B.pack9[i]);
+                        by_cls[cls].push_back(B.pack9[i + 1]);
+                    }
+                    B.pack9.clear();
+                    for (int c = 0; c < 9; ++c) {
+                        reorder_pairs_for_banks(by_cls[c], (unsigned)acc9);
+                        B.pack9.insert(B.pack9.end(), by_cls[c].begin(), by_cls[c].end());
+                    }
+                }
                 {
                     std::vector<unsigned long long> sp;
                     for (unsigned long long w : singles) { sp.push_back(w); sp.push_back(null_word); }
@@ -1212,7 +1253,19 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
         size_t pp_off = 0, po_off = 0;
         for (int64_t t = 0; t < n_tiles; ++t) {
             const TileDesc8& d8 = p->tiles8[t];
-            std::copy(p->pair_pack.begin() + pp_off, p->pair_pack.begin() + pp_off + 2 * (size_t)d8.n_pent, d_pair.begin() + (size_t)t * SP * 2);
+            for (int32_t i = 0; i < d8.n_pent; ++i) {      // device format of the second word (tri_plan.h)
+                const unsigned long long w1 = p->pair_pack[pp_off + 2 * (size_t)i], w2 = p->pair_pack[pp_off + 2 * (size_t)i + 1];
+                const int cls = pair_class(w1, w2);
+                unsigned long long dw = (unsigned long long)kPairSingle << (kLidBits + kPosBits);
+                if (cls != kPairSingle) {
+                    const int r = cls % 3;
+                    dw = ((w2 >> (kLidBits * r)) & ((1ull << kLidBits) - 1ull)) |
+                         (((w2 >> (3 * kLidBits + kPosBits * r)) & ((1ull << kPosBits) - 1ull)) << kLidBits) |
+                         ((unsigned long long)cls << (kLidBits + kPosBits)) | (w2 & (1ull << kOwnerBit));
+                }
+                d_pair[((size_t)t * SP + i) * 2] = w1;
+                d_pair[((size_t)t * SP + i) * 2 + 1] = dw;
+            }
             std::copy(p->entry_off9.begin() + po_off, p->entry_off9.begin() + po_off + d8.n_owned, d_off9.begin() + (size_t)t * SO);
             pp_off += 2 * (size_t)d8.n_pent;
             po_off += d8.n_owned;

@@ -51,6 +51,13 @@ struct TileDesc8 {           // 64 B
 // in registers, so that node receives ONE partial for the pair: 4 instead of 6 partial stores and fold reads per pair.
 // pair_pack holds two 64-bit words of the elem_pack format per entry (first element = smaller element id; corners of
 // the second element that are merged carry the dump position; a single element has the null word kNullPack second).
+// Partners run through their shared edge in opposite directions (both counter-clockwise or both clockwise), so with the
+// first element's corners Q0 Q1 Q2 and the second element's new corner Q3 a pair is one of 9 classes
+//   cls = 3 i + r:   second element: corner r = Q3, corner r+1 = Q(i+1), corner r+2 = Q(i)      (indices mod 3)
+// and the kernel has one compile-time register wiring per class (the reference's J^-1 D_N quirk makes an element's result
+// depend on its own corner order, so the corners cannot be rotated into a canonical position).  Entries are listed class
+// by class.  On the DEVICE the second word is  lid(Q3) | pos(Q3) << 10 | cls << 21 | owner << 63  (cls = kPairSingle for
+// a single element); the host copy keeps the two elem_pack words (tests replay them).
 struct TriPlan8Dev {
     const TileDesc8* tiles;
     const int2* t_halo;                    // [n_tiles, stride_halo]: (xslot, uslot) of the halo nodes, ascending node id
@@ -63,6 +70,8 @@ struct TriPlan8Dev {
     int32_t stride_pent, max_entries9, pad2, pad3;
 };
 constexpr unsigned long long kNullPack = 0x3FFFFFFFull;      // local ids 1023,1023,1023: no element
+constexpr int kPairSingle = 9;
+int pair_class(unsigned long long w1, unsigned long long w2);
 
 struct TriPlanDev {
     const TileDesc* tiles;

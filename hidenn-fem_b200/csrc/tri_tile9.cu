@@ -45,7 +45,7 @@ namespace hidenn {
 #if HIDENN_PROF9
 #define PROF_DECL long long pf_t0 = clock64(), pf_a = 0, pf_b = 0
 #define PROF_WAIT(acc, stmt) { const long long pf_s = clock64(); stmt; acc += clock64() - pf_s; }
-#define PROF_END(ntiles) if (lane == 0) { double* o = e_dom + ((size_t)blockIdx.x * 24 + wid) * 4; o[0] = (double)(clock64() - pf_t0); o[1] = (double)pf_a; o[2] = (double)pf_b; o[3] = (double)(ntiles); }
+#define PROF_END(ntiles) if (lane == 0) { double* o = e_dom + ((size_t)blockIdx.x * kWarps9 + wid) * 4; o[0] = (double)(clock64() - pf_t0); o[1] = (double)pf_a; o[2] = (double)pf_b; o[3] = (double)(ntiles); }
 #else
 #define PROF_DECL
 #define PROF_WAIT(acc, stmt) stmt;
@@ -58,8 +58,18 @@ namespace hidenn {
 #define HIDENN_WS_LWARPS 2
 #endif
 constexpr int kLWarps = HIDENN_WS_LWARPS;
-constexpr int kEWarps = HIDENN_WS_EWARPS, kFWarps = 24 - kLWarps - kEWarps, kThreads9 = 24 * 32;      // 768 threads = 6 warpgroups
-constexpr int kRedWarp0 = 16;      // the last 8 warps (small-register groups in every configuration) do the final reduction
+// CTA size: 24 warps (launch pool 768 x 80 registers) or 32 warps (1024 x 64).  Registers after setmaxnreg:
+//   24 warps: 12 element warps x 120 + 12 x 40;   32 warps: 16 x 80 + 16 x 40  or  12 x 104 + 20 x 40   (all <= 65536 / 32)
+#ifndef HIDENN_WS_WARPS
+#define HIDENN_WS_WARPS 24
+#endif
+constexpr int kWarps9 = HIDENN_WS_WARPS;
+constexpr int kEWarps = HIDENN_WS_EWARPS, kFWarps = kWarps9 - kLWarps - kEWarps, kThreads9 = kWarps9 * 32;
+constexpr int kERegs = kWarps9 == 24 ? (kEWarps == 16 ? 96 : 120) : (kEWarps == 16 ? 80 : 104);
+constexpr int kORegs = kWarps9 == 24 ? (kEWarps == 16 ? 48 : 40) : 40;
+static_assert(kWarps9 == 24 || kWarps9 == 32, "768 or 1024 threads");
+static_assert((kEWarps * kERegs + (kWarps9 - kEWarps) * kORegs) * 32 <= 65536, "register pool");
+constexpr int kRedWarp0 = 16;      // warps 16..23 (small-register groups in every configuration) do the final reduction
 static_assert(kEWarps % 4 == 0 && kEWarps <= 16, "element warps come in warpgroups; 512 x 104 + 256 x 32 or 384 x 128 + 384 x 32 registers");
 constexpr int kMaxStages = 4;
 constexpr int kEnSlots = kEWarps * 32 + 16;
@@ -160,8 +170,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
 
     if (wid < kEWarps) {
         // ------------------------------------------------------------------ element warps
-        if (kEWarps == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
-        else asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kERegs));
         const TriConsts<R> K = load_consts<R, BODY>(consts);
         const bool with_edges = (flags & HIDENN_WITH_EDGES) != 0;
         const int etid = tid;
@@ -183,22 +192,63 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
             PROF_WAIT(pf_b, bar_wait(&part_empty[pb], ((k >> 1) & 1) ^ 1))
             const unsigned dumpv = (unsigned)(PAIRS ? d->n_entries9 : d->n_entries);
             R e_acc = R(0), ee_acc = R(0);
-            // one entry = an edge-sharing element pair (or a single element): both elements are evaluated by this thread,
-            // the partials of the two shared nodes are added in registers (first element + second), so each shared node
-            // gets one partial store / one fold read for the pair
+            // one entry = an edge-sharing element pair (or a single element): both elements are evaluated by this thread
+            // from FOUR gathered nodes; the partials of the two shared nodes are added in registers (first element +
+            // second), so the pair costs 4 gathers, 4 partial stores and 4 fold reads instead of 6 / 6 / 6
             for (int i = etid; i < n_pent; i += kEWarps * 32) {
-                ulonglong2 pw;
-                if (PAIRS) pw = s_pack[i];
-                else {
-                    pw.x = pw_next; pw.y = kNullPack;
-                    pw_next = (i + kEWarps * 32 < n_pent) ? s_pack1[i + kEWarps * 32] : 0ull;
-                }
                 R2 gu[3], gx[3];
                 unsigned l0, l1, l2, p0, p1, p2;
-                {
+                if (PAIRS) {
+                    const ulonglong2 pw = s_pack[i];
                     const unsigned lo = (unsigned)pw.x, hi = (unsigned)(pw.x >> 32);
                     l0 = lo & LM; l1 = (lo >> kLidBits) & LM; l2 = (lo >> (2 * kLidBits)) & LM;
                     p0 = (unsigned)(pw.x >> (3 * kLidBits)) & PM; p1 = (hi >> (3 * kLidBits + kPosBits - 32)) & PM;
+                    p2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
+                    const unsigned w2 = (unsigned)pw.y;
+                    const unsigned l3 = w2 & LM, p3 = (w2 >> kLidBits) & PM, cls = (w2 >> (kLidBits + kPosBits)) & 15u;
+                    R2 Q0, Q1, Q2, Q3, V0, V1, V2, V3;
+                    nodes.load(l0, Q0, V0); nodes.load(l1, Q1, V1); nodes.load(l2, Q2, V2);
+                    if (cls != (unsigned)kPairSingle) nodes.load(l3, Q3, V3);
+                    R e;
+                    if (cls == (unsigned)kPairSingle) {
+                        tri_element<R, BODY, ISO>(Q0, Q1, Q2, V0, V1, V2, K, e, gu, gx, JT);
+                        e_acc += (hi >> 31) ? e : R(0);
+                    } else {
+                        R2 g3u, g3x;
+                        R e2;
+                        // second element of class 3 i + r: corner r = Q3, corner r+1 = Q(i+1), corner r+2 = Q(i).  Both
+                        // elements are evaluated inside the case, so their two dependent FP64 chains interleave
+#define HIDENN_PAIR_CASE(I_, R_)                                                                                              \
+    case 3 * I_ + R_: {                                                                                                       \
+        const R2 A = I_ == 0 ? Q1 : I_ == 1 ? Q2 : Q0, AU = I_ == 0 ? V1 : I_ == 1 ? V2 : V0;                                 \
+        const R2 B = I_ == 0 ? Q0 : I_ == 1 ? Q1 : Q2, BU = I_ == 0 ? V0 : I_ == 1 ? V1 : V2;                                 \
+        R2 hu[3], hx[3];                                                                                                      \
+        tri_element<R, BODY, ISO>(Q0, Q1, Q2, V0, V1, V2, K, e, gu, gx, JT);                                                  \
+        if (R_ == 0) tri_element<R, BODY, ISO>(Q3, A, B, V3, AU, BU, K, e2, hu, hx, JT);                                      \
+        else if (R_ == 1) tri_element<R, BODY, ISO>(B, Q3, A, BU, V3, AU, K, e2, hu, hx, JT);                                 \
+        else tri_element<R, BODY, ISO>(A, B, Q3, AU, BU, V3, K, e2, hu, hx, JT);                                              \
+        constexpr int ia = (I_ + 1) % 3, ib = I_, ca = (R_ + 1) % 3, cb = (R_ + 2) % 3;                                       \
+        gu[ia].x += hu[ca].x; gu[ia].y += hu[ca].y; gx[ia].x += hx[ca].x; gx[ia].y += hx[ca].y;                               \
+        gu[ib].x += hu[cb].x; gu[ib].y += hu[cb].y; gx[ib].x += hx[cb].x; gx[ib].y += hx[cb].y;                               \
+        g3u = hu[R_]; g3x = hx[R_];                                                                                           \
+    } break;
+                        switch (cls) {
+                            HIDENN_PAIR_CASE(0, 0) HIDENN_PAIR_CASE(0, 1) HIDENN_PAIR_CASE(0, 2)
+                            HIDENN_PAIR_CASE(1, 0) HIDENN_PAIR_CASE(1, 1) HIDENN_PAIR_CASE(1, 2)
+                            HIDENN_PAIR_CASE(2, 0) HIDENN_PAIR_CASE(2, 1)
+                            default: HIDENN_PAIR_CASE(2, 2)
+                        }
+#undef HIDENN_PAIR_CASE
+                        e_acc += (hi >> 31) ? e : R(0);
+                        e_acc += (pw.y >> 63) ? e2 : R(0);
+                        if (p3 != dumpv) part.store(p3, g3u, g3x);
+                    }
+                } else {
+                    const unsigned long long pw = pw_next;
+                    pw_next = (i + kEWarps * 32 < n_pent) ? s_pack1[i + kEWarps * 32] : 0ull;
+                    const unsigned lo = (unsigned)pw, hi = (unsigned)(pw >> 32);
+                    l0 = lo & LM; l1 = (lo >> kLidBits) & LM; l2 = (lo >> (2 * kLidBits)) & LM;
+                    p0 = (unsigned)(pw >> (3 * kLidBits)) & PM; p1 = (hi >> (3 * kLidBits + kPosBits - 32)) & PM;
                     p2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
                     R e;
                     R2 v0, v1, v2, U0, U1, U2;
@@ -227,28 +277,6 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
 #if HIDENN_ABL >= 3
                     e_acc += gu[0].x + gu[0].y + gx[0].x + gx[0].y;
 #endif
-                }
-                if (PAIRS && ((unsigned)pw.y & 0x3FFFFFFFu) != 0x3FFFFFFFu) {
-                    const unsigned lo = (unsigned)pw.y, hi = (unsigned)(pw.y >> 32);
-                    const unsigned m0 = lo & LM, m1 = (lo >> kLidBits) & LM, m2 = (lo >> (2 * kLidBits)) & LM;
-                    const unsigned q0 = (unsigned)(pw.y >> (3 * kLidBits)) & PM, q1 = (hi >> (3 * kLidBits + kPosBits - 32)) & PM,
-                                   q2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
-                    R e;
-                    R2 hu[3], hx[3], v0, v1, v2, U0, U1, U2;
-                    nodes.load(m0, v0, U0); nodes.load(m1, v1, U1); nodes.load(m2, v2, U2);
-                    tri_element<R, BODY, ISO>(v0, v1, v2, U0, U1, U2, K, e, hu, hx, JT);
-                    e_acc += (hi >> 31) ? e : R(0);
-                    const unsigned ll[3] = {l0, l1, l2}, mm[3] = {m0, m1, m2};
-#pragma unroll
-                    for (int a = 0; a < 3; ++a)
-#pragma unroll
-                        for (int c = 0; c < 3; ++c)
-                            if (ll[a] == mm[c]) {      // same node: one partial for the pair
-                                gu[a].x += hu[c].x; gu[a].y += hu[c].y; gx[a].x += hx[c].x; gx[a].y += hx[c].y;
-                            }
-                    if (q0 != dumpv) part.store(q0, hu[0], hx[0]);
-                    if (q1 != dumpv) part.store(q1, hu[1], hx[1]);
-                    if (q2 != dumpv) part.store(q2, hu[2], hx[2]);
                 }
 #if HIDENN_ABL <= 2
                 if (p0 != dumpv) part.store(p0, gu[0], gx[0]);
@@ -311,8 +339,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
         }
         PROF_END(n_mine)
     } else {
-        if (kEWarps == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
-        else asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kORegs));
         if (wid >= kEWarps + kFWarps) {
             // -------------------------------------------------------------- loader warp
             // The per-tile chain  descriptor -> bulk copies, halo records -> gathers  is two dependent global loads; the
@@ -460,7 +487,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
         *s_flag = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
     }
     __syncthreads();
-    if (*s_flag && wid >= kRedWarp0) {        // 8 warps of the small-register groups do the reduction (256 threads)
+    if (*s_flag && wid >= kRedWarp0 && wid < kRedWarp0 + 8) {        // 8 warps of the small-register groups do the reduction (256 threads)
         __threadfence();
         const int t0 = tid - kRedWarp0 * 32;
         double dsum = 0.0, esum = 0.0;

@@ -28,17 +28,21 @@ def run_one():
     import torch, bench
     args = bench.parse()
     dev = torch.device("cuda:0")
-    m, model, loss_fn, _ = bench.make_workload(args, 0, 1, dev, torch.float64, "tiles", args.elems)
+    m, model, loss_fn, _ = bench.make_workload(args, 0, 1, dev, torch.float64, "tiles", args.elems, args.tile_nodes)
     ms = min(bench.time_kernel(model, loss_fn, 20, 5) for _ in range(3))
-    rec = {"lib": os.path.basename(os.environ.get("HIDENN_LIB", "default")), "kernel_us": round(ms * 1e3, 1)}
+    info = model._plan().info
+    rec = {"lib": os.path.basename(os.environ.get("HIDENN_LIB", "default")), "kernel_us": round(ms * 1e3, 1),
+           "pairs": os.environ.get("HIDENN_PLAN_PAIRS", "0"), "tile_nodes": args.tile_nodes, "n_tiles": info["n_tiles"],
+           "entries_per_tile": round(info.get("pair_entries", 0) / info["n_tiles"], 1), "n_pairs": info.get("n_pairs", 0)}
+    import re
     if "prof" in rec["lib"]:      # HIDENN_PROF9 build: per-warp wait cycles sit in the tile-energy scratch
         torch.cuda.synchronize()
         plan = model._plan()
-        sc = loss_fn._scratch(plan, dev, torch.float64)[:148 * 24 * 4].reshape(148, 24, 4).cpu().numpy()
-        import re
+        nw = int((re.search(r"_w(\d+)", rec["lib"]) or [0, "24"])[1])
+        sc = loss_fn._scratch(plan, dev, torch.float64)[:148 * nw * 4].reshape(148, nw, 4).cpu().numpy()
         ew = int((re.search(r"_e(\d+)", rec["lib"]) or [0, "12"])[1])      # tags: prof_e12_l2 ...
         lw = int((re.search(r"_l(\d+)", rec["lib"]) or [0, "2"])[1])
-        for name, sl in (("element", slice(0, ew)), ("fold", slice(ew, 24 - lw)), ("loader", slice(24 - lw, 24))):
+        for name, sl in (("element", slice(0, ew)), ("fold", slice(ew, nw - lw)), ("loader", slice(nw - lw, nw))):
             w = sc[:, sl]
             tot = w[..., 0].mean()
             rec[name] = {"total_cyc": round(float(tot)), "waitA_frac": round(float((w[..., 1] / w[..., 0]).mean()), 3),
