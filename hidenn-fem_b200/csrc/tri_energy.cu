@@ -821,7 +821,7 @@ extern "C" int hidenn_tri_plan_kernel(const hidenn_tri_plan* plan) {
 extern "C" int hidenn_tri_plan_overlap_target(const hidenn_tri_plan* plan) {
     static const bool ws_off = [] { const char* e = getenv("HIDENN_TILE_WS"); return e && atoi(e) == 0; }();
     if (!plan || !plan->tile_order || plan->n_first_tiles <= 0 || ws_off || !tile9_fits(plan)) return 0;
-    return plan->n_first_tiles * tile9_fold_warps();
+    return plan->n_first_tiles * tile9_fold_warps(plan);
 }
 extern "C" int hidenn_tri_energy_finish_f64(const hidenn_tri_plan* plan, double* scratch, double* out, void* stream) {
     HIDENN_REQUIRE(plan && plan->tile_order && scratch && out, "tri_energy_finish: needs a tile-ordered FP64 plan, scratch and out");

@@ -168,6 +168,7 @@ static void reorder_for_banks(TileBuild& B, int real_bytes) {
 // a single element; -1 if the two words are not such a pair.
 int pair_class(unsigned long long w1, unsigned long long w2) {
     constexpr unsigned LM = (1u << kLidBits) - 1u;
+    if (((unsigned)w1 & 0x3FFFFFFFu) == 0x3FFFFFFFu) return kPairSkip;
     if (((unsigned)w2 & 0x3FFFFFFFu) == 0x3FFFFFFFu) return kPairSingle;
     unsigned l[3], m[3];
     for (int c = 0; c < 3; ++c) { l[c] = (unsigned)(w1 >> (kLidBits * c)) & LM; m[c] = (unsigned)(w2 >> (kLidBits * c)) & LM; }
@@ -588,11 +589,13 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
     // neighbours left (ties: smallest id).
     const int32_t* c32g = p->conn32.data();
     auto elem_has = [c32g](int32_t f, int32_t n) { return c32g[3 * (int64_t)f] == n || c32g[3 * (int64_t)f + 1] == n || c32g[3 * (int64_t)f + 2] == n; };
-    // opt-in: measured slower than one element per thread on B200 (profiles/README.md: the twelve accesses of a pair cannot
-    // be kept bank-conflict free, and the merge costs issue slots); kept for the record and for meshes where it may pay
-    const bool want_pairs = getenv("HIDENN_PLAN_PAIRS") != nullptr && atoi(getenv("HIDENN_PLAN_PAIRS")) != 0;
+    // HIDENN_PLAN_PAIRS: unset = automatic (the paired layout is kept when at least 80 % of the elements find a partner),
+    // 0 = never, 1 = always.  C4 on B200: 161 us per launch paired against 173 us with one element per entry.
+    const char* pairs_env = getenv("HIDENN_PLAN_PAIRS");
+    const bool want_pairs = pairs_env == nullptr || atoi(pairs_env) != 0;
+    const bool force_pairs = pairs_env != nullptr && atoi(pairs_env) != 0;
     if (want_pairs && real_bytes == 8 && !no_v8 && Ne > 0) {
-        std::vector<int32_t> nb(3 * Ne, -1);
+        std::vector<int32_t> nb(3 * Ne, -1);      // neighbour across the edge (corner c -> c+1): f * 4 + (corner of f at the edge's start node)
         auto nb_range = [&](int64_t e0, int64_t e1) {
             for (int64_t e = e0; e < e1; ++e)
                 for (int c = 0; c < 3; ++c) {
@@ -603,7 +606,7 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
                     for (int64_t k = p->n2e_off[a]; k < p->n2e_off[a + 1]; ++k) {
                         const int32_t f = p->n2e_ent[k] >> 2;
                         const int cf = p->n2e_ent[k] & 3;      // corner of f that is a
-                        if (f != e && c32g[3 * (int64_t)f + (cf + 2) % 3] == b) { nb[3 * e + c] = f; break; }
+                        if (f != e && c32g[3 * (int64_t)f + (cf + 2) % 3] == b) { nb[3 * e + c] = f * 4 + cf; break; }
                     }
                 }
         };
@@ -618,22 +621,67 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
             }
             for (auto& t : th) t.join();
         }
+        // wiring class of the pair (e, neighbour across e's edge c), first element = smaller id (tri_plan.h)
+        auto cls_of = [&](int64_t e, int c) -> int {
+            const int32_t v = nb[3 * e + c];
+            if (v < 0) return -1;
+            const int64_t f = v >> 2;
+            const int cf = v & 3;
+            return e < f ? 3 * c + (cf + 1) % 3 : 3 * ((cf + 2) % 3) + (c + 2) % 3;
+        };
+        // Which classes?  Meshes from generators number their corners by a few patterns, and a tile's entries are listed
+        // class by class with every class padded to whole warps, so the matching should live in as few classes as
+        // possible: the PAIR of classes whose greedy matching (element order, free neighbour of an allowed class) covers
+        // most of a sample of the mesh goes first, then the remaining classes one at a time, most frequent first.
+        int64_t hist[9] = {};
+        for (int64_t e = 0; e < Ne; ++e)
+            for (int c = 0; c < 3; ++c) {
+                const int32_t v = nb[3 * e + c];
+                if (v >= 0 && e < (v >> 2)) hist[cls_of(e, c)]++;
+            }
         p->mate.assign(Ne, -1);
         std::vector<int32_t>& mate = p->mate;
-        for (int64_t e = 0; e < Ne; ++e) {
-            if (mate[e] >= 0) continue;
-            int32_t best = -1, best_deg = 99;
-            for (int c = 0; c < 3; ++c) {
-                const int32_t f = nb[3 * e + c];
-                if (f < 0 || mate[f] >= 0 || f == best) continue;
-                int deg = 0;
-                for (int c2 = 0; c2 < 3; ++c2) {
-                    const int32_t g = nb[3 * (int64_t)f + c2];
-                    if (g >= 0 && g != e && mate[g] < 0) ++deg;
+        auto greedy = [&](unsigned mask, int64_t e_end, std::vector<int32_t>& mt) -> int64_t {
+            int64_t n = 0;
+            for (int64_t e = 0; e < e_end; ++e) {
+                if (mt[e] >= 0) continue;
+                for (int c = 0; c < 3; ++c) {
+                    const int32_t v = nb[3 * e + c];
+                    if (v < 0 || (v >> 2) >= e_end || mt[v >> 2] >= 0 || !((mask >> cls_of(e, c)) & 1u)) continue;
+                    mt[e] = v >> 2; mt[v >> 2] = (int32_t)e; ++n;
+                    break;
                 }
-                if (deg < best_deg || (deg == best_deg && f < best)) { best = f; best_deg = deg; }
             }
-            if (best >= 0) { mate[e] = best; mate[best] = (int32_t)e; p->n_pairs++; }
+            return n;
+        };
+        unsigned best_mask = 0;
+        {
+            const int64_t ns = std::min<int64_t>(Ne, 1 << 20);
+            std::vector<int32_t> tmp;
+            int64_t best = -1;
+            for (int x = 0; x < 9; ++x)
+                for (int y = x; y < 9; ++y) {
+                    if (hist[x] == 0 || hist[y] == 0) continue;
+                    tmp.assign(ns, -1);
+                    const int64_t n = greedy((1u << x) | (1u << y), ns, tmp);
+                    if (n > best) { best = n; best_mask = (1u << x) | (1u << y); }
+                }
+        }
+        static const int max_classes = [] { const char* e = getenv("HIDENN_PLAN_PAIR_CLASSES"); return e ? std::max(1, std::min(9, atoi(e))) : 9; }();
+        p->n_pairs += greedy(best_mask, Ne, mate);
+        int corder[9];
+        std::iota(corder, corder + 9, 0);
+        std::stable_sort(corder, corder + 9, [&](int x, int y) { return hist[x] > hist[y]; });
+        int used = __builtin_popcount(best_mask);
+        for (int ci = 0; ci < 9 && used < max_classes; ++ci) {
+            const int cls = corder[ci];
+            if (hist[cls] == 0 || ((best_mask >> cls) & 1u)) continue;
+            p->n_pairs += greedy(1u << cls, Ne, mate);
+            ++used;
+        }
+        if (!force_pairs && p->n_pairs * 10 < Ne * 4) {      // too few partners: one element per entry
+            p->mate.clear();
+            p->n_pairs = 0;
         }
     }
 
@@ -932,9 +980,13 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
                         by_cls[cls].push_back(B.pack9[i + 1]);
                     }
                     B.pack9.clear();
+                    // every class starts at a multiple of 32 entries (padding = skip entries): a warp that ran two wirings
+                    // one after the other would take twice as long, and the tile waits for its slowest warp
+                    static const bool pad_cls = [] { const char* e = getenv("HIDENN_PLAN_PAIR_PAD"); return !e || atoi(e) != 0; }();
                     for (int c = 0; c < 9; ++c) {
                         reorder_pairs_for_banks(by_cls[c], (unsigned)acc9);
                         B.pack9.insert(B.pack9.end(), by_cls[c].begin(), by_cls[c].end());
+                        while (pad_cls && (B.pack9.size() / 2) % 32 != 0) { B.pack9.push_back(null_word); B.pack9.push_back(null_word); }
                     }
                 }
                 {
@@ -1256,8 +1308,8 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
             for (int32_t i = 0; i < d8.n_pent; ++i) {      // device format of the second word (tri_plan.h)
                 const unsigned long long w1 = p->pair_pack[pp_off + 2 * (size_t)i], w2 = p->pair_pack[pp_off + 2 * (size_t)i + 1];
                 const int cls = pair_class(w1, w2);
-                unsigned long long dw = (unsigned long long)kPairSingle << (kLidBits + kPosBits);
-                if (cls != kPairSingle) {
+                unsigned long long dw = (unsigned long long)cls << (kLidBits + kPosBits);
+                if (cls < kPairSingle) {
                     const int r = cls % 3;
                     dw = ((w2 >> (kLidBits * r)) & ((1ull << kLidBits) - 1ull)) |
                          (((w2 >> (3 * kLidBits + kPosBits * r)) & ((1ull << kPosBits) - 1ull)) << kLidBits) |

@@ -70,7 +70,7 @@ struct TriPlan8Dev {
     int32_t stride_pent, max_entries9, pad2, pad3;
 };
 constexpr unsigned long long kNullPack = 0x3FFFFFFFull;      // local ids 1023,1023,1023: no element
-constexpr int kPairSingle = 9;
+constexpr int kPairSingle = 9, kPairSkip = 10;      // skip: padding entry (both words null), no work
 int pair_class(unsigned long long w1, unsigned long long w2);
 
 struct TriPlanDev {

@@ -18,13 +18,13 @@ int tile8_launch(const hidenn_tri_plan* p, const double* x_free, const double* x
 size_t tile9_smem_bytes(const hidenn_tri_plan* p);
 bool tile9_fits(const hidenn_tri_plan* p);
 // first_done (may be NULL): device counter every fold warp increments once per finished tile among the plan's first
-// n_first_tiles (multi-GPU overlap: it reaches n_first_tiles * tile9_fold_warps() when the shared rows are final);
+// n_first_tiles (multi-GPU overlap: it reaches n_first_tiles * tile9_fold_warps(plan) when the shared rows are final);
 // reserve_sms: leave that many SMs to kernels running beside this one.
 int tile9_launch(const hidenn_tri_plan* p, const double* x_free, const double* x_fixed, const double* u_free, const double* u_fixed,
                  const double* consts, const double* t_table, int flags, double* out, double* gx, double* gu, double* gt, double* scratch,
                  unsigned* ticket, cudaStream_t stream, int tile_begin, int tile_end, unsigned* first_done = nullptr, int reserve_sms = 0,
                  const P2PLossArgs* loss_args = nullptr);      // loss_args: exchange the loss partials over peer memory in the kernel's tail
-int tile9_fold_warps();
+int tile9_fold_warps(const hidenn_tri_plan* p);
 // fixed-order reduction of the tile energies alone (after ranged launches)
 int tile8_reduce(const hidenn_tri_plan* p, double* scratch, double* out, cudaStream_t stream);
 }  // namespace hidenn

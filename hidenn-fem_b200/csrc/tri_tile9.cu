@@ -58,21 +58,34 @@ namespace hidenn {
 #define HIDENN_WS_LWARPS 2
 #endif
 constexpr int kLWarps = HIDENN_WS_LWARPS;
-// CTA size: 24 warps (launch pool 768 x 80 registers) or 32 warps (1024 x 64).  Registers after setmaxnreg:
-//   24 warps: 12 element warps x 120 + 12 x 40;   32 warps: 16 x 80 + 16 x 40  or  12 x 104 + 20 x 40   (all <= 65536 / 32)
+// CTA size and register split (setmaxnreg works on warpgroups of 4 warps; the launch pool is threads x the launch
+// register count, and the split may not exceed it):
+//   24 warps (pool 768 x 80):  12 element warps x 120 + 12 x 40,  or 16 x 96 + 8 x 48
+//   28 warps (pool 896 x 72):  16 x 96 + 12 x 40
+//   32 warps (pool 1024 x 64): 16 x 80 + 16 x 40,  or 12 x 104 + 20 x 40
 #ifndef HIDENN_WS_WARPS
 #define HIDENN_WS_WARPS 24
 #endif
-constexpr int kWarps9 = HIDENN_WS_WARPS;
-constexpr int kEWarps = HIDENN_WS_EWARPS, kFWarps = kWarps9 - kLWarps - kEWarps, kThreads9 = kWarps9 * 32;
-constexpr int kERegs = kWarps9 == 24 ? (kEWarps == 16 ? 96 : 120) : (kEWarps == 16 ? 80 : 104);
-constexpr int kORegs = kWarps9 == 24 ? (kEWarps == 16 ? 48 : 40) : 40;
-static_assert(kWarps9 == 24 || kWarps9 == 32, "768 or 1024 threads");
-static_assert((kEWarps * kERegs + (kWarps9 - kEWarps) * kORegs) * 32 <= 65536, "register pool");
+constexpr int kWarps9 = HIDENN_WS_WARPS, kThreads9 = kWarps9 * 32;
+constexpr int kPoolRegs = kWarps9 == 24 ? 80 : kWarps9 == 28 ? 72 : 64;
+static_assert(kWarps9 == 24 || kWarps9 == 28 || kWarps9 == 32, "768, 896 or 1024 threads");
+// Roles per layout.  One element per entry: 12 element warps (two passes over a tile's ~720 visits), 10 fold warps (one
+// owned node per thread).  Pairs: an entry is two elements and needs ~95 registers, a tile has ~410 entries (classes padded
+// to whole warps), so 16 element warps take it in one pass; the fold is a third shorter and runs on 6 warps (two passes).
+#ifndef HIDENN_WS_EWARPS_PAIRS
+#define HIDENN_WS_EWARPS_PAIRS 16
+#endif
+template <bool PAIRS> struct Roles9 {
+    static constexpr int E = PAIRS ? HIDENN_WS_EWARPS_PAIRS : HIDENN_WS_EWARPS;
+    static constexpr int F = kWarps9 - kLWarps - E;
+    static constexpr int ERegs = kWarps9 == 24 ? (E == 16 ? 96 : 120) : kWarps9 == 28 ? 96 : (E == 16 ? 80 : 104);
+    static constexpr int ORegs = kWarps9 == 24 ? (E == 16 ? 48 : 40) : 40;
+    static constexpr int EnSlots = E * 32 + 16;
+    static_assert(E % 4 == 0 && E <= 16 && F >= 1, "element warps come in warpgroups");
+    static_assert(E * ERegs + (kWarps9 - E) * ORegs <= kWarps9 * kPoolRegs, "register split exceeds the launch pool");
+};
 constexpr int kRedWarp0 = 16;      // warps 16..23 (small-register groups in every configuration) do the final reduction
-static_assert(kEWarps % 4 == 0 && kEWarps <= 16, "element warps come in warpgroups; 512 x 104 + 256 x 32 or 384 x 128 + 384 x 32 registers");
 constexpr int kMaxStages = 4;
-constexpr int kEnSlots = kEWarps * 32 + 16;
 
 namespace {
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,7 +133,7 @@ struct Smem9 {          // offsets (bytes) into the dynamic shared memory
     int stage_bytes, node_off, pack_off, offs_off, desc_off;      // inside a stage
     int part_bytes, part0, en0, bar0, total;
 };
-__host__ __device__ inline Smem9 smem9_layout(int max_local, int max_entries9, int pack_bytes, int stride_owned, int n_stages) {
+__host__ __device__ inline Smem9 smem9_layout(int max_local, int max_entries9, int pack_bytes, int stride_owned, int n_stages, int e_warps) {
     Smem9 L;
     L.node_off = 0;
     L.pack_off = max_local * 32;
@@ -130,7 +143,7 @@ __host__ __device__ inline Smem9 smem9_layout(int max_local, int max_entries9, i
     L.part_bytes = (max_entries9 + 1) * 32;
     L.part0 = n_stages * L.stage_bytes;
     L.en0 = L.part0 + 2 * L.part_bytes;
-    L.bar0 = L.en0 + 2 * kEnSlots * 8;      // per partial buffer: one energy slot per element lane + 16 edge-energy warp sums
+    L.bar0 = L.en0 + 2 * (e_warps * 32 + 16) * 8;      // per partial buffer: one energy slot per element lane + 16 edge-energy warp sums
     L.total = L.bar0 + 16 * 8 + 16;
     return L;
 }
@@ -149,7 +162,9 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
     using R2 = double2;
     extern __shared__ __align__(128) unsigned char smem[];
     const int max_entries = PAIRS ? P8.max_entries9 : P.max_entries;
-    const Smem9 L = smem9_layout(P.max_local, max_entries, PAIRS ? P8.stride_pent * 16 : P.stride_elem * 8, P.stride_owned, kStages);
+    constexpr int kEWarps = Roles9<PAIRS>::E, kFWarps = Roles9<PAIRS>::F, kERegs = Roles9<PAIRS>::ERegs, kORegs = Roles9<PAIRS>::ORegs,
+                  kEnSlots = Roles9<PAIRS>::EnSlots;
+    const Smem9 L = smem9_layout(P.max_local, max_entries, PAIRS ? P8.stride_pent * 16 : P.stride_elem * 8, P.stride_owned, kStages, kEWarps);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar0);
     uint64_t* full_stage = bars;                  // [kStages] loader -> element / fold warps
     uint64_t* empty_stage = bars + kMaxStages;    // [kStages] fold warps -> loader
@@ -206,6 +221,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     p2 = (hi >> (3 * kLidBits + 2 * kPosBits - 32)) & PM;
                     const unsigned w2 = (unsigned)pw.y;
                     const unsigned l3 = w2 & LM, p3 = (w2 >> kLidBits) & PM, cls = (w2 >> (kLidBits + kPosBits)) & 15u;
+                    if (cls == (unsigned)kPairSkip) continue;      // padding up to the next class boundary
                     R2 Q0, Q1, Q2, Q3, V0, V1, V2, V3;
                     nodes.load(l0, Q0, V0); nodes.load(l1, Q1, V1); nodes.load(l2, Q2, V2);
                     if (cls != (unsigned)kPairSingle) nodes.load(l3, Q3, V3);
@@ -516,8 +532,8 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
 
 static bool pairs9(const hidenn_tri_plan* p) { return p->dev8.pair_pack != nullptr; }
 static size_t smem9_for(const hidenn_tri_plan* p, int n_stages) {
-    return pairs9(p) ? (size_t)smem9_layout(p->dev.max_local, p->dev8.max_entries9, p->dev8.stride_pent * 16, p->dev.stride_owned, n_stages).total
-                     : (size_t)smem9_layout(p->dev.max_local, p->dev.max_entries, p->dev.stride_elem * 8, p->dev.stride_owned, n_stages).total;
+    return pairs9(p) ? (size_t)smem9_layout(p->dev.max_local, p->dev8.max_entries9, p->dev8.stride_pent * 16, p->dev.stride_owned, n_stages, Roles9<true>::E).total
+                     : (size_t)smem9_layout(p->dev.max_local, p->dev.max_entries, p->dev.stride_elem * 8, p->dev.stride_owned, n_stages, Roles9<false>::E).total;
 }
 // as many tile stages as fit (4 if possible: one more tile of slack between the bulk copies and the element warps)
 static int stages9_for(const hidenn_tri_plan* p) {
@@ -561,7 +577,7 @@ static int launch9(const hidenn_tri_plan* p, const double* x_free, const double*
     return 0;
 }
 
-int tile9_fold_warps() { return kFWarps; }
+int tile9_fold_warps(const hidenn_tri_plan* p) { return pairs9(p) ? Roles9<true>::F : Roles9<false>::F; }
 bool tile9_fits(const hidenn_tri_plan* p) { return tile9_smem_bytes(p) <= (size_t)227 * 1024; }
 
 int tile9_launch(const hidenn_tri_plan* p, const double* x_free, const double* x_fixed, const double* u_free, const double* u_fixed,

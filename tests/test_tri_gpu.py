@@ -556,7 +556,7 @@ def test_paired_layout_opt_in(monkeypatch):
     g = _mesh_case(120_000, torch.float64, "tiles", invert=0.2, u_scale=1e-3)
     model = build(g)
     info = model._plan().info
-    assert info["tile_ordered"] and info["n_pairs"] > 0.4 * g["connectivity"].shape[0]
+    assert info["tile_ordered"] and info["n_pairs"] > 0.3 * g["connectivity"].shape[0]      # 20 % inverted: fewer opposite-direction neighbours
     loss_fn = loss_of(g, torch.float64)
     loss = loss_fn(model, forces.b_force_test, None)
     loss.backward()
