@@ -598,8 +598,11 @@ def main():
     alg_bytes = 12 * ne_local + 2 * sz * (2 * nn_local) + 2 * sz * (nfree_x + nfree_u)
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": {9: "tri_tile9_kernel<double> (warp-specialised: 12 element warps, 11 fold warps, 1 loader warp; "
-                                               "bulk-copy stage ring; tile-ordered numbering)",
+                "traffic": None, "kernel": {9: ("tri_tile9_kernel<double> (warp-specialised: 16 element warps on edge-sharing element pairs, "
+                                                "6 fold warps, 2 loader warps; bulk-copy stage ring; tile-ordered numbering)"
+                                                if plan.info.get("n_pairs", 0) > 0 else
+                                                "tri_tile9_kernel<double> (warp-specialised: 12 element warps, 10 fold warps, 2 loader warps; "
+                                                "bulk-copy stage ring; tile-ordered numbering)"),
                                             8: "tri_tile8_kernel<double> (two CTAs per SM, bulk-copy staging; tile-ordered numbering)"}.get(
                                                 plan.info.get("kernel"), "tri_tile_persistent_kernel<%s>" % ("double" if sz == 8 else "float")),
                 "kernel_ms": ms_kernel, "algorithmic_bytes_per_launch": alg_bytes,
