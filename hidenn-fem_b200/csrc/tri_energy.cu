@@ -560,6 +560,9 @@ static int tri_energy_launch(const hidenn_tri_plan* p, const R* x_free, const R*
             if (tile_end > tile_begin) {
                 HIDENN_REQUIRE(first_done == nullptr || (!ws_off && tile9_fits(p)),
                                "tri_energy_overlap: needs the warp-specialised tile kernel (hidenn_tri_plan_overlap_target > 0)");
+                HIDENN_REQUIRE(p->unpaired_ok || (!ws_off && tile9_fits(p)),
+                               "tri_energy: this plan's tiles are sized for the paired layout (kernel v9 only); build it with "
+                               "HIDENN_PLAN_PAIRS=0 to run the other tile kernels");
                 const int rc = (!ws_off && tile9_fits(p))
                                    ? tile9_launch(p, x_free, x_fixed, u_free, u_fixed, consts, t_table, flags, out, gx, gu, gt, scratch, ticket,
                                                   stream, tile_begin, tile_end, first_done, reserve_sms, loss_args)

@@ -30,6 +30,13 @@ namespace hidenn {
 
 // default owned nodes per tile: close to the largest tile whose fold slots fit the 11-bit position fields at valence ~6
 constexpr int kDefaultTileNodes = 320;
+// with the paired layout a node has ~4 fold slots instead of 6 and an entry is two elements: tiles are sized so that a
+// tile's entries (pairs + singles + class padding) fill the 512 element lanes of kernel v9 in ONE pass -- the time of a tile
+// hardly depends on how full that pass is, so fewer, fuller tiles are faster (C4: 160 us at 320 nodes, 173 us at 288)
+#ifndef HIDENN_TILE_NODES_PAIRS
+#define HIDENN_TILE_NODES_PAIRS 352
+#endif
+constexpr int kDefaultTileNodesPairs = HIDENN_TILE_NODES_PAIRS;
 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
@@ -96,6 +103,7 @@ struct TileBuild {
     int err = 0;
     std::vector<unsigned long long> epack;   // tile-ordered layout: Neumann edge visits
     std::vector<int32_t> eid;
+    bool unpaired_overflow = false;                  // one-element-per-entry packs unusable (plan is pairs-only)
     std::vector<unsigned long long> pack9, epack9;   // paired layout (2 words per entry)
     std::vector<uint32_t> off9;
     int32_t n_entries9 = 0;
@@ -319,12 +327,127 @@ struct EdgeEnds {       // Neumann edge ends by node: (node, edge*2+end), sorted
     }
 };
 
+// Global matching of the elements into edge-sharing pairs whose partners run through the shared edge in opposite
+// directions (tri_plan.h).  Depends only on the mesh (connectivity + node->element lists), never on the tiling.
+// HIDENN_PLAN_PAIRS: unset = automatic (kept when at least 80 % of the elements find a partner), 0 = never, 1 = always.
+// Returns the number of pairs; `mate` stays empty when the paired layout is not used.
+static int64_t match_elements(const int32_t* c32g, int64_t Ne, const int64_t* n2o, const int32_t* n2e, std::vector<int32_t>& mate) {
+    mate.clear();
+    const char* pairs_env = getenv("HIDENN_PLAN_PAIRS");
+    const bool want_pairs = pairs_env == nullptr || atoi(pairs_env) != 0;
+    const bool force_pairs = pairs_env != nullptr && atoi(pairs_env) != 0;
+    if (!want_pairs || Ne <= 0) return 0;
+    int64_t n_pairs = 0;
+    {
+        std::vector<int32_t> nb(3 * Ne, -1);      // neighbour across the edge (corner c -> c+1): f * 4 + (corner of f at the edge's start node)
+        auto nb_range = [&](int64_t e0, int64_t e1) {
+            for (int64_t e = e0; e < e1; ++e)
+                for (int c = 0; c < 3; ++c) {
+                    // only a neighbour that runs through the shared edge in the opposite direction (b -> a; both elements
+                    // counter-clockwise or both clockwise) can be this element's partner: the kernel has one register wiring
+                    // per (edge of the first element, position of the new corner in the second) = 9 classes
+                    const int32_t a = c32g[3 * e + c], b = c32g[3 * e + (c + 1) % 3];
+                    for (int64_t k = n2o[a]; k < n2o[a + 1]; ++k) {
+                        const int32_t f = n2e[k] >> 2;
+                        const int cf = n2e[k] & 3;      // corner of f that is a
+                        if (f != e && c32g[3 * (int64_t)f + (cf + 2) % 3] == b) { nb[3 * e + c] = f * 4 + cf; break; }
+                    }
+                }
+        };
+        {
+            unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+            if (Ne < 100000) nthr = 1;
+            std::vector<std::thread> th;
+            const int64_t per = (Ne + nthr - 1) / nthr;
+            for (unsigned i = 0; i < nthr; ++i) {
+                const int64_t a = i * per, b = std::min<int64_t>(Ne, a + per);
+                if (a < b) th.emplace_back(nb_range, a, b);
+            }
+            for (auto& t : th) t.join();
+        }
+        // wiring class of the pair (e, neighbour across e's edge c), first element = smaller id (tri_plan.h)
+        auto cls_of = [&](int64_t e, int c) -> int {
+            const int32_t v = nb[3 * e + c];
+            if (v < 0) return -1;
+            const int64_t f = v >> 2;
+            const int cf = v & 3;
+            return e < f ? 3 * c + (cf + 1) % 3 : 3 * ((cf + 2) % 3) + (c + 2) % 3;
+        };
+        // Which classes?  Meshes from generators number their corners by a few patterns, and a tile's entries are listed
+        // class by class with every class padded to whole warps, so the matching should live in as few classes as
+        // possible: the PAIR of classes whose greedy matching (element order, free neighbour of an allowed class) covers
+        // most of a sample of the mesh goes first, then the remaining classes one at a time, most frequent first.
+        int64_t hist[9] = {};
+        for (int64_t e = 0; e < Ne; ++e)
+            for (int c = 0; c < 3; ++c) {
+                const int32_t v = nb[3 * e + c];
+                if (v >= 0 && e < (v >> 2)) hist[cls_of(e, c)]++;
+            }
+        mate.assign(Ne, -1);
+        auto greedy = [&](unsigned mask, int64_t e_end, std::vector<int32_t>& mt) -> int64_t {
+            int64_t n = 0;
+            for (int64_t e = 0; e < e_end; ++e) {
+                if (mt[e] >= 0) continue;
+                for (int c = 0; c < 3; ++c) {
+                    const int32_t v = nb[3 * e + c];
+                    if (v < 0 || (v >> 2) >= e_end || mt[v >> 2] >= 0 || !((mask >> cls_of(e, c)) & 1u)) continue;
+                    mt[e] = v >> 2; mt[v >> 2] = (int32_t)e; ++n;
+                    break;
+                }
+            }
+            return n;
+        };
+        unsigned best_mask = 0;
+        {
+            const int64_t ns = std::min<int64_t>(Ne, 1 << 20);
+            std::vector<int32_t> tmp;
+            int64_t best = -1;
+            for (int x = 0; x < 9; ++x)
+                for (int y = x; y < 9; ++y) {
+                    if (hist[x] == 0 || hist[y] == 0) continue;
+                    tmp.assign(ns, -1);
+                    const int64_t n = greedy((1u << x) | (1u << y), ns, tmp);
+                    if (n > best) { best = n; best_mask = (1u << x) | (1u << y); }
+                }
+        }
+        static const int max_classes = [] { const char* e = getenv("HIDENN_PLAN_PAIR_CLASSES"); return e ? std::max(1, std::min(9, atoi(e))) : 9; }();
+        n_pairs += greedy(best_mask, Ne, mate);
+        int corder[9];
+        std::iota(corder, corder + 9, 0);
+        std::stable_sort(corder, corder + 9, [&](int x, int y) { return hist[x] > hist[y]; });
+        int used = __builtin_popcount(best_mask);
+        for (int ci = 0; ci < 9 && used < max_classes; ++ci) {
+            const int cls = corder[ci];
+            if (hist[cls] == 0 || ((best_mask >> cls) & 1u)) continue;
+            n_pairs += greedy(1u << cls, Ne, mate);
+            ++used;
+        }
+        if (!force_pairs && n_pairs * 10 < Ne * 4) {      // too few partners: one element per entry
+            mate.clear();
+            n_pairs = 0;
+        }
+    }
+    return n_pairs;
+}
+
+// fold slots of node n in the paired layout: one per incident element whose partial is not merged into its (smaller-id)
+// partner's, i.e. one per pair or single
+static inline int32_t paired_elem_slots(int32_t n, const int32_t* c32, const int64_t* n2o, const int32_t* n2e, const std::vector<int32_t>& mate) {
+    int32_t c = 0;
+    for (int64_t k = n2o[n]; k < n2o[n + 1]; ++k) {
+        const int32_t e = n2e[k] >> 2, f = mate[e];
+        const bool merged = f >= 0 && f < e && (c32[3 * (int64_t)f] == n || c32[3 * (int64_t)f + 1] == n || c32[3 * (int64_t)f + 2] == n);
+        c += merged ? 0 : 1;
+    }
+    return c;
+}
+
 // Does a leaf of the bisection fit the pack limits (local ids <= 1022, fold slots <= 2047)?  Depends only on the set of
 // owned nodes, not on the numbering: local nodes = owned + nodes of incident elements + other ends of incident Neumann
 // edges; slots by canon_padded_entries.
 static bool leaf_feasible(const int32_t* ids, int64_t n, const int32_t* c32, const int64_t* n2o, const int32_t* n2e, const uint8_t* bmask,
                           const uint8_t* dmask, const EdgeEnds& ee, const int64_t* edges, std::vector<int32_t>& owned,
-                          std::vector<int32_t>& loc, std::vector<std::pair<int32_t, int32_t>>& cs) {
+                          std::vector<int32_t>& loc, std::vector<std::pair<int32_t, int32_t>>& cs, const std::vector<int32_t>& mate) {
     owned.assign(ids, ids + n);
     std::sort(owned.begin(), owned.end());
     loc.clear();
@@ -336,7 +459,10 @@ static bool leaf_feasible(const int32_t* ids, int64_t n, const int32_t* c32, con
         }
         auto r = ee.of(nd);
         for (auto it = r.first; it != r.second; ++it) loc.push_back((int32_t)edges[it->second ^ 1]);
-        cs.push_back({node_class(bmask[nd], dmask[nd]), (int32_t)(n2o[nd + 1] - n2o[nd] + (r.second - r.first))});
+        // with a matching only the paired layout has to fit (the one-element-per-entry packs of such a plan may overflow
+        // and are then marked unusable)
+        const int32_t es = mate.empty() ? (int32_t)(n2o[nd + 1] - n2o[nd]) : paired_elem_slots(nd, c32, n2o, n2e, mate);
+        cs.push_back({node_class(bmask[nd], dmask[nd]), (int32_t)(es + (r.second - r.first))});
         loc.push_back(nd);
     }
     std::sort(loc.begin(), loc.end());
@@ -351,6 +477,7 @@ extern "C" int hidenn_tri_locality_order(const int64_t* conn, int64_t Ne, int64_
     HIDENN_REQUIRE(conn && coords && bmask && dmask && new_to_old && elem_new_to_old, "locality_order: NULL argument");
     HIDENN_REQUIRE(Ne >= 0 && Nn > 0 && Nn < (int64_t)2147483000, "locality_order: sizes out of range");
     HIDENN_REQUIRE(Ned == 0 || edges != nullptr, "locality_order: edges NULL");
+    const bool tile_nodes_given = tile_nodes > 0;
     if (tile_nodes <= 0) tile_nodes = kDefaultTileNodes;
     HIDENN_REQUIRE(tile_nodes >= 8 && tile_nodes <= 2048, "locality_order: tile_nodes must be in [8,2048]");
     for (int64_t i = 0; i < 3 * Ne; ++i) HIDENN_REQUIRE(conn[i] >= 0 && conn[i] < Nn, "locality_order: connectivity index out of range");
@@ -369,8 +496,16 @@ extern "C" int hidenn_tri_locality_order(const int64_t* conn, int64_t Ne, int64_
     }
     EdgeEnds ee;
     ee.build(edges, Ned);
+    // the same global matching the plan will compute: with it the tiles are sized for the paired layout
+    std::vector<int32_t> mate;
+    if (!getenv("HIDENN_PLAN_NO_V8")) match_elements(c32.data(), Ne, n2o.data(), n2e.data(), mate);
+    if (!mate.empty() && !tile_nodes_given) tile_nodes = kDefaultTileNodesPairs;
     std::vector<int32_t> slots(Nn);
-    for (int64_t n = 0; n < Nn; ++n) { auto r = ee.of((int32_t)n); slots[n] = (int32_t)(n2o[n + 1] - n2o[n] + (r.second - r.first)); }
+    for (int64_t n = 0; n < Nn; ++n) {
+        auto r = ee.of((int32_t)n);
+        const int32_t es = mate.empty() ? (int32_t)(n2o[n + 1] - n2o[n]) : paired_elem_slots((int32_t)n, c32.data(), n2o.data(), n2e.data(), mate);
+        slots[n] = (int32_t)(es + (r.second - r.first));
+    }
     int64_t n_tiles = 0;
     std::vector<int32_t> order(Nn);
     std::vector<int64_t> tile_begin;
@@ -401,7 +536,7 @@ extern "C" int hidenn_tri_locality_order(const int64_t* conn, int64_t Ne, int64_
             std::vector<std::pair<int32_t, int32_t>> cs;
             for (int64_t t = t0; t < t1 && !bad.load(std::memory_order_relaxed); ++t)
                 if (!leaf_feasible(order.data() + tile_begin[t], tile_begin[t + 1] - tile_begin[t], c32.data(), n2o.data(), n2e.data(), bmask,
-                                   dmask, ee, edges, owned, loc, cs))
+                                   dmask, ee, edges, owned, loc, cs, mate))
                     bad.store(1);
         });
         if (!bad.load()) break;
@@ -535,6 +670,7 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
     HIDENN_REQUIRE(Ned == 0 || edges != nullptr, "plan_create: edges NULL");
     HIDENN_REQUIRE(n_first == 0 || first_nodes != nullptr, "plan_create: first_nodes NULL");
     for (int64_t i = 0; i < n_first; ++i) HIDENN_REQUIRE(first_nodes[i] >= 0 && first_nodes[i] < Nn, "plan_create: first_nodes index out of range");
+    const bool tile_nodes_given = tile_nodes > 0;
     if (tile_nodes <= 0) tile_nodes = kDefaultTileNodes;
     HIDENN_REQUIRE(tile_nodes >= 8 && tile_nodes <= 2048, "plan_create: tile_nodes must be in [8,2048]");
 
@@ -583,107 +719,13 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
     auto ends_of = [&](int32_t n) { return edge_ends.of(n); };
     const bool no_v8 = getenv("HIDENN_PLAN_NO_V8") != nullptr;      // A/B: treat a tile-ordered mesh like any other
     bool tile_order = false, force_generic = false;
-    // Global matching of the elements into edge-sharing pairs (paired layout of kernel v9; tri_plan.h).  It depends only
-    // on the mesh, not on the tiling: the neighbour across each edge is looked up through the node->element lists, then a
-    // greedy pass in element order matches every free element with its free neighbour that has the fewest free
-    // neighbours left (ties: smallest id).
+    // Global matching of the elements into edge-sharing pairs (paired layout of kernel v9; match_elements above).  It
+    // depends only on the mesh, so hidenn_tri_locality_order computes the same one and sizes the tiles by it.
     const int32_t* c32g = p->conn32.data();
     auto elem_has = [c32g](int32_t f, int32_t n) { return c32g[3 * (int64_t)f] == n || c32g[3 * (int64_t)f + 1] == n || c32g[3 * (int64_t)f + 2] == n; };
-    // HIDENN_PLAN_PAIRS: unset = automatic (the paired layout is kept when at least 80 % of the elements find a partner),
-    // 0 = never, 1 = always.  C4 on B200: 161 us per launch paired against 173 us with one element per entry.
-    const char* pairs_env = getenv("HIDENN_PLAN_PAIRS");
-    const bool want_pairs = pairs_env == nullptr || atoi(pairs_env) != 0;
-    const bool force_pairs = pairs_env != nullptr && atoi(pairs_env) != 0;
-    if (want_pairs && real_bytes == 8 && !no_v8 && Ne > 0) {
-        std::vector<int32_t> nb(3 * Ne, -1);      // neighbour across the edge (corner c -> c+1): f * 4 + (corner of f at the edge's start node)
-        auto nb_range = [&](int64_t e0, int64_t e1) {
-            for (int64_t e = e0; e < e1; ++e)
-                for (int c = 0; c < 3; ++c) {
-                    // only a neighbour that runs through the shared edge in the opposite direction (b -> a; both elements
-                    // counter-clockwise or both clockwise) can be this element's partner: the kernel has one register wiring
-                    // per (edge of the first element, position of the new corner in the second) = 9 classes
-                    const int32_t a = c32g[3 * e + c], b = c32g[3 * e + (c + 1) % 3];
-                    for (int64_t k = p->n2e_off[a]; k < p->n2e_off[a + 1]; ++k) {
-                        const int32_t f = p->n2e_ent[k] >> 2;
-                        const int cf = p->n2e_ent[k] & 3;      // corner of f that is a
-                        if (f != e && c32g[3 * (int64_t)f + (cf + 2) % 3] == b) { nb[3 * e + c] = f * 4 + cf; break; }
-                    }
-                }
-        };
-        {
-            unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-            if (Ne < 100000) nthr = 1;
-            std::vector<std::thread> th;
-            const int64_t per = (Ne + nthr - 1) / nthr;
-            for (unsigned i = 0; i < nthr; ++i) {
-                const int64_t a = i * per, b = std::min<int64_t>(Ne, a + per);
-                if (a < b) th.emplace_back(nb_range, a, b);
-            }
-            for (auto& t : th) t.join();
-        }
-        // wiring class of the pair (e, neighbour across e's edge c), first element = smaller id (tri_plan.h)
-        auto cls_of = [&](int64_t e, int c) -> int {
-            const int32_t v = nb[3 * e + c];
-            if (v < 0) return -1;
-            const int64_t f = v >> 2;
-            const int cf = v & 3;
-            return e < f ? 3 * c + (cf + 1) % 3 : 3 * ((cf + 2) % 3) + (c + 2) % 3;
-        };
-        // Which classes?  Meshes from generators number their corners by a few patterns, and a tile's entries are listed
-        // class by class with every class padded to whole warps, so the matching should live in as few classes as
-        // possible: the PAIR of classes whose greedy matching (element order, free neighbour of an allowed class) covers
-        // most of a sample of the mesh goes first, then the remaining classes one at a time, most frequent first.
-        int64_t hist[9] = {};
-        for (int64_t e = 0; e < Ne; ++e)
-            for (int c = 0; c < 3; ++c) {
-                const int32_t v = nb[3 * e + c];
-                if (v >= 0 && e < (v >> 2)) hist[cls_of(e, c)]++;
-            }
-        p->mate.assign(Ne, -1);
-        std::vector<int32_t>& mate = p->mate;
-        auto greedy = [&](unsigned mask, int64_t e_end, std::vector<int32_t>& mt) -> int64_t {
-            int64_t n = 0;
-            for (int64_t e = 0; e < e_end; ++e) {
-                if (mt[e] >= 0) continue;
-                for (int c = 0; c < 3; ++c) {
-                    const int32_t v = nb[3 * e + c];
-                    if (v < 0 || (v >> 2) >= e_end || mt[v >> 2] >= 0 || !((mask >> cls_of(e, c)) & 1u)) continue;
-                    mt[e] = v >> 2; mt[v >> 2] = (int32_t)e; ++n;
-                    break;
-                }
-            }
-            return n;
-        };
-        unsigned best_mask = 0;
-        {
-            const int64_t ns = std::min<int64_t>(Ne, 1 << 20);
-            std::vector<int32_t> tmp;
-            int64_t best = -1;
-            for (int x = 0; x < 9; ++x)
-                for (int y = x; y < 9; ++y) {
-                    if (hist[x] == 0 || hist[y] == 0) continue;
-                    tmp.assign(ns, -1);
-                    const int64_t n = greedy((1u << x) | (1u << y), ns, tmp);
-                    if (n > best) { best = n; best_mask = (1u << x) | (1u << y); }
-                }
-        }
-        static const int max_classes = [] { const char* e = getenv("HIDENN_PLAN_PAIR_CLASSES"); return e ? std::max(1, std::min(9, atoi(e))) : 9; }();
-        p->n_pairs += greedy(best_mask, Ne, mate);
-        int corder[9];
-        std::iota(corder, corder + 9, 0);
-        std::stable_sort(corder, corder + 9, [&](int x, int y) { return hist[x] > hist[y]; });
-        int used = __builtin_popcount(best_mask);
-        for (int ci = 0; ci < 9 && used < max_classes; ++ci) {
-            const int cls = corder[ci];
-            if (hist[cls] == 0 || ((best_mask >> cls) & 1u)) continue;
-            p->n_pairs += greedy(1u << cls, Ne, mate);
-            ++used;
-        }
-        if (!force_pairs && p->n_pairs * 10 < Ne * 4) {      // too few partners: one element per entry
-            p->mate.clear();
-            p->n_pairs = 0;
-        }
-    }
+    if (real_bytes == 8 && !no_v8 && Ne > 0) p->n_pairs = match_elements(c32g, Ne, p->n2e_off.data(), p->n2e_ent.data(), p->mate);
+    bool pairs_on = !p->mate.empty();
+    if (pairs_on && !tile_nodes_given) tile_nodes = kDefaultTileNodesPairs;
 
     // RCB tiling of the nodes
     int64_t n_tiles = 0;
@@ -708,6 +750,16 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
         if ((int64_t)mx - mn + 1 != tile_begin[t + 1] - tile_begin[t]) { tile_order = false; break; }
         for (int32_t n = mn; n < mx; ++n)
             if (node_class(bmask[n], dmask[n]) > node_class(bmask[n + 1], dmask[n + 1])) { tile_order = false; break; }
+    }
+
+    if (pairs_on && !tile_order) {
+        // the paired layout only serves the tile-ordered kernel: without such a numbering drop it and size the tiles for
+        // one element per entry
+        p->mate.clear();
+        p->n_pairs = 0;
+        pairs_on = false;
+        if (!tile_nodes_given) tile_nodes = kDefaultTileNodes;
+        continue;
     }
 
     // per-tile packs, in parallel over tiles
@@ -768,7 +820,8 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
                 cs.clear();
                 for (int32_t n : owned_sorted) {
                     auto r = ends_of(n);
-                    cs.push_back({node_class(bmask[n], dmask[n]), (int32_t)(n2o[n + 1] - n2o[n] + (r.second - r.first))});
+                    const int32_t es = pairs_on ? paired_elem_slots(n, c32, n2o, n2e, p->mate) : (int32_t)(n2o[n + 1] - n2o[n]);
+                    cs.push_back({node_class(bmask[n], dmask[n]), (int32_t)(es + (r.second - r.first))});
                 }
                 if (canon_padded_entries(cs) > kMaxEntries) { B.err = 2; continue; }
             }
@@ -843,9 +896,16 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
                     B.off[l] = (uint32_t)(acc + (l - g0)) | ((uint32_t)cnt << 16);
                 }
                 acc += mx * G;
-                if (acc > kMaxEntries) { B.err = 3; break; }      // only a tile-ordered numbering that is not slot-sorted can get here
+                if (acc > kMaxEntries) {
+                    // a plan with a paired layout sizes its tiles for that layout: the one-element-per-entry packs of this
+                    // tile do not fit their 11-bit position fields and the plan is marked pairs-only (kernel v9 only);
+                    // otherwise only a tile-ordered numbering that is not slot-sorted can get here
+                    if (pairs_on && tile_order) B.unpaired_overflow = true;
+                    else { B.err = 3; break; }
+                }
             }
             if (B.err) continue;
+            if (B.unpaired_overflow) acc = kMaxEntries;      // positions below are masked garbage, never used
             B.n_entries = (int32_t)acc;
             B.pack.resize(B.elems.size());
             for (size_t i = 0; i < B.elems.size(); ++i) {
@@ -863,7 +923,7 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
                         lid = halo_lid[std::lower_bound(halo.begin(), halo.end(), n) - halo.begin()];
                     }
                     w |= (unsigned long long)lid << (kLidBits * c);
-                    w |= pos << (3 * kLidBits + kPosBits * c);
+                    w |= (pos & (unsigned long long)kMaxEntries) << (3 * kLidBits + kPosBits * c);
                 }
                 if (owned_id(c32[3 * (int64_t)e]) >= 0) w |= 1ull << kOwnerBit;
                 B.pack[i] = w;
@@ -896,7 +956,7 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
                             lid = halo_lid[std::lower_bound(halo.begin(), halo.end(), n) - halo.begin()];
                         }
                         w |= (unsigned long long)lid << (kLidBits * k);
-                        w |= pos << (2 * kLidBits + kPosBits * k);
+                        w |= (pos & (unsigned long long)kMaxEntries) << (2 * kLidBits + kPosBits * k);
                     }
                     B.epack.push_back(w);
                     B.eid.push_back(e);
@@ -926,6 +986,7 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
                         B.off9[l] = (uint32_t)(acc9 + (l - g0)) | ((uint32_t)slots9(B.nodes[l]) << 16);
                     acc9 += mx * G;
                 }
+                if (acc9 > kMaxEntries) { B.err = 2; continue; }      // the bound above is by class and count, the layout by id
                 B.n_entries9 = (int32_t)acc9;
                 auto word9 = [&](int32_t e) {
                     unsigned long long w = 0;
@@ -1042,6 +1103,8 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
     }
     int32_t max_local = 0, max_entries = 0, max_owned = 0, max_elem = 0;
     int64_t node_visits = 0, elem_visits = 0, off_total = 0;
+    bool any_unpaired_overflow = false;
+    for (auto& B : tb) any_unpaired_overflow |= B.unpaired_overflow;
     for (auto& B : tb) {
         node_visits += (int64_t)B.nodes.size();
         elem_visits += (int64_t)B.elems.size();
@@ -1133,6 +1196,7 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
     p->node_visits = node_visits;
     p->elem_visits = elem_visits;
     p->tile_order = tile_order;
+    p->unpaired_ok = !any_unpaired_overflow;
 
     // device layout: fixed-stride records per tile
     const int32_t SL = (max_local + 1) & ~1, SE = (max_elem + 1) & ~1, SO = (max_owned + 3) & ~3;
@@ -1443,6 +1507,7 @@ extern "C" int hidenn_tri_plan_tiles(const hidenn_tri_plan* p, int64_t* node_off
 extern "C" int hidenn_tri_plan_fold_tables(const hidenn_tri_plan* p, int64_t* elem_off, uint64_t* packs, int64_t* elems, int64_t* owned_off,
                                            uint32_t* entry_off, int32_t* n_entries) {
     HIDENN_REQUIRE(p && elem_off && packs && elems && owned_off && entry_off && n_entries, "plan_fold_tables: NULL");
+    HIDENN_REQUIRE(p->unpaired_ok, "plan_fold_tables: the plan is pairs-only (tiles sized for the paired layout); use hidenn_tri_plan_pair_tables or HIDENN_PLAN_PAIRS=0");
     const size_t nt = p->tiles.size();
     for (size_t t = 0; t < nt; ++t) {
         elem_off[t] = p->tiles[t].elem_off;
@@ -1508,6 +1573,7 @@ extern "C" int hidenn_tri_plan_stage_stats(const hidenn_tri_plan* p, int64_t* ou
 
 extern "C" int hidenn_tri_plan_bank_stats(const hidenn_tri_plan* p, int real_bytes, int64_t* out4) {
     HIDENN_REQUIRE(p && out4 && (real_bytes == 8 || real_bytes == 4), "plan_bank_stats: bad arguments");
+    HIDENN_REQUIRE(p->unpaired_ok, "plan_bank_stats: the plan is pairs-only (tiles sized for the paired layout)");
     (void)real_bytes;
     const int G = 8;
     constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;

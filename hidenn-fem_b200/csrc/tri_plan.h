@@ -126,6 +126,8 @@ struct hidenn_tri_plan {
     std::vector<int32_t> edges32;
     hidenn::TriPlanDev dev{};
     bool tile_order = false;                // numbering is tile-ordered -> kernel v8 (FP64)
+    bool unpaired_ok = true;                // false: tiles sized for the paired layout, the one-element-per-entry packs overflow
+                                            // their position fields -> only kernel v9 (paired) can run this plan
     hidenn::TriPlan8Dev dev8{};
     std::vector<hidenn::TileDesc8> tiles8;
     std::vector<unsigned long long> edge_pack, edge_pack9;

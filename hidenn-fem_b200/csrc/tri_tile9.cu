@@ -84,6 +84,13 @@ template <bool PAIRS> struct Roles9 {
     static_assert(E % 4 == 0 && E <= 16 && F >= 1, "element warps come in warpgroups");
     static_assert(E * ERegs + (kWarps9 - E) * ORegs <= kWarps9 * kPoolRegs, "register split exceeds the launch pool");
 };
+#ifndef HIDENN_WS_SLEEP_SHORT
+#define HIDENN_WS_SLEEP_SHORT 32
+#endif
+#ifndef HIDENN_WS_SLEEP_IDLE
+#define HIDENN_WS_SLEEP_IDLE 256
+#endif
+constexpr unsigned kSleepShort = HIDENN_WS_SLEEP_SHORT, kSleepIdle = HIDENN_WS_SLEEP_IDLE;      // ns, mbarrier wait back-off
 constexpr int kRedWarp0 = 16;      // warps 16..23 (small-register groups in every configuration) do the final reduction
 constexpr int kMaxStages = 4;
 
@@ -114,17 +121,22 @@ __device__ __forceinline__ double2 lds_pair(const double2* p) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(s32(p)));
     return v;
 }
-__device__ __forceinline__ void bar_wait(uint64_t* bar, unsigned parity) {
+// Spinning warps take issue slots from the working warps of their scheduler (the ncu source page of the first paired
+// kernel: 22 M of 126 M warp instructions were try_wait retries), so a failed try backs off with nanosleep: a few tens of
+// ns where the waiter is on the critical path (fold warps waiting for partials), longer where it is not (element warps
+// without entries in this tile, loader warps waiting for an empty stage).
+__device__ __forceinline__ void bar_wait(uint64_t* bar, unsigned parity, unsigned sleep_ns) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE_%=;\n"
+        "nanosleep.u32 %2;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(s32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(sleep_ns)
         : "memory");
 }
 }  // namespace
@@ -200,11 +212,11 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
             const unsigned long long* s_pack1 = reinterpret_cast<const unsigned long long*>(stage + L.pack_off);
             const NodeBuf<R> nodes(stage + L.node_off, P.max_local);
             const PartBuf<R> part(smem + L.part0 + pb * L.part_bytes, max_entries + 1);
-            PROF_WAIT(pf_a, bar_wait(&full_stage[st], st_ph))
+            PROF_WAIT(pf_a, bar_wait(&full_stage[st], st_ph, kSleepShort))
             const int n_pent = PAIRS ? d->n_pent : d->n_elem, n_edge = d->n_edge;
             // the pack of the next pass is loaded one pass ahead (the first one before the wait for the partial buffer)
             unsigned long long pw_next = (!PAIRS && etid < n_pent) ? s_pack1[etid] : 0ull;
-            PROF_WAIT(pf_b, bar_wait(&part_empty[pb], ((k >> 1) & 1) ^ 1))
+            PROF_WAIT(pf_b, bar_wait(&part_empty[pb], ((k >> 1) & 1) ^ 1, (wid * 32 < n_pent || n_edge > 0) ? kSleepShort : kSleepIdle))
             const unsigned dumpv = (unsigned)(PAIRS ? d->n_entries9 : d->n_entries);
             R e_acc = R(0), ee_acc = R(0);
             // one entry = an edge-sharing element pair (or a single element): both elements are evaluated by this thread
@@ -382,7 +394,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                 if (lane < n_halo) h0 = __ldg(hrec + lane);
                 if (lane + 32 < n_halo) h1 = __ldg(hrec + lane + 32);
                 if (lane + 64 < n_halo) h2 = __ldg(hrec + lane + 64);
-                PROF_WAIT(pf_a, bar_wait(&empty_stage[st], st_ph ^ 1u))
+                PROF_WAIT(pf_a, bar_wait(&empty_stage[st], st_ph ^ 1u, kSleepIdle))
                 R2* xy = reinterpret_cast<R2*>(stage + L.node_off);
                 R2* uv = xy + P.max_local;
                 if (lane == 0) {
@@ -429,8 +441,8 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                 const TileDesc8* d = reinterpret_cast<const TileDesc8*>(stage + L.desc_off);
                 const uint32_t* s_off = reinterpret_cast<const uint32_t*>(stage + L.offs_off);
                 const PartBuf<R> part(smem + L.part0 + pb * L.part_bytes, max_entries + 1);
-                PROF_WAIT(pf_a, bar_wait(&full_stage[st], st_ph))
-                PROF_WAIT(pf_b, bar_wait(&part_full[pb], (k >> 1) & 1))
+                PROF_WAIT(pf_a, bar_wait(&full_stage[st], st_ph, kSleepShort))
+                PROF_WAIT(pf_b, bar_wait(&part_full[pb], (k >> 1) & 1, kSleepShort))
                 const int n_owned = d->n_owned, nA = d->nA, nAB = nA + d->nB, nBC = d->nB + d->nC, nABC = nAB + d->nC;
                 const int rx = d->rx_free, ru = d->ru_free;
                 // one node per thread and pass, two slots in flight per step (summed pairwise: acc += (s_q + s_q+1)).  More
