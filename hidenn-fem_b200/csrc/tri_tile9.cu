@@ -368,7 +368,14 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
         PROF_END(n_mine)
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kORegs));
-        if (wid >= kEWarps + kFWarps) {
+        // which of the non-element warps load: the schedulers (warp id mod 4) that carry four busy element warps of a
+        // paired tile (~14 of 16 warps have entries: schedulers 0 and 1) get a loader and one fold warp, the others two
+        // fold warps
+        constexpr int kLoaderPos = (PAIRS && kWarps9 - kEWarps == 8 && kLWarps == 2) ? 4 : kFWarps;
+        const int oj = wid - kEWarps;
+        const bool is_loader = oj >= kLoaderPos && oj < kLoaderPos + kLWarps;
+        const int fwarp = oj < kLoaderPos ? oj : oj - kLWarps;      // fold warp index
+        if (is_loader) {
             // -------------------------------------------------------------- loader warp
             // The per-tile chain  descriptor -> bulk copies, halo records -> gathers  is two dependent global loads; the
             // records of the tile kAhead iterations later are pulled into L2 now, so the chain costs L2 hits, not DRAM misses.
@@ -378,7 +385,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                 if (lane == 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(P8.tiles + t));
                 else if (lane * 128 < P8.stride_halo * 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + lane * 128));
             };
-            const int lw = wid - (kEWarps + kFWarps);
+            const int lw = oj - kLoaderPos;
             for (int k = lw; k < kAhead * kLWarps && k < n_mine; k += kLWarps) prefetch_tile(blockIdx.x + k * nct);
             PROF_DECL;
             int st = lw % kStages;
@@ -428,7 +435,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
             PROF_END(n_mine)
         } else {
             // -------------------------------------------------------------- fold warps
-            const int ftid = tid - kEWarps * 32;
+            const int ftid = fwarp * 32 + lane;
             const bool need_gx = flags & HIDENN_NEED_GX, need_gu = flags & HIDENN_NEED_GU;
             constexpr unsigned G = 8u;
             PROF_DECL;
@@ -474,7 +481,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     if (need_gu && l < nAB) gu_free[ru + l] = mk2<R>(ax, ay);
                     if (need_gx && (l < nA || l >= nABC)) gx_free[rx + (l < nA ? l : l - nBC)] = mk2<R>(bx, by);
                 }
-                if (wid == kEWarps + kFWarps - 1 && !HIDENN_PROF9) {
+                if (fwarp == kFWarps - 1 && !HIDENN_PROF9) {
                     // tile energies in fixed order: lane j adds the slots of lane j of the element warps 0, 1, ..., then a
                     // shuffle tree (this fold warp has the fewest second-pass nodes)
                     const R* s_en = reinterpret_cast<const R*>(smem + L.en0) + pb * kEnSlots;
