@@ -25,8 +25,8 @@
 namespace hidenn {
 
 #ifndef HIDENN_WS_FOLD
-#define HIDENN_WS_FOLD 2      // slots in flight per fold step (1: one at a time)
-#endif
+#define HIDENN_WS_FOLD 1      // slots in flight per fold step.  1 (u and x pair of one slot) is fastest for the WHOLE kernel:
+#endif                        // 2: +2 %, two nodes per thread side by side: +24 %, one load at a time: +10 % (profiles/README.md)
 #ifndef HIDENN_WS_EWARPS
 #define HIDENN_WS_EWARPS 12
 #endif
@@ -200,6 +200,10 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kERegs));
         const TriConsts<R> K = load_consts<R, BODY>(consts);
         const bool with_edges = (flags & HIDENN_WITH_EDGES) != 0;
+#ifdef HIDENN_WS_STAGGER
+        // measurement switch: de-phase the element warps of a scheduler once, at the start
+        if ((wid >> 2) > 0) asm volatile("nanosleep.u32 %0;" ::"r"((unsigned)((wid >> 2) * HIDENN_WS_STAGGER)));
+#endif
         const int etid = tid;
         PROF_DECL;
         int st = 0;
@@ -371,7 +375,16 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
         // which of the non-element warps load: the schedulers (warp id mod 4) that carry four busy element warps of a
         // paired tile (~14 of 16 warps have entries: schedulers 0 and 1) get a loader and one fold warp, the others two
         // fold warps
-        constexpr int kLoaderPos = (PAIRS && kWarps9 - kEWarps == 8 && kLWarps == 2) ? 4 : kFWarps;
+#ifndef HIDENN_WS_LPOS
+#define HIDENN_WS_LPOS 4
+#endif
+#ifndef HIDENN_WS_FROT
+#define HIDENN_WS_FROT 0
+#endif
+#ifndef HIDENN_WS_FOLD2N
+#define HIDENN_WS_FOLD2N 0
+#endif
+        constexpr int kLoaderPos = (PAIRS && kWarps9 - kEWarps == 8 && kLWarps == 2) ? HIDENN_WS_LPOS : kFWarps;
         const int oj = wid - kEWarps;
         const bool is_loader = oj >= kLoaderPos && oj < kLoaderPos + kLWarps;
         const int fwarp = oj < kLoaderPos ? oj : oj - kLWarps;      // fold warp index
@@ -455,7 +468,42 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                 // one node per thread and pass, two slots in flight per step (summed pairwise: acc += (s_q + s_q+1)).  More
                 // loads in flight (two nodes per thread, four slots) make the WHOLE kernel slower: the fold warps have slack,
                 // the element warps do not, and both share the SM's load/store pipe (profiles/README.md)
+                // (HIDENN_WS_FROT: measurement switch -- the fold warps that take the short last pass)
+#if HIDENN_WS_FOLD2N
+                // two nodes per thread side by side (l and l + fold threads), one slot of each per step
+                if (PAIRS) {
+                    for (int l = ftid; l < n_owned; l += 2 * kFWarps * 32) {
+                        const int lb = l + kFWarps * 32;
+                        const bool hb = lb < n_owned;
+                        const uint32_t oa = s_off[l], ob = hb ? s_off[lb] : 0u;
+                        unsigned qa = oa & 0xFFFFu, qb = ob & 0xFFFFu;
+                        const unsigned ea = qa + (oa >> 16) * G, eb = qb + (ob >> 16) * G;
+                        R aax = R(0), aay = R(0), abx = R(0), aby = R(0), bax = R(0), bay = R(0), bbx = R(0), bby = R(0);
+#pragma unroll 1
+                        while (qa < ea || qb < eb) {
+                            R2 ua = mk2<R>(R(0), R(0)), xa = ua, ub = ua, xb = ua;
+                            if (qa < ea) { ua = lds_pair(part.pu + qa); xa = lds_pair(part.px + qa); }
+                            if (qb < eb) { ub = lds_pair(part.pu + qb); xb = lds_pair(part.px + qb); }
+                            aax += ua.x; aay += ua.y; abx += xa.x; aby += xa.y;
+                            bax += ub.x; bay += ub.y; bbx += xb.x; bby += xb.y;
+                            qa += G; qb += G;
+                        }
+                        if (need_gu && l < nAB) gu_free[ru + l] = mk2<R>(aax, aay);
+                        if (need_gx && (l < nA || l >= nABC)) gx_free[rx + (l < nA ? l : l - nBC)] = mk2<R>(abx, aby);
+                        if (hb) {
+                            if (need_gu && lb < nAB) gu_free[ru + lb] = mk2<R>(bax, bay);
+                            if (need_gx && (lb < nA || lb >= nABC)) gx_free[rx + (lb < nA ? lb : lb - nBC)] = mk2<R>(bbx, bby);
+                        }
+                    }
+                } else
+#endif
+#if HIDENN_WS_FROT
+                for (int l0 = 0, pass = 0; l0 < n_owned; l0 += kFWarps * 32, ++pass) {
+                    const int l = l0 + ((PAIRS && pass == 1) ? (ftid + HIDENN_WS_FROT * 32) % (kFWarps * 32) : ftid);
+                    if (l >= n_owned) continue;
+#else
                 for (int l = ftid; l < n_owned; l += kFWarps * 32) {
+#endif
                     const uint32_t oc = s_off[l];
 #if HIDENN_ABL == 0
                     const unsigned fb = oc & 0xFFFFu, fe = fb + (oc >> 16) * G;
@@ -474,8 +522,14 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
 #endif
 #pragma unroll 1
                     for (; q < fe; q += G) {
+#if HIDENN_WS_FOLD == 0
+                        // ONE shared-memory load in flight: the second address is made to depend on the first value
+                        const R2 u = lds_pair(part.pu + q);
+                        const R2 x = lds_pair(part.px + q + (__double2hiint(u.x) == 0x7ff8dead ? 1 : 0));
+#else
                         R2 u, x;
                         part.load(q, u, x);
+#endif
                         ax += u.x; ay += u.y; bx += x.x; by += x.y;
                     }
                     if (need_gu && l < nAB) gu_free[ru + l] = mk2<R>(ax, ay);
