@@ -42,7 +42,12 @@ def run_one():
         sc = loss_fn._scratch(plan, dev, torch.float64)[:148 * nw * 4].reshape(148, nw, 4).cpu().numpy()
         ew = int((re.search(r"_e(\d+)", rec["lib"]) or [0, "12"])[1])      # tags: prof_e12_l2 ...
         lw = int((re.search(r"_l(\d+)", rec["lib"]) or [0, "2"])[1])
-        for name, sl in (("element", slice(0, ew)), ("fold", slice(ew, nw - lw)), ("loader", slice(nw - lw, nw))):
+        # paired builds: 16 element warps; of the 8 others, warps 20 and 21 load (HIDENN_WS_LPOS = 4)
+        if "_pe" in rec["lib"]:
+            roles = (("element_active", list(range(0, 13))), ("element_idle", [14, 15]), ("fold", [16, 17, 18, 19, 22, 23]), ("loader", [20, 21]))
+        else:
+            roles = (("element", list(range(0, ew))), ("fold", list(range(ew, nw - lw))), ("loader", list(range(nw - lw, nw))))
+        for name, sl in roles:
             w = sc[:, sl]
             tot = w[..., 0].mean()
             rec[name] = {"total_cyc": round(float(tot)), "waitA_frac": round(float((w[..., 1] / w[..., 0]).mean()), 3),
