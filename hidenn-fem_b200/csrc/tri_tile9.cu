@@ -30,6 +30,11 @@ namespace hidenn {
 #ifndef HIDENN_WS_EWARPS
 #define HIDENN_WS_EWARPS 12
 #endif
+// halo rows as 16-byte bulk copies (the copy engine writes shared memory without passing the SM's LSU data pipe, which the
+// element warps need) instead of per-lane cp.async
+#ifndef HIDENN_WS_HALO_BULK
+#define HIDENN_WS_HALO_BULK 0
+#endif
 // Measurement-only ablations (profiles/v9_ablate.py; results are WRONG on purpose, never shipped): fraction of the
 // shared-memory exchange kept per element -- 1: two of three corners (what edge-sharing pairs would move), 2: one of
 // three (triangle strips), 3: none (FP64 + issue + global traffic floor).  The FP64 work is unchanged.
@@ -189,7 +194,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
     constexpr unsigned LM = (1u << kLidBits) - 1u, PM = (1u << kPosBits) - 1u;
 
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { bar_init(&full_stage[s], 1 + 32); bar_init(&empty_stage[s], kFWarps); }
+        for (int s = 0; s < kStages; ++s) { bar_init(&full_stage[s], HIDENN_WS_HALO_BULK ? 1 : 1 + 32); bar_init(&empty_stage[s], kFWarps); }
         for (int s = 0; s < 2; ++s) { bar_init(&part_full[s], kEWarps); bar_init(&part_empty[s], kFWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -421,7 +426,7 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     const int nBC = d.nB + d.nC, nAB = d.nA + d.nB, nCD = d.nC + d.nD;
                     const unsigned pack_bytes = PAIRS ? 16u * (unsigned)d.n_pent : 8u * (unsigned)((d.n_elem + 1) & ~1);
                     const unsigned off_bytes = 4u * (unsigned)((d.n_owned + 3) & ~3);
-                    bar_expect_tx(&full_stage[st], 32u * (unsigned)d.n_owned + pack_bytes + off_bytes + 64u);
+                    bar_expect_tx(&full_stage[st], 32u * (unsigned)(HIDENN_WS_HALO_BULK ? d.n_local : d.n_owned) + pack_bytes + off_bytes + 64u);
                     bulk(stage + L.desc_off, P8.tiles + tile, 64u, &full_stage[st]);
                     const void* pack_src = PAIRS ? (const void*)(P8.pair_pack + (size_t)tile * P8.stride_pent * 2)
                                                  : (const void*)(P.elem_pack + (size_t)tile * P.stride_elem);
@@ -433,15 +438,25 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                     if (nAB) bulk(uv, u_free + d.ru_free, 16u * nAB, &full_stage[st]);
                     if (nCD) bulk(uv + nAB, u_fixed + d.ru_fixed, 16u * nCD, &full_stage[st]);
                 }
+#if HIDENN_WS_HALO_BULK
+                __syncwarp();      // lane 0's expect_tx (with the halo bytes) is posted before any halo copy can complete
+#endif
                 auto gather = [&](const int j, const int2 h) {      // consecutive lanes land at consecutive local ids
+#if HIDENN_WS_HALO_BULK
+                    bulk(xy + d.n_owned + j, h.x >= 0 ? (const void*)(x_free + h.x) : (const void*)(x_fixed + (~h.x)), 16u, &full_stage[st]);
+                    bulk(uv + d.n_owned + j, h.y >= 0 ? (const void*)(u_free + h.y) : (const void*)(u_fixed + (~h.y)), 16u, &full_stage[st]);
+#else
                     cp_async_pair(xy + d.n_owned + j, h.x >= 0 ? (const void*)(x_free + h.x) : (const void*)(x_fixed + (~h.x)), 16);
                     cp_async_pair(uv + d.n_owned + j, h.y >= 0 ? (const void*)(u_free + h.y) : (const void*)(u_fixed + (~h.y)), 16);
+#endif
                 };
                 if (lane < n_halo) gather(lane, h0);
                 if (lane + 32 < n_halo) gather(lane + 32, h1);
                 if (lane + 64 < n_halo) gather(lane + 64, h2);
                 for (int j = lane + 96; j < n_halo; j += 32) gather(j, __ldg(hrec + j));
+#if !HIDENN_WS_HALO_BULK
                 bar_arrive_cp_async(&full_stage[st]);
+#endif
                 st += kLWarps;
                 while (st >= kStages) { st -= kStages; st_ph ^= 1u; }
             }
