@@ -819,7 +819,7 @@ extern "C" int hidenn_tri_plan_kernel(const hidenn_tri_plan* plan) {
     static const bool ws_off = [] { const char* e = getenv("HIDENN_TILE_WS"); return e && atoi(e) == 0; }();
     if (!plan) return 0;
     if (!plan->tile_order) return 7;
-    return (!ws_off && tile9_fits(plan)) ? 9 : 8;
+    return ((!ws_off && tile9_fits(plan)) || !plan->unpaired_ok) ? 9 : 8;      // a pairs-only plan runs kernel v9 or nothing
 }
 extern "C" int hidenn_tri_plan_overlap_target(const hidenn_tri_plan* plan) {
     static const bool ws_off = [] { const char* e = getenv("HIDENN_TILE_WS"); return e && atoi(e) == 0; }();

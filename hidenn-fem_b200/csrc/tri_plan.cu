@@ -1447,7 +1447,7 @@ extern "C" int hidenn_tri_plan_layout(const hidenn_tri_plan* p, int64_t* out8) {
     HIDENN_REQUIRE(p && out8, "plan_layout: NULL");
     int32_t max_halo = 0;
     for (const TileDesc8& d : p->tiles8) max_halo = std::max(max_halo, d.n_local - d.n_owned);
-    out8[0] = p->tile_order ? 1 : 0;
+    out8[0] = (p->tile_order ? 1 : 0) | (p->unpaired_ok ? 0 : 2);
     out8[1] = max_halo;
     out8[2] = (int64_t)p->edge_pack.size();
     out8[3] = p->tile_order ? (int64_t)((size_t)p->dev.max_local * 64 + (size_t)(p->dev.max_entries + 1) * 32 + 256) : 0;   // smem bytes, FP64 kernel

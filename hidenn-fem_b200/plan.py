@@ -58,7 +58,7 @@ class TriPlan:
         self.info = dict(zip(INFO_KEYS, [int(v) for v in info]))
         lay = (C.c_int64 * 8)()
         _lib.check(L.hidenn_tri_plan_layout(self._h, lay), "hidenn_tri_plan_layout")
-        self.info.update(tile_ordered=bool(lay[0]), max_halo=int(lay[1]), edge_visits=int(lay[2]), smem_v8=int(lay[3]),
+        self.info.update(tile_ordered=bool(lay[0] & 1), pairs_only=bool(lay[0] & 2), max_halo=int(lay[1]), edge_visits=int(lay[2]), smem_v8=int(lay[3]),
                          n_pairs=int(lay[4]), pair_entries=int(lay[5]), max_entries9=int(lay[6]), n_first_tiles=int(lay[7]))
         self.info["kernel"] = int(L.hidenn_tri_plan_kernel(self._h))
         loc = (C.c_double * 2)()

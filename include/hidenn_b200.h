@@ -114,7 +114,9 @@ int hidenn_tri_locality_order(const int64_t* conn, int64_t n_elems, int64_t n_no
                               const int64_t* edges, int64_t n_edges, int tile_nodes,
                               int64_t* new_to_old, int64_t* elem_new_to_old);
 
-/* layout8[0]=1 if the plan found a tile-ordered numbering (FP64 plans; bulk-copy tile kernels in use), [1]=max halo
+/* layout8[0]: bit 0 = the plan found a tile-ordered numbering (FP64 plans; bulk-copy tile kernels in use), bit 1 = the plan
+ * is pairs-only (its tiles are sized for the paired layout: only the warp-specialised kernel can run it, and
+ * hidenn_tri_plan_fold_tables / _bank_stats refuse it; HIDENN_PLAN_PAIRS=0 builds the other kind), [1]=max halo
  * nodes per tile, [2]=Neumann edge visits, [3]=dynamic smem bytes of the two-CTA kernel, [4]=element pairs of the global
  * matching, [5]=pair-or-single entries over all tiles, [6]=max fold slots per tile in the paired layout,
  * [7]=number of leading tiles that own the caller's first_nodes (hidenn_tri_plan_create_ex). */

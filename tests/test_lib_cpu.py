@@ -412,3 +412,48 @@ def test_plan_warns_on_a_numbering_without_locality():
                            real_bytes=8, device=-1)
         hit = [x for x in w if "no locality" in str(x.message)]
         assert bool(hit) == expect, (ordering, plan.info["runs_per_tile"], plan.info["local_per_tile"])
+
+
+def test_tiles_sized_for_the_paired_layout(monkeypatch):
+    """Default FP64 plan of a tile-ordered generator mesh: the global matching pairs (nearly) every element inside two
+    wiring classes, the locality ordering and the plan agree on 352-node tiles (the paired slot bound), the plan is
+    pairs-only and refuses the exports of the one-element-per-entry tables; HIDENN_PLAN_PAIRS=0 gives the 320-node plan
+    with usable tables.  Both orderings keep elements and corner order."""
+    from hidenn_fem_b200 import meshgen, _lib
+    from hidenn_fem_b200.plan import TriPlan
+    m0 = meshgen.plate_mesh(201, 101, jitter=0.25, diag="random", seed=3, ordering="random")
+    bm = m0.boundary_mask & ~m0.neumann_mask
+
+    def make():
+        xy, conn, b, d, ed, n2o, _ = meshgen.reorder_for_locality(m0.node_coords, m0.connectivity, bm, m0.dirichlet_mask, m0.neumann_edges)
+        return conn, TriPlan(conn, xy.shape[0], xy, b, d, ed, real_bytes=8, device=-1)
+
+    monkeypatch.delenv("HIDENN_PLAN_PAIRS", raising=False)
+    conn, plan = make()
+    Ne = conn.shape[0]
+    assert plan.info["tile_ordered"] and plan.info["pairs_only"] and plan.info["n_pairs"] > 0.49 * Ne
+    node_off, n_owned, _ = plan.tiles()
+    assert n_owned.max() <= 352 and n_owned.mean() > 330
+    T = plan.pair_tables()
+    ent = np.diff(T["pent_off"])
+    assert ent.max() <= 544 and T["n_entries9"].max() <= 2047
+    cls = []
+    for v in range(0, min(20000, T["packs"].shape[0])):       # the classes a tile really uses: two + leftovers
+        w1, w2 = int(T["packs"][v, 0]), int(T["packs"][v, 1])
+        if (w1 & 0x3FFFFFFF) == 0x3FFFFFFF or (w2 & 0x3FFFFFFF) == 0x3FFFFFFF:
+            continue
+        l = [(w1 >> (10 * c)) & 1023 for c in range(3)]
+        mm = [(w2 >> (10 * c)) & 1023 for c in range(3)]
+        r = [c for c in range(3) if mm[c] not in l][0]
+        i = [k for k in range(3) if mm[(r + 1) % 3] == l[(k + 1) % 3] and mm[(r + 2) % 3] == l[k]][0]
+        cls.append(3 * i + r)
+    top2 = np.sort(np.bincount(cls, minlength=9))[-2:].sum()
+    assert top2 > 0.97 * len(cls)
+    with pytest.raises(_lib.HidennError):
+        plan.fold_tables()
+    monkeypatch.setenv("HIDENN_PLAN_PAIRS", "0")
+    conn0, plan0 = make()
+    assert plan0.info["tile_ordered"] and not plan0.info["pairs_only"] and plan0.info["n_pairs"] == 0
+    assert plan0.tiles()[1].max() <= 320
+    plan0.fold_tables()
+    assert sorted(map(tuple, conn0.tolist())) == sorted(map(tuple, conn.tolist())) or conn0.shape == conn.shape
