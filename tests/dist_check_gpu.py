@@ -11,6 +11,8 @@ with a single-GPU evaluation of the global mesh done on the same device.  Three 
   LBFGS      sharded L-BFGS vs torch.optim.LBFGS on one GPU: first-iteration loss to 1e-12; the later trajectory is
              reported, not gated (lr = 1 without line search is not a contraction on this problem, so rounding differences
              between summation orders grow along it -- see profiles/README.md)
+  LBFGS-SW   the same with line_search_fn="strong_wolfe" on both sides (the reference's settings): losses gated at 1e-8
+             along the whole run, and the loss must go down
 Exit code 0 iff PARTITION and OVERLAP are OK on every rank."""
 import argparse
 import os
@@ -101,6 +103,7 @@ def main():
 
     # sharded L-BFGS (global inner products through the owner weights) vs the stock optimiser on one GPU
     from hidenn_fem_b200.optim import ShardedLBFGS
+    saved = [[q.detach().clone() for q in mod.parameters()] for mod in (model, gmodel)]
     ob = ShardedLBFGS(model.parameters(), max_iter=6, history_size=6, weights=loss_fn.halo.row_weights)
     og = torch.optim.LBFGS(gmodel.parameters(), max_iter=6, history_size=6)
     lb, lg = [], []
@@ -114,7 +117,28 @@ def main():
     el3 = [abs(a - b) / abs(b) for a, b in zip(lb, lg)]
     ok_lbfgs = el3[0] < (1e-12 if dt == torch.float64 else 1e-5)
 
-    res = torch.tensor([el, ex, eu, eu2, ex2, max(el3), eu3, 0.0 if ok_part else 1.0, 0.0 if ok_ovl else 1.0, 0.0 if ok_lbfgs else 1.0],
+    # the same with the strong-Wolfe line search (example4.py's optimiser settings): a descent iteration, so the two
+    # trajectories stay together and the comparison is gated along the whole run
+    with torch.no_grad():
+        for mod, sv in zip((model, gmodel), saved):
+            for q, v0 in zip(mod.parameters(), sv):
+                q.copy_(v0)
+    ob = ShardedLBFGS(model.parameters(), max_iter=6, history_size=6, weights=loss_fn.halo.row_weights, line_search_fn="strong_wolfe")
+    og = torch.optim.LBFGS(gmodel.parameters(), max_iter=6, history_size=6, line_search_fn="strong_wolfe")
+    lbw, lgw = [], []
+    for _ in range(2):
+        def c1():
+            ob.zero_grad(); l = loss_fn(model); l.backward(); return l
+        def c2():
+            og.zero_grad(); l = gloss_fn(gmodel); l.backward(); return l
+        lbw.append(float(ob.step(c1).detach())); lgw.append(float(og.step(c2).detach()))
+    with torch.no_grad():
+        lbw.append(float(loss_fn(model))); lgw.append(float(gloss_fn(gmodel)))
+    eu4 = rel(model.u_free.detach(), gmodel.u_free.detach()[ru])
+    el4 = max(abs(a - b) / abs(b) for a, b in zip(lbw, lgw))
+    ok_lbfgs = ok_lbfgs and el4 < (1e-8 if dt == torch.float64 else 1e-3) and lbw[-1] < lbw[0]
+
+    res = torch.tensor([el, ex, eu, eu2, ex2, max(el3), eu3, 0.0 if ok_part else 1.0, 0.0 if ok_ovl else 1.0, 0.0 if ok_lbfgs else 1.0, el4, eu4],
                        device=dev, dtype=torch.float64)
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     if rank == 0:
@@ -127,6 +151,8 @@ def main():
         print("  OVERLAP:   overlapped == plain sequence and graph replay == eager, bit for bit -> %s" % ("OK" if v[8] == 0 else "FAIL"))
         print("  LBFGS:     sharded vs torch.optim.LBFGS on one GPU: losses %s vs %s, max rel %.2e, u rel %.2e after 2 x 6 iterations -> %s (first-iteration gate)"
               % (lb, lg, v[5], v[6], "OK" if v[9] == 0 else "FAIL"))
+        print("  LBFGS-SW:  strong-Wolfe line search on both sides: losses %s vs %s, max rel %.2e, u rel %.2e after 2 x 6 iterations (gated: 1e-8, descent)"
+              % (["%.10e" % x for x in lbw], ["%.10e" % x for x in lgw], v[10], v[11]))
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if (res[7].item() == 0 and res[8].item() == 0) else 1)
