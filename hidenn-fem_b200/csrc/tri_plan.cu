@@ -928,7 +928,9 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
                 if (owned_id(c32[3 * (int64_t)e]) >= 0) w |= 1ull << kOwnerBit;
                 B.pack[i] = w;
             }
-            reorder_for_banks(B, real_bytes);
+            // (a plan with the paired layout runs kernel v9 on the pair entries: its one-element packs serve only the
+            // energy-only kernel and the fall-backs, and are left in element order)
+            if (!(pairs_on && tile_order)) reorder_for_banks(B, real_bytes);
             if (tile_order && Ned > 0) {
                 // Neumann edge visits: every edge with an owned end; the partial of an owned end goes to the slot after
                 // the node's element slots (rank among the node's edge ends), a halo end to the dump slot
