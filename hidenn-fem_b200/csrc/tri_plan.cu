@@ -329,10 +329,13 @@ struct EdgeEnds {       // Neumann edge ends by node: (node, edge*2+end), sorted
 
 // Global matching of the elements into edge-sharing pairs whose partners run through the shared edge in opposite
 // directions (tri_plan.h).  Depends only on the mesh (connectivity + node->element lists), never on the tiling.
-// HIDENN_PLAN_PAIRS: unset = automatic (kept when at least 80 % of the elements find a partner), 0 = never, 1 = always.
+// HIDENN_PLAN_PAIRS: unset = automatic (kept when at least 80 % of the elements find a partner inside at most three wiring
+// classes), 0 = never, 1 = always.
 // Returns the number of pairs; `mate` stays empty when the paired layout is not used.
-static int64_t match_elements(const int32_t* c32g, int64_t Ne, const int64_t* n2o, const int32_t* n2e, std::vector<int32_t>& mate) {
+static int64_t match_elements(const int32_t* c32g, int64_t Ne, const int64_t* n2o, const int32_t* n2e, std::vector<int32_t>& mate,
+                              int* n_classes_out = nullptr) {
     mate.clear();
+    if (n_classes_out) *n_classes_out = 0;
     const char* pairs_env = getenv("HIDENN_PLAN_PAIRS");
     const bool want_pairs = pairs_env == nullptr || atoi(pairs_env) != 0;
     const bool force_pairs = pairs_env != nullptr && atoi(pairs_env) != 0;
@@ -422,12 +425,39 @@ static int64_t match_elements(const int32_t* c32g, int64_t Ne, const int64_t* n2
             n_pairs += greedy(1u << cls, Ne, mate);
             ++used;
         }
-        if (!force_pairs && n_pairs * 10 < Ne * 4) {      // too few partners: one element per entry
+        // classes that hold at least 1 % of the pairs: each costs a tile up to 31 padding entries and the kernel one more
+        // wiring to keep in the instruction cache
+        int n_classes = 0;
+        {
+            int64_t cnt[9] = {};
+            for (int64_t e = 0; e < Ne; ++e)
+                if (mate[e] > e)
+                    for (int c = 0; c < 3; ++c)
+                        if (nb[3 * e + c] >= 0 && (nb[3 * e + c] >> 2) == mate[e]) { cnt[cls_of(e, c)]++; break; }
+            for (int c = 0; c < 9; ++c) n_classes += (cnt[c] * 100 >= n_pairs && cnt[c] > 0) ? 1 : 0;
+        }
+        if (n_classes_out) *n_classes_out = n_classes;
+        // Automatic mode keeps the paired layout only where it wins: at least 80 % of the elements paired, inside at most
+        // three classes.  Measured on B200 (C4 geometry, 10 M elements): generator mesh (two classes) 147 us paired /
+        // 173 us one element per entry; the same mesh with every element's corners rotated at random (all nine classes,
+        // 240-node tiles) 284 us paired / 176 us one element per entry.
+        if (!force_pairs && (n_pairs * 10 < Ne * 4 || n_classes > 3)) {
             mate.clear();
             n_pairs = 0;
         }
     }
     return n_pairs;
+}
+
+// Owned nodes per tile for the paired layout: a tile of T nodes visits ~2.25 T elements, i.e. ~2.25 T (1 - pf / 2) entries
+// when a fraction pf of the elements is paired (a few per cent more: partners the tile does not visit), plus ~16 padding
+// entries per class and for the singles; the entries should
+// fill the 512 element lanes of kernel v9 in ONE pass (352 nodes for a generator mesh with two classes, ~290 when the
+// corner order is random and all nine classes occur).
+static int pairs_tile_nodes(int64_t Ne, int64_t n_pairs, int n_classes) {
+    const double pf = Ne > 0 ? 2.0 * (double)n_pairs / (double)Ne : 0.0;
+    const double t = (500.0 - 16.0 * (n_classes + 1)) / (2.25 * (1.0 - 0.5 * pf + 0.06));      // + 6 %: partners outside the tile
+    return (int)std::max(128.0, std::min((double)kDefaultTileNodesPairs, t)) / 8 * 8;
 }
 
 // fold slots of node n in the paired layout: one per incident element whose partial is not merged into its (smaller-id)
@@ -498,8 +528,10 @@ extern "C" int hidenn_tri_locality_order(const int64_t* conn, int64_t Ne, int64_
     ee.build(edges, Ned);
     // the same global matching the plan will compute: with it the tiles are sized for the paired layout
     std::vector<int32_t> mate;
-    if (!getenv("HIDENN_PLAN_NO_V8")) match_elements(c32.data(), Ne, n2o.data(), n2e.data(), mate);
-    if (!mate.empty() && !tile_nodes_given) tile_nodes = kDefaultTileNodesPairs;
+    int n_classes = 0;
+    int64_t n_pairs_lo = 0;
+    if (!getenv("HIDENN_PLAN_NO_V8")) n_pairs_lo = match_elements(c32.data(), Ne, n2o.data(), n2e.data(), mate, &n_classes);
+    if (!mate.empty() && !tile_nodes_given) tile_nodes = pairs_tile_nodes(Ne, n_pairs_lo, n_classes);
     std::vector<int32_t> slots(Nn);
     for (int64_t n = 0; n < Nn; ++n) {
         auto r = ee.of((int32_t)n);
@@ -723,9 +755,10 @@ extern "C" int hidenn_tri_plan_create_ex(const int64_t* conn, int64_t Ne, int64_
     // depends only on the mesh, so hidenn_tri_locality_order computes the same one and sizes the tiles by it.
     const int32_t* c32g = p->conn32.data();
     auto elem_has = [c32g](int32_t f, int32_t n) { return c32g[3 * (int64_t)f] == n || c32g[3 * (int64_t)f + 1] == n || c32g[3 * (int64_t)f + 2] == n; };
-    if (real_bytes == 8 && !no_v8 && Ne > 0) p->n_pairs = match_elements(c32g, Ne, p->n2e_off.data(), p->n2e_ent.data(), p->mate);
+    int n_classes = 0;
+    if (real_bytes == 8 && !no_v8 && Ne > 0) p->n_pairs = match_elements(c32g, Ne, p->n2e_off.data(), p->n2e_ent.data(), p->mate, &n_classes);
     bool pairs_on = !p->mate.empty();
-    if (pairs_on && !tile_nodes_given) tile_nodes = kDefaultTileNodesPairs;
+    if (pairs_on && !tile_nodes_given) tile_nodes = pairs_tile_nodes(Ne, p->n_pairs, n_classes);
 
     // RCB tiling of the nodes
     int64_t n_tiles = 0;

@@ -28,6 +28,17 @@ def run_one():
     import torch, bench
     args = bench.parse()
     dev = torch.device("cuda:0")
+    if os.environ.get("ABLATE_ROTATE"):      # every element's corners rotated at random: all nine pair classes occur (gmsh-like)
+        import numpy as np
+        from hidenn_fem_b200 import meshgen
+        orig = meshgen.plate_mesh
+
+        def rotated(*a, **k):
+            mm = orig(*a, **k)
+            rot = np.random.default_rng(0).integers(0, 3, mm.connectivity.shape[0])
+            mm.connectivity = np.take_along_axis(mm.connectivity, (np.arange(3)[None, :] + rot[:, None]) % 3, axis=1)
+            return mm
+        meshgen.plate_mesh = rotated
     m, model, loss_fn, _ = bench.make_workload(args, 0, 1, dev, torch.float64, "tiles", args.elems, args.tile_nodes)
     ms = min(bench.time_kernel(model, loss_fn, 20, 5) for _ in range(3))
     info = model._plan().info

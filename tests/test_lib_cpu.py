@@ -457,3 +457,12 @@ def test_tiles_sized_for_the_paired_layout(monkeypatch):
     assert plan0.tiles()[1].max() <= 320
     plan0.fold_tables()
     assert sorted(map(tuple, conn0.tolist())) == sorted(map(tuple, conn.tolist())) or conn0.shape == conn.shape
+    # every element's corners rotated at random (what an arbitrary mesher hands over): all nine classes occur, the padding
+    # and the nine wirings cost more than the pairs save (measured), so the automatic mode keeps one element per entry
+    monkeypatch.delenv("HIDENN_PLAN_PAIRS", raising=False)
+    rot = np.random.default_rng(0).integers(0, 3, m0.connectivity.shape[0])
+    crot = np.take_along_axis(m0.connectivity, (np.arange(3)[None, :] + rot[:, None]) % 3, axis=1)
+    xy, c2, b, d, ed, _, _ = meshgen.reorder_for_locality(m0.node_coords, crot, bm, m0.dirichlet_mask, m0.neumann_edges)
+    plan9 = TriPlan(c2, xy.shape[0], xy, b, d, ed, real_bytes=8, device=-1)
+    assert plan9.info["tile_ordered"] and not plan9.info["pairs_only"] and plan9.info["n_pairs"] == 0
+    assert plan9.tiles()[1].max() <= 320
