@@ -152,10 +152,15 @@ def make_workload(args, rank, world, device, dtype, ordering, n_elems_per_gpu, t
     splits = balanced_splits(nx, ny, world, meshgen.DEFAULT_HOLES)
     # "tiles": generator output (Z-curve numbered, cheap to build) passed through the ingestion helper;
     # "random+reorder": the same helper on a randomly numbered mesh (what a gmsh mesh looks like)
-    gen_order = {"tiles": "morton", "random+reorder": "random"}.get(ordering, ordering)
+    # "tiles+rotated": every element's corners rotated at random (an arbitrary mesher's corner order: all nine pair classes
+    # occur, so the plan keeps one element per entry -- DESIGN.md 3.1)
+    gen_order = {"tiles": "morton", "random+reorder": "random", "tiles+rotated": "morton"}.get(ordering, ordering)
     m = meshgen.plate_mesh(nx, ny, jitter=0.25, diag="random", seed=0, ordering=gen_order,
                            col_range=(splits[rank], splits[rank + 1]))
-    if ordering in ("tiles", "random+reorder"):
+    if ordering == "tiles+rotated":
+        rot = np.random.default_rng(0).integers(0, 3, m.connectivity.shape[0])
+        m.connectivity = np.take_along_axis(m.connectivity, (np.arange(3)[None, :] + rot[:, None]) % 3, axis=1)
+    if ordering in ("tiles", "random+reorder", "tiles+rotated"):
         m = meshgen.reorder_mesh(m, mode="tiles", tile_nodes=tile_nodes)
     T = torch.tensor
     torch.manual_seed(0)
@@ -601,7 +606,7 @@ def main():
                 "traffic": None, "kernel": {9: ("tri_tile9_kernel<double> (warp-specialised: 16 element warps on edge-sharing element pairs, "
                                                 "6 fold warps, 2 loader warps; bulk-copy stage ring; tile-ordered numbering)"
                                                 if plan.info.get("n_pairs", 0) > 0 else
-                                                "tri_tile9_kernel<double> (warp-specialised: 12 element warps, 10 fold warps, 2 loader warps; "
+                                                "tri_tile9_kernel<double> (warp-specialised, one element per entry: 12 element warps, 10 fold warps, 2 loader warps; "
                                                 "bulk-copy stage ring; tile-ordered numbering)"),
                                             8: "tri_tile8_kernel<double> (two CTAs per SM, bulk-copy staging; tile-ordered numbering)"}.get(
                                                 plan.info.get("kernel"), "tri_tile_persistent_kernel<%s>" % ("double" if sz == 8 else "float")),
@@ -650,6 +655,7 @@ def main():
         for tag, dt2, ordr in (("f64_morton", torch.float64, "morton"), ("f64_natural", torch.float64, "natural"),
                                ("f64_random_numbering", torch.float64, "random"),
                                ("f64_random_numbering_after_reorder_for_locality", torch.float64, "random+reorder"),
+                               ("f64_tiles_corners_rotated_at_random", torch.float64, "tiles+rotated"),
                                ("f32_tiles", torch.float32, "tiles"), ("f32_morton", torch.float32, "morton")):
             del model, loss_fn
             torch.cuda.empty_cache()
