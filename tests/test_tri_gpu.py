@@ -573,6 +573,58 @@ def test_paired_layout_opt_in(monkeypatch):
     assert relmax(model.u_free.grad.cpu().numpy(), dU[um]) < 1e-10
 
 
+def test_all_nine_pair_wirings_vs_oracle(monkeypatch):
+    """Every element's corners rotated at random: all nine (edge of the first element, position of the new corner in the
+    second) classes occur.  Forced paired layout (the automatic mode would keep one element per entry here): each of the
+    kernel's nine compile-time wirings is checked against the oracle at the FP64 contract tolerance, and the automatic
+    plan of the same mesh (one element per entry) gives the same numbers."""
+    from hidenn_fem_b200 import meshgen
+    g = _mesh_case(60_000, torch.float64, "natural", u_scale=1e-3)
+    rot = np.random.default_rng(3).integers(0, 3, g["connectivity"].shape[0])
+    g["connectivity"] = np.take_along_axis(g["connectivity"], (np.arange(3)[None, :] + rot[:, None]) % 3, axis=1)
+    g0 = g
+    results = []
+    for forced in (True, False):
+        if forced:
+            monkeypatch.setenv("HIDENN_PLAN_PAIRS", "1")
+        else:
+            monkeypatch.delenv("HIDENN_PLAN_PAIRS", raising=False)
+        # the numbering is made under the same setting as the plan (both size their tiles by the same matching)
+        xy, conn, bm, dm, ed, n2o, _ = meshgen.reorder_for_locality(g0["node_coords"], g0["connectivity"], g0["boundary_mask"],
+                                                                    g0["dirichlet_mask"], g0["neumann_edges"])
+        u_old = 1e-3 * np.random.default_rng(0).standard_normal((g0["node_coords"].shape[0], 2))      # per ORIGINAL node
+        u_new = u_old[n2o]
+        g = dict(g0, node_coords=xy, connectivity=conn, boundary_mask=bm, dirichlet_mask=dm, neumann_edges=ed,
+                 node_coords_free=xy[~bm], node_coords_fixed=xy[bm], u_free=u_new[~dm])
+        lo, gx, gu = tri_oracle(g, "default", dtype=np.float64)
+        model = build(g)
+        info = model._plan().info
+        assert info["tile_ordered"] and (info["n_pairs"] > 0) == forced
+        if forced:
+            T = model._plan().pair_tables()
+            seen = set()
+            for v in range(T["packs"].shape[0]):
+                w1, w2 = int(T["packs"][v, 0]), int(T["packs"][v, 1])
+                if (w1 & 0x3FFFFFFF) == 0x3FFFFFFF or (w2 & 0x3FFFFFFF) == 0x3FFFFFFF:
+                    continue
+                l = [(w1 >> (10 * c)) & 1023 for c in range(3)]
+                mm = [(w2 >> (10 * c)) & 1023 for c in range(3)]
+                r = [c for c in range(3) if mm[c] not in l][0]
+                i = [k for k in range(3) if mm[(r + 1) % 3] == l[(k + 1) % 3] and mm[(r + 2) % 3] == l[k]][0]
+                seen.add(3 * i + r)
+                if len(seen) == 9:
+                    break
+            assert seen == set(range(9))
+        loss_fn = loss_of(g, torch.float64)
+        loss = loss_fn(model)
+        loss.backward()
+        assert abs(loss.item() - float(lo)) <= 1e-10 * abs(float(lo))
+        assert relmax(model.node_coords_free.grad.cpu().numpy(), gx) < 1e-10
+        assert relmax(model.u_free.grad.cpu().numpy(), gu) < 1e-10
+        results.append((loss.item(), model.node_coords_free.grad.clone(), model.u_free.grad.clone()))
+    assert abs(results[0][0] - results[1][0]) <= 1e-12 * abs(results[1][0])
+
+
 @pytest.mark.parametrize("numbering", ["as_is", "tiles"])
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 def test_correct_math_switches(numbering, dtype):
