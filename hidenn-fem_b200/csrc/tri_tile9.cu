@@ -205,10 +205,6 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kERegs));
         const TriConsts<R> K = load_consts<R, BODY>(consts);
         const bool with_edges = (flags & HIDENN_WITH_EDGES) != 0;
-#ifdef HIDENN_WS_STAGGER
-        // measurement switch: de-phase the element warps of a scheduler once, at the start
-        if ((wid >> 2) > 0) asm volatile("nanosleep.u32 %0;" ::"r"((unsigned)((wid >> 2) * HIDENN_WS_STAGGER)));
-#endif
         const int etid = tid;
         PROF_DECL;
         int st = 0;
@@ -383,12 +379,6 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
 #ifndef HIDENN_WS_LPOS
 #define HIDENN_WS_LPOS 4
 #endif
-#ifndef HIDENN_WS_FROT
-#define HIDENN_WS_FROT 0
-#endif
-#ifndef HIDENN_WS_FOLD2N
-#define HIDENN_WS_FOLD2N 0
-#endif
         // (one element per entry: loaders on warps 12, 13 = schedulers 0, 1, and the fold warps that take the nodes with the
         // most slots on schedulers 2, 3, whose element warps run out of second-pass entries first: 172.6 -> 166.2 us)
 #ifndef HIDENN_WS_LPOS_SINGLE
@@ -485,45 +475,11 @@ tri_tile9_kernel(const TriPlanDev P, const TriPlan8Dev P8, const double2* __rest
                 PROF_WAIT(pf_b, bar_wait(&part_full[pb], (k >> 1) & 1, kSleepShort))
                 const int n_owned = d->n_owned, nA = d->nA, nAB = nA + d->nB, nBC = d->nB + d->nC, nABC = nAB + d->nC;
                 const int rx = d->rx_free, ru = d->ru_free;
-                // one node per thread and pass, two slots in flight per step (summed pairwise: acc += (s_q + s_q+1)).  More
-                // loads in flight (two nodes per thread, four slots) make the WHOLE kernel slower: the fold warps have slack,
-                // the element warps do not, and both share the SM's load/store pipe (profiles/README.md)
-                // (HIDENN_WS_FROT: measurement switch -- the fold warps that take the short last pass)
-#if HIDENN_WS_FOLD2N
-                // two nodes per thread side by side (l and l + fold threads), one slot of each per step
-                if (PAIRS) {
-                    for (int l = ftid; l < n_owned; l += 2 * kFWarps * 32) {
-                        const int lb = l + kFWarps * 32;
-                        const bool hb = lb < n_owned;
-                        const uint32_t oa = s_off[l], ob = hb ? s_off[lb] : 0u;
-                        unsigned qa = oa & 0xFFFFu, qb = ob & 0xFFFFu;
-                        const unsigned ea = qa + (oa >> 16) * G, eb = qb + (ob >> 16) * G;
-                        R aax = R(0), aay = R(0), abx = R(0), aby = R(0), bax = R(0), bay = R(0), bbx = R(0), bby = R(0);
-#pragma unroll 1
-                        while (qa < ea || qb < eb) {
-                            R2 ua = mk2<R>(R(0), R(0)), xa = ua, ub = ua, xb = ua;
-                            if (qa < ea) { ua = lds_pair(part.pu + qa); xa = lds_pair(part.px + qa); }
-                            if (qb < eb) { ub = lds_pair(part.pu + qb); xb = lds_pair(part.px + qb); }
-                            aax += ua.x; aay += ua.y; abx += xa.x; aby += xa.y;
-                            bax += ub.x; bay += ub.y; bbx += xb.x; bby += xb.y;
-                            qa += G; qb += G;
-                        }
-                        if (need_gu && l < nAB) gu_free[ru + l] = mk2<R>(aax, aay);
-                        if (need_gx && (l < nA || l >= nABC)) gx_free[rx + (l < nA ? l : l - nBC)] = mk2<R>(abx, aby);
-                        if (hb) {
-                            if (need_gu && lb < nAB) gu_free[ru + lb] = mk2<R>(bax, bay);
-                            if (need_gx && (lb < nA || lb >= nABC)) gx_free[rx + (lb < nA ? lb : lb - nBC)] = mk2<R>(bbx, bby);
-                        }
-                    }
-                } else
-#endif
-#if HIDENN_WS_FROT
-                for (int l0 = 0, pass = 0; l0 < n_owned; l0 += kFWarps * 32, ++pass) {
-                    const int l = l0 + ((PAIRS && pass == 1) ? (ftid + HIDENN_WS_FROT * 32) % (kFWarps * 32) : ftid);
-                    if (l >= n_owned) continue;
-#else
+                // one node per thread and pass, ONE slot (its u and x pair) in flight per step.  More loads in flight make the
+                // WHOLE kernel slower: the fold warps have slack, the element warps do not, and both queue at the SM's
+                // load/store pipe (two slots +2 %, two nodes side by side +24 %; one load at a time is too slow, +10 %;
+                // even the same loop written with a pass counter cost 4 % -- profiles/README.md)
                 for (int l = ftid; l < n_owned; l += kFWarps * 32) {
-#endif
                     const uint32_t oc = s_off[l];
 #if HIDENN_ABL == 0
                     const unsigned fb = oc & 0xFFFFu, fe = fb + (oc >> 16) * G;
